@@ -1,0 +1,275 @@
+/*
+ * ngp_b200.h -- C ABI of libngp_b200.so: the sm_100a (B200) implementation of
+ * raw_ngp's data-parallel NeRF hot path.
+ *
+ * Every entry point replaces one native function that the reference binds through
+ * pybind11 (gridencoder/src/bindings.cpp:5-10, raymarching/src/bindings.cpp:5-20,
+ * shencoder/src/bindings.cpp:5-8); the reference declaration it stands in for is cited
+ * above each prototype as  <file>:<line>  relative to the reference tree.
+ *
+ * Conventions (differences from the reference's at::Tensor interface):
+ *   - plain device pointers + sizes; the caller owns and allocates every buffer, the
+ *     library allocates nothing and keeps no state (re-entrant, thread-safe);
+ *   - every call takes the CUDA stream to launch on (the reference always used the
+ *     legacy default stream) as an opaque pointer (cudaStream_t);
+ *   - every call returns NGP_OK (0) or a negative NGP_ERR_* code and never throws;
+ *     launch errors are collected with cudaPeekAtLastError() (the reference never checked);
+ *   - `dtype` selects the element type of hash-table-typed buffers: NGP_F32 / NGP_F16 /
+ *     NGP_BF16 (the reference dispatched float/double/half from the tensor; double is
+ *     not provided, bf16 is new).  Ray-marching and SH buffers are always fp32: the
+ *     reference wrappers cast them with custom_fwd(cast_inputs=float32)
+ *     (raymarching/raymarching.py:34,254,336,399,450; shencoder/sphere_harmonics.py:16).
+ *   - layouts are the *user-visible* layouts of the Python operators, so the wrappers do
+ *     no permute copies: encoder outputs and their gradients are [B, L*C] (the reference
+ *     kernel used [L,B,C] and the wrapper permuted, gridencoder/grid.py:49,63,81).
+ */
+#ifndef NGP_B200_H
+#define NGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_B200_ABI_VERSION 1
+
+typedef void* ngp_stream_t; /* cudaStream_t */
+
+enum ngp_dtype { NGP_F32 = 0, NGP_F16 = 1, NGP_BF16 = 2 };
+
+enum ngp_status {
+    NGP_OK = 0,
+    NGP_ERR_BAD_DTYPE = -1,   /* dtype not one of ngp_dtype                               */
+    NGP_ERR_UNSUPPORTED = -2, /* D not in {2,3} / C not in {1,2,4,8} / degree not in 1..8  */
+    NGP_ERR_NULL = -3,        /* required pointer is NULL                                 */
+    NGP_ERR_ALIGN = -4,       /* pointer not aligned for the vector width of the kernel   */
+    NGP_ERR_CUDA = -5,        /* cudaPeekAtLastError() != cudaSuccess after the launch    */
+    NGP_ERR_BAD_ARG = -6      /* size / flag out of range                                 */
+};
+
+/* library identity */
+int ngp_abi_version(void);
+const char* ngp_status_string(int status);
+/* last CUDA error string seen by this thread's most recent failing call ("" if none) */
+const char* ngp_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Grid encoder  (reference: gridencoder/src/gridencoder.h:12-15)
+ * ---------------------------------------------------------------------------------------- */
+
+/* flags for ngp_grid_encode_forward / backward */
+#define NGP_GRID_REF_ROUNDING 1u /* fp16 tables: accumulate in half exactly like the reference
+                                    (gridencoder.cu:168,191); without it: fp32 accumulate, one rounding */
+
+/* replaces grid_encode_forward            gridencoder/src/gridencoder.h:12, gridencoder.cu:467-490
+ * inputs      [B, D]       fp32 in [0,1]
+ * embeddings  [sO, C]      dtype
+ * offsets     [L+1]        int32
+ * outputs     [B, L*C]     dtype   (levels >= max_level are written as zeros)
+ * dy_dx       [B, L*D*C]   dtype or NULL  (same layout as the reference's dy_dx, gridencoder.cu:207)
+ */
+int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                            void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                            uint32_t max_level, float S, uint32_t H, void* dy_dx,
+                            uint32_t gridtype, int align_corners, uint32_t interp,
+                            int dtype, uint32_t flags, ngp_stream_t stream);
+
+/* replaces grid_encode_backward           gridencoder/src/gridencoder.h:13, gridencoder.cu:492-522
+ * grad             [B, L*C]  dtype
+ * grad_embeddings  [sO, C]   dtype, must be zero-filled by the caller (as gridencoder/grid.py:83)
+ * grad_inputs      [B, D]    fp32 or NULL; must be zero-filled by the caller.  It is recomputed
+ *                            from the table (fuses kernel_input_backward, gridencoder.cu:352-378,
+ *                            without the [B, L*D*C] dy_dx round trip).
+ */
+int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                             const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D,
+                             uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                             float* grad_inputs, uint32_t gridtype, int align_corners,
+                             uint32_t interp, int dtype, uint32_t flags, ngp_stream_t stream);
+
+/* reference-layout variant of the input gradient: grad_inputs[b,d] = sum_{l,c} grad[b,l,c]*dy_dx[b,l,d,c]
+ * replaces kernel_input_backward          gridencoder.cu:352-378 (called from :421-441)
+ * grad [B, L*C] dtype, dy_dx [B, L*D*C] dtype, grad_inputs [B, D] fp32 (overwritten) */
+int ngp_grid_input_backward(const void* grad, const void* dy_dx, float* grad_inputs, uint32_t B,
+                            uint32_t D, uint32_t C, uint32_t L, int dtype, ngp_stream_t stream);
+
+/* replaces grad_total_variation           gridencoder/src/gridencoder.h:14, gridencoder.cu:525-668
+ * inputs [B, D] dtype (the reference reads inputs as table dtype, gridencoder.cu:666), in [0,1];
+ * grad [sO, C] dtype is accumulated in place. */
+int ngp_grid_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                                  const int32_t* offsets, float weight, uint32_t B, uint32_t D,
+                                  uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                  int align_corners, int dtype, ngp_stream_t stream);
+
+/* replaces grad_weight_decay              gridencoder/src/gridencoder.h:15, gridencoder.cu:670-713
+ * n_entries = embeddings.shape[0] (the reference calls it B) */
+int ngp_grid_grad_weight_decay(const void* embeddings, void* grad, const int32_t* offsets,
+                               float weight, uint32_t n_entries, uint32_t C, uint32_t L, int dtype,
+                               ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spherical-harmonics encoder  (reference: shencoder/src/shencoder.h:9-10)
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces sh_encode_forward              shencoder/src/shencoder.h:9, shencoder.cu:400-417
+ * inputs [B,3] fp32, outputs [B, degree^2] fp32, dy_dx [B, 3*degree^2] fp32 or NULL
+ * out_dtype: NGP_F32 (reference behaviour) or NGP_F16/NGP_BF16 to emit the encoding directly in the
+ * MLP's activation type (dy_dx stays fp32). */
+int ngp_sh_encode_forward(const float* inputs, void* outputs, uint32_t B, uint32_t degree,
+                          float* dy_dx, int out_dtype, ngp_stream_t stream);
+
+/* replaces sh_encode_backward             shencoder/src/shencoder.h:10, shencoder.cu:419-439
+ * grad [B, degree^2] (grad_dtype), inputs [B,3] fp32.  The derivative basis is recomputed from
+ * `inputs` (no saved dy_dx); grad_inputs [B,3] fp32 is *accumulated into* like the reference
+ * (shencoder.cu:377-379), so the caller zero-fills it (shencoder/sphere_harmonics.py:50). */
+int ngp_sh_encode_backward(const void* grad, const float* inputs, uint32_t B, uint32_t degree,
+                           float* grad_inputs, int grad_dtype, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ray marching utilities  (reference: raymarching/src/raymarching.h:7-12)
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces near_far_from_aabb             raymarching/src/raymarching.h:7, raymarching.cu:91-156 */
+int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                           float min_near, float* nears, float* fars, ngp_stream_t stream);
+
+/* replaces sph_from_ray                   raymarching/src/raymarching.h:8, raymarching.cu:162-209 */
+int ngp_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N,
+                     float* coords, ngp_stream_t stream);
+
+/* replaces morton3D                       raymarching/src/raymarching.h:9, raymarching.cu:214-232 */
+int ngp_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, ngp_stream_t stream);
+
+/* replaces morton3D_invert                raymarching/src/raymarching.h:10, raymarching.cu:237-260 */
+int ngp_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, ngp_stream_t stream);
+
+/* replaces packbits                       raymarching/src/raymarching.h:11, raymarching.cu:267-300
+ * grid [8*N] fp32, bitfield [N] uint8.  If thresh_dev != NULL the threshold is
+ * min(*thresh_dev, density_thresh) read on the device (renderer.py:892 without the .item() sync). */
+int ngp_packbits(const float* grid, uint32_t N, float density_thresh, const float* thresh_dev,
+                 uint8_t* bitfield, ngp_stream_t stream);
+
+/* replaces flatten_rays                   raymarching/src/raymarching.h:12, raymarching.cu:303-326 */
+int ngp_flatten_rays(const int32_t* rays, uint32_t N, uint32_t M, int32_t* res, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training march / composite  (reference: raymarching/src/raymarching.h:14-16)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Pass 1 of march_rays_train              raymarching/src/raymarching.h:14, raymarching.cu:337-508
+ * (the reference calls its kernel with xyzs == nullptr, raymarching/raymarching.py:301).
+ * Writes rays[n,1] = sample count of ray n, then rays[n,0] = exclusive prefix sum of the counts in
+ * ray order (a legal outcome of the reference's atomicAdd(counter) and the only one its backward is
+ * correct for, raymarching/raymarching.py:325), and counter[0] = M = total samples.
+ * counter: int32[2] scratch, zero-filled by the caller ([1] is a block ticket). */
+int ngp_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                               float bound, int contract, float dt_gamma, uint32_t max_steps,
+                               uint32_t N, uint32_t C, uint32_t H, const float* nears,
+                               const float* fars, const float* noises, int32_t* rays,
+                               int32_t* counter, ngp_stream_t stream);
+
+/* Pass 2 of march_rays_train              raymarching.cu:337-508 with xyzs != nullptr
+ * (raymarching/raymarching.py:311).  xyzs/dirs [M,3], ts [M,2], ldirs [M,3] or NULL (with rays_ldir). */
+int ngp_march_rays_train_write(const float* rays_o, const float* rays_d, const float* rays_ldir,
+                               const uint8_t* grid, float bound, int contract, float dt_gamma,
+                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                               const float* nears, const float* fars, const float* noises,
+                               const int32_t* rays, uint32_t M, float* xyzs, float* dirs, float* ts,
+                               float* ldirs, ngp_stream_t stream);
+
+/* replaces composite_rays_train_forward   raymarching/src/raymarching.h:15, raymarching.cu:519-608
+ * weights [M] must be zero-filled by the caller (raymarching/raymarching.py:356). */
+int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ts,
+                                     const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                     float* weights, float* weights_sum, float* depth, float* image,
+                                     ngp_stream_t stream);
+
+/* replaces composite_rays_train_backward  raymarching/src/raymarching.h:16, raymarching.cu:623-723
+ * grad_sigmas [M], grad_rgbs [M,3] must be zero-filled by the caller (raymarching.py:382-383). */
+int ngp_composite_rays_train_backward(const float* grad_weights, const float* grad_weights_sum,
+                                      const float* grad_depth, const float* grad_image,
+                                      const float* sigmas, const float* rgbs, const float* ts,
+                                      const int32_t* rays, const float* weights_sum,
+                                      const float* depth, const float* image, uint32_t M, uint32_t N,
+                                      float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                      ngp_stream_t stream);
+
+/* Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329, which used
+ * torch_scatter.segment_csr): dL/drays_o[n] = sum_seg dL/dxyz ; dL/drays_d[n] = sum_seg (dL/dxyz * t + dL/ddirs).
+ * dL_ddirs may be NULL.  ts [M,2] (column 0 is used). */
+int ngp_march_rays_train_backward(const float* dL_dxyzs, const float* dL_ddirs, const float* ts,
+                                  const int32_t* rays, uint32_t N, uint32_t M, float* dL_drays_o,
+                                  float* dL_drays_d, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inference march / composite  (reference: raymarching/src/raymarching.h:18-19)
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces march_rays                     raymarching/src/raymarching.h:18, raymarching.cu:730-856
+ * xyzs/dirs [n_alive*n_step,3], ts [n_alive*n_step,2]; the kernel zero-fills the unwritten tail of
+ * every ray itself (the reference relied on torch.zeros, raymarching/raymarching.py:429-431). */
+int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, float bound, int contract, float dt_gamma,
+                   uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                   const float* nears, const float* fars, float* xyzs, float* dirs, float* ts,
+                   const float* noises, ngp_stream_t stream);
+
+/* replaces composite_rays                 raymarching/src/raymarching.h:19, raymarching.cu:859-950 */
+int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                       float* rays_t, const float* sigmas, const float* rgbs, const float* ts,
+                       float* weights_sum, float* depth, float* image, ngp_stream_t stream);
+
+/* Device-side stream compaction of rays_alive (replaces `rays_alive[rays_alive >= 0]`,
+ * nerf/renderer.py:612): writes the surviving ids, in order, to alive_out and their number to
+ * n_out[0].  n_out int32[1]. */
+int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* alive_out,
+                           int32_t* n_out, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Occupancy-grid update  (reference: nerf/renderer.py:811-897, Python loop over torch ops)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Sample positions for one cascade of update_extra_state (renderer.py:824-848 full / :854-876 partial).
+ * cell_indices == NULL : full update, cell n = n-th cell of the H^3 grid in x-major order (custom_meshgrid
+ *                        order of renderer.py:835), indices_out[n] = morton3D(coords);
+ * cell_indices != NULL : partial update, Morton indices given; coords = morton3D_invert(index).
+ * noise [n,3] uniform [0,1).  xyzs_out[n,3] = (2c/(H-1)-1)*(bound-hgs) + (2*noise-1)*hgs, hgs = bound/H. */
+int ngp_occ_sample_positions(const int32_t* cell_indices, const float* noise, uint32_t n, uint32_t H,
+                             float bound, float* xyzs_out, int32_t* indices_out, ngp_stream_t stream);
+
+/* EMA-max update of one cascade (renderer.py:848,883-885): for each i: j = indices[i];
+ * tmp[j] = sigmas[i] (last writer wins on duplicates, as torch index_put);  then for every cell with
+ * density_grid[j] >= 0 and tmp[j] >= 0: density_grid[j] = max(density_grid[j]*decay, tmp[j]).
+ * tmp_grid [H3] scratch is filled with -1 by the caller; this call does the scatter. */
+int ngp_occ_scatter_sigmas(const int32_t* indices, const float* sigmas, uint32_t n, float* tmp_grid,
+                           ngp_stream_t stream);
+/* density_grid/tmp_grid [n_cells]; mean_out[0] = mean(clamp(density_grid,min=0)) after the update
+ * (renderer.py:887).  mean_out fp32[1]; accum fp64[2] scratch (running sum + block ticket), 16-byte aligned
+ * and zero-filled by the caller. */
+int ngp_occ_ema_update(float* density_grid, const float* tmp_grid, uint32_t n_cells, float decay,
+                       double* accum, float* mean_out, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused optimizer over the flat parameter buffer (reference: torch.optim.Adam, main.py:245;
+ * GradScaler unscale + inf check, nerf/train_utils.py:897-904) -- SURVEY 8(f) row 1.
+ * ---------------------------------------------------------------------------------------- */
+
+/* One Adam step (eps outside sqrt, no amsgrad, L2 weight_decay folded into grad like torch) over n
+ * elements.  master/exp_avg/exp_avg_sq fp32; grad in grad_dtype, multiplied by *inv_scale_dev (device
+ * fp32, e.g. 1/(loss_scale*world_size)); if *found_inf_dev != 0 the step is skipped (GradScaler semantics).
+ * param_lp (optional, lp_dtype) receives the low-precision copy of the updated parameters; if
+ * zero_grad != 0 the gradient buffer is cleared in the same pass.  step = 1-based step count. */
+int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype,
+                   float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, uint32_t step, const float* inv_scale_dev,
+                   const float* found_inf_dev, int zero_grad, ngp_stream_t stream);
+
+/* found_inf_dev[0] = 1.0f if any element of grad is inf/nan (accumulates; caller zero-fills). */
+int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev,
+                     ngp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H */

@@ -1,0 +1,570 @@
+// grid_encode.cu -- multiresolution hash / tiled grid encoder for sm_100a.
+//
+// Implements the semantics of the reference kernels kernel_grid, kernel_grid_backward,
+// kernel_input_backward, kernel_grad_tv and kernel_grad_wd (gridencoder/src/gridencoder.cu:82-249,
+// 252-349, 352-378, 525-631, 670-703) with a different data path:
+//   * one thread per (point, level), blocks of one level are scheduled together (blockIdx.y = level)
+//     so that a level's slice of the table (<= 2 MiB fp16) is what the SM's L1 and the 126 MB L2 see;
+//   * every corner is ONE vector load of the whole C-wide row through ld.global.nc (half2 for the
+//     fp16 F=2 table) and every gradient corner is ONE packed reduction (red.global.add.noftz.f16x2 /
+//     red.global.add.v2.f32), never a per-element atomic;
+//   * outputs and incoming gradients use the operator's own [B, L*C] layout, so the wrapper does no
+//     permute copies (gridencoder/grid.py:63,81);
+//   * the input gradient is recomputed from the table inside the backward kernel instead of being
+//     streamed out as dy_dx [B, L*D*C] in forward and back in (gridencoder/grid.py:54, gridencoder.cu:352-378).
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+constexpr uint32_t kFwdThreads = 256;
+constexpr uint32_t kBwdThreads = 256;
+
+// Spatial hash of tcnn / torch-ngp: xor of coordinate * prime (first prime is 1, which keeps x-neighbours
+// in the same sector most of the time).  gridencoder.cu:45-58.
+template <uint32_t D>
+__device__ __forceinline__ uint32_t coherent_prime_hash(const uint32_t (&p)[D]) {
+    constexpr uint32_t kPrimes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+    uint32_t h = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) h ^= p[d] * kPrimes[d];
+    return h;
+}
+
+// Entry index (row number inside the level) of an integer grid position.  gridencoder.cu:61-79:
+// dense strides are accumulated only while stride <= hashmap_size; the level is hashed iff
+// gridtype == hash and the (possibly truncated) stride product exceeds hashmap_size.
+template <uint32_t D>
+__device__ __forceinline__ uint32_t entry_index(uint32_t gridtype, uint32_t hashmap_size, uint32_t res,
+                                                const uint32_t (&p)[D]) {
+    uint32_t stride = 1, idx = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        if (stride <= hashmap_size) {
+            idx += p[d] * stride;
+            stride *= res;
+        }
+    }
+    if (gridtype == 0 && stride > hashmap_size) idx = coherent_prime_hash<D>(p);
+    // idx % hashmap_size; dense levels never wrap and hashed levels are powers of two in practice.
+    if (idx >= hashmap_size) idx = ((hashmap_size & (hashmap_size - 1)) == 0) ? (idx & (hashmap_size - 1)) : (idx % hashmap_size);
+    return idx;
+}
+
+// Per-level resolution exactly as the device code of the reference computes it (fp32, gridencoder.cu:133).
+__device__ __forceinline__ uint32_t level_resolution(uint32_t level, float S, uint32_t H) {
+    return (uint32_t)ceilf(exp2f(level * S) * H);
+}
+
+__device__ __forceinline__ float smoothstep_f(float v) { return v * v * (3.0f - 2.0f * v); }
+__device__ __forceinline__ float smoothstep_df(float v) { return 6 * v * (1.0f - v); }
+
+// Position of the sample inside level `res`: integer base corner, fractional offset (after optional
+// smoothstep) and d(frac)/d(pos).  gridencoder.cu:140-160.  Returns false if the point is outside [0,1]^D.
+template <uint32_t D>
+__device__ __forceinline__ bool locate(const float* __restrict__ x, uint32_t res, bool align_corners, uint32_t interp,
+                                       uint32_t (&base)[D], float (&frac)[D], float (&dfrac)[D]) {
+    float xin[D];
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        xin[d] = __ldg(x + d);
+        if (xin[d] < 0 || xin[d] > 1) oob = true;
+    }
+    if (oob) return false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        float p;
+        if (align_corners) {
+            p = xin[d] * (float)(res - 1);
+            base[d] = min((uint32_t)floorf(p), res - 2);
+        } else {
+            p = fminf(fmaxf(xin[d] * (float)res - 0.5f, 0.0f), (float)(res - 1));
+            base[d] = (uint32_t)floorf(p);
+        }
+        p -= (float)base[d];
+        if (interp == 1) {
+            dfrac[d] = smoothstep_df(p);
+            frac[d] = smoothstep_f(p);
+        } else {
+            dfrac[d] = 1.0f;
+            frac[d] = p;
+        }
+    }
+    return true;
+}
+
+// Accumulators.  RefRound on fp16 tables reproduces the reference's at::Half arithmetic
+// (product rounded to half, then a half+half add evaluated in fp32 and rounded; gridencoder.cu:168,191).
+template <typename T, bool RefRound> struct Acc {
+    float v;
+    __device__ __forceinline__ Acc() : v(0.f) {}
+    __device__ __forceinline__ void fma(float w, float g) { v += w * g; }
+    __device__ __forceinline__ T get() const { return from_f32<T>(v); }
+};
+template <> struct Acc<__half, true> {
+    __half v;
+    __device__ __forceinline__ Acc() : v(__float2half_rn(0.f)) {}
+    __device__ __forceinline__ void fma(float w, float g) {
+        __half t = __float2half_rn(w * g);
+        v = __float2half_rn(__half2float(v) + __half2float(t));
+    }
+    __device__ __forceinline__ __half get() const { return v; }
+};
+
+template <typename T, uint32_t D, uint32_t C, bool RefRound>
+__global__ void __launch_bounds__(kFwdThreads)
+grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ table, const int* __restrict__ offsets,
+                    T* __restrict__ outputs, T* __restrict__ dy_dx, uint32_t B, uint32_t L, uint32_t max_level,
+                    float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+
+    T* out = outputs + (size_t)b * (L * C) + level * C;
+    T* dout = dy_dx ? dy_dx + ((size_t)b * L + level) * (D * C) : nullptr;
+
+    T zero[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) zero[c] = from_f32<T>(0.f);
+
+    uint32_t base[D];
+    float frac[D], dfrac[D];
+    const uint32_t res = level_resolution(level, S, H);
+    if (level >= max_level || !locate<D>(inputs + (size_t)b * D, res, align_corners, interp, base, frac, dfrac)) {
+        store_row<T, C>(out, zero);
+        if (dout) {
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) store_row<T, C>(dout + d * C, zero);
+        }
+        return;
+    }
+
+    const uint32_t off = (uint32_t)__ldg(offsets + level);
+    const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
+    const T* __restrict__ lvl = table + (size_t)off * C;
+
+    // gather the 2^D corner rows (independent loads, all in flight together)
+    float val[1u << D][C];
+#pragma unroll
+    for (uint32_t k = 0; k < (1u << D); k++) {
+        uint32_t p[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) p[d] = (k & (1u << d)) ? min(base[d] + 1, res - 1) : base[d];
+        load_row<T, C>(lvl + (size_t)entry_index<D>(gridtype, hashmap_size, res, p) * C, val[k]);
+    }
+
+    Acc<T, RefRound> acc[C];
+#pragma unroll
+    for (uint32_t k = 0; k < (1u << D); k++) {
+        float w = 1;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) acc[c].fma(w, val[k][c]);
+    }
+    T res_out[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) res_out[c] = acc[c].get();
+    store_row<T, C>(out, res_out);
+
+    if (dout) {
+        // d out / d x_g = scale * dfrac_g * sum over the 2^(D-1) corner pairs along g (gridencoder.cu:205-247)
+        const float scale = (float)(align_corners ? res - 1 : res);
+#pragma unroll
+        for (uint32_t g = 0; g < D; g++) {
+            Acc<T, RefRound> dacc[C];
+#pragma unroll
+            for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
+                float w = scale;
+                uint32_t lo = 0;  // corner id with bit g clear
+#pragma unroll
+                for (uint32_t nd = 0; nd < D - 1; nd++) {
+                    const uint32_t d = (nd >= g) ? nd + 1 : nd;
+                    if (j & (1u << nd)) { w *= frac[d]; lo |= (1u << d); }
+                    else w *= 1 - frac[d];
+                }
+                const uint32_t hi = lo | (1u << g);
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) {
+                    float diff = val[hi][c] - val[lo][c];
+                    if (RefRound && std::is_same<T, __half>::value) diff = __half2float(__float2half_rn(diff));
+                    dacc[c].fma(w * diff, dfrac[g]);
+                }
+            }
+            T dres[C];
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) dres[c] = dacc[c].get();
+            store_row<T, C>(dout + g * C, dres);
+        }
+    }
+}
+
+// Backward: scatter w * grad into the table gradient with one packed reduction per corner and, if asked,
+// recompute d out / d x from the table and reduce over the level's channels into grad_inputs.
+template <typename T, uint32_t D, uint32_t C, bool InputGrad>
+__global__ void __launch_bounds__(kBwdThreads)
+grid_backward_kernel(const T* __restrict__ grad, const float* __restrict__ inputs, const T* __restrict__ table,
+                     const int* __restrict__ offsets, T* __restrict__ grad_table, float* __restrict__ grad_inputs,
+                     uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                     uint32_t interp) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+
+    uint32_t base[D];
+    float frac[D], dfrac[D];
+    const uint32_t res = level_resolution(level, S, H);
+    if (!locate<D>(inputs + (size_t)b * D, res, align_corners, interp, base, frac, dfrac)) return;
+
+    const uint32_t off = (uint32_t)__ldg(offsets + level);
+    const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
+
+    float g[C];
+    load_row<T, C>(grad + (size_t)b * (L * C) + level * C, g);
+
+    uint32_t row[1u << D];
+#pragma unroll
+    for (uint32_t k = 0; k < (1u << D); k++) {
+        uint32_t p[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) p[d] = (k & (1u << d)) ? min(base[d] + 1, res - 1) : base[d];
+        row[k] = entry_index<D>(gridtype, hashmap_size, res, p);
+    }
+
+    float val[1u << D][C];
+    if (InputGrad) {
+        const T* __restrict__ lvl = table + (size_t)off * C;
+#pragma unroll
+        for (uint32_t k = 0; k < (1u << D); k++) load_row<T, C>(lvl + (size_t)row[k] * C, val[k]);
+    }
+
+    T* glvl = grad_table + (size_t)off * C;
+#pragma unroll
+    for (uint32_t k = 0; k < (1u << D); k++) {
+        float w = 1;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
+        float wg[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) wg[c] = w * g[c];
+        red_add_row<T, C>(glvl + (size_t)row[k] * C, wg);
+    }
+
+    if (InputGrad) {
+        const float scale = (float)(align_corners ? res - 1 : res);
+#pragma unroll
+        for (uint32_t gd = 0; gd < D; gd++) {
+            float s = 0.f;
+#pragma unroll
+            for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
+                float w = scale;
+                uint32_t lo = 0;
+#pragma unroll
+                for (uint32_t nd = 0; nd < D - 1; nd++) {
+                    const uint32_t d = (nd >= gd) ? nd + 1 : nd;
+                    if (j & (1u << nd)) { w *= frac[d]; lo |= (1u << d); }
+                    else w *= 1 - frac[d];
+                }
+                const uint32_t hi = lo | (1u << gd);
+                float dot = 0.f;
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) dot += g[c] * (val[hi][c] - val[lo][c]);
+                s += w * dot;
+            }
+            red_add_f32(grad_inputs + (size_t)b * D + gd, s * dfrac[gd]);
+        }
+    }
+}
+
+// grad_inputs[b,d] = sum_{l,c} grad[b,l,c] * dy_dx[b,l,d,c]   (reference layout; gridencoder.cu:352-378)
+template <typename T, uint32_t D, uint32_t C>
+__global__ void grid_input_backward_kernel(const T* __restrict__ grad, const T* __restrict__ dy_dx,
+                                           float* __restrict__ grad_inputs, uint32_t B, uint32_t L) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const T* gr = grad + (size_t)b * L * C;
+    const T* dd = dy_dx + (size_t)b * L * D * C + d * C;
+    float s = 0.f;
+    for (uint32_t l = 0; l < L; l++) {
+        float gv[C], dv[C];
+        load_row<T, C>(gr + l * C, gv);
+        load_row<T, C>(dd + (size_t)l * D * C, dv);
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) s += gv[c] * dv[c];
+    }
+    grad_inputs[t] = s;
+}
+
+// Total-variation gradient at B sample positions per level.  gridencoder.cu:525-631.
+template <typename T, uint32_t D, uint32_t C>
+__global__ void grid_tv_kernel(const T* __restrict__ inputs, const T* __restrict__ table, T* __restrict__ grad,
+                               const int* __restrict__ offsets, float weight, uint32_t B, uint32_t L, float S,
+                               uint32_t H, uint32_t gridtype, bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    float x[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        x[d] = to_f32(inputs[(size_t)b * D + d]);
+        if (x[d] < 0 || x[d] > 1) return;
+    }
+    const uint32_t off = (uint32_t)__ldg(offsets + level);
+    const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
+    const uint32_t res = level_resolution(level, S, H);
+    const T* __restrict__ lvl = table + (size_t)off * C;
+
+    uint32_t cell[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        if (align_corners) cell[d] = min((uint32_t)floorf(x[d] * (float)(res - 1)), res - 2);
+        else cell[d] = (uint32_t)floorf(fminf(fmaxf(x[d] * (float)res - 0.5f, 0.0f), (float)(res - 1)));
+    }
+    const uint32_t centre = entry_index<D>(gridtype, hashmap_size, res, cell);
+    float vc[C];
+    load_row<T, C>(lvl + (size_t)centre * C, vc);
+
+    float sum[C], sq[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) sum[c] = sq[c] = 0.f;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const uint32_t cur = cell[d];
+        float vn[C];
+        if (cur < res) {  // always true, kept: the "+1" neighbour may be res (wraps through the index map)
+            cell[d] = cur + 1;
+            load_row<T, C>(lvl + (size_t)entry_index<D>(gridtype, hashmap_size, res, cell) * C, vn);
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) { float df = vc[c] - vn[c]; sum[c] += df; sq[c] += df * df; }
+        }
+        if (cur > 0) {
+            cell[d] = cur - 1;
+            load_row<T, C>(lvl + (size_t)entry_index<D>(gridtype, hashmap_size, res, cell) * C, vn);
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) { float df = vc[c] - vn[c]; sum[c] += df; sq[c] += df * df; }
+        }
+        cell[d] = cur;
+    }
+    const float w = weight / (2 * D);
+    float upd[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) upd[c] = w * sum[c] * rsqrtf(sq[c] + 1e-9f);
+    red_add_row<T, C>(grad + ((size_t)off + centre) * C, upd);
+}
+
+// Level-wise mean weight decay: grad += 2*w*table / hashmap_size(level).  gridencoder.cu:670-703.
+template <typename T>
+__global__ void grid_wd_kernel(const T* __restrict__ table, T* __restrict__ grad, const int* __restrict__ offsets,
+                               float weight, uint32_t n_elems, uint32_t L, uint32_t C) {
+    extern __shared__ int s_off[];
+    for (uint32_t i = threadIdx.x; i <= L; i += blockDim.x) s_off[i] = offsets[i];
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += stride) {
+        const uint32_t n = e / C;
+        uint32_t lo = 0, hi = L, level = 0;
+        while (lo < hi) {
+            const uint32_t m = (lo + hi) / 2;
+            if ((uint32_t)s_off[m] <= n) { level = m; lo = m + 1; } else hi = m;
+        }
+        const uint32_t hashmap_size = (uint32_t)(s_off[level + 1] - s_off[level]);
+        grad[e] = from_f32<T>(to_f32(grad[e]) + 2 * weight * to_f32(table[e]) / hashmap_size);
+    }
+}
+
+template <typename T, uint32_t D>
+int launch_forward(const float* inputs, const T* table, const int* offsets, T* outputs, T* dy_dx, uint32_t B,
+                   uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H, uint32_t gridtype,
+                   bool align_corners, uint32_t interp, bool ref_round, cudaStream_t st) {
+    const dim3 grid(div_up(B, kFwdThreads), L, 1);
+#define NGP_FWD(CC)                                                                                              \
+    if (ref_round)                                                                                               \
+        grid_forward_kernel<T, D, CC, true><<<grid, kFwdThreads, 0, st>>>(inputs, table, offsets, outputs, dy_dx, B, L, \
+                                                                          max_level, S, H, gridtype, align_corners, interp); \
+    else                                                                                                         \
+        grid_forward_kernel<T, D, CC, false><<<grid, kFwdThreads, 0, st>>>(inputs, table, offsets, outputs, dy_dx, B, L, \
+                                                                           max_level, S, H, gridtype, align_corners, interp);
+    switch (C) {
+        case 1: NGP_FWD(1); break;
+        case 2: NGP_FWD(2); break;
+        case 4: NGP_FWD(4); break;
+        case 8: NGP_FWD(8); break;
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+#undef NGP_FWD
+    return finish_launch();
+}
+
+template <typename T, uint32_t D>
+int launch_backward(const T* grad, const float* inputs, const T* table, const int* offsets, T* grad_table,
+                    float* grad_inputs, uint32_t B, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                    uint32_t gridtype, bool align_corners, uint32_t interp, cudaStream_t st) {
+    const dim3 grid(div_up(B, kBwdThreads), max_level, 1);
+#define NGP_BWD(CC)                                                                                              \
+    if (grad_inputs)                                                                                             \
+        grid_backward_kernel<T, D, CC, true><<<grid, kBwdThreads, 0, st>>>(grad, inputs, table, offsets, grad_table, \
+                                                                           grad_inputs, B, L, S, H, gridtype, align_corners, interp); \
+    else                                                                                                         \
+        grid_backward_kernel<T, D, CC, false><<<grid, kBwdThreads, 0, st>>>(grad, inputs, table, offsets, grad_table, \
+                                                                            grad_inputs, B, L, S, H, gridtype, align_corners, interp);
+    switch (C) {
+        case 1: NGP_BWD(1); break;
+        case 2: NGP_BWD(2); break;
+        case 4: NGP_BWD(4); break;
+        case 8: NGP_BWD(8); break;
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+#undef NGP_BWD
+    return finish_launch();
+}
+
+template <typename T, uint32_t D>
+int launch_input_backward(const T* grad, const T* dy_dx, float* grad_inputs, uint32_t B, uint32_t C, uint32_t L,
+                          cudaStream_t st) {
+    const uint32_t blocks = div_up(B * D, 256u);
+    switch (C) {
+        case 1: grid_input_backward_kernel<T, D, 1><<<blocks, 256, 0, st>>>(grad, dy_dx, grad_inputs, B, L); break;
+        case 2: grid_input_backward_kernel<T, D, 2><<<blocks, 256, 0, st>>>(grad, dy_dx, grad_inputs, B, L); break;
+        case 4: grid_input_backward_kernel<T, D, 4><<<blocks, 256, 0, st>>>(grad, dy_dx, grad_inputs, B, L); break;
+        case 8: grid_input_backward_kernel<T, D, 8><<<blocks, 256, 0, st>>>(grad, dy_dx, grad_inputs, B, L); break;
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+    return finish_launch();
+}
+
+template <typename T, uint32_t D>
+int launch_tv(const T* inputs, const T* table, T* grad, const int* offsets, float weight, uint32_t B, uint32_t C,
+              uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners, cudaStream_t st) {
+    const dim3 grid(div_up(B, 256u), L, 1);
+    switch (C) {
+        case 1: grid_tv_kernel<T, D, 1><<<grid, 256, 0, st>>>(inputs, table, grad, offsets, weight, B, L, S, H, gridtype, align_corners); break;
+        case 2: grid_tv_kernel<T, D, 2><<<grid, 256, 0, st>>>(inputs, table, grad, offsets, weight, B, L, S, H, gridtype, align_corners); break;
+        case 4: grid_tv_kernel<T, D, 4><<<grid, 256, 0, st>>>(inputs, table, grad, offsets, weight, B, L, S, H, gridtype, align_corners); break;
+        case 8: grid_tv_kernel<T, D, 8><<<grid, 256, 0, st>>>(inputs, table, grad, offsets, weight, B, L, S, H, gridtype, align_corners); break;
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+    return finish_launch();
+}
+
+// table rows must be aligned to their own width for the vector loads / packed reductions
+static inline bool row_aligned(const void* p, uint32_t C, size_t elem) {
+    size_t w = C * elem;
+    if (w > 16) w = 16;
+    return aligned(p, w);
+}
+
+}  // namespace
+}  // namespace ngp
+
+using namespace ngp;
+
+#define NGP_DISPATCH_DTYPE(dtype, ...)                                  \
+    switch (dtype) {                                                    \
+        case NGP_F32: { using T = float; __VA_ARGS__; } break;          \
+        case NGP_F16: { using T = __half; __VA_ARGS__; } break;         \
+        case NGP_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break; \
+        default: return NGP_ERR_BAD_DTYPE;                              \
+    }
+
+static inline size_t dtype_size(int dtype) { return dtype == NGP_F32 ? 4 : 2; }
+
+extern "C" int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                                       void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                                       uint32_t max_level, float S, uint32_t H, void* dy_dx, uint32_t gridtype,
+                                       int align_corners, uint32_t interp, int dtype, uint32_t flags,
+                                       ngp_stream_t stream) {
+    if (dtype < NGP_F32 || dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+    if (B == 0 || L == 0) return NGP_OK;
+    if (!inputs || !embeddings || !offsets || !outputs) return NGP_ERR_NULL;
+    if (gridtype > 1 || interp > 1 || max_level > L) return NGP_ERR_BAD_ARG;
+    if (C != 1 && C != 2 && C != 4 && C != 8) return NGP_ERR_UNSUPPORTED;
+    const size_t es = dtype_size(dtype);
+    if (!row_aligned(embeddings, C, es) || !row_aligned(outputs, C, es) || (dy_dx && !row_aligned(dy_dx, C, es)) ||
+        !aligned(inputs, 4))
+        return NGP_ERR_ALIGN;
+    const bool ref_round = (flags & NGP_GRID_REF_ROUNDING) && dtype == NGP_F16;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = NGP_ERR_UNSUPPORTED;
+    NGP_DISPATCH_DTYPE(dtype, {
+        if (D == 3) rc = launch_forward<T, 3>(inputs, (const T*)embeddings, offsets, (T*)outputs, (T*)dy_dx, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, ref_round, st);
+        else if (D == 2) rc = launch_forward<T, 2>(inputs, (const T*)embeddings, offsets, (T*)outputs, (T*)dy_dx, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, ref_round, st);
+    });
+    return rc;
+}
+
+extern "C" int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                        const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D,
+                                        uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                                        float* grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                                        int dtype, uint32_t flags, ngp_stream_t stream) {
+    (void)flags;
+    if (dtype < NGP_F32 || dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+    if (B == 0 || L == 0 || max_level == 0) return NGP_OK;
+    if (!grad || !inputs || !embeddings || !offsets || !grad_embeddings) return NGP_ERR_NULL;
+    if (gridtype > 1 || interp > 1 || max_level > L) return NGP_ERR_BAD_ARG;
+    if (C != 1 && C != 2 && C != 4 && C != 8) return NGP_ERR_UNSUPPORTED;
+    const size_t es = dtype_size(dtype);
+    if (!row_aligned(embeddings, C, es) || !row_aligned(grad, C, es) || !row_aligned(grad_embeddings, C, es) ||
+        !aligned(inputs, 4) || (grad_inputs && !aligned(grad_inputs, 4)))
+        return NGP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = NGP_ERR_UNSUPPORTED;
+    NGP_DISPATCH_DTYPE(dtype, {
+        if (D == 3) rc = launch_backward<T, 3>((const T*)grad, inputs, (const T*)embeddings, offsets, (T*)grad_embeddings, grad_inputs, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, st);
+        else if (D == 2) rc = launch_backward<T, 2>((const T*)grad, inputs, (const T*)embeddings, offsets, (T*)grad_embeddings, grad_inputs, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, st);
+    });
+    return rc;
+}
+
+extern "C" int ngp_grid_input_backward(const void* grad, const void* dy_dx, float* grad_inputs, uint32_t B,
+                                       uint32_t D, uint32_t C, uint32_t L, int dtype, ngp_stream_t stream) {
+    if (dtype < NGP_F32 || dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+    if (B == 0) return NGP_OK;
+    if (!grad || !dy_dx || !grad_inputs) return NGP_ERR_NULL;
+    const size_t es = dtype_size(dtype);
+    if (!row_aligned(grad, C, es) || !row_aligned(dy_dx, C, es)) return NGP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = NGP_ERR_UNSUPPORTED;
+    NGP_DISPATCH_DTYPE(dtype, {
+        if (D == 3) rc = launch_input_backward<T, 3>((const T*)grad, (const T*)dy_dx, grad_inputs, B, C, L, st);
+        else if (D == 2) rc = launch_input_backward<T, 2>((const T*)grad, (const T*)dy_dx, grad_inputs, B, C, L, st);
+    });
+    return rc;
+}
+
+extern "C" int ngp_grid_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                                             const int32_t* offsets, float weight, uint32_t B, uint32_t D,
+                                             uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                             int align_corners, int dtype, ngp_stream_t stream) {
+    if (dtype < NGP_F32 || dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+    if (B == 0 || L == 0) return NGP_OK;
+    if (!inputs || !embeddings || !grad || !offsets) return NGP_ERR_NULL;
+    if (gridtype > 1) return NGP_ERR_BAD_ARG;
+    const size_t es = dtype_size(dtype);
+    if (!row_aligned(embeddings, C, es) || !row_aligned(grad, C, es)) return NGP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = NGP_ERR_UNSUPPORTED;
+    NGP_DISPATCH_DTYPE(dtype, {
+        if (D == 3) rc = launch_tv<T, 3>((const T*)inputs, (const T*)embeddings, (T*)grad, offsets, weight, B, C, L, S, H, gridtype, align_corners != 0, st);
+        else if (D == 2) rc = launch_tv<T, 2>((const T*)inputs, (const T*)embeddings, (T*)grad, offsets, weight, B, C, L, S, H, gridtype, align_corners != 0, st);
+    });
+    return rc;
+}
+
+extern "C" int ngp_grid_grad_weight_decay(const void* embeddings, void* grad, const int32_t* offsets, float weight,
+                                          uint32_t n_entries, uint32_t C, uint32_t L, int dtype,
+                                          ngp_stream_t stream) {
+    if (dtype < NGP_F32 || dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+    if (n_entries == 0) return NGP_OK;
+    if (!embeddings || !grad || !offsets) return NGP_ERR_NULL;
+    if (L == 0 || L > 1024) return NGP_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n = n_entries * C;
+    const uint32_t blocks = min(div_up(n, 256u), (uint32_t)(kNumSMs * 8));
+    NGP_DISPATCH_DTYPE(dtype, {
+        grid_wd_kernel<T><<<blocks, 256, (L + 1) * sizeof(int), st>>>((const T*)embeddings, (T*)grad, offsets, weight, n, L, C);
+    });
+    return finish_launch();
+}

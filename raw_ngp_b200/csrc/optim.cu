@@ -1,0 +1,99 @@
+// optim.cu -- fused Adam over the flat parameter buffer (hash table + MLP weights): GradScaler unscale,
+// inf/nan skip, Adam update on fp32 master weights, low-precision parameter copy and gradient clearing in
+// ONE pass over memory (7 streams instead of torch's foreach chain + separate zero_grad + .half() cast).
+// Reference behaviour: torch.optim.Adam(eps=1e-15) (main.py:245) under torch.cuda.amp.GradScaler
+// (nerf/train_utils.py:897-904).
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+template <typename G> __device__ __forceinline__ float load_g(const G* p, uint64_t i) { return to_f32(p[i]); }
+
+template <typename G, typename P, bool HasLP>
+__global__ void __launch_bounds__(256)
+fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __restrict__ grad, float* __restrict__ m,
+                  float* __restrict__ v, uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float bias1, float bias2_sqrt, const float* __restrict__ inv_scale_dev,
+                  const float* __restrict__ found_inf_dev, bool zero_grad) {
+    const bool skip = found_inf_dev && (__ldg(found_inf_dev) != 0.f);
+    const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
+    const float step_size = lr / bias1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (!skip) {
+            float g = to_f32(grad[i]) * inv_scale;
+            float p = master[i];
+            if (weight_decay != 0.f) g += weight_decay * p;
+            const float mi = beta1 * m[i] + (1.f - beta1) * g;
+            const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+            m[i] = mi;
+            v[i] = vi;
+            const float denom = sqrtf(vi) / bias2_sqrt + eps;
+            p -= step_size * (mi / denom);
+            master[i] = p;
+            if (HasLP) param_lp[i] = from_f32<P>(p);
+        }
+        if (zero_grad) grad[i] = from_f32<G>(0.f);
+    }
+}
+
+template <typename G>
+__global__ void __launch_bounds__(256)
+check_finite_kernel(const G* __restrict__ grad, uint64_t n, float* __restrict__ found_inf) {
+    bool bad = false;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float g = to_f32(grad[i]);
+        bad |= !isfinite(g);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
+}
+
+}  // namespace
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype, float* exp_avg,
+                              float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, uint32_t step, const float* inv_scale_dev,
+                              const float* found_inf_dev, int zero_grad, ngp_stream_t stream) {
+    if (n == 0) return NGP_OK;
+    if (!master || !grad || !exp_avg || !exp_avg_sq) return NGP_ERR_NULL;
+    if (step == 0) return NGP_ERR_BAD_ARG;
+    if (grad_dtype < NGP_F32 || grad_dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+    if (param_lp && (lp_dtype != NGP_F16 && lp_dtype != NGP_BF16)) return NGP_ERR_BAD_DTYPE;
+    const float bias1 = 1.f - powf(beta1, (float)step);
+    const float bias2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(n, 256), (uint64_t)kNumSMs * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+#define NGP_ADAM(G, P, HAS)                                                                                      \
+    fused_adam_kernel<G, P, HAS><<<blocks, 256, 0, st>>>(master, (P*)param_lp, (G*)grad, exp_avg, exp_avg_sq, n, lr, \
+                                                         beta1, beta2, eps, weight_decay, bias1, bias2_sqrt,      \
+                                                         inv_scale_dev, found_inf_dev, zero_grad != 0)
+#define NGP_ADAM_G(G)                                                             \
+    if (!param_lp) NGP_ADAM(G, __half, false);                                    \
+    else if (lp_dtype == NGP_F16) NGP_ADAM(G, __half, true);                      \
+    else NGP_ADAM(G, __nv_bfloat16, true)
+    if (grad_dtype == NGP_F32) { NGP_ADAM_G(float); }
+    else if (grad_dtype == NGP_F16) { NGP_ADAM_G(__half); }
+    else { NGP_ADAM_G(__nv_bfloat16); }
+#undef NGP_ADAM_G
+#undef NGP_ADAM
+    return finish_launch();
+}
+
+extern "C" int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev, ngp_stream_t stream) {
+    if (n == 0) return NGP_OK;
+    if (!grad || !found_inf_dev) return NGP_ERR_NULL;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(n, 256), (uint64_t)kNumSMs * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (grad_dtype) {
+        case NGP_F32: check_finite_kernel<float><<<blocks, 256, 0, st>>>((const float*)grad, n, found_inf_dev); break;
+        case NGP_F16: check_finite_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)grad, n, found_inf_dev); break;
+        case NGP_BF16: check_finite_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)grad, n, found_inf_dev); break;
+        default: return NGP_ERR_BAD_DTYPE;
+    }
+    return finish_launch();
+}

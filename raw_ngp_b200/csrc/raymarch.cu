@@ -1,0 +1,767 @@
+// raymarch.cu -- occupancy-grid ray marching and volume compositing for sm_100a.
+//
+// Operator semantics follow raymarching/src/raymarching.cu of the reference (kernel line ranges are cited
+// at each function).  What is different:
+//   * the occupancy bitfield (256 KiB per cascade at H=128) is read through ld.global.nc so it lives in
+//     L1/L2; the cascade is selected in registers;
+//   * the voxel index needs no FP64: 0.5*v is exact in fp32 and (0.5*v)*H rounds the exact product once,
+//     which is the value the reference obtains through its double detour (raymarching.cu:432-434);
+//   * sample offsets are an exclusive prefix sum in ray order (deterministic) computed by the last block
+//     of the counting kernel, not an atomicAdd ticket in arrival order (raymarching.cu:486-490);
+//   * compositing is one warp per ray: coalesced 32-sample chunks, transmittance by a shuffle product scan,
+//     early termination by ballot;
+//   * inference marching zero-fills its own tail, there is no memset per iteration.
+// Do NOT build this file with --use_fast_math: sample counts are compared bit-exactly with the reference.
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
+__device__ __forceinline__ float sign1(float x) { return copysignf(1.0f, x); }
+
+// 10-bit-per-axis Morton code.  raymarching.cu:56-81.
+__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton_encode(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t compact3(uint32_t v) {
+    v &= 0x49249249u;
+    v = (v | (v >> 2)) & 0xc30c30c3u;
+    v = (v | (v >> 4)) & 0x0f00f00fu;
+    v = (v | (v >> 8)) & 0xff0000ffu;
+    v = (v | (v >> 16)) & 0x0000ffffu;
+    return v;
+}
+
+// cascade level from position / from step size.  raymarching.cu:42-54.
+__device__ __forceinline__ int cascade_from_pos(float x, float y, float z, float n_cascades) {
+    const float m = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    int e;
+    frexpf(m, &e);
+    return fminf(n_cascades - 1, fmaxf(0, e));
+}
+__device__ __forceinline__ int cascade_from_dt(float dt, float H, float n_cascades) {
+    const float m = dt * H * 0.5f;
+    int e;
+    frexpf(m, &e);
+    return fminf(n_cascades - 1, fmaxf(0, e));
+}
+
+// Per-ray constants shared by the training and inference marchers.
+struct MarchParams {
+    const uint8_t* __restrict__ grid;
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf;
+    uint32_t H;
+    bool contract;
+};
+
+__device__ __forceinline__ MarchParams make_params(const uint8_t* grid, float bound, bool contract, float dt_gamma,
+                                                   uint32_t max_steps, uint32_t C, uint32_t H) {
+    MarchParams p;
+    p.grid = grid;
+    p.bound = bound;
+    p.contract = contract;
+    p.dt_gamma = dt_gamma;
+    p.dt_min = 2 * 1.7320508075688772f / max_steps;      // raymarching.cu:396
+    p.dt_max = 2 * 1.7320508075688772f * bound / H;      // raymarching.cu:397
+    p.rH = 1 / (float)H;
+    p.H3 = H * H * H;
+    p.Hf = (float)H;
+    p.Cf = (float)C;
+    p.H = H;
+    return p;
+}
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+};
+
+// One probe of the marching loop at parameter t (raymarching.cu:407-437 / 778-808): clamps the position,
+// picks the cascade, contracts, finds the voxel and tests its bit.  Returns true when the sample is kept.
+struct Probe {
+    float cx, cy, cz, dt, mip_bound;
+    int nx, ny, nz;
+};
+__device__ __forceinline__ bool probe(const MarchParams& p, const Ray& r, float t, Probe& q) {
+    const float x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
+    const float y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
+    const float z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
+    q.dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+
+    const int level = max(cascade_from_pos(x, y, z, p.Cf), cascade_from_dt(q.dt, p.Hf, p.Cf));
+    q.mip_bound = fminf(scalbnf(1.0f, level), p.bound);
+    const float mip_rbound = 1 / q.mip_bound;
+
+    q.cx = x; q.cy = y; q.cz = z;
+    const float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    const bool outer = p.contract && mag > 1;
+    if (outer) {  // L-inf contraction, all axes scaled (raymarching.cu:423-429)
+        const float s = (2 - 1 / mag) / mag;
+        q.cx *= s; q.cy *= s; q.cz *= s;
+    }
+    // 0.5*(c/mip_bound + 1)*H, clamped to [0, H-1], truncated
+    q.nx = (int)clampf((0.5f * (q.cx * mip_rbound + 1)) * p.Hf, 0.0f, (float)(p.H - 1));
+    q.ny = (int)clampf((0.5f * (q.cy * mip_rbound + 1)) * p.Hf, 0.0f, (float)(p.H - 1));
+    q.nz = (int)clampf((0.5f * (q.cz * mip_rbound + 1)) * p.Hf, 0.0f, (float)(p.H - 1));
+
+    // bit index is evaluated in fp32 like the reference (raymarching.cu:436)
+    const uint32_t index = level * p.H3 + morton_encode(q.nx, q.ny, q.nz);
+    const bool occ = __ldg(p.grid + index / 8) & (1 << (index % 8));
+    return occ || outer;
+}
+
+// Advance t past the current (empty) voxel in dt-sized steps.  raymarching.cu:468-480.
+__device__ __forceinline__ float skip_voxel(const MarchParams& p, const Ray& r, float t, const Probe& q) {
+    const float tx = (((q.nx + 0.5f + 0.5f * sign1(r.dx)) * p.rH * 2 - 1) * q.mip_bound - q.cx) * r.rdx;
+    const float ty = (((q.ny + 0.5f + 0.5f * sign1(r.dy)) * p.rH * 2 - 1) * q.mip_bound - q.cy) * r.rdy;
+    const float tz = (((q.nz + 0.5f + 0.5f * sign1(r.dz)) * p.rH * 2 - 1) * q.mip_bound - q.cz) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    do {
+        const float dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+        t += dt;
+    } while (t < tt);
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------------------
+
+// raymarching.cu:91-145
+__global__ void near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                const float* __restrict__ aabb, uint32_t N, float min_near, float* __restrict__ nears,
+                                float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float lo[3] = {__ldg(aabb), __ldg(aabb + 1), __ldg(aabb + 2)};
+    const float hi[3] = {__ldg(aabb + 3), __ldg(aabb + 4), __ldg(aabb + 5)};
+    float tn = 0.f, tf = 0.f;
+    bool miss = false;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float o = __ldg(rays_o + (size_t)n * 3 + a);
+        const float rd = 1 / __ldg(rays_d + (size_t)n * 3 + a);
+        float t0 = (lo[a] - o) * rd, t1 = (hi[a] - o) * rd;
+        if (t0 > t1) { const float s = t0; t0 = t1; t1 = s; }
+        if (a == 0) { tn = t0; tf = t1; }
+        else if (!miss) {
+            if (tn > t1 || t0 > tf) miss = true;
+            else { if (t0 > tn) tn = t0; if (t1 < tf) tf = t1; }
+        }
+    }
+    if (miss) { nears[n] = fars[n] = 3.402823466e+38f; return; }  // numeric_limits<float>::max()
+    if (tn < min_near) tn = min_near;
+    nears[n] = tn;
+    fars[n] = tf;
+}
+
+// raymarching.cu:162-198
+__global__ void sph_from_ray_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+                                    uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bh = ox * dx + oy * dy + oz * dz;
+    const float Cc = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-Bh + sqrtf(Bh * Bh - A * Cc)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    coords[n * 2] = 2 * theta * 0.3183098861837907f - 1;
+    coords[n * 2 + 1] = phi * 0.3183098861837907f;
+}
+
+// raymarching.cu:214-226
+__global__ void morton3d_kernel(const int* __restrict__ coords, uint32_t N, int* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int)morton_encode(__ldg(coords + (size_t)n * 3), __ldg(coords + (size_t)n * 3 + 1), __ldg(coords + (size_t)n * 3 + 2));
+}
+
+// raymarching.cu:237-254
+__global__ void morton3d_invert_kernel(const int* __restrict__ indices, uint32_t N, int* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int ind = __ldg(indices + n);   // arithmetic shifts of a signed value, like the reference
+    coords[(size_t)n * 3] = (int)compact3(ind >> 0);
+    coords[(size_t)n * 3 + 1] = (int)compact3(ind >> 1);
+    coords[(size_t)n * 3 + 2] = (int)compact3(ind >> 2);
+}
+
+// raymarching.cu:267-289.  One thread packs 8 densities (two 16-byte loads) into one byte.
+__global__ void packbits_kernel(const float* __restrict__ grid, uint32_t N, float density_thresh,
+                                const float* __restrict__ thresh_dev, uint8_t* __restrict__ bitfield) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float th = density_thresh;
+    if (thresh_dev) th = fminf(__ldg(thresh_dev), density_thresh);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(grid) + (size_t)n * 2);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(grid) + (size_t)n * 2 + 1);
+    uint32_t bits = 0;
+    bits |= (a.x > th) ? 1u : 0u;   bits |= (a.y > th) ? 2u : 0u;
+    bits |= (a.z > th) ? 4u : 0u;   bits |= (a.w > th) ? 8u : 0u;
+    bits |= (b.x > th) ? 16u : 0u;  bits |= (b.y > th) ? 32u : 0u;
+    bits |= (b.z > th) ? 64u : 0u;  bits |= (b.w > th) ? 128u : 0u;
+    bitfield[n] = (uint8_t)bits;
+}
+
+// raymarching.cu:303-319; one warp per ray so the stores coalesce.
+__global__ void flatten_rays_kernel(const int* __restrict__ rays, uint32_t N, uint32_t M, int* __restrict__ res) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = __ldg(rays + (size_t)n * 2), num = __ldg(rays + (size_t)n * 2 + 1);
+    for (uint32_t i = lane; i < num; i += 32)
+        if (offset + i < M) res[offset + i] = (int)n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training march
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, size_t n, bool eps) {
+    Ray r;
+    r.ox = __ldg(rays_o + n * 3); r.oy = __ldg(rays_o + n * 3 + 1); r.oz = __ldg(rays_o + n * 3 + 2);
+    r.dx = __ldg(rays_d + n * 3); r.dy = __ldg(rays_d + n * 3 + 1); r.dz = __ldg(rays_d + n * 3 + 2);
+    if (eps) {  // inference marcher: raymarching.cu:762
+        r.rdx = 1 / (r.dx + 1e-10f); r.rdy = 1 / (r.dy + 1e-10f); r.rdz = 1 / (r.dz + 1e-10f);
+    } else {    // training marcher: raymarching.cu:388
+        r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+    }
+    return r;
+}
+
+constexpr uint32_t kMarchThreads = 64;
+
+// Pass 1 (raymarching.cu:337-491 with xyzs == nullptr) + ray-ordered exclusive scan by the last block.
+__global__ void __launch_bounds__(kMarchThreads)
+march_train_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+                         float bound, bool contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                         const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+                         int* __restrict__ rays, int* __restrict__ counter) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) {
+        const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
+        const Ray r = load_ray(rays_o, rays_d, n, false);
+        const float far = __ldg(fars + n);
+        float t = __ldg(nears + n);
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
+        uint32_t step = 0;
+        while (t < far && step < max_steps) {
+            Probe q;
+            if (probe(p, r, t, q)) { step++; t += q.dt; }
+            else t = skip_voxel(p, r, t, q);
+        }
+        rays[(size_t)n * 2 + 1] = (int)step;
+    }
+
+    // last block to arrive turns the counts into ray-ordered offsets
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x >= 32) return;
+    const uint32_t lane = threadIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < N; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t cnt = (i < N) ? (uint32_t)__ldcg(rays + (size_t)i * 2 + 1) : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= (uint32_t)s) incl += v;
+        }
+        if (i < N) rays[(size_t)i * 2] = (int)(carry + incl - cnt);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { counter[0] = (int)carry; counter[1] = 0; }
+}
+
+// Pass 2 (raymarching.cu:337-491 with output buffers): re-march and write the samples of each ray.
+template <bool LDIR>
+__global__ void __launch_bounds__(kMarchThreads)
+march_train_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ rays_ldir,
+                         const uint8_t* __restrict__ grid, float bound, bool contract, float dt_gamma, uint32_t max_steps,
+                         uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears, const float* __restrict__ fars,
+                         const float* __restrict__ noises, const int* __restrict__ rays, uint32_t M, float* __restrict__ xyzs,
+                         float* __restrict__ dirs, float* __restrict__ ts, float* __restrict__ ldirs) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2);
+    const uint32_t num_steps = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    if (num_steps == 0 || offset + num_steps > M) return;
+
+    const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n, false);
+    float lx = 0, ly = 0, lz = 0;
+    if (LDIR) { lx = __ldg(rays_ldir + (size_t)n * 3); ly = __ldg(rays_ldir + (size_t)n * 3 + 1); lz = __ldg(rays_ldir + (size_t)n * 3 + 2); }
+    const float far = __ldg(fars + n);
+    float t = __ldg(nears + n);
+    t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
+
+    float* px = xyzs + (size_t)offset * 3;
+    float* pd = dirs + (size_t)offset * 3;
+    float* pt = ts + (size_t)offset * 2;
+    float* pl = LDIR ? ldirs + (size_t)offset * 3 : nullptr;
+    uint32_t step = 0;
+    while (t < far && step < num_steps) {
+        Probe q;
+        if (probe(p, r, t, q)) {
+            step++;
+            t += q.dt;
+            px[0] = q.cx; px[1] = q.cy; px[2] = q.cz;   // contracted coordinates (raymarching.cu:446)
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            *reinterpret_cast<float2*>(pt) = make_float2(t, q.dt);  // t AFTER the step (raymarching.cu:458)
+            if (LDIR) { pl[0] = lx; pl[1] = ly; pl[2] = lz; pl += 3; }
+            px += 3; pd += 3; pt += 2;
+        } else {
+            t = skip_voxel(p, r, t, q);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training composite: one warp per ray
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kCompThreads = 128;  // 4 rays per block
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, uint32_t lane) {
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, s);
+        if (lane >= (uint32_t)s) v += u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_incl_prod(float v, uint32_t lane) {
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, s);
+        if (lane >= (uint32_t)s) v *= u;
+    }
+    return v;
+}
+
+// raymarching.cu:519-597
+__global__ void __launch_bounds__(kCompThreads)
+composite_train_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ts,
+                           const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, float* __restrict__ weights,
+                           float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    if (count != 0 && offset + count <= M) {
+        float T = 1.0f;  // transmittance entering the chunk
+        for (uint32_t base = 0; base < count; base += 32) {
+            const uint32_t k = base + lane;
+            const bool valid = k < count;
+            const size_t i = (size_t)offset + k;
+            float alpha = 0.f, tk = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (valid) {
+                const float2 tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
+                tk = tt.x;
+                alpha = 1.0f - __expf(-__ldg(sigmas + i) * tt.y);
+                cr = __ldg(rgbs + i * 3); cg = __ldg(rgbs + i * 3 + 1); cb = __ldg(rgbs + i * 3 + 2);
+            }
+            const float incl = warp_incl_prod(1.0f - alpha, lane);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            const float T_before = T * excl, T_after = T * incl;
+            // the reference stops AFTER accumulating the first sample whose outgoing T < T_thresh
+            const uint32_t dead = __ballot_sync(0xffffffffu, valid && T_after < T_thresh);
+            const uint32_t last_live = dead ? (uint32_t)(__ffs(dead) - 1) : 31u;
+            if (valid && lane <= last_live) {
+                const float w = alpha * T_before;
+                weights[i] = w;
+                r += w * cr; g += w * cg; b += w * cb; ws += w; d += w * tk;
+            }
+            if (dead) break;
+            T = __shfl_sync(0xffffffffu, T_after, 31);
+        }
+        r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+    }
+    if (lane == 0) {
+        weights_sum[n] = ws;
+        depth[n] = d;
+        image[(size_t)n * 3] = r; image[(size_t)n * 3 + 1] = g; image[(size_t)n * 3 + 2] = b;
+    }
+}
+
+// raymarching.cu:623-712
+__global__ void __launch_bounds__(kCompThreads)
+composite_train_bwd_kernel(const float* __restrict__ grad_weights, const float* __restrict__ grad_weights_sum,
+                           const float* __restrict__ grad_depth, const float* __restrict__ grad_image,
+                           const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ts,
+                           const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ depth,
+                           const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+                           float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    if (count == 0 || offset + count > M) return;
+
+    const float gi_r = __ldg(grad_image + (size_t)n * 3), gi_g = __ldg(grad_image + (size_t)n * 3 + 1), gi_b = __ldg(grad_image + (size_t)n * 3 + 2);
+    const float g_ws = __ldg(grad_weights_sum + n), g_d = __ldg(grad_depth + n);
+    const float r_fin = __ldg(image + (size_t)n * 3), g_fin = __ldg(image + (size_t)n * 3 + 1), b_fin = __ldg(image + (size_t)n * 3 + 2);
+    const float ws_fin = __ldg(weights_sum + n), d_fin = __ldg(depth + n);
+
+    float T = 1.0f, r0 = 0, g0 = 0, b0 = 0, ws0 = 0, d0 = 0;  // running prefixes entering the chunk
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t k = base + lane;
+        const bool valid = k < count;
+        const size_t i = (size_t)offset + k;
+        float alpha = 0.f, tk = 0.f, dtk = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, gw = 0.f;
+        if (valid) {
+            const float2 tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
+            tk = tt.x; dtk = tt.y;
+            alpha = 1.0f - __expf(-__ldg(sigmas + i) * dtk);
+            cr = __ldg(rgbs + i * 3); cg = __ldg(rgbs + i * 3 + 1); cb = __ldg(rgbs + i * 3 + 2);
+            gw = __ldg(grad_weights + i);
+        }
+        const float incl = warp_incl_prod(1.0f - alpha, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float T_before = T * excl, T_after = T * incl;
+        const uint32_t dead = __ballot_sync(0xffffffffu, valid && T_after < T_thresh);
+        const uint32_t last_live = dead ? (uint32_t)(__ffs(dead) - 1) : 31u;
+        const bool live = valid && lane <= last_live;
+        const float w = live ? alpha * T_before : 0.f;
+        const float pr = r0 + warp_incl_sum(w * cr, lane);
+        const float pg = g0 + warp_incl_sum(w * cg, lane);
+        const float pb = b0 + warp_incl_sum(w * cb, lane);
+        const float pw = ws0 + warp_incl_sum(w, lane);
+        const float pd = d0 + warp_incl_sum(w * tk, lane);
+        if (live) {
+            grad_rgbs[i * 3] = gi_r * w; grad_rgbs[i * 3 + 1] = gi_g * w; grad_rgbs[i * 3 + 2] = gi_b * w;
+            grad_sigmas[i] = dtk * (gi_r * (T_after * cr - (r_fin - pr)) + gi_g * (T_after * cg - (g_fin - pg)) +
+                                    gi_b * (T_after * cb - (b_fin - pb)) + (g_ws + gw) * (T_after - (ws_fin - pw)) +
+                                    g_d * (T_after * tk - (d_fin - pd)));
+        }
+        if (dead) break;
+        T = __shfl_sync(0xffffffffu, T_after, 31);
+        r0 = __shfl_sync(0xffffffffu, pr, 31); g0 = __shfl_sync(0xffffffffu, pg, 31); b0 = __shfl_sync(0xffffffffu, pb, 31);
+        ws0 = __shfl_sync(0xffffffffu, pw, 31); d0 = __shfl_sync(0xffffffffu, pd, 31);
+    }
+}
+
+// Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329); one warp per ray.
+__global__ void __launch_bounds__(kCompThreads)
+march_train_bwd_kernel(const float* __restrict__ dL_dxyzs, const float* __restrict__ dL_ddirs, const float* __restrict__ ts,
+                       const int* __restrict__ rays, uint32_t N, uint32_t M, float* __restrict__ dL_do, float* __restrict__ dL_dd) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
+    for (uint32_t k = lane; k < count; k += 32) {
+        const size_t i = (size_t)offset + k;
+        if (i >= M) break;
+        const float gx = __ldg(dL_dxyzs + i * 3), gy = __ldg(dL_dxyzs + i * 3 + 1), gz = __ldg(dL_dxyzs + i * 3 + 2);
+        const float t = __ldg(ts + i * 2);
+        ox += gx; oy += gy; oz += gz;
+        dx += gx * t; dy += gy * t; dz += gz * t;
+        if (dL_ddirs) { dx += __ldg(dL_ddirs + i * 3); dy += __ldg(dL_ddirs + i * 3 + 1); dz += __ldg(dL_ddirs + i * 3 + 2); }
+    }
+    ox = warp_sum(ox); oy = warp_sum(oy); oz = warp_sum(oz);
+    dx = warp_sum(dx); dy = warp_sum(dy); dz = warp_sum(dz);
+    if (lane == 0) {
+        dL_do[(size_t)n * 3] = ox; dL_do[(size_t)n * 3 + 1] = oy; dL_do[(size_t)n * 3 + 2] = oz;
+        dL_dd[(size_t)n * 3] = dx; dL_dd[(size_t)n * 3 + 1] = dy; dL_dd[(size_t)n * 3 + 2] = dz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inference march / composite
+// ---------------------------------------------------------------------------------------------------
+
+// raymarching.cu:730-846
+__global__ void __launch_bounds__(128)
+march_infer_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
+                   const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, bool contract, float dt_gamma,
+                   uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ nears,
+                   const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ ts,
+                   const float* __restrict__ noises) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = __ldg(rays_alive + n);
+    const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, (size_t)index, true);
+    const float far = __ldg(fars + index);
+    (void)nears;
+    float t = __ldg(rays_t + index);
+    t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
+
+    float* px = xyzs + (size_t)n * n_step * 3;
+    float* pd = dirs + (size_t)n * n_step * 3;
+    float* pt = ts + (size_t)n * n_step * 2;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        Probe q;
+        if (probe(p, r, t, q)) {
+            px[0] = q.cx; px[1] = q.cy; px[2] = q.cz;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += q.dt;
+            *reinterpret_cast<float2*>(pt) = make_float2(t, q.dt);
+            px += 3; pd += 3; pt += 2;
+            step++;
+        } else {
+            t = skip_voxel(p, r, t, q);
+        }
+    }
+    // unwritten tail: ts[0] == 0 is the "ray finished" sentinel read by composite_rays (raymarching.cu:893-894)
+    for (; step < n_step; step++) {
+        px[0] = px[1] = px[2] = 0.f;
+        pd[0] = pd[1] = pd[2] = 0.f;
+        *reinterpret_cast<float2*>(pt) = make_float2(0.f, 0.f);
+        px += 3; pd += 3; pt += 2;
+    }
+}
+
+// raymarching.cu:859-941
+__global__ void __launch_bounds__(128)
+composite_infer_kernel(uint32_t n_alive, uint32_t n_step, float T_thresh, int* __restrict__ rays_alive, float* __restrict__ rays_t,
+                       const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ts,
+                       float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float* sg = sigmas + (size_t)n * n_step;
+    const float* cl = rgbs + (size_t)n * n_step * 3;
+    const float* tp = ts + (size_t)n * n_step * 2;
+    float t = 0.f;
+    float d = depth[index], r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+    float wsum = weights_sum[index];
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float2 tt = __ldg(reinterpret_cast<const float2*>(tp) + step);
+        if (tt.x == 0) break;  // finished ray
+        const float alpha = 1.0f - __expf(-__ldg(sg + step) * tt.y);
+        const float T = 1 - wsum;
+        const float w = alpha * T;
+        wsum += w;
+        t = tt.x;
+        d += w * t;
+        r += w * __ldg(cl + step * 3); g += w * __ldg(cl + step * 3 + 1); b += w * __ldg(cl + step * 3 + 2);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (step < n_step) rays_alive[n] = -1;
+    else rays_t[index] = t;
+    weights_sum[index] = wsum;
+    depth[index] = d;
+    image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+}
+
+// Ordered compaction of the surviving ray ids by a single block (inference batches are <= a few million ids:
+// 8 MB read, one pass).  Replaces `rays_alive[rays_alive >= 0]` (nerf/renderer.py:612).
+__global__ void __launch_bounds__(1024)
+compact_alive_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* __restrict__ out, int* __restrict__ n_out) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_alive; base += 1024) {
+        const uint32_t i = base + tid;
+        const int v = (i < n_alive) ? __ldg(rays_alive + i) : -1;
+        const bool keep = v >= 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(m);
+        __syncthreads();
+        uint32_t wsum = s_warp[lane];   // warp 0..31 totals
+        uint32_t incl = wsum;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= (uint32_t)s) incl += u;
+        }
+        const uint32_t warp_excl = __shfl_sync(0xffffffffu, incl - wsum, wid);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t carry = s_carry;
+        if (keep) out[carry + warp_excl + __popc(m & ((1u << lane) - 1))] = v;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (tid == 0) n_out[0] = (int)s_carry;
+}
+
+}  // namespace
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                      float min_near, float* nears, float* fars, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_NULL;
+    near_far_kernel<<<div_up(N, 128u), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return finish_launch();
+}
+
+extern "C" int ngp_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                                ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays_o || !rays_d || !coords) return NGP_ERR_NULL;
+    sph_from_ray_kernel<<<div_up(N, 128u), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+    return finish_launch();
+}
+
+extern "C" int ngp_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!coords || !indices) return NGP_ERR_NULL;
+    morton3d_kernel<<<div_up(N, 256u), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    return finish_launch();
+}
+
+extern "C" int ngp_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!coords || !indices) return NGP_ERR_NULL;
+    morton3d_invert_kernel<<<div_up(N, 256u), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    return finish_launch();
+}
+
+extern "C" int ngp_packbits(const float* grid, uint32_t N, float density_thresh, const float* thresh_dev,
+                            uint8_t* bitfield, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!grid || !bitfield) return NGP_ERR_NULL;
+    if (!aligned(grid, 16)) return NGP_ERR_ALIGN;
+    packbits_kernel<<<div_up(N, 256u), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, thresh_dev, bitfield);
+    return finish_launch();
+}
+
+extern "C" int ngp_flatten_rays(const int32_t* rays, uint32_t N, uint32_t M, int32_t* res, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays || !res) return NGP_ERR_NULL;
+    flatten_rays_kernel<<<div_up(N * 32u, 128u), 128, 0, (cudaStream_t)stream>>>(rays, N, M, res);
+    return finish_launch();
+}
+
+extern "C" int ngp_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                          int contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
+                                          uint32_t H, const float* nears, const float* fars, const float* noises,
+                                          int32_t* rays, int32_t* counter, ngp_stream_t stream) {
+    if (!counter) return NGP_ERR_NULL;
+    if (N == 0) return NGP_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !noises || !rays) return NGP_ERR_NULL;
+    if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
+    march_train_count_kernel<<<div_up(N, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter);
+    return finish_launch();
+}
+
+extern "C" int ngp_march_rays_train_write(const float* rays_o, const float* rays_d, const float* rays_ldir,
+                                          const uint8_t* grid, float bound, int contract, float dt_gamma,
+                                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears,
+                                          const float* fars, const float* noises, const int32_t* rays, uint32_t M,
+                                          float* xyzs, float* dirs, float* ts, float* ldirs, ngp_stream_t stream) {
+    if (N == 0 || M == 0) return NGP_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !noises || !rays || !xyzs || !dirs || !ts) return NGP_ERR_NULL;
+    if ((rays_ldir != nullptr) != (ldirs != nullptr)) return NGP_ERR_NULL;
+    if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
+    if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
+    const uint32_t blocks = div_up(N, kMarchThreads);
+    if (rays_ldir)
+        march_train_write_kernel<true><<<blocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, M, xyzs, dirs, ts, ldirs);
+    else
+        march_train_write_kernel<false><<<blocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, M, xyzs, dirs, ts, ldirs);
+    return finish_launch();
+}
+
+extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ts,
+                                                const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                                float* weights, float* weights_sum, float* depth, float* image,
+                                                ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays || !weights_sum || !depth || !image) return NGP_ERR_NULL;
+    if (M > 0 && (!sigmas || !rgbs || !ts || !weights)) return NGP_ERR_NULL;
+    if (M > 0 && !aligned(ts, 8)) return NGP_ERR_ALIGN;
+    composite_train_fwd_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, ts, rays, M, N, T_thresh, weights, weights_sum, depth, image);
+    return finish_launch();
+}
+
+extern "C" int ngp_composite_rays_train_backward(const float* grad_weights, const float* grad_weights_sum,
+                                                 const float* grad_depth, const float* grad_image,
+                                                 const float* sigmas, const float* rgbs, const float* ts,
+                                                 const int32_t* rays, const float* weights_sum, const float* depth,
+                                                 const float* image, uint32_t M, uint32_t N, float T_thresh,
+                                                 float* grad_sigmas, float* grad_rgbs, ngp_stream_t stream) {
+    if (N == 0 || M == 0) return NGP_OK;
+    if (!grad_weights || !grad_weights_sum || !grad_depth || !grad_image || !sigmas || !rgbs || !ts || !rays ||
+        !weights_sum || !depth || !image || !grad_sigmas || !grad_rgbs)
+        return NGP_ERR_NULL;
+    if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
+    composite_train_bwd_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
+        grad_weights, grad_weights_sum, grad_depth, grad_image, sigmas, rgbs, ts, rays, weights_sum, depth, image, M, N,
+        T_thresh, grad_sigmas, grad_rgbs);
+    return finish_launch();
+}
+
+extern "C" int ngp_march_rays_train_backward(const float* dL_dxyzs, const float* dL_ddirs, const float* ts,
+                                             const int32_t* rays, uint32_t N, uint32_t M, float* dL_drays_o,
+                                             float* dL_drays_d, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays || !dL_drays_o || !dL_drays_d) return NGP_ERR_NULL;
+    if (M > 0 && (!dL_dxyzs || !ts)) return NGP_ERR_NULL;
+    march_train_bwd_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
+        dL_dxyzs, dL_ddirs, ts, rays, N, M, dL_drays_o, dL_drays_d);
+    return finish_launch();
+}
+
+extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                              const float* rays_o, const float* rays_d, float bound, int contract, float dt_gamma,
+                              uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                              const float* fars, float* xyzs, float* dirs, float* ts, const float* noises,
+                              ngp_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return NGP_OK;
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !ts || !noises) return NGP_ERR_NULL;
+    if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
+    if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
+    march_infer_kernel<<<div_up(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, contract != 0, dt_gamma, max_steps, C, H, grid, nears, fars,
+        xyzs, dirs, ts, noises);
+    return finish_launch();
+}
+
+extern "C" int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                  const float* sigmas, const float* rgbs, const float* ts, float* weights_sum,
+                                  float* depth, float* image, ngp_stream_t stream) {
+    if (n_alive == 0 || n_step == 0) return NGP_OK;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !ts || !weights_sum || !depth || !image) return NGP_ERR_NULL;
+    if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
+    composite_infer_kernel<<<div_up(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, ts, weights_sum, depth, image);
+    return finish_launch();
+}
+
+extern "C" int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* alive_out, int32_t* n_out,
+                                      ngp_stream_t stream) {
+    if (!n_out) return NGP_ERR_NULL;
+    if (n_alive > 0 && (!rays_alive || !alive_out)) return NGP_ERR_NULL;
+    compact_alive_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, alive_out, n_out);
+    return finish_launch();
+}

@@ -1,0 +1,198 @@
+"""GridEncoder -- multiresolution hash / tiled grid encoding, B200 backend.
+
+Host-side mirror of the reference operator surface (gridencoder/grid.py:24-211): same class, function and
+argument names, same autograd / autocast contract.  The native work goes through the C ABI of
+libngp_b200.so (include/ngp_b200.h); there is no other backend.
+
+Differences that are deliberate:
+  * the kernel writes / reads the [B, L*C] layout directly (no [L,B,C] staging + permute copies,
+    reference grid.py:49,63,81);
+  * no dy_dx [B, L*D*C] tensor is saved for backward; the input gradient is recomputed from the table inside
+    the backward kernel (reference grid.py:54-55, gridencoder.cu:352-378).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
+
+from .. import _lib
+
+_gridtype_to_id = {"hash": 0, "tiled": 1}
+_interp_to_id = {"linear": 0, "smoothstep": 1}
+
+# fp16 tables: reproduce the reference's half-precision accumulation bit for bit (gridencoder.cu:168,191).
+# Set to False for fp32 accumulation with a single final rounding (more accurate, not bit-identical).
+REFERENCE_ROUNDING = True
+
+
+def _flags():
+    return _lib.NGP_GRID_REF_ROUNDING if REFERENCE_ROUNDING else 0
+
+
+class _grid_encode(Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False,
+                gridtype=0, align_corners=False, interpolation=0, max_level=None):
+        # inputs [B, D] float in [0, 1]; embeddings [sO, C]; offsets [L + 1] int32  ->  [B, L * C] in table dtype
+        _lib.require_cuda(inputs, embeddings, offsets)
+        inputs = inputs.contiguous()
+        if inputs.dtype != torch.float32:
+            inputs = inputs.float()
+        embeddings = embeddings.contiguous()
+        if offsets.dtype != torch.int32:
+            raise RuntimeError("offsets must be an int tensor")
+        offsets = offsets.contiguous()
+
+        B, D = inputs.shape
+        L = offsets.shape[0] - 1
+        C = embeddings.shape[1]
+        S = float(np.log2(per_level_scale))
+        H = int(base_resolution)
+        max_level = L if max_level is None else min(int(max_level), L)
+        dt = _lib.dtype_id(embeddings.dtype)
+
+        outputs = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
+        _lib.call("ngp_grid_encode_forward", _lib.ptr(inputs), _lib.ptr(embeddings), _lib.ptr(offsets),
+                  _lib.ptr(outputs), B, D, C, L, max_level, S, H, None, int(gridtype), int(bool(align_corners)),
+                  int(interpolation), dt, _flags(), _lib.stream())
+
+        ctx.save_for_backward(inputs, embeddings, offsets)
+        ctx.dims = (B, D, C, L, S, H, int(gridtype), int(interpolation), max_level)
+        ctx.align_corners = bool(align_corners)
+        ctx.calc_grad_inputs = bool(calc_grad_inputs)
+        return outputs
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad):
+        inputs, embeddings, offsets = ctx.saved_tensors
+        B, D, C, L, S, H, gridtype, interpolation, max_level = ctx.dims
+
+        grad = grad.contiguous()
+        if grad.dtype != embeddings.dtype:
+            grad = grad.to(embeddings.dtype)
+        grad_embeddings = torch.zeros_like(embeddings)
+        grad_inputs = torch.zeros(B, D, device=inputs.device, dtype=torch.float32) if ctx.calc_grad_inputs else None
+
+        _lib.call("ngp_grid_encode_backward", _lib.ptr(grad), _lib.ptr(inputs), _lib.ptr(embeddings),
+                  _lib.ptr(offsets), _lib.ptr(grad_embeddings), B, D, C, L, max_level, S, H, _lib.ptr(grad_inputs),
+                  gridtype, int(ctx.align_corners), interpolation, _lib.dtype_id(embeddings.dtype), _flags(),
+                  _lib.stream())
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None
+
+
+grid_encode = _grid_encode.apply
+
+
+def grid_encode_with_jacobian(inputs, embeddings, offsets, per_level_scale, base_resolution, gridtype=0,
+                              align_corners=False, interpolation=0, max_level=None):
+    """Forward that also materialises dy_dx [B, L*D*C] in the reference's layout (gridencoder.cu:207).
+    Not used by the autograd path; kept so the kernel can be compared with the reference's dy_dx."""
+    inputs = inputs.contiguous().float()
+    B, D = inputs.shape
+    L = offsets.shape[0] - 1
+    C = embeddings.shape[1]
+    S = float(np.log2(per_level_scale))
+    max_level = L if max_level is None else min(int(max_level), L)
+    outputs = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
+    dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype)
+    _lib.call("ngp_grid_encode_forward", _lib.ptr(inputs), _lib.ptr(embeddings), _lib.ptr(offsets), _lib.ptr(outputs),
+              B, D, C, L, max_level, S, int(base_resolution), _lib.ptr(dy_dx), int(gridtype), int(bool(align_corners)),
+              int(interpolation), _lib.dtype_id(embeddings.dtype), _flags(), _lib.stream())
+    return outputs, dy_dx
+
+
+def level_table_offsets(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size):
+    """Per-level entry offsets, float64 on the host exactly as the reference (grid.py:124-134)."""
+    max_params = 2 ** log2_hashmap_size
+    offsets, offset = [], 0
+    for i in range(num_levels):
+        resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+        params_in_level = min(max_params, resolution ** input_dim)
+        params_in_level = int(np.ceil(params_in_level / 8) * 8)
+        offsets.append(offset)
+        offset += params_in_level
+    offsets.append(offset)
+    return offsets
+
+
+class GridEncoder(nn.Module):
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16,
+                 log2_hashmap_size=19, desired_resolution=None, gridtype="hash", align_corners=False,
+                 interpolation="linear"):
+        super().__init__()
+        if desired_resolution is not None:
+            per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+
+        self.input_dim = input_dim
+        self.num_levels = num_levels
+        self.level_dim = level_dim
+        self.per_level_scale = per_level_scale
+        self.log2_hashmap_size = log2_hashmap_size
+        self.base_resolution = base_resolution
+        self.output_dim = num_levels * level_dim
+        self.gridtype = gridtype
+        self.gridtype_id = _gridtype_to_id[gridtype]
+        self.interpolation = interpolation
+        self.interp_id = _interp_to_id[interpolation]
+        self.align_corners = align_corners
+        self.max_params = 2 ** log2_hashmap_size
+
+        offsets = level_table_offsets(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size)
+        self.register_buffer("offsets", torch.from_numpy(np.array(offsets, dtype=np.int32)))
+        self.n_params = self.offsets[-1] * level_dim
+        self.embeddings = nn.Parameter(torch.empty(offsets[-1], level_dim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        std = 1e-4
+        self.embeddings.data.uniform_(-std, std)
+
+    def __repr__(self):
+        return (f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "
+                f"resolution={self.base_resolution} -> "
+                f"{int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))} "
+                f"per_level_scale={self.per_level_scale:.4f} params={tuple(self.embeddings.shape)} "
+                f"gridtype={self.gridtype} align_corners={self.align_corners} interpolation={self.interpolation}")
+
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(self, inputs, bound=1, max_level=None):
+        # inputs [..., input_dim] in [-bound, bound]  ->  [..., num_levels * level_dim]
+        inputs = (inputs + bound) / (2 * bound)
+        prefix_shape = list(inputs.shape[:-1])
+        inputs = inputs.view(-1, self.input_dim)
+        outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
+                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id, max_level)
+        return outputs.view(prefix_shape + [self.output_dim])
+
+    @torch.amp.autocast("cuda", enabled=False)
+    def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
+        D = self.input_dim
+        C = self.embeddings.shape[1]
+        L = self.offsets.shape[0] - 1
+        S = float(np.log2(self.per_level_scale))
+        H = self.base_resolution
+        if inputs is None:
+            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
+        else:
+            inputs = (inputs + bound) / (2 * bound)
+            inputs = inputs.view(-1, self.input_dim)
+            B = inputs.shape[0]
+        if self.embeddings.grad is None:
+            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
+        inputs = inputs.to(self.embeddings.dtype).contiguous()
+        _lib.call("ngp_grid_grad_total_variation", _lib.ptr(inputs), _lib.ptr(self.embeddings),
+                  _lib.ptr(self.embeddings.grad), _lib.ptr(self.offsets), float(weight), B, D, C, L, S, H,
+                  self.gridtype_id, int(self.align_corners), _lib.dtype_id(self.embeddings.dtype), _lib.stream())
+
+    @torch.amp.autocast("cuda", enabled=False)
+    def grad_weight_decay(self, weight=0.1):
+        B = self.embeddings.shape[0]
+        C = self.embeddings.shape[1]
+        L = self.offsets.shape[0] - 1
+        if self.embeddings.grad is None:
+            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
+        _lib.call("ngp_grid_grad_weight_decay", _lib.ptr(self.embeddings), _lib.ptr(self.embeddings.grad),
+                  _lib.ptr(self.offsets), float(weight), B, C, L, _lib.dtype_id(self.embeddings.dtype), _lib.stream())
