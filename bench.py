@@ -1,0 +1,392 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the raw_ngp hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours:       BASELINE.json configs[1] -- synthetic NeRF training step (bound 1, cascade 1, grid 128^3, 4096 rays per
+            GPU, max_steps 1024, fp16 hash table, 64-wide MLPs) through raw_ngp_b200 (libngp_b200.so).  One JSON line:
+            value = training rays/s over all ranks (device-timed, inputs resident in HBM); e2e = the same step fed
+            from pinned host buffers with the loss read back each step; roofline = the dominant kernel of the step
+            timed alone on the step's own sample batch; grid_encode = the configs[0] micro-benchmark (2^18 points);
+            cpu_baseline = the PyTorch-on-CPU port of the same step (oracle/cpu_pipeline.py) on a bounded ray sample.
+reference:  the same step in the CPU port (the reference has no CPU path of its own; kind "port"), rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 4096
+CPU_SAMPLE_RAYS = 96
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(device, rank, seed=2):
+    from raw_ngp_b200 import raymarching, synthetic
+    from raw_ngp_b200.nerf import NeRFNetwork, default_opt
+    torch.manual_seed(0)
+    opt = default_opt(bound=1, grid_size=128, max_steps=1024, dt_gamma=0, T_thresh=1e-8, min_near=0.05, fp16=True,
+                      density_thresh=10, hashmap_size=19, hashgrid_resolution=2048)
+    model = NeRFNetwork(opt).to(device)
+    grid = synthetic.ball_density_grid(H=128, cascade=1, bound=1.0, radius=0.5, sigma=50.0).to(device)
+    model.density_grid.copy_(grid)
+    thresh = min(grid.clamp(min=0).mean().item(), 10.0)
+    model.density_bitfield = raymarching.packbits(model.density_grid, thresh, model.density_bitfield)
+    model.mean_density = grid.clamp(min=0).mean().item()
+    o, d = synthetic.sphere_rays(RAYS_PER_GPU, seed=seed + 1000 * rank)
+    g = torch.Generator().manual_seed(7 + rank)
+    target = torch.rand(RAYS_PER_GPU, 3, generator=g)
+    return model, o, d, target
+
+
+def time_kernel(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(iters):
+        fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters  # ms
+
+
+def encoder_micro(device, hbm_peak):
+    """BASELINE configs[0]: GridEncoder fwd / bwd on 2^18 points, fp16 table, L2-warm (the table is resident in the
+    126 MB L2 in the training steady state) and with an L2 flush between launches."""
+    from raw_ngp_b200 import synthetic
+    from raw_ngp_b200.gridencoder import GridEncoder, grid_encode
+    B = 2 ** 18
+    enc = GridEncoder(desired_resolution=2048).to(device)
+    table = enc.embeddings.data.half().contiguous()
+    x = ((synthetic.uniform_points(B, seed=0) + 1) / 2).to(device)
+    grad = (torch.randn(B, 32, generator=torch.Generator().manual_seed(1)) * 1e-3).half().to(device)
+    sink = torch.zeros_like(table)
+    args = (enc.per_level_scale, enc.base_resolution)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def fwd():
+        return grid_encode(x, table, enc.offsets, *args, False, 0, False, 0, None)
+
+    tab_g = table.clone().requires_grad_(True)
+
+    def bwd_only():
+        from raw_ngp_b200 import _lib
+        _lib.call("ngp_grid_encode_backward", grad.data_ptr(), x.data_ptr(), table.data_ptr(), enc.offsets.data_ptr(),
+                  sink.data_ptr(), B, 3, 2, 16, 16, float(__import__("numpy").log2(enc.per_level_scale)), 16, None, 0, 0, 0,
+                  _lib.NGP_F16, 0, _lib.stream())
+
+    res = {}
+    t_f = time_kernel(fwd)
+    t_b = time_kernel(bwd_only)
+
+    def flushed(fn):
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+    bytes_pt = 12 + 256 * 2 + 32 * 2   # xyz + corner payload + output, fp16
+    res = {
+        "points": B, "dtype": "f16",
+        "fwd_mpts_s": B / t_f / 1e3, "bwd_mpts_s": B / t_b / 1e3,
+        "fwd_ms_l2_warm": t_f, "bwd_ms_l2_warm": t_b,
+        "fwd_ms_l2_flushed": flushed(fwd), "bwd_ms_l2_flushed": flushed(bwd_only),
+        "algorithmic_bytes_per_point": bytes_pt,
+        "fwd_frac_of_hbm_peak": bytes_pt * B / (t_f * 1e-3) / 1e9 / hbm_peak,
+        "bwd_frac_of_hbm_peak": bytes_pt * B / (t_b * 1e-3) / 1e9 / hbm_peak,
+    }
+    try:
+        from oracle import ref_cuda
+        if ref_cuda.available():
+            t_rf = time_kernel(lambda: ref_cuda.grid_forward(x, table, enc.offsets, *args))
+            t_rb = time_kernel(lambda: ref_cuda.grid_backward(grad, x, table, enc.offsets, *args))
+            res["reference_cuda"] = {"fwd_ms": t_rf, "bwd_ms": t_rb, "fwd_mpts_s": B / t_rf / 1e3, "bwd_mpts_s": B / t_rb / 1e3,
+                                     "note": "reference extension (unmodified source, sm_100a) incl. its wrapper's permute/zero-fill"}
+    except Exception as e:  # the reference build is optional
+        res["reference_cuda"] = {"unavailable": str(e)[:120]}
+    return res
+
+
+def cpu_baseline(steps=1, rays=CPU_SAMPLE_RAYS):
+    """The CPU port on a bounded sample of the same workload (same scene, same ray distribution)."""
+    from oracle import cpu_pipeline, raymarch_oracle
+    from raw_ngp_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    grid = synthetic.ball_density_grid(H=128, cascade=1)
+    bitfield = synthetic.packbits_torch(grid, min(grid.clamp(min=0).mean().item(), 10.0))
+    o, d = synthetic.sphere_rays(rays, seed=2)
+    aabb = torch.tensor([-1.0] * 3 + [1.0] * 3)
+    nears, fars = synthetic.near_far_torch(o, d, aabb, 0.05)
+    nears, fars = nears.view(-1).contiguous(), fars.view(-1).contiguous()
+    target = torch.rand(rays, 3, generator=torch.Generator().manual_seed(7))
+    model = cpu_pipeline.CpuNeRF()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    g = torch.Generator().manual_seed(3)
+    times, M = [], 0
+    for i in range(steps + 1):
+        noises = torch.rand(rays, generator=g)
+        t0 = time.perf_counter()
+        _, M = cpu_pipeline.train_step(model, optim, o, d, target, bitfield, nears, fars, noises)
+        times.append(time.perf_counter() - t0)
+    best = min(times[1:]) if steps >= 1 else times[0]
+    return {"value": rays / best, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{rays} rays ({M} samples) per step of the configs[1] scene, full step incl. Adam over the 12.2M-entry table; best of {steps} after 1 warm-up",
+            "ms_per_step": best * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    from oracle import cpu_pipeline
+    from raw_ngp_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    rays = CPU_SAMPLE_RAYS
+    grid = synthetic.ball_density_grid(H=128, cascade=1)
+    bitfield = synthetic.packbits_torch(grid, min(grid.clamp(min=0).mean().item(), 10.0))
+    o, d = synthetic.sphere_rays(rays, seed=2)
+    nears, fars = synthetic.near_far_torch(o, d, torch.tensor([-1.0] * 3 + [1.0] * 3), 0.05)
+    nears, fars = nears.view(-1).contiguous(), fars.view(-1).contiguous()
+    target = torch.rand(rays, 3, generator=torch.Generator().manual_seed(7))
+    model = cpu_pipeline.CpuNeRF()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    g = torch.Generator().manual_seed(3)
+    M = 0
+    for _ in range(W):
+        cpu_pipeline.train_step(model, optim, o, d, target, bitfield, nears, fars, torch.rand(rays, generator=g))
+    t0 = time.perf_counter()
+    for _ in range(K):
+        _, M = cpu_pipeline.train_step(model, optim, o, d, target, bitfield, nears, fars, torch.rand(rays, generator=g))
+    dt = time.perf_counter() - t0
+    v = rays * K / dt
+    line = {
+        "impl": "reference", "metric": "training rays/s", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] NeRF training step (bound 1, cascade 1, grid 128^3, max_steps 1024, hash grid L16 F2 T2^19 + 64-wide MLPs)",
+                   "rays_per_step": rays, "samples_per_step": M},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{rays} rays ({M} samples) per step; the reference has no CPU implementation, this is oracle/cpu_pipeline.py (PyTorch on the host cores)"},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from raw_ngp_b200 import _lib
+    from raw_ngp_b200.trainer import TrainStep
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (ours) needs a CUDA device: the hot path has no CPU fallback")
+    _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    K, W = args.steps, args.warmup
+    hbm_peak, peak_src = _peaks()
+
+    model, o_cpu, d_cpu, tgt_cpu = build_scene(device, rank)
+    step = TrainStep(model, lr=1e-2, table_dtype=torch.float16, loss_scale=128.0, update_extra_interval=16)
+    o, d, tgt = o_cpu.to(device), d_cpu.to(device), tgt_cpu.to(device)
+    # the occupancy grid of the synthetic scene is fixed (random-init weights would empty it): update_extra_state is
+    # exercised once per 16 steps on a scratch copy so its cost is inside the timed region without changing M
+    scratch = dict(grid=model.density_grid.clone(), bits=model.density_bitfield.clone())
+
+    def one_step(ro, rd, tg):
+        if step.global_step % step.update_extra_interval == 0:
+            model.update_extra_state()
+            model.density_grid.copy_(scratch["grid"])
+            model.density_bitfield.copy_(scratch["bits"])
+            model.iter_density = 0
+        return step.step(ro, rd, tg, update_grid=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(W):
+        one_step(o, d, tgt)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = one_step(o, d, tgt)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    M = step.last_num_points
+
+    # ---------------- end to end: pinned host inputs, loss read back ----------------
+    o_pin, d_pin, t_pin = o_cpu.pin_memory(), d_cpu.pin_memory(), tgt_cpu.pin_memory()
+    loss_host = torch.empty(1, pin_memory=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        ro = o_pin.to(device, non_blocking=True)
+        rd = d_pin.to(device, non_blocking=True)
+        tg = t_pin.to(device, non_blocking=True)
+        loss = one_step(ro, rd, tg)
+        loss_host.copy_(loss.reshape(1), non_blocking=False)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel, on the step's own sample batch ----------------
+        import numpy as np
+        from raw_ngp_b200 import raymarching
+        enc = model.grid_encoder
+        with torch.no_grad():
+            nears, fars = __import__("raw_ngp_b200.nerf", fromlist=["near_far_from_aabb"]).near_far_from_aabb(o, d, model.aabb_train, 0.05)
+            xyzs, dirs, ts_, rays_, _ = raymarching.march_rays_train(o, d, None, 1.0, False, model.density_bitfield, 1, 128,
+                                                                     nears, fars, True, 0, 1024)
+        Mk = xyzs.shape[0]
+        x01 = ((xyzs + 1) / 2).contiguous()
+        gradk = (torch.randn(Mk, 32, device=device) * 1e-3).half()
+        S = float(np.log2(enc.per_level_scale))
+
+        def k_bwd():
+            _lib.call("ngp_grid_encode_backward", gradk.data_ptr(), x01.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
+                      step.table_grad.data_ptr(), Mk, 3, 2, 16, 16, S, 16, None, 0, 0, 0, _lib.NGP_F16, 0, _lib.stream())
+        outk = torch.empty(Mk, 32, device=device, dtype=torch.float16)
+
+        def k_fwd():
+            _lib.call("ngp_grid_encode_forward", x01.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(), outk.data_ptr(),
+                      Mk, 3, 2, 16, 16, S, 16, None, 0, 0, 0, _lib.NGP_F16, 1, _lib.stream())
+        t_bwd, t_fwd = time_kernel(k_bwd), time_kernel(k_fwd)
+        step.table_grad.zero_()
+        bytes_pt = 12 + 256 * 2 + 32 * 2
+        dom, t_dom = ("grid_backward_kernel", t_bwd) if t_bwd >= t_fwd else ("grid_forward_kernel", t_fwd)
+        achieved = bytes_pt * Mk / (t_dom * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else peak_src,
+                    "algorithmic_bytes_per_launch": bytes_pt * Mk, "ms_per_launch": t_dom, "points_per_launch": Mk,
+                    "other": {"grid_forward_ms": t_fwd, "grid_backward_ms": t_bwd}}
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            tj = json.load(open(prof))
+            if dom in tj:
+                roofline["traffic"] = tj[dom].get("dram_bytes_per_launch")
+                roofline["traffic_note"] = tj[dom].get("note")
+        micro = encoder_micro(device, hbm_peak)
+        cpu = cpu_baseline() if world == 1 else None
+        total_rays = RAYS_PER_GPU * world
+        line = {
+            "metric": "training rays/s", "value": total_rays * K / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "configs[1] NeRF training step (bound 1, cascade 1, grid 128^3, max_steps 1024, fp16 hash grid L16 F2 T2^19 + 64-wide MLPs)",
+                       "rays_per_gpu": RAYS_PER_GPU, "samples_per_step_per_gpu": M, "samples_per_ray": M / RAYS_PER_GPU,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": "inputs re-read each step; table 23 MiB + grads are L2 resident by design (steady state of training); no flush",
+                       "occupancy_update": "update_extra_state every 16 steps inside the timed region"},
+            "samples_per_s": M * world * K / (ms * 1e-3),
+            "e2e": {"value": total_rays * K / (ms_e2e * 1e-3), "unit": "rays/s",
+                    "h2d_bytes_per_step": int(o_pin.numel() * 4 + d_pin.numel() * 4 + t_pin.numel() * 4), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "grid_encode": micro,
+            "final_loss": float(loss.item()),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

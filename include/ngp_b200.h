@@ -108,6 +108,11 @@ int ngp_grid_grad_weight_decay(const void* embeddings, void* grad, const int32_t
                                float weight, uint32_t n_entries, uint32_t C, uint32_t L, int dtype,
                                ngp_stream_t stream);
 
+/* Per-level grid resolution exactly as the kernels evaluate it on the device, in fp32:
+ * ceil(exp2f(level * S) * H)  (gridencoder.cu:133; the host computes table offsets in float64, grid.py:128,
+ * and the two can disagree by one at the finest level).  out_dev uint32[L]. */
+int ngp_grid_level_resolutions(uint32_t L, float S, uint32_t H, uint32_t* out_dev, ngp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Spherical-harmonics encoder  (reference: shencoder/src/shencoder.h:9-10)
  * ---------------------------------------------------------------------------------------- */

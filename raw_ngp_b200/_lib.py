@@ -26,6 +26,7 @@ SIGNATURES = {
     "ngp_grid_input_backward": [_p, _p, _p, _u32, _u32, _u32, _u32, _i, _p],
     "ngp_grid_grad_total_variation": [_p, _p, _p, _p, _f32, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i, _i, _p],
     "ngp_grid_grad_weight_decay": [_p, _p, _p, _f32, _u32, _u32, _u32, _i, _p],
+    "ngp_grid_level_resolutions": [_u32, _f32, _u32, _p, _p],
     "ngp_sh_encode_forward": [_p, _p, _u32, _u32, _p, _i, _p],
     "ngp_sh_encode_backward": [_p, _p, _u32, _u32, _p, _i, _p],
     "ngp_near_far_from_aabb": [_p, _p, _p, _u32, _f32, _p, _p, _p],
@@ -106,9 +107,14 @@ def require_cuda(*tensors):
             raise RuntimeError("raw_ngp_b200: operator called with a CPU tensor; these operators are CUDA-only (sm_100a)")
 
 
+launch_count = 0  # kernels launched through the C ABI by this process (every entry point is one launch)
+
+
 def call(name, *args):
     """Calls an entry point on the current stream's device and raises on a non-zero status."""
+    global launch_count
     lib = load()
+    launch_count += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.ngp_status_string(rc).decode()

@@ -374,6 +374,11 @@ __global__ void grid_wd_kernel(const T* __restrict__ table, T* __restrict__ grad
     }
 }
 
+__global__ void level_resolution_kernel(uint32_t L, float S, uint32_t H, uint32_t* __restrict__ out) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < L) out[l] = level_resolution(l, S, H);
+}
+
 template <typename T, uint32_t D>
 int launch_forward(const float* inputs, const T* table, const int* offsets, T* outputs, T* dy_dx, uint32_t B,
                    uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H, uint32_t gridtype,
@@ -566,5 +571,12 @@ extern "C" int ngp_grid_grad_weight_decay(const void* embeddings, void* grad, co
     NGP_DISPATCH_DTYPE(dtype, {
         grid_wd_kernel<T><<<blocks, 256, (L + 1) * sizeof(int), st>>>((const T*)embeddings, (T*)grad, offsets, weight, n, L, C);
     });
+    return finish_launch();
+}
+
+extern "C" int ngp_grid_level_resolutions(uint32_t L, float S, uint32_t H, uint32_t* out_dev, ngp_stream_t stream) {
+    if (L == 0) return NGP_OK;
+    if (!out_dev) return NGP_ERR_NULL;
+    level_resolution_kernel<<<div_up(L, 64u), 64, 0, (cudaStream_t)stream>>>(L, S, H, out_dev);
     return finish_launch();
 }

@@ -27,8 +27,11 @@ __device__ __forceinline__ uint32_t compact3(uint32_t v) {
 }
 
 // renderer.py:833-846 (full) / :857-876 (partial)
+// Arithmetic mirrors the torch expression chain of the reference op for op (every product / sum rounded
+// separately, hence the explicit __fmul_rn/__fadd_rn: no FMA contraction), so that with the same torch RNG
+// stream the sample positions are the reference's.
 __global__ void occ_sample_kernel(const int* __restrict__ cell_indices, const float* __restrict__ noise, uint32_t n,
-                                  uint32_t H, float bound, float* __restrict__ xyzs, int* __restrict__ indices_out) {
+                                  uint32_t H, float span, float hgs, float* __restrict__ xyzs, int* __restrict__ indices_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t cx, cy, cz, morton;
@@ -40,14 +43,13 @@ __global__ void occ_sample_kernel(const int* __restrict__ cell_indices, const fl
         cz = i % H; cy = (i / H) % H; cx = i / (H * H);
         morton = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
     }
-    const float hgs = bound / H;          // half grid size
-    const float span = bound - hgs;
     const float c[3] = {(float)cx, (float)cy, (float)cz};
+    const float hm1 = (float)(H - 1);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const float w = 2 * c[a] / (H - 1) - 1;                 // [-1, 1]
-        const float jitter = (__ldg(noise + (size_t)i * 3 + a) * 2 - 1) * hgs;
-        xyzs[(size_t)i * 3 + a] = w * span + jitter;
+        const float w = __fadd_rn(__fdiv_rn(__fmul_rn(2.0f, c[a]), hm1), -1.0f);           // 2*c/(H-1) - 1 in [-1, 1]
+        const float jitter = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(noise + (size_t)i * 3 + a), 2.0f), -1.0f), hgs);
+        xyzs[(size_t)i * 3 + a] = __fadd_rn(__fmul_rn(w, span), jitter);
     }
     if (indices_out) indices_out[i] = (int)morton;
 }
@@ -104,7 +106,10 @@ extern "C" int ngp_occ_sample_positions(const int32_t* cell_indices, const float
     if (n == 0) return NGP_OK;
     if (!noise || !xyzs_out) return NGP_ERR_NULL;
     if (H < 2 || H > 1024) return NGP_ERR_BAD_ARG;
-    occ_sample_kernel<<<div_up(n, 256u), 256, 0, (cudaStream_t)stream>>>(cell_indices, noise, n, H, bound, xyzs_out, indices_out);
+    // python-double arithmetic of the reference (renderer.py:841-844), cast to fp32 where torch casts the scalar
+    const double hgs = (double)bound / (double)H;
+    const double span = (double)bound - hgs;
+    occ_sample_kernel<<<div_up(n, 256u), 256, 0, (cudaStream_t)stream>>>(cell_indices, noise, n, H, (float)span, (float)hgs, xyzs_out, indices_out);
     return finish_launch();
 }
 

@@ -34,8 +34,10 @@ class _grid_encode(Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
     def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False,
-                gridtype=0, align_corners=False, interpolation=0, max_level=None):
+                gridtype=0, align_corners=False, interpolation=0, max_level=None, grad_sink=None):
         # inputs [B, D] float in [0, 1]; embeddings [sO, C]; offsets [L + 1] int32  ->  [B, L * C] in table dtype
+        # grad_sink (extension, optional): persistent [sO, C] buffer the table gradient is ACCUMULATED into instead of
+        # returning a fresh zero-filled tensor (no 24-48 MB memset + allocation per step; see raw_ngp_b200/trainer.py)
         _lib.require_cuda(inputs, embeddings, offsets)
         inputs = inputs.contiguous()
         if inputs.dtype != torch.float32:
@@ -62,6 +64,7 @@ class _grid_encode(Function):
         ctx.dims = (B, D, C, L, S, H, int(gridtype), int(interpolation), max_level)
         ctx.align_corners = bool(align_corners)
         ctx.calc_grad_inputs = bool(calc_grad_inputs)
+        ctx.grad_sink = grad_sink
         return outputs
 
     @staticmethod
@@ -73,14 +76,20 @@ class _grid_encode(Function):
         grad = grad.contiguous()
         if grad.dtype != embeddings.dtype:
             grad = grad.to(embeddings.dtype)
-        grad_embeddings = torch.zeros_like(embeddings)
+        sink = ctx.grad_sink
+        if sink is not None:
+            if sink.shape != embeddings.shape or sink.dtype != embeddings.dtype or not sink.is_contiguous():
+                raise RuntimeError("grad_sink must be a contiguous tensor with the table's shape and dtype")
+            grad_embeddings = sink
+        else:
+            grad_embeddings = torch.zeros_like(embeddings)
         grad_inputs = torch.zeros(B, D, device=inputs.device, dtype=torch.float32) if ctx.calc_grad_inputs else None
 
         _lib.call("ngp_grid_encode_backward", _lib.ptr(grad), _lib.ptr(inputs), _lib.ptr(embeddings),
                   _lib.ptr(offsets), _lib.ptr(grad_embeddings), B, D, C, L, max_level, S, H, _lib.ptr(grad_inputs),
                   gridtype, int(ctx.align_corners), interpolation, _lib.dtype_id(embeddings.dtype), _flags(),
                   _lib.stream())
-        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None
+        return grad_inputs, (None if sink is not None else grad_embeddings), None, None, None, None, None, None, None, None, None
 
 
 grid_encode = _grid_encode.apply
@@ -144,6 +153,7 @@ class GridEncoder(nn.Module):
         self.register_buffer("offsets", torch.from_numpy(np.array(offsets, dtype=np.int32)))
         self.n_params = self.offsets[-1] * level_dim
         self.embeddings = nn.Parameter(torch.empty(offsets[-1], level_dim))
+        self.grad_sink = None   # set by raw_ngp_b200.trainer: table gradients accumulate here, embeddings.grad stays None
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -164,7 +174,8 @@ class GridEncoder(nn.Module):
         prefix_shape = list(inputs.shape[:-1])
         inputs = inputs.view(-1, self.input_dim)
         outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
-                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id, max_level)
+                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id, max_level,
+                              self.grad_sink)
         return outputs.view(prefix_shape + [self.output_dim])
 
     @torch.amp.autocast("cuda", enabled=False)

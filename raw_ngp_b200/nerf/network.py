@@ -1,0 +1,129 @@
+"""NeRFNetwork -- hash grid + tiny MLPs (nerf/network.py:12-184) on the B200 operators.
+
+Same module / parameter names as the reference so that checkpoints keep their keys:
+grid_encoder.embeddings, grid_encoder.offsets, grid_mlp.net.{0,1,2}.weight, view_mlp.net.{0,1,2}.weight
+(SURVEY.md 5.4).  The camera pose optimizer (barf/) is outside the hot path; the BARF / BAA-NGP feature annealing
+that lives inside common_forward (network.py:77-109) is kept.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..activation import trunc_exp
+from ..encoding import get_encoder
+from .renderer import NeRFRenderer
+
+
+class MLP(nn.Module):
+    def __init__(self, dim_in, dim_out, dim_hidden, num_layers, opt, bias=True):
+        super().__init__()
+        self.dim_in = dim_in
+        self.dim_out = dim_out
+        self.dim_hidden = dim_hidden
+        self.num_layers = num_layers
+        self.opt = opt
+        self.net = nn.ModuleList([
+            nn.Linear(self.dim_in if l == 0 else self.dim_hidden,
+                      self.dim_out if l == num_layers - 1 else self.dim_hidden, bias=bias)
+            for l in range(num_layers)])
+
+    def forward(self, x):
+        for l in range(self.num_layers):
+            x = self.net[l](x)
+            if l != self.num_layers - 1:
+                if self.opt.internal_activation == "relu":
+                    x = F.relu(x, inplace=True)
+                if self.opt.internal_activation == "softplus":
+                    x = F.softplus(x, beta=self.opt.beta, threshold=20)
+        return x
+
+
+class NeRFNetwork(NeRFRenderer):
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.annealing = 0.0
+        if opt.pose_opt != "none" and getattr(opt, "pose_optimizer_factory", None) is not None:
+            # barf/camera_optimizers.CameraOptimizer is not part of the hot path; plug one in through the factory
+            self.pose_optimizer = opt.pose_optimizer_factory(opt)
+
+        self.level_dim = 2
+        self.grid_encoder, self.grid_in_dim = get_encoder(
+            "hashgrid", input_dim=3, level_dim=self.level_dim, num_levels=16, log2_hashmap_size=self.opt.hashmap_size,
+            desired_resolution=self.opt.hashgrid_resolution * self.bound)
+        self.grid_mlp = MLP(self.grid_in_dim, 16, 64, 3, opt, bias=False)
+
+        self.view_encoder, self.view_in_dim = get_encoder("sh", input_dim=3, degree=4)
+        ldir_dim = self.view_in_dim if self.opt.rfield else 0
+        self.view_mlp = MLP(15 + self.view_in_dim + ldir_dim, 3, 64 + ldir_dim, 3, opt, bias=False)
+
+    def _annealing_window(self, L, device):
+        start, end = self.opt.start_annealing, self.opt.end_annealing
+        k = torch.arange(L, dtype=torch.float32, device=device)
+        if end == 0:
+            end = 1e-12
+        alpha = (self.annealing - start) / (end - start) * L
+        return (1 - (alpha - k).clamp_(min=0, max=1).mul_(np.pi).cos_()) / 2
+
+    def common_forward(self, x):
+        f = self.grid_encoder(x, bound=self.bound)
+        if self.opt.pose_opt == "baangp":      # network.py:77-97
+            L = self.grid_mlp.dim_out - 1
+            weight = self._annealing_window(L, f.device)
+            weights = torch.cat([torch.ones(self.level_dim, device=f.device), weight.repeat_interleave(self.level_dim)])
+            assert f.shape[-1] == len(weights)
+            available_features = f[..., weights > 0]
+            assert len(available_features) > 0, "no features are selected!"
+            coarse_features = available_features[..., -self.level_dim:]
+            coarse_f = coarse_features.repeat(1, L + 1)
+            weights[0:2] = 1
+            f = f * weights + coarse_f * (1 - weights)
+        if self.opt.pose_opt == "barf":        # network.py:99-109
+            L = self.grid_mlp.dim_out
+            weights = self._annealing_window(L, f.device).repeat_interleave(self.level_dim)
+            weights[0:2] = 1
+            f = f * weights
+
+        f = self.grid_mlp(f)
+        if self.opt.density_activation == "clamped_exp":
+            sigma = trunc_exp(f[..., 0])
+        else:
+            sigma = F.softplus(f[..., 0], beta=self.opt.beta, threshold=20)
+        return sigma, f[..., 1:]
+
+    def forward(self, x, d, ld=None, **kwargs):
+        # x [N, 3] in [-bound, bound], d [N, 3] unit view directions, ld [N, 3] unit light directions (rfield)
+        sigma, feat = self.common_forward(x)
+        d = self.view_encoder(d)
+        if self.opt.rfield:
+            ld = self.view_encoder(ld)
+            color = self.view_mlp(torch.cat([feat, d, ld], dim=-1))
+        else:
+            color = self.view_mlp(torch.cat([feat, d], dim=-1))
+        if self.opt.color_activation == "exp":
+            color = torch.exp(color - 5.0)
+        if self.opt.color_activation == "sigmoid":
+            color = torch.sigmoid(color)
+        if self.opt.color_activation == "clamped_exp":
+            color = torch.clamp(torch.exp(color - 5.0), max=5.0)
+        return {"sigma": sigma, "color": color}
+
+    def density(self, x, proposal=-1):
+        sigma, _ = self.common_forward(x)
+        return {"sigma": sigma}
+
+    def apply_total_variation(self, w):
+        self.grid_encoder.grad_total_variation(w)
+
+    def apply_weight_decay(self, w):
+        self.grid_encoder.grad_weight_decay(w)
+
+    def update_annealing(self, new_value):
+        self.annealing = new_value
+
+    def get_params(self, lr):
+        return [
+            {"params": self.grid_encoder.parameters(), "lr": lr},
+            {"params": self.grid_mlp.parameters(), "lr": lr},
+            {"params": self.view_mlp.parameters(), "lr": lr},
+        ]

@@ -1,0 +1,298 @@
+"""NeRFRenderer -- the cuda_ray rendering path of the reference (nerf/renderer.py) on the B200 operators.
+
+In scope: __init__ (:161-198), update_aabb (:211-217), render/run_cuda (:374-377, :515-676),
+mark_untrained_grid (:716-809), update_extra_state (:811-897) and the differentiable near_far_from_aabb (:139-158).
+The proposal-network path (`run`) and mesh export are not part of the hot path and are not provided.
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, raymarching
+
+
+def default_opt(**overrides):
+    """The hot-path relevant defaults of the reference CLI (main.py:31-92)."""
+    opt = SimpleNamespace(
+        bound=2, contract=False, grid_size=128, min_near=0.05, density_thresh=10, cuda_ray=True, dt_gamma=0,
+        max_steps=1024, T_thresh=1e-8, fp16=True, hashmap_size=19, hashgrid_resolution=2048, rfield=False,
+        pose_opt="none", internal_activation="relu", beta=1.0, density_activation="clamped_exp",
+        color_activation="clamped_exp", start_annealing=0.0, end_annealing=0.5, lambda_orientation=0,
+        compute_normals=False, device="cuda", num_cameras=0, update_extra_interval=16,
+    )
+    for k, v in overrides.items():
+        setattr(opt, k, v)
+    return opt
+
+
+@torch.amp.autocast("cuda", enabled=False)
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.05):
+    """Differentiable slab test, returns near [N,1], far [N,1] (renderer.py:139-158)."""
+    tmin = (aabb[:3] - rays_o) / (rays_d + 1e-15)
+    tmax = (aabb[3:] - rays_o) / (rays_d + 1e-15)
+    near = torch.where(tmin < tmax, tmin, tmax).amax(dim=-1, keepdim=True)
+    far = torch.where(tmin > tmax, tmin, tmax).amin(dim=-1, keepdim=True)
+    mask = far < near
+    near = torch.where(mask, torch.full_like(near, 1e9), near)
+    far = torch.where(mask, torch.full_like(far, 1e9), far)
+    near = torch.clamp(near, min=min_near)
+    return near, far
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.real_bound = opt.bound                       # bound for ray marching (world space)
+        self.bound = 2 if self.opt.contract else opt.bound  # bound for grid querying
+        self.cascade = 1 + math.ceil(math.log2(self.bound))
+        self.grid_size = opt.grid_size
+        self.min_near = opt.min_near
+        self.density_thresh = opt.density_thresh
+
+        aabb_train = torch.FloatTensor([-self.real_bound] * 3 + [self.real_bound] * 3)
+        self.register_buffer("aabb_train", aabb_train)
+        self.register_buffer("aabb_infer", aabb_train.clone())
+
+        self.cuda_ray = opt.cuda_ray
+        if not self.cuda_ray:
+            raise NotImplementedError("only the cuda_ray path is part of the B200 hot path")
+        self.register_buffer("density_grid", torch.zeros([self.cascade, self.grid_size ** 3]))
+        self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+        self._mean_density = 0.0        # python float or a 1-element device tensor (synced lazily)
+        self.iter_density = 0
+
+    # mean_density stays a plain attribute for checkpoints (train_utils.py:1156-1157) but is produced on the device;
+    # reading it is the only host sync of update_extra_state.
+    @property
+    def mean_density(self):
+        if torch.is_tensor(self._mean_density):
+            self._mean_density = float(self._mean_density.item())
+        return self._mean_density
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density = v
+
+    def forward(self, x, d, **kwargs):
+        raise NotImplementedError()
+
+    def density(self, x, **kwargs):
+        raise NotImplementedError()
+
+    def update_aabb(self, aabb):
+        if not torch.is_tensor(aabb):
+            aabb = torch.from_numpy(np.asarray(aabb)).float()
+        self.aabb_train = aabb.clamp(-self.real_bound, self.real_bound).to(self.aabb_train.device)
+        self.aabb_infer = self.aabb_train.clone()
+
+    def render(self, rays_o, rays_d, **kwargs):
+        return self.run_cuda(rays_o, rays_d, **kwargs)
+
+    def run_cuda(self, rays_o, rays_d, rays_ldir=None, bg_color=None, perturb=False, cam_near_far=None,
+                 update_proposal=True, shading="full", **kwargs):
+        # rays_o, rays_d [N, 3] -> image [N, 3], depth [N]
+        rays_o = rays_o.contiguous()
+        rays_d = rays_d.contiguous()
+        N = rays_o.shape[0]
+        device = rays_o.device
+
+        nears, fars = near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer,
+                                         self.min_near)
+        if cam_near_far is not None:
+            nears = torch.maximum(nears, cam_near_far[:, 0])
+            fars = torch.minimum(fars, cam_near_far[:, 1])
+        if bg_color is None:
+            bg_color = 0
+        results = {}
+        amp = torch.amp.autocast("cuda", enabled=self.opt.fp16)
+
+        if self.training:
+            xyzs, dirs, ts, rays, ldirs = raymarching.march_rays_train(
+                rays_o, rays_d, rays_ldir, self.real_bound, self.opt.contract, self.density_bitfield, self.cascade,
+                self.grid_size, nears, fars, perturb, self.opt.dt_gamma, self.opt.max_steps)
+            dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+            with amp:
+                outputs = self(xyzs, dirs, ldirs, shading=shading)
+                sigmas = outputs["sigma"]
+                rgbs = outputs["color"]
+            weights, weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, ts, rays,
+                                                                                  self.opt.T_thresh)
+            results["num_points"] = xyzs.shape[0]
+            results["weights"] = weights
+            results["weights_sum"] = weights_sum
+            if self.opt.lambda_orientation > 0:
+                pos = xyzs.clone().requires_grad_(True)
+                normals = torch.autograd.grad(self(pos, dirs, shading=shading)["sigma"], pos,
+                                              grad_outputs=torch.ones_like(sigmas), retain_graph=True)[0]
+                normals = (-torch.nn.functional.normalize(normals, dim=-1) + 1) / 2
+                zero = torch.tensor(0.0, dtype=torch.float32, device=device)
+                n_dot_v = (normals * -dirs).sum(dim=-1)
+                results["orientation_loss"] = torch.mean((weights * torch.min(zero, n_dot_v) ** 2).sum(dim=-1))
+        else:
+            dtype = torch.float32
+            weights_sum = torch.zeros(N, dtype=dtype, device=device)
+            depth = torch.zeros(N, dtype=dtype, device=device)
+            image = torch.zeros(N, 3, dtype=dtype, device=device)
+            self._march_composite_loop(N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, weights_sum,
+                                       depth, image, normals=False)
+            if getattr(self.opt, "compute_normals", False):
+                ws_n = torch.zeros(N, dtype=dtype, device=device)
+                depth_n = torch.zeros(N, dtype=dtype, device=device)
+                normalmap = torch.zeros(N, 3, dtype=dtype, device=device)
+                self._march_composite_loop(N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, ws_n,
+                                           depth_n, normalmap, normals=True)
+                results["normals"] = normalmap + (1 - weights_sum).unsqueeze(-1) * bg_color
+
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results["depth"] = depth
+        results["image"] = image
+        return results
+
+    def _march_composite_loop(self, N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, weights_sum,
+                              depth, image, normals):
+        """The alive-ray loop of renderer.py:588-616 (:626-668 for normals).  Compaction of the surviving ray ids
+        happens on the device; only the surviving count comes back to the host (it sizes the next launch)."""
+        device = rays_o.device
+        n_alive = N
+        rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+        rays_t = nears.clone().view(-1).contiguous()
+        step = 0
+        while step < self.opt.max_steps:
+            if n_alive <= 0:
+                break
+            n_step = max(min(N // n_alive, 8), 1)
+            xyzs, dirs, ts = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.real_bound,
+                                                    self.opt.contract, self.density_bitfield, self.cascade,
+                                                    self.grid_size, nears, fars, perturb if step == 0 else False,
+                                                    self.opt.dt_gamma, self.opt.max_steps)
+            dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+            with amp:
+                ldirs = rays_ldir.repeat(xyzs.shape[0], 1) if self.opt.rfield else None
+                outputs = self(xyzs, dirs, ldirs, shading=shading)
+                sigmas = outputs["sigma"]
+                if normals:
+                    with torch.enable_grad():
+                        pos = xyzs.clone().requires_grad_(True)
+                        nrm = torch.autograd.grad(self(pos, dirs, ldirs, shading=shading)["sigma"], pos,
+                                                  grad_outputs=torch.ones_like(sigmas), retain_graph=True)[0]
+                        rgbs = (-torch.nn.functional.normalize(nrm, dim=-1) + 1) / 2
+                else:
+                    rgbs = outputs["color"]
+            raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, ts, weights_sum, depth, image,
+                                       self.opt.T_thresh)
+            rays_alive, count = raymarching.compact_rays_alive(rays_alive, n_alive)
+            n_alive = int(count.item())
+            step += n_step
+
+    @torch.no_grad()
+    def mark_untrained_grid(self, dataset, S=64):
+        """Cells seen by no training camera, or outside the training AABB, get density -1 and never become occupied
+        (renderer.py:716-809).  `dataset` provides poses [B,4,4] (camera-to-world), intrinsics (fx, fy, cx, cy) and
+        optionally cam_near_far [B,2]."""
+        poses = dataset.poses
+        intrinsics = dataset.intrinsics
+        cam_near_far = dataset.cam_near_far if hasattr(dataset, "cam_near_far") else None
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        B = poses.shape[0]
+        dev = self.aabb_train.device
+        if isinstance(intrinsics, np.ndarray):
+            fx, fy, cx, cy = [torch.as_tensor(float(v)) for v in intrinsics]
+        else:
+            fx, fy, cx, cy = torch.chunk(intrinsics, 4, dim=-1)
+        fx, fy, cx, cy = fx.to(dev).float(), fy.to(dev).float(), cx.to(dev).float(), cy.to(dev).float()
+        per_cam = fx.numel() > 1
+        poses = poses.to(dev).float()
+        mask_cam = torch.zeros_like(self.density_grid)
+        mask_aabb = torch.zeros_like(self.density_grid)
+        H = self.grid_size
+        ar = torch.arange(H, dtype=torch.int32, device=dev)
+        for xs in ar.split(S):
+            for ys in ar.split(S):
+                for zs in ar.split(S):
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+                    coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+                    indices = raymarching.morton3D(coords).long()
+                    world_xyzs = (2 * coords.float() / (H - 1) - 1).unsqueeze(0)
+                    for cas in range(self.cascade):
+                        bound = min(2 ** cas, self.bound)
+                        hgs = bound / H
+                        cas_world_xyzs = world_xyzs * (bound - hgs)
+                        mask_min = (cas_world_xyzs >= (self.aabb_train[:3] - hgs)).sum(-1) == 3
+                        mask_max = (cas_world_xyzs <= (self.aabb_train[3:] + hgs)).sum(-1) == 3
+                        mask_aabb[cas, indices] += (mask_min & mask_max).reshape(-1)
+                        head = 0
+                        while head < B:
+                            tail = min(head + S, B)
+                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
+                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]   # world -> camera
+                            cam_xyzs[:, :, 2] *= -1                          # camera looks down -z
+                            cx_div_fx = (cx[head:tail] / fx[head:tail]) if per_cam else cx / fx
+                            cy_div_fy = (cy[head:tail] / fy[head:tail]) if per_cam else cy / fy
+                            if cam_near_far is None:
+                                min_near = torch.as_tensor(float(self.opt.min_near), device=dev)
+                            else:
+                                min_near = torch.as_tensor(cam_near_far[head:tail, 0]).to(dev).float().unsqueeze(1)
+                            mask_z = cam_xyzs[:, :, 2] > min_near
+                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < (cx_div_fx * cam_xyzs[:, :, 2] + hgs * 2)
+                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < (cy_div_fy * cam_xyzs[:, :, 2] + hgs * 2)
+                            mask_cam[cas, indices] += (mask_z & mask_x & mask_y).sum(0).bool().reshape(-1)
+                            head += S
+        self.density_grid[(mask_cam == 0) | (mask_aabb == 0)] = -1
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """EMA-max update of the density grid + bitfield (renderer.py:811-897).
+
+        Full update (first 16 calls): every cell of every cascade is queried once at a jittered position.  Partial
+        update: H^3/4 uniform cells + H^3/4 occupied cells per cascade.  The per-cascade torch op chains of the
+        reference are replaced by three kernels (sample positions, sigma scatter, fused EMA-max + clamped mean) and
+        packbits reads min(mean, density_thresh) on the device."""
+        if not self.cuda_ray:
+            return
+        H = self.grid_size
+        H3 = H ** 3
+        dev = self.density_grid.device
+        st = _lib.stream()
+        tmp_grid = torch.full_like(self.density_grid, -1.0)
+        amp = torch.amp.autocast("cuda", enabled=self.opt.fp16)
+
+        for cas in range(self.cascade):
+            bound = float(min(2 ** cas, self.bound))
+            if self.iter_density < 16:
+                n = H3
+                cells = None
+                noise = torch.rand(n, 3, device=dev)
+            else:
+                quarter = H3 // 4
+                coords = torch.randint(0, H, (quarter, 3), device=dev)
+                uniform_idx = raymarching.morton3D(coords)
+                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                if occ_indices.shape[0] > 0:
+                    rand_mask = torch.randint(0, occ_indices.shape[0], [quarter], dtype=torch.long, device=dev)
+                    cells = torch.cat([uniform_idx, occ_indices[rand_mask].int()], dim=0).contiguous()
+                else:
+                    cells = uniform_idx
+                n = cells.shape[0]
+                noise = torch.rand(n, 3, device=dev)
+            xyzs = torch.empty(n, 3, device=dev)
+            indices = cells if cells is not None else torch.empty(n, dtype=torch.int32, device=dev)
+            _lib.call("ngp_occ_sample_positions", _lib.ptr(cells), _lib.ptr(noise), n, H, bound, _lib.ptr(xyzs),
+                      None if cells is not None else _lib.ptr(indices), st)
+            with amp:
+                sigmas = self.density(xyzs)["sigma"].reshape(-1).detach().float().contiguous()
+            _lib.call("ngp_occ_scatter_sigmas", _lib.ptr(indices), _lib.ptr(sigmas), n, _lib.ptr(tmp_grid[cas]), st)
+
+        accum = torch.zeros(2, dtype=torch.float64, device=dev)
+        mean = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("ngp_occ_ema_update", _lib.ptr(self.density_grid), _lib.ptr(tmp_grid), self.cascade * H3, float(decay),
+                  _lib.ptr(accum), _lib.ptr(mean), st)
+        self._mean_density = mean
+        self.iter_density += 1
+        self.density_bitfield = raymarching.packbits(self.density_grid.detach(), (mean, float(self.density_thresh)),
+                                                     self.density_bitfield)
+        return None
