@@ -256,6 +256,32 @@ int ngp_occ_ema_update(float* density_grid, const float* tmp_grid, uint32_t n_ce
                        double* accum, float* mean_out, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused MLP (reference: nerf/network.py:12-35, nn.Linear stack -> cuBLAS)
+ * ---------------------------------------------------------------------------------------- */
+
+#define NGP_MLP_MAX_LAYERS 4
+enum ngp_activation { NGP_ACT_NONE = 0, NGP_ACT_RELU = 1 };
+
+/* Bias-free MLP forward, all layers in one kernel, activations stay on chip.
+ * x [M, dims[0]] f16 row-major (ldx elements per row), weights[l] [dims[l+1], dims[l]] f16 row-major
+ * (nn.Linear layout), y [M, dims[n_layers]] f16.  hidden activation = `act` (network.py:30-34).
+ * acts_out: optional [n_layers-1][M, dims[l+1]] f16 post-activation hidden states saved for backward
+ * (pointer array on the host; entries may be NULL).  Dimensions must be multiples of 16 and <= 128 (callers
+ * zero-pad, e.g. 31 -> 32 inputs, 3 -> 16 outputs).  Implementation: tcgen05.mma (M = 128 samples per CTA tile),
+ * accumulators in TMEM, one persistent CTA loop over tiles. */
+int ngp_mlp_forward(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
+                    uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy,
+                    void* const* acts_out, ngp_stream_t stream);
+
+/* Backward: given dy [M, dims[n]] f16 and the saved hidden states, computes dx [M, dims[0]] f16 (or NULL)
+ * and dW[l] [dims[l+1], dims[l]] fp32 (accumulated with atomics; zero-filled by the caller).  acts[l] is the
+ * post-ReLU output of layer l as written by ngp_mlp_forward (row stride dims[l+1]). */
+int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx,
+                     const void* const* weights, const void* const* acts, const uint32_t* dims,
+                     uint32_t n_layers, uint32_t M, int act, void* dx, uint32_t lddx,
+                     float* const* dweights, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (reference: torch.optim.Adam, main.py:245;
  * GradScaler unscale + inf check, nerf/train_utils.py:897-904) -- SURVEY 8(f) row 1.
  * ---------------------------------------------------------------------------------------- */

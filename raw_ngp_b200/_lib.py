@@ -46,6 +46,8 @@ SIGNATURES = {
     "ngp_occ_sample_positions": [_p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_occ_scatter_sigmas": [_p, _p, _u32, _p, _p],
     "ngp_occ_ema_update": [_p, _p, _u32, _f32, _p, _p, _p],
+    "ngp_mlp_forward": [_p, _u32, _p, _p, _u32, _u32, _i, _p, _u32, _p, _p],
+    "ngp_mlp_backward": [_p, _u32, _p, _u32, _p, _p, _p, _u32, _u32, _i, _p, _u32, _p, _p],
     "ngp_fused_adam": [_p, _p, _i, _p, _i, _p, _p, c_uint64, _f32, _f32, _f32, _f32, _f32, _u32, _p, _p, _i, _p],
     "ngp_check_finite": [_p, _i, c_uint64, _p, _p],
 }

@@ -1,0 +1,378 @@
+// mlp.cu -- fully fused bias-free ReLU MLP (network.py:12-35) on the 5th-generation tensor cores.
+//
+// One CTA (128 threads) owns a tile of 128 samples.  Every layer is a tcgen05.mma with M = 128 (samples on the
+// TMEM lanes), the fp32 accumulator lives in TMEM, and the epilogue thread of each sample row reads its row with
+// tcgen05.ld, applies ReLU, converts to fp16 and writes it back to shared memory as the A operand of the next
+// layer -- hidden activations never leave the SM in the forward pass (they are only streamed out once, for the
+// backward pass).  The backward kernel keeps the weight-gradient accumulators of all layers resident in TMEM
+// across the CTA's whole persistent loop and reduces them to global memory once at the end.
+//
+// The reference runs these layers as separate cuBLAS GEMMs + elementwise kernels (nn.Linear, F.relu), with the
+// [M, 64] activations round-tripping through HBM between them.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace ngp {
+namespace {
+
+constexpr uint32_t kTile = 128;          // samples per tile == UMMA M == threads per CTA
+constexpr uint32_t kPanel = kTile * 16;  // bytes of one 8-column panel of a 128-row tile
+constexpr uint32_t kMaxLayers = 4;
+
+struct MlpArgs {
+    const __half* w[kMaxLayers];   // [dims[l+1], dims[l]] row-major fp16
+    __half* acts[kMaxLayers];      // forward: hidden activations out; backward: hidden activations in
+    float* dw[kMaxLayers];         // backward: [dims[l+1], dims[l]] fp32, accumulated with atomics
+    uint32_t dims[kMaxLayers + 1];
+    uint32_t n_layers;
+};
+
+// weights -> shared memory in row-panel layout (R = N_l rows)
+__device__ __forceinline__ void load_weight_tile(uint8_t* dst, const __half* __restrict__ w, uint32_t N, uint32_t K) {
+    const uint32_t chunks = K / 8;
+    for (uint32_t i = threadIdx.x; i < N * chunks; i += blockDim.x) {
+        const uint32_t n = i / chunks, c = i - n * chunks;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * K + c * 8));
+        *reinterpret_cast<uint4*>(dst + (size_t)c * (N * 16) + n * 16) = v;
+    }
+}
+
+// one row of a [M, F] fp16 matrix -> this thread's row of a 128-row tile (cp.async, zero-fill past M)
+__device__ __forceinline__ void load_row_tile(uint8_t* tile, const __half* __restrict__ src, uint32_t ld, uint32_t F,
+                                              uint32_t row, uint32_t M) {
+    const uint32_t t = threadIdx.x;
+    if (row < M) {
+        const __half* p = src + (size_t)row * ld;
+        for (uint32_t c = 0; c < F / 8; c++) tc::cp_async16(tc::smem_u32(tile + c * kPanel + t * 16), p + c * 8);
+    } else {
+        for (uint32_t c = 0; c < F / 8; c++) *reinterpret_cast<uint4*>(tile + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+__device__ __forceinline__ void pack16(const float (&v)[16], uint4& lo, uint4& hi) {
+    __half2 h[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    lo = *reinterpret_cast<uint4*>(&h[0]);
+    hi = *reinterpret_cast<uint4*>(&h[4]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kFwdTmemCols = 128;
+
+__global__ void __launch_bounds__(kTile)
+mlp_forward_kernel(const __half* __restrict__ x, uint32_t ldx, MlpArgs p, uint32_t M, __half* __restrict__ y, uint32_t ldy,
+                   uint32_t a_tile_off, uint32_t ctrl_off) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t t = threadIdx.x, warp = t >> 5;
+    uint8_t* a_tile = smem + a_tile_off;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
+
+    uint32_t w_off[kMaxLayers];
+    {
+        uint32_t o = 0;
+        for (uint32_t l = 0; l < p.n_layers; l++) { w_off[l] = o; o += p.dims[l] * p.dims[l + 1] * 2; }
+    }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kFwdTmemCols);
+    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    for (uint32_t l = 0; l < p.n_layers; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t a_saddr = tc::smem_u32(a_tile), mbar_saddr = tc::smem_u32(mbar);
+
+    uint32_t phase = 0;
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTile + t;
+        load_row_tile(a_tile, x, ldx, p.dims[0], row, M);
+        tc::cp_async_wait_all();
+        tc::fence_async_smem();
+        __syncthreads();
+        for (uint32_t l = 0; l < p.n_layers; l++) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            if (t == 0) {
+                tc::fence_after_sync();
+                const uint32_t idesc = tc::instr_desc(kTile, N, false, false);
+                const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
+                for (uint32_t ks = 0; ks < K / 16; ks++) {
+                    const uint64_t ad = tc::smem_desc(a_saddr + ks * 2 * kPanel, kPanel, 128);
+                    const uint64_t bd = tc::smem_desc(w_saddr + ks * 2 * (N * 16), N * 16, 128);
+                    tc::mma_f16_ss(tmem, ad, bd, idesc, ks > 0);
+                }
+                tc::mma_commit(mbar_saddr);
+            }
+            tc::mbar_wait(mbar_saddr, phase);
+            phase ^= 1;
+            tc::fence_after_sync();
+            const bool last = (l + 1 == p.n_layers);
+            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(lane_addr + c0, v);
+                if (!last) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                }
+                uint4 lo, hi;
+                pack16(v, lo, hi);
+                if (!last) {
+                    *reinterpret_cast<uint4*>(a_tile + (c0 / 8) * kPanel + t * 16) = lo;
+                    *reinterpret_cast<uint4*>(a_tile + (c0 / 8 + 1) * kPanel + t * 16) = hi;
+                    if (p.acts[l] && row < M) {
+                        uint4* g = reinterpret_cast<uint4*>(p.acts[l] + (size_t)row * N + c0);
+                        g[0] = lo; g[1] = hi;
+                    }
+                } else if (row < M) {
+                    uint4* g = reinterpret_cast<uint4*>(y + (size_t)row * ldy + c0);
+                    g[0] = lo; g[1] = hi;
+                }
+            }
+            if (!last) tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kFwdTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kBwdTmemCols = 256;
+
+__global__ void __launch_bounds__(kTile)
+mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* __restrict__ x, uint32_t ldx, MlpArgs p,
+                    uint32_t M, __half* __restrict__ dx, uint32_t lddx, uint32_t dz_off, uint32_t dz_bytes,
+                    uint32_t w_base, uint32_t ctrl_off) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t t = threadIdx.x, warp = t >> 5;
+    const uint32_t L = p.n_layers;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
+
+    // shared memory: [in tiles l = 0..L-1 (X, H1, ...)] [dZ ping] [dZ pong] [weights] [ctrl]
+    uint32_t in_off[kMaxLayers], w_off[kMaxLayers], acc_col[kMaxLayers];
+    uint32_t work_cols = 0;
+    {
+        uint32_t o = 0, wo = w_base, col = 0;
+        for (uint32_t l = 0; l < L; l++) {
+            in_off[l] = o; o += kTile * p.dims[l] * 2;
+            w_off[l] = wo; wo += p.dims[l] * p.dims[l + 1] * 2;
+            work_cols = max(work_cols, p.dims[l]);
+        }
+        col = work_cols;
+        for (uint32_t l = 0; l < L; l++) { acc_col[l] = col; col += p.dims[l + 1]; }
+    }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kBwdTmemCols);
+    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t mbar_saddr = tc::smem_u32(mbar);
+
+    uint32_t phase = 0, iter = 0;
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
+        const uint32_t row = tile * kTile + t;
+        uint32_t cur = 0;  // which dZ buffer holds dZ of the layer being processed
+        load_row_tile(smem + dz_off, dy, lddy, p.dims[L], row, M);
+        load_row_tile(smem + in_off[0], x, ldx, p.dims[0], row, M);
+        for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
+        tc::cp_async_wait_all();
+        tc::fence_async_smem();
+        __syncthreads();
+        for (int l = (int)L - 1; l >= 0; l--) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            const bool need_dh = (l > 0) || (dx != nullptr);
+            const uint32_t dz_saddr = tc::smem_u32(smem + dz_off + cur * dz_bytes);
+            if (t == 0) {
+                tc::fence_after_sync();
+                // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]   (both operands MN-major views of row tiles)
+                const uint32_t in_saddr = tc::smem_u32(smem + in_off[l]);
+                const uint32_t idw = tc::instr_desc(kTile, N, true, true);
+                for (uint32_t ks = 0; ks < kTile / 16; ks++) {
+                    const uint64_t ad = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
+                    const uint64_t bd = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
+                    tc::mma_f16_ss(tmem + acc_col[l], ad, bd, idw, (iter > 0 || ks > 0) ? 1u : 0u);
+                }
+                if (need_dh) {
+                    // dH [128 x K] = dZ_l [128 x N] * W_l [N x K]   (A K-major, B = MN-major view of the weight tile)
+                    const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
+                    const uint32_t idh = tc::instr_desc(kTile, K, false, true);
+                    for (uint32_t ks = 0; ks < N / 16; ks++) {
+                        const uint64_t ad = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
+                        const uint64_t bd = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
+                        tc::mma_f16_ss(tmem, ad, bd, idh, ks > 0);
+                    }
+                }
+                tc::mma_commit(mbar_saddr);
+            }
+            tc::mbar_wait(mbar_saddr, phase);
+            phase ^= 1;
+            tc::fence_after_sync();
+            if (need_dh) {
+                uint8_t* nxt = smem + dz_off + (cur ^ 1) * dz_bytes;
+                const uint8_t* in_tile = smem + in_off[l];
+                for (uint32_t c0 = 0; c0 < K; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + c0, v);
+                    if (l > 0) {
+                        // ReLU mask from the saved post-activation input of layer l
+                        const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8) * kPanel + t * 16);
+                        const uint4 m1 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8 + 1) * kPanel + t * 16);
+                        const __half* h0 = reinterpret_cast<const __half*>(&m0);
+                        const __half* h1 = reinterpret_cast<const __half*>(&m1);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (!(__half2float(h0[i]) > 0.f)) v[i] = 0.f;
+                            if (!(__half2float(h1[i]) > 0.f)) v[8 + i] = 0.f;
+                        }
+                        uint4 lo, hi;
+                        pack16(v, lo, hi);
+                        *reinterpret_cast<uint4*>(nxt + (c0 / 8) * kPanel + t * 16) = lo;
+                        *reinterpret_cast<uint4*>(nxt + (c0 / 8 + 1) * kPanel + t * 16) = hi;
+                    } else if (row < M) {
+                        uint4 lo, hi;
+                        pack16(v, lo, hi);
+                        uint4* g = reinterpret_cast<uint4*>(dx + (size_t)row * lddx + c0);
+                        g[0] = lo; g[1] = hi;
+                    }
+                }
+                if (l > 0) tc::fence_async_smem();
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+    // reduce this CTA's weight-gradient accumulators (TMEM lane i = input feature i) into global memory
+    if (iter > 0) {
+        tc::fence_after_sync();
+        for (uint32_t l = 0; l < L; l++) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(lane_addr + acc_col[l] + c0, v);   // warp-collective: every lane participates
+                if (t < K) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) red_add_f32(p.dw[l] + (size_t)(c0 + i) * K + t, v[i]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kBwdTmemCols);
+}
+
+bool dims_ok(const uint32_t* dims, uint32_t n_layers) {
+    if (n_layers < 1 || n_layers > kMaxLayers) return false;
+    for (uint32_t l = 0; l <= n_layers; l++)
+        if (dims[l] == 0 || dims[l] % 16 != 0 || dims[l] > 128) return false;
+    return true;
+}
+
+}  // namespace
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_mlp_forward(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
+                               uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy, void* const* acts_out,
+                               ngp_stream_t stream) {
+    if (M == 0) return NGP_OK;
+    if (!x || !weights || !dims || !y) return NGP_ERR_NULL;
+    if (act != NGP_ACT_RELU) return NGP_ERR_UNSUPPORTED;
+    if (!dims_ok(dims, n_layers)) return NGP_ERR_UNSUPPORTED;
+    if (ldx < dims[0] || ldy < dims[n_layers] || ldx % 8 || ldy % 8) return NGP_ERR_BAD_ARG;
+    if (!aligned(x, 16) || !aligned(y, 16)) return NGP_ERR_ALIGN;
+    MlpArgs p = {};
+    p.n_layers = n_layers;
+    uint32_t w_bytes = 0, max_k = 0;
+    for (uint32_t l = 0; l < n_layers; l++) {
+        if (!weights[l] || !aligned(weights[l], 16)) return weights[l] ? NGP_ERR_ALIGN : NGP_ERR_NULL;
+        p.w[l] = (const __half*)weights[l];
+        p.acts[l] = (acts_out && l + 1 < n_layers) ? (__half*)acts_out[l] : nullptr;
+        if (p.acts[l] && !aligned(p.acts[l], 16)) return NGP_ERR_ALIGN;
+        w_bytes += dims[l] * dims[l + 1] * 2;
+        max_k = std::max(max_k, dims[l]);
+    }
+    for (uint32_t l = 0; l <= n_layers; l++) p.dims[l] = dims[l];
+    const uint32_t a_off = (w_bytes + 127) & ~127u;
+    const uint32_t ctrl_off = a_off + kTile * max_k * 2;
+    const uint32_t smem_bytes = ctrl_off + 16;
+    static thread_local uint32_t configured = 0;
+    if (smem_bytes > configured) {
+        if (cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+            set_last_cuda_error(cudaGetLastError());
+            return NGP_ERR_CUDA;
+        }
+        configured = smem_bytes;
+    }
+    const uint32_t n_tiles = div_up(M, kTile);
+    const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 4);   // 4 CTAs/SM: 4 x 128 TMEM columns
+    mlp_forward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)x, ldx, p, M, (__half*)y, ldy, a_off, ctrl_off);
+    return finish_launch();
+}
+
+extern "C" int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
+                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
+                                void* dx, uint32_t lddx, float* const* dweights, ngp_stream_t stream) {
+    if (M == 0) return NGP_OK;
+    if (!dy || !x || !weights || !dims || !dweights) return NGP_ERR_NULL;
+    if (n_layers > 1 && !acts) return NGP_ERR_NULL;
+    if (act != NGP_ACT_RELU) return NGP_ERR_UNSUPPORTED;
+    if (!dims_ok(dims, n_layers)) return NGP_ERR_UNSUPPORTED;
+    if (ldx < dims[0] || lddy < dims[n_layers] || ldx % 8 || lddy % 8 || (dx && (lddx < dims[0] || lddx % 8))) return NGP_ERR_BAD_ARG;
+    if (!aligned(x, 16) || !aligned(dy, 16) || (dx && !aligned(dx, 16))) return NGP_ERR_ALIGN;
+    MlpArgs p = {};
+    p.n_layers = n_layers;
+    uint32_t w_bytes = 0, in_bytes = 0, max_n = 0, max_k = 0, acc_cols = 0;
+    for (uint32_t l = 0; l < n_layers; l++) {
+        if (!weights[l] || !dweights[l]) return NGP_ERR_NULL;
+        if (l + 1 < n_layers && !acts[l]) return NGP_ERR_NULL;
+        p.w[l] = (const __half*)weights[l];
+        p.acts[l] = (l + 1 < n_layers) ? (__half*)acts[l] : nullptr;
+        p.dw[l] = dweights[l];
+        w_bytes += dims[l] * dims[l + 1] * 2;
+        in_bytes += kTile * dims[l] * 2;
+        max_n = std::max(max_n, dims[l + 1]);
+        max_k = std::max(max_k, dims[l]);
+        acc_cols += dims[l + 1];
+    }
+    for (uint32_t l = 0; l <= n_layers; l++) p.dims[l] = dims[l];
+    if (max_k + acc_cols > kBwdTmemCols) return NGP_ERR_UNSUPPORTED;
+    const uint32_t dz_bytes = kTile * std::max(max_n, max_k) * 2;
+    const uint32_t dz_off = in_bytes;
+    const uint32_t w_base = dz_off + 2 * dz_bytes;
+    const uint32_t ctrl_off = (w_base + w_bytes + 127) & ~127u;
+    // the M = 128 MN-major A view of an input tile spans 16 panels (32 KiB) from the tile start: keep that inside the
+    // allocation (rows past dims[l] only feed TMEM lanes that are never read)
+    const uint32_t last_in_off = in_bytes - kTile * dims[n_layers - 1] * 2;
+    const uint32_t smem_bytes = std::max(ctrl_off + 16, last_in_off + 16 * kPanel + 2 * kPanel);
+    if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
+    static thread_local uint32_t configured = 0;
+    if (smem_bytes > configured) {
+        if (cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+            set_last_cuda_error(cudaGetLastError());
+            return NGP_ERR_CUDA;
+        }
+        configured = smem_bytes;
+    }
+    const uint32_t n_tiles = div_up(M, kTile);
+    const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
+    mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
+                                                                          (__half*)dx, lddx, dz_off, dz_bytes, w_base, ctrl_off);
+    return finish_launch();
+}

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from ..activation import trunc_exp
 from ..encoding import get_encoder
+from ..ffmlp import fused_mlp
 from .renderer import NeRFRenderer
 
 
@@ -28,7 +29,16 @@ class MLP(nn.Module):
                       self.dim_out if l == num_layers - 1 else self.dim_hidden, bias=bias)
             for l in range(num_layers)])
 
+    def _fusable(self, x):
+        # The tcgen05 kernel computes in fp16 with fp32 accumulation, i.e. what the nn.Linear stack does under autocast
+        # (renderer.py:546).  fp32 runs (--fp16 off) and softplus hidden activations use the library path below.
+        return (x.is_cuda and x.dim() == 2 and self.opt.internal_activation == "relu" and self.num_layers <= 4
+                and all(l.bias is None for l in self.net) and (x.dtype == torch.float16 or torch.is_autocast_enabled("cuda"))
+                and max(self.dim_in, self.dim_hidden, self.dim_out) <= 128)
+
     def forward(self, x):
+        if self._fusable(x):
+            return fused_mlp(x, *[l.weight for l in self.net])
         for l in range(self.num_layers):
             x = self.net[l](x)
             if l != self.num_layers - 1:
