@@ -167,21 +167,26 @@ int ngp_flatten_rays(const int32_t* rays, uint32_t N, uint32_t M, int32_t* res, 
  * Writes rays[n,1] = sample count of ray n, then rays[n,0] = exclusive prefix sum of the counts in
  * ray order (a legal outcome of the reference's atomicAdd(counter) and the only one its backward is
  * correct for, raymarching/raymarching.py:325), and counter[0] = M = total samples.
- * counter: int32[2] scratch, zero-filled by the caller ([1] is a block ticket). */
+ * counter: int32[2] scratch, zero-filled by the caller ([1] is a block ticket).
+ * t_scratch: fp32 [N * max_steps] workspace or NULL.  With it the march is warp-cooperative (one warp per ray,
+ * 32 lattice points probed per instruction) and the t of every kept sample is left in t_scratch[n*max_steps + i]
+ * for pass 2; without it the kernel is the one-thread-per-ray loop of the reference.  Same results either way. */
 int ngp_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
                                float bound, int contract, float dt_gamma, uint32_t max_steps,
                                uint32_t N, uint32_t C, uint32_t H, const float* nears,
                                const float* fars, const float* noises, int32_t* rays,
-                               int32_t* counter, ngp_stream_t stream);
+                               int32_t* counter, float* t_scratch, ngp_stream_t stream);
 
 /* Pass 2 of march_rays_train              raymarching.cu:337-508 with xyzs != nullptr
- * (raymarching/raymarching.py:311).  xyzs/dirs [M,3], ts [M,2], ldirs [M,3] or NULL (with rays_ldir). */
+ * (raymarching/raymarching.py:311).  xyzs/dirs [M,3], ts [M,2], ldirs [M,3] or NULL (with rays_ldir).
+ * t_scratch: the workspace filled by ngp_march_rays_train_count (samples are then written in parallel from their
+ * stored t, no second march) or NULL (re-march like the reference). */
 int ngp_march_rays_train_write(const float* rays_o, const float* rays_d, const float* rays_ldir,
                                const uint8_t* grid, float bound, int contract, float dt_gamma,
                                uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                const float* nears, const float* fars, const float* noises,
-                               const int32_t* rays, uint32_t M, float* xyzs, float* dirs, float* ts,
-                               float* ldirs, ngp_stream_t stream);
+                               const int32_t* rays, uint32_t M, const float* t_scratch, float* xyzs,
+                               float* dirs, float* ts, float* ldirs, ngp_stream_t stream);
 
 /* replaces composite_rays_train_forward   raymarching/src/raymarching.h:15, raymarching.cu:519-608
  * weights [M] must be zero-filled by the caller (raymarching/raymarching.py:356). */

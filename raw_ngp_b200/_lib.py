@@ -35,8 +35,8 @@ SIGNATURES = {
     "ngp_morton3D_invert": [_p, _u32, _p, _p],
     "ngp_packbits": [_p, _u32, _f32, _p, _p, _p],
     "ngp_flatten_rays": [_p, _u32, _u32, _p, _p],
-    "ngp_march_rays_train_count": [_p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p],
-    "ngp_march_rays_train_write": [_p, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _u32, _p, _p, _p, _p, _p],
+    "ngp_march_rays_train_count": [_p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p],
+    "ngp_march_rays_train_write": [_p, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _u32, _p, _p, _p, _p, _p, _p],
     "ngp_composite_rays_train_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p, _p],
     "ngp_composite_rays_train_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_march_rays_train_backward": [_p, _p, _p, _p, _u32, _u32, _p, _p, _p],

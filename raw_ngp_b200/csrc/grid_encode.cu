@@ -200,8 +200,59 @@ grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ tabl
     }
 }
 
-// Backward: scatter w * grad into the table gradient with one packed reduction per corner and, if asked,
-// recompute d out / d x from the table and reduce over the level's channels into grad_inputs.
+// ---- backward helpers ------------------------------------------------------------------------------------------
+// Two corners that are x-neighbours usually live in the same 16-byte block of the table (dense levels: consecutive
+// rows; hashed levels: the first hash prime is 1, so x and x+1 differ only in the low row bits unless x ends in
+// ...11).  scatter_pair sends both contributions with ONE 16-byte vector reduction when they share a block
+// (red.global.add.noftz.v4.f16x2 = 4 rows of an fp16 F=2 table, red.global.add.v4.f32 = 2 rows of an fp32 one)
+// and falls back to one packed reduction per corner otherwise.
+template <typename T, uint32_t C>
+__device__ __forceinline__ void scatter_pair(T* glvl, uint32_t row0, uint32_t row1, const float (&v0)[C], const float (&v1)[C]) {
+    if constexpr (C == 2 && sizeof(T) == 2) {
+        if ((row0 >> 2) == (row1 >> 2)) {
+            const uint32_t a = row0 & 3u, b = row1 & 3u;
+            uint32_t p0, p1;
+            if (a == b) {
+                p0 = std::is_same<T, __half>::value ? pack_h2(v0[0] + v1[0], v0[1] + v1[1]) : pack_bf2(v0[0] + v1[0], v0[1] + v1[1]);
+                p1 = 0u;
+            } else {
+                p0 = std::is_same<T, __half>::value ? pack_h2(v0[0], v0[1]) : pack_bf2(v0[0], v0[1]);
+                p1 = std::is_same<T, __half>::value ? pack_h2(v1[0], v1[1]) : pack_bf2(v1[0], v1[1]);
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (uint32_t s = 0; s < 4; s++) w[s] = (s == a ? p0 : 0u) | ((s == b && a != b) ? p1 : 0u);
+            T* blk = glvl + (size_t)(row0 >> 2) * 8;
+            if constexpr (std::is_same<T, __half>::value) red_add_v4_h2(blk, w[0], w[1], w[2], w[3]);
+            else red_add_v4_bf2(blk, w[0], w[1], w[2], w[3]);
+            return;
+        }
+    } else if constexpr (C == 2 && sizeof(T) == 4) {
+        if ((row0 >> 1) == (row1 >> 1)) {
+            const uint32_t a = row0 & 1u, b = row1 & 1u;
+            float f[4];
+            if (a == b) {
+                f[2 * a] = v0[0] + v1[0]; f[2 * a + 1] = v0[1] + v1[1];
+                f[2 * (a ^ 1)] = 0.f; f[2 * (a ^ 1) + 1] = 0.f;
+            } else {
+                f[2 * a] = v0[0]; f[2 * a + 1] = v0[1];
+                f[2 * b] = v1[0]; f[2 * b + 1] = v1[1];
+            }
+            red_add_v4_f32(reinterpret_cast<float*>(glvl) + (size_t)(row0 >> 1) * 4, f[0], f[1], f[2], f[3]);
+            return;
+        }
+    }
+    red_add_row<T, C>(glvl + (size_t)row0 * C, v0);
+    red_add_row<T, C>(glvl + (size_t)row1 * C, v1);
+}
+
+// Backward: scatter w * grad into the table gradient and, if asked, recompute d out / d x from the table and reduce
+// over the level's channels into grad_inputs.
+//
+// Consecutive samples of a ray fall into the same cell on the coarse levels (about 37 samples per cell at
+// resolution 16 with dt = 2*sqrt(3)/1024), so every warp first merges runs of lanes that share a cell with a
+// segmented shuffle reduction and only the head lane of each run issues reductions (warp-aggregated atomics);
+// levels where no two neighbouring lanes share a cell skip the merge (one ballot of overhead).
 template <typename T, uint32_t D, uint32_t C, bool InputGrad>
 __global__ void __launch_bounds__(kBwdThreads)
 grid_backward_kernel(const T* __restrict__ grad, const float* __restrict__ inputs, const T* __restrict__ table,
@@ -209,49 +260,80 @@ grid_backward_kernel(const T* __restrict__ grad, const float* __restrict__ input
                      uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
                      uint32_t interp) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t level = blockIdx.y;
 
     uint32_t base[D];
     float frac[D], dfrac[D];
     const uint32_t res = level_resolution(level, S, H);
-    if (!locate<D>(inputs + (size_t)b * D, res, align_corners, interp, base, frac, dfrac)) return;
+    const bool valid = (b < B) && locate<D>(inputs + (size_t)(b < B ? b : 0) * D, res, align_corners, interp, base, frac, dfrac);
 
     const uint32_t off = (uint32_t)__ldg(offsets + level);
     const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
 
     float g[C];
-    load_row<T, C>(grad + (size_t)b * (L * C) + level * C, g);
-
-    uint32_t row[1u << D];
 #pragma unroll
-    for (uint32_t k = 0; k < (1u << D); k++) {
-        uint32_t p[D];
-#pragma unroll
-        for (uint32_t d = 0; d < D; d++) p[d] = (k & (1u << d)) ? min(base[d] + 1, res - 1) : base[d];
-        row[k] = entry_index<D>(gridtype, hashmap_size, res, p);
-    }
+    for (uint32_t c = 0; c < C; c++) g[c] = 0.f;
+    if (valid) load_row<T, C>(grad + (size_t)b * (L * C) + level * C, g);
 
-    float val[1u << D][C];
-    if (InputGrad) {
-        const T* __restrict__ lvl = table + (size_t)off * C;
-#pragma unroll
-        for (uint32_t k = 0; k < (1u << D); k++) load_row<T, C>(lvl + (size_t)row[k] * C, val[k]);
-    }
-
-    T* glvl = grad_table + (size_t)off * C;
+    // weighted contributions of this sample to its 2^D corners
+    float wg[1u << D][C];
 #pragma unroll
     for (uint32_t k = 0; k < (1u << D); k++) {
         float w = 1;
 #pragma unroll
         for (uint32_t d = 0; d < D; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
-        float wg[C];
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) wg[c] = w * g[c];
-        red_add_row<T, C>(glvl + (size_t)row[k] * C, wg);
+        for (uint32_t c = 0; c < C; c++) wg[k][c] = valid ? w * g[c] : 0.f;
     }
 
-    if (InputGrad) {
+    // ---- warp aggregation over runs of lanes in the same cell --------------------------------------------------
+    uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFF00u | lane;   // invalid lanes never match a neighbour
+    if (valid) {
+        key0 = base[0] | (base[1] << 16);                      // resolutions are < 65536
+        key1 = (D > 2) ? base[D - 1] : 0u;
+    }
+    const uint32_t pk0 = __shfl_up_sync(0xffffffffu, key0, 1), pk1 = __shfl_up_sync(0xffffffffu, key1, 1);
+    const bool head = (lane == 0) || (pk0 != key0) || (pk1 != key1);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    if (heads != 0xffffffffu) {
+        const uint32_t above = heads & ~((2u << lane) - 1u);          // heads strictly above this lane
+        const uint32_t end = (lane == 31 || above == 0) ? 31u : (uint32_t)__ffs(above) - 2u;  // last lane of my run
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (uint32_t k = 0; k < (1u << D); k++) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) {
+                    const float o = __shfl_down_sync(0xffffffffu, wg[k][c], d);
+                    if (lane + d <= end) wg[k][c] += o;
+                }
+            }
+        }
+    }
+
+    uint32_t row[1u << D];
+    if (valid) {
+#pragma unroll
+        for (uint32_t k = 0; k < (1u << D); k++) {
+            uint32_t p[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) p[d] = (k & (1u << d)) ? min(base[d] + 1, res - 1) : base[d];
+            row[k] = entry_index<D>(gridtype, hashmap_size, res, p);
+        }
+    }
+
+    if (valid && head) {
+        T* glvl = grad_table + (size_t)off * C;
+#pragma unroll
+        for (uint32_t k = 0; k < (1u << D); k += 2) scatter_pair<T, C>(glvl, row[k], row[k + 1], wg[k], wg[k + 1]);
+    }
+
+    if (InputGrad && valid) {
+        float val[1u << D][C];
+        const T* __restrict__ lvl = table + (size_t)off * C;
+#pragma unroll
+        for (uint32_t k = 0; k < (1u << D); k++) load_row<T, C>(lvl + (size_t)row[k] * C, val[k]);
         const float scale = (float)(align_corners ? res - 1 : res);
 #pragma unroll
         for (uint32_t gd = 0; gd < D; gd++) {

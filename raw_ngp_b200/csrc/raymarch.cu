@@ -334,6 +334,172 @@ march_train_write_kernel(const float* __restrict__ rays_o, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// warp-cooperative training march
+// ---------------------------------------------------------------------------------------------------
+// The reference loop is serial per ray, but the sequence of t values it can ever visit is a fixed lattice
+// u_0 = t0, u_{i+1} = u_i + clamp(u_i * dt_gamma, dt_min, dt_max): a kept sample advances by one lattice step and
+// the empty-voxel skip `do { t += dt } while (t < tt)` advances to the first lattice point >= tt.  So one warp per ray
+//   (1) builds a window of kWin lattice points (the only serial fp32 chain, identical adds to the reference),
+//   (2) probes all of them in parallel (32 per instruction): keep flag, or the jump target found by binary search,
+//   (3) lets one lane chase the next[] pointers (no memory traffic beyond shared memory),
+// and repeats from the t where the chase left the window.  The t of every kept sample is stored so that pass 2
+// writes all samples of a ray in parallel with coalesced stores and never re-marches.  Results are bit-identical
+// to the serial loop: the same fp32 operations produce every t, and keep/skip decisions are taken on those t.
+constexpr uint32_t kWin = 1024;
+constexpr uint32_t kCoopWarps = 4;
+
+// tt of an empty probe (raymarching.cu:470-474)
+__device__ __forceinline__ float voxel_exit(const MarchParams& p, const Ray& r, float t, const Probe& q) {
+    const float tx = (((q.nx + 0.5f + 0.5f * sign1(r.dx)) * p.rH * 2 - 1) * q.mip_bound - q.cx) * r.rdx;
+    const float ty = (((q.ny + 0.5f + 0.5f * sign1(r.dy)) * p.rH * 2 - 1) * q.mip_bound - q.cy) * r.rdy;
+    const float tz = (((q.nz + 0.5f + 0.5f * sign1(r.dz)) * p.rH * 2 - 1) * q.mip_bound - q.cz) * r.rdz;
+    return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+}
+
+__global__ void __launch_bounds__(kCoopWarps * 32)
+march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+                              float bound, bool contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                              const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+                              int* __restrict__ rays, int* __restrict__ counter, float* __restrict__ t_scratch) {
+    __shared__ float s_u[kCoopWarps][kWin];
+    __shared__ uint16_t s_next[kCoopWarps][kWin];   // bit 15: keep, low bits: next lattice index (kWin = leaves the window)
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x * kCoopWarps + warp;
+    if (n < N) {
+        const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
+        const Ray r = load_ray(rays_o, rays_d, n, false);
+        const float far = __ldg(fars + n);
+        float t = __ldg(nears + n);
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
+        float* u = s_u[warp];
+        uint16_t* nx = s_next[warp];
+        float* tout = t_scratch + (size_t)n * max_steps;
+        uint32_t step = 0;
+        while (t < far && step < max_steps) {       // warp-uniform
+            // (1) lattice window starting at t: every lane runs the same chain, lane i%32 keeps u_i
+            uint32_t cnt = 0;
+            {
+                float tt = t, mine = 0.f;
+                while (cnt < kWin && tt < far) {
+                    if ((cnt & 31u) == lane) mine = tt;
+                    tt += clampf(tt * p.dt_gamma, p.dt_min, p.dt_max);
+                    cnt++;
+                    if ((cnt & 31u) == 0) u[cnt - 32 + lane] = mine;
+                }
+                if ((cnt & 31u) != 0 && lane < (cnt & 31u)) u[(cnt & ~31u) + lane] = mine;
+            }
+            __syncwarp();
+            // (2) parallel probes
+            for (uint32_t i = lane; i < cnt; i += 32) {
+                Probe q;
+                const float ti = u[i];
+                uint32_t code;
+                if (probe(p, r, ti, q)) {
+                    code = 0x8000u | (i + 1);
+                } else {
+                    const float tt = voxel_exit(p, r, ti, q);
+                    uint32_t lo = i + 1, hi = cnt;          // first j in (i, cnt) with u[j] >= tt, else cnt
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (u[mid] < tt) lo = mid + 1; else hi = mid;
+                    }
+                    code = lo;
+                }
+                nx[i] = (uint16_t)code;
+            }
+            __syncwarp();
+            // (3) pointer chase (all lanes redundantly: uniform, no divergence), kept t's go to the scratch list
+            uint32_t i = 0;
+            int exit_skip = -1;                     // lattice index of a skip whose target lies beyond the window
+            while (i < cnt && step < max_steps) {
+                const uint32_t code = nx[i];
+                if (code & 0x8000u) {
+                    if (lane == 0) tout[step] = u[i];
+                    step++;
+                    i++;
+                } else {
+                    if (code >= cnt) exit_skip = (int)i;
+                    i = code;
+                }
+            }
+            if (step >= max_steps) break;
+            if (cnt < kWin) break;                  // the window reached `far`: the ray is finished
+            // leave the window exactly as the reference loop would continue
+            if (exit_skip >= 0) {
+                // finish the skip serially: every u in the window is < tt, keep stepping from the last one
+                Probe q;
+                const float ts = u[exit_skip];
+                probe(p, r, ts, q);
+                const float tt = voxel_exit(p, r, ts, q);
+                float tc = u[cnt - 1];
+                do { tc += clampf(tc * p.dt_gamma, p.dt_min, p.dt_max); } while (tc < tt);
+                t = tc;
+            } else {
+                // the last point of the window was kept: one more lattice step
+                const float tl = u[cnt - 1];
+                t = tl + clampf(tl * p.dt_gamma, p.dt_min, p.dt_max);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) rays[(size_t)n * 2 + 1] = (int)step;
+    }
+
+    // last block to arrive turns the counts into ray-ordered offsets
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x >= 32) return;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < N; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t c = (i < N) ? (uint32_t)__ldcg(rays + (size_t)i * 2 + 1) : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= (uint32_t)s) incl += v;
+        }
+        if (i < N) rays[(size_t)i * 2] = (int)(carry + incl - c);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { counter[0] = (int)carry; counter[1] = 0; }
+}
+
+// Pass 2 from the stored sample t's: one warp per ray, samples written in parallel (coalesced).
+template <bool LDIR>
+__global__ void __launch_bounds__(kCoopWarps * 32)
+march_train_write_coop_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ rays_ldir,
+                              const uint8_t* __restrict__ grid, float bound, bool contract, float dt_gamma, uint32_t max_steps,
+                              uint32_t N, uint32_t C, uint32_t H, const int* __restrict__ rays, uint32_t M,
+                              const float* __restrict__ t_scratch, float* __restrict__ xyzs, float* __restrict__ dirs,
+                              float* __restrict__ ts, float* __restrict__ ldirs) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x * kCoopWarps + warp;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    if (count == 0 || offset + count > M) return;
+    const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n, false);
+    float lx = 0, ly = 0, lz = 0;
+    if (LDIR) { lx = __ldg(rays_ldir + (size_t)n * 3); ly = __ldg(rays_ldir + (size_t)n * 3 + 1); lz = __ldg(rays_ldir + (size_t)n * 3 + 2); }
+    const float* tin = t_scratch + (size_t)n * max_steps;
+    for (uint32_t k = lane; k < count; k += 32) {
+        const float t = __ldg(tin + k);
+        Probe q;
+        probe(p, r, t, q);
+        const size_t i = (size_t)offset + k;
+        xyzs[i * 3] = q.cx; xyzs[i * 3 + 1] = q.cy; xyzs[i * 3 + 2] = q.cz;
+        dirs[i * 3] = r.dx; dirs[i * 3 + 1] = r.dy; dirs[i * 3 + 2] = r.dz;
+        *reinterpret_cast<float2*>(ts + i * 2) = make_float2(t + q.dt, q.dt);
+        if (LDIR) { ldirs[i * 3] = lx; ldirs[i * 3 + 1] = ly; ldirs[i * 3 + 2] = lz; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // training composite: one warp per ray
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kCompThreads = 128;  // 4 rays per block
@@ -661,13 +827,17 @@ extern "C" int ngp_flatten_rays(const int32_t* rays, uint32_t N, uint32_t M, int
 extern "C" int ngp_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                           int contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
                                           uint32_t H, const float* nears, const float* fars, const float* noises,
-                                          int32_t* rays, int32_t* counter, ngp_stream_t stream) {
+                                          int32_t* rays, int32_t* counter, float* t_scratch, ngp_stream_t stream) {
     if (!counter) return NGP_ERR_NULL;
     if (N == 0) return NGP_OK;
     if (!rays_o || !rays_d || !grid || !nears || !fars || !noises || !rays) return NGP_ERR_NULL;
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
-    march_train_count_kernel<<<div_up(N, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter);
+    if (t_scratch)
+        march_train_count_coop_kernel<<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, t_scratch);
+    else
+        march_train_count_kernel<<<div_up(N, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter);
     return finish_launch();
 }
 
@@ -675,12 +845,23 @@ extern "C" int ngp_march_rays_train_write(const float* rays_o, const float* rays
                                           const uint8_t* grid, float bound, int contract, float dt_gamma,
                                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears,
                                           const float* fars, const float* noises, const int32_t* rays, uint32_t M,
-                                          float* xyzs, float* dirs, float* ts, float* ldirs, ngp_stream_t stream) {
+                                          const float* t_scratch, float* xyzs, float* dirs, float* ts, float* ldirs,
+                                          ngp_stream_t stream) {
     if (N == 0 || M == 0) return NGP_OK;
     if (!rays_o || !rays_d || !grid || !nears || !fars || !noises || !rays || !xyzs || !dirs || !ts) return NGP_ERR_NULL;
     if ((rays_ldir != nullptr) != (ldirs != nullptr)) return NGP_ERR_NULL;
     if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
+    if (t_scratch) {
+        const uint32_t cb = div_up(N, kCoopWarps);
+        if (rays_ldir)
+            march_train_write_coop_kernel<true><<<cb, kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
+                rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, rays, M, t_scratch, xyzs, dirs, ts, ldirs);
+        else
+            march_train_write_coop_kernel<false><<<cb, kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
+                rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, rays, M, t_scratch, xyzs, dirs, ts, ldirs);
+        return finish_launch();
+    }
     const uint32_t blocks = div_up(N, kMarchThreads);
     if (rays_ldir)
         march_train_write_kernel<true><<<blocks, kMarchThreads, 0, (cudaStream_t)stream>>>(

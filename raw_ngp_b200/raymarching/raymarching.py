@@ -15,6 +15,9 @@ __all__ = [
 ]
 
 
+COOPERATIVE_MARCH = True
+
+
 def _cuda(t):
     return t if t.is_cuda else t.cuda()
 
@@ -174,11 +177,14 @@ class _march_rays_train(Function):
         else:
             noises = torch.zeros(N, dtype=torch.float32, device=dev)
         rays = torch.empty(N, 2, dtype=torch.int32, device=dev)
+        # workspace of the warp-cooperative marcher: t of every kept sample (COOPERATIVE_MARCH = False selects the
+        # one-thread-per-ray kernels; both give identical results)
+        scratch = torch.empty(N * int(max_steps), dtype=torch.float32, device=dev) if COOPERATIVE_MARCH else None
 
         st = _lib.stream()
         _lib.call("ngp_march_rays_train_count", _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(density_bitfield),
                   float(bound), int(bool(contract)), float(dt_gamma), int(max_steps), N, int(C), int(H),
-                  _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(noises), _lib.ptr(rays), _lib.ptr(counter), st)
+                  _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(noises), _lib.ptr(rays), _lib.ptr(counter), _lib.ptr(scratch), st)
         M = int(counter[0].item())  # the one host sync of the op (reference: raymarching.py:303)
 
         xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
@@ -187,7 +193,7 @@ class _march_rays_train(Function):
         ldirs = torch.empty(M, 3, dtype=torch.float32, device=dev) if rays_ldir is not None else None
         _lib.call("ngp_march_rays_train_write", _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(rays_ldir),
                   _lib.ptr(density_bitfield), float(bound), int(bool(contract)), float(dt_gamma), int(max_steps), N,
-                  int(C), int(H), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(noises), _lib.ptr(rays), M,
+                  int(C), int(H), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(noises), _lib.ptr(rays), M, _lib.ptr(scratch),
                   _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ts), _lib.ptr(ldirs), st)
 
         ctx.save_for_backward(rays, ts)

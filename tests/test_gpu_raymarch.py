@@ -74,12 +74,15 @@ MARCH_CASES = [
     dict(name="cfg3-contract-C2", N=8192, H=128, cascade=2, bound=2.0, contract=True, dt_gamma=0.0, perturb=True, ldir=True),
     dict(name="H64-odd-bound", N=3001, H=64, cascade=2, bound=1.5, contract=False, dt_gamma=0.0, perturb=True, ldir=False),
     dict(name="maxsteps64", N=2048, H=128, cascade=1, bound=1.0, contract=False, dt_gamma=0.0, perturb=True, ldir=False, max_steps=64),
+    # lattice far longer than one 1024-point window of the cooperative marcher (8x the cube diagonal at dt_min)
+    dict(name="long-lattice-bound8", N=4096, H=128, cascade=4, bound=8.0, contract=False, dt_gamma=0.0, perturb=True, ldir=False),
+    dict(name="long-lattice-sparse", N=4096, H=128, cascade=4, bound=8.0, contract=False, dt_gamma=0.0, perturb=True, ldir=False, radius=0.05),
 ]
 
 
 def _march_both(case):
     from oracle import ref_cuda
-    grid, thresh = _scene(H=case["H"], cascade=case["cascade"], bound=case["bound"])
+    grid, thresh = _scene(H=case["H"], cascade=case["cascade"], bound=case["bound"], radius=case.get("radius", 0.5))
     bitfield = raymarching.packbits(grid, thresh)
     o, d, aabb, nears, fars = _rays(case["N"], bound=case["bound"])
     ldir = synthetic.unit_vectors(case["N"], seed=3).cuda() if case["ldir"] else None
@@ -95,8 +98,11 @@ def _march_both(case):
     return ours, ref
 
 
+@pytest.mark.parametrize("coop", [True, False], ids=["warp-cooperative", "thread-per-ray"])
 @pytest.mark.parametrize("case", MARCH_CASES, ids=lambda c: c["name"])
-def test_march_rays_train_bit_exact(case, ref_march):
+def test_march_rays_train_bit_exact(case, coop, ref_march, monkeypatch):
+    from raw_ngp_b200.raymarching import raymarching as rm_mod
+    monkeypatch.setattr(rm_mod, "COOPERATIVE_MARCH", coop)
     (xyzs, dirs, ts, rays, ldirs), (rx, rd, rt, rrays, rl) = _march_both(case)
     N = rays.shape[0]
     # counts and total bit-exact
