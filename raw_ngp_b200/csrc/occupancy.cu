@@ -44,10 +44,12 @@ __global__ void occ_sample_kernel(const int* __restrict__ cell_indices, const fl
         morton = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
     }
     const float c[3] = {(float)cx, (float)cy, (float)cz};
-    const float hm1 = (float)(H - 1);
+    // torch divides a tensor by a host scalar as a * (1/b) with the reciprocal rounded to fp32
+    // (BinaryDivTrueKernel.cu), so 2*c/(H-1) is mirrored as a multiplication
+    const float inv_hm1 = __fdiv_rn(1.0f, (float)(H - 1));
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const float w = __fadd_rn(__fdiv_rn(__fmul_rn(2.0f, c[a]), hm1), -1.0f);           // 2*c/(H-1) - 1 in [-1, 1]
+        const float w = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, c[a]), inv_hm1), -1.0f);       // 2*c/(H-1) - 1 in [-1, 1]
         const float jitter = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(noise + (size_t)i * 3 + a), 2.0f), -1.0f), hgs);
         xyzs[(size_t)i * 3 + a] = __fadd_rn(__fmul_rn(w, span), jitter);
     }

@@ -12,7 +12,7 @@ What is native here:
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, parallel
 
 
 class FusedAdam:
@@ -90,9 +90,7 @@ class TrainStep:
         self.last_num_points = 0
 
     def _all_reduce_grads(self):
-        if self.world > 1:
-            dist.all_reduce(self.table_grad, op=dist.ReduceOp.SUM, group=self.pg)
-            dist.all_reduce(self.mlp_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        parallel.all_reduce_gradients([self.table_grad, self.mlp_grad], None, self.pg)
 
     def step(self, rays_o, rays_d, target_rgb, rays_ldir=None, update_grid=True):
         """One optimisation step on N rays; returns the (unscaled) loss as a 0-d device tensor."""
@@ -113,7 +111,7 @@ class TrainStep:
         _lib.call("ngp_check_finite", _lib.ptr(self.mlp_grad), _lib.NGP_F32, self.mlp_grad.numel(), _lib.ptr(self.found_inf), st)
         if self.world > 1:
             dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
-        self.inv_scale.fill_(1.0 / (self.loss_scale * self.world))
+        self.inv_scale.fill_(parallel.unscale_factor(self.loss_scale, self.world))
         self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
         if self.dynamic:  # GradScaler growth / backoff (one sync, only in dynamic mode)
             if self.found_inf.item() != 0:
