@@ -287,6 +287,51 @@ int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx,
                      float* const* dweights, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused NeRF field (reference: nerf/network.py:74-143 -- GridEncoder -> grid_mlp -> trunc_exp / SHEncoder -> view_mlp ->
+ * colour activation, each a separate PyTorch op there).  Four launches per training step:
+ *   ngp_field_forward_density : xyz -> encode -> grid_mlp -> sigma, in2 = [feat(15), SH(dir), (SH(ldir)), 0]
+ *   ngp_mlp_forward_rgb       : in2 -> view_mlp -> colour activation -> rgb
+ *   ngp_mlp_backward_rgb      : d rgb -> view_mlp backward -> d in2
+ *   ngp_field_backward_density: [d sigma, d in2[:, :15]] -> grid_mlp backward -> hash-table gradient (accumulated)
+ * Table fp16 with F = 2, D = 3; MLP dims as ngp_mlp_forward (dims[0] = 2L, dims[n] = 16).
+ * ---------------------------------------------------------------------------------------- */
+
+enum ngp_density_activation { NGP_DENSITY_EXP = 0, NGP_DENSITY_SOFTPLUS = 1 };           /* network.py:112-115 */
+enum ngp_color_activation { NGP_COLOR_EXP = 1, NGP_COLOR_SIGMOID = 2, NGP_COLOR_CLAMPED_EXP = 3 }; /* network.py:131-138 */
+
+/* xyzs [M,3] fp32 in [-bound, bound]; dirs [M,3] fp32 (any length, normalised inside like renderer.py:544 +
+ * sphere_harmonics.py:81); ldirs [M,3] or NULL; feat_weights [2L] fp32 or NULL (BARF window, network.py:99-109).
+ * Outputs: sigma_out [M] fp32; in2 [M, ld2] fp16 (ld2 >= 32, or 48 with ldirs); saved for backward: enc_out [M, 2L]
+ * fp16 (or NULL) and acts_out[l] [M, dims[l+1]] fp16.  in2 == NULL computes the density only (NeRFNetwork.density). */
+int ngp_field_forward_density(const float* xyzs, const float* dirs, const float* ldirs, const void* table,
+                              const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
+                              uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,
+                              const void* const* weights, const uint32_t* dims, uint32_t n_layers, uint32_t M,
+                              int density_act, float beta, void* enc_out, void* const* acts_out, float* sigma_out,
+                              void* in2, uint32_t ld2, ngp_stream_t stream);
+
+/* d_sigma, sigma [M] fp32; d_in2 [M, ld2] fp16 (columns 0..14 are used); enc / acts as saved by the forward;
+ * grad_table [sO, 2] fp16 is ACCUMULATED into; dweights[l] fp32 accumulated with atomics. */
+int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
+                               uint32_t ld2, const void* enc, const void* table, const int32_t* offsets,
+                               const float* feat_weights, float bound, float S, uint32_t H, uint32_t L,
+                               uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
+                               const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
+                               int density_act, float beta, void* grad_table, float* const* dweights,
+                               ngp_stream_t stream);
+
+/* ngp_mlp_forward whose last epilogue applies the colour activation to output columns 0..2 and writes rgb_out [M,3] fp32 */
+int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
+                        uint32_t n_layers, uint32_t M, int act, int color_act, float* rgb_out,
+                        void* const* acts_out, ngp_stream_t stream);
+
+/* ngp_mlp_backward whose incoming gradient is computed from d_rgb [M,3] fp32 and the activated rgb [M,3] fp32 */
+int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
+                         const void* const* weights, const void* const* acts, const uint32_t* dims,
+                         uint32_t n_layers, uint32_t M, int act, void* dx, uint32_t lddx, float* const* dweights,
+                         ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (reference: torch.optim.Adam, main.py:245;
  * GradScaler unscale + inf check, nerf/train_utils.py:897-904) -- SURVEY 8(f) row 1.
  * ---------------------------------------------------------------------------------------- */

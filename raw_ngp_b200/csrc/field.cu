@@ -1,0 +1,582 @@
+// field.cu -- the NeRF field of nerf/network.py:74-143 fused around the tensor-core MLP kernels.
+//
+//   forward 1 (density):  xyz -> hash-grid encode (gathers into the A tile, no HBM round trip) -> grid_mlp
+//                         -> sigma = act(out[0]) ; in2 = [out[1:16], SH(dir), (SH(light dir)), 0]
+//   forward 2 (colour):   in2 -> view_mlp -> colour activation -> rgb           (mlp.cu, head epilogue)
+//   backward 2:           d rgb -> d out2 -> view_mlp backward -> d in2          (mlp.cu, head prologue)
+//   backward 1:           [d sigma * sigma', d in2[:, :15]] -> grid_mlp backward -> d enc (TMEM)
+//                         -> warp-aggregated packed reductions straight into the table gradient
+//
+// Every elementwise op the reference runs as its own PyTorch kernel between these stages (input scaling, direction
+// normalisation, slicing, cat, casts, exp/clamp and all their autograd mirrors) happens in registers here.
+// Rounding points follow the autocast pipeline of the reference (fp16 linear outputs, fp32 exp, fp16 features).
+#include "common.cuh"
+#include "grid_core.cuh"
+#include "mlp_core.cuh"
+#include "tcgen05.cuh"
+
+namespace ngp {
+namespace {
+
+using namespace mlpcore;
+using namespace gridcore;
+
+constexpr uint32_t kMaxLevels = 32;
+
+struct GridArgs {
+    const __half* table;        // [sO, 2] fp16
+    const int* offsets;         // [L+1]
+    const float* feat_weights;  // [2L] or nullptr (BARF annealing window, network.py:99-109)
+    float S, bound;
+    uint32_t H, L, gridtype, interp;
+    bool align_corners;
+};
+
+struct LevelConst { uint32_t res, hashmap_size, offset; };
+
+__device__ __forceinline__ void load_level_consts(LevelConst* s_lv, const GridArgs& g) {
+    for (uint32_t l = threadIdx.x; l < g.L; l += blockDim.x) {
+        const uint32_t off = (uint32_t)__ldg(g.offsets + l);
+        s_lv[l].res = level_resolution(l, g.S, g.H);
+        s_lv[l].offset = off;
+        s_lv[l].hashmap_size = (uint32_t)__ldg(g.offsets + l + 1) - off;
+    }
+}
+
+// position in [0,1]^3 the way GridEncoder.forward computes it: (x + bound) / (2*bound), the division by a host
+// scalar being a multiplication by its fp32 reciprocal in torch (grid.py:160).
+__device__ __forceinline__ void unit_cube(const float* __restrict__ xyz, float bound, float (&x)[3]) {
+    const float inv = __fdiv_rn(1.0f, 2.0f * bound);
+#pragma unroll
+    for (int d = 0; d < 3; d++) x[d] = __fmul_rn(__fadd_rn(__ldg(xyz + d), bound), inv);
+}
+
+__device__ __forceinline__ bool locate3(const float (&x)[3], uint32_t res, bool align_corners, uint32_t interp,
+                                        uint32_t (&base)[3], float (&frac)[3]) {
+    if (x[0] < 0 || x[0] > 1 || x[1] < 0 || x[1] > 1 || x[2] < 0 || x[2] > 1) return false;
+#pragma unroll
+    for (uint32_t d = 0; d < 3; d++) {
+        float p;
+        if (align_corners) {
+            p = x[d] * (float)(res - 1);
+            base[d] = min((uint32_t)floorf(p), res - 2);
+        } else {
+            p = fminf(fmaxf(x[d] * (float)res - 0.5f, 0.0f), (float)(res - 1));
+            base[d] = (uint32_t)floorf(p);
+        }
+        p -= (float)base[d];
+        frac[d] = (interp == 1) ? smoothstep_f(p) : p;
+    }
+    return true;
+}
+
+__device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
+
+// ---------------------------------------------------------------------------------------------------
+// forward 1: encode -> grid_mlp -> sigma, in2
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kFwdTmemCols = 128;
+
+template <bool LDIR>
+__global__ void __launch_bounds__(kTile)
+field_forward_density_kernel(const float* __restrict__ xyzs, const float* __restrict__ dirs, const float* __restrict__ ldirs,
+                             GridArgs g, MlpArgs p, uint32_t M, __half* __restrict__ enc_out, float* __restrict__ sigma_out,
+                             __half* __restrict__ in2, uint32_t ld2, int density_act, float beta, uint32_t a_tile_off,
+                             uint32_t ctrl_off) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t t = threadIdx.x, warp = t >> 5;
+    uint8_t* a_tile = smem + a_tile_off;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
+    LevelConst* s_lv = reinterpret_cast<LevelConst*>(smem + ctrl_off + 16);
+
+    uint32_t w_off[kMaxLayers];
+    {
+        uint32_t o = 0;
+        for (uint32_t l = 0; l < p.n_layers; l++) { w_off[l] = o; o += p.dims[l] * p.dims[l + 1] * 2; }
+    }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kFwdTmemCols);
+    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    for (uint32_t l = 0; l < p.n_layers; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
+    load_level_consts(s_lv, g);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t a_saddr = tc::smem_u32(a_tile), mbar_saddr = tc::smem_u32(mbar);
+    const uint32_t F = p.dims[0];  // = 2 * L
+
+    uint32_t phase = 0;
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTile + t;
+        const bool live = row < M;
+        // ---- hash-grid encode of this thread's sample, 4 levels (8 features = one 16-byte chunk) at a time ----
+        float x[3] = {2.f, 2.f, 2.f};
+        if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
+        for (uint32_t lg = 0; lg < g.L; lg += 4) {
+            __align__(16) __half2 feat[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                const uint32_t level = lg + j;
+                const LevelConst lv = s_lv[level];
+                uint32_t base[3];
+                float frac[3];
+                float f0 = 0.f, f1 = 0.f;
+                if (live && locate3(x, lv.res, g.align_corners, g.interp, base, frac)) {
+                    const __half* __restrict__ lvl = g.table + (size_t)lv.offset * 2;
+                    float val[8][2];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; k++) {
+                        uint32_t q[3];
+#pragma unroll
+                        for (uint32_t d = 0; d < 3; d++) q[d] = (k & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
+                        load_row<__half, 2>(lvl + (size_t)entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q) * 2, val[k]);
+                    }
+                    // same half-precision accumulation as grid_forward_kernel with NGP_GRID_REF_ROUNDING
+                    __half a0 = __float2half_rn(0.f), a1 = a0;
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; k++) {
+                        float w = 1;
+#pragma unroll
+                        for (uint32_t d = 0; d < 3; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
+                        a0 = __float2half_rn(__half2float(a0) + __half2float(__float2half_rn(w * val[k][0])));
+                        a1 = __float2half_rn(__half2float(a1) + __half2float(__float2half_rn(w * val[k][1])));
+                    }
+                    f0 = __half2float(a0); f1 = __half2float(a1);
+                    if (g.feat_weights) {
+                        f0 *= __ldg(g.feat_weights + 2 * level);
+                        f1 *= __ldg(g.feat_weights + 2 * level + 1);
+                    }
+                }
+                feat[j] = __floats2half2_rn(f0, f1);
+            }
+            const uint4 chunk = *reinterpret_cast<uint4*>(feat);
+            *reinterpret_cast<uint4*>(a_tile + (lg / 4) * kPanel + t * 16) = chunk;
+            if (live && enc_out) *reinterpret_cast<uint4*>(enc_out + (size_t)row * F + lg * 2) = chunk;
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+
+        float out[16];
+        for (uint32_t l = 0; l < p.n_layers; l++) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            if (t == 0) {
+                tc::fence_after_sync();
+                const uint32_t idesc = tc::instr_desc(kTile, N, false, false);
+                const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
+                for (uint32_t ks = 0; ks < K / 16; ks++) {
+                    const uint64_t ad = tc::smem_desc(a_saddr + ks * 2 * kPanel, kPanel, 128);
+                    const uint64_t bd = tc::smem_desc(w_saddr + ks * 2 * (N * 16), N * 16, 128);
+                    tc::mma_f16_ss(tmem, ad, bd, idesc, ks > 0);
+                }
+                tc::mma_commit(mbar_saddr);
+            }
+            tc::mbar_wait(mbar_saddr, phase);
+            phase ^= 1;
+            tc::fence_after_sync();
+            const bool last = (l + 1 == p.n_layers);
+            if (!last) {
+                for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                    uint4 lo, hi;
+                    pack16(v, lo, hi);
+                    *reinterpret_cast<uint4*>(a_tile + (c0 / 8) * kPanel + t * 16) = lo;
+                    *reinterpret_cast<uint4*>(a_tile + (c0 / 8 + 1) * kPanel + t * 16) = hi;
+                    if (p.acts[l] && live) {
+                        uint4* gp = reinterpret_cast<uint4*>(p.acts[l] + (size_t)row * N + c0);
+                        gp[0] = lo; gp[1] = hi;
+                    }
+                }
+                tc::fence_async_smem();
+            } else {
+                tc::tmem_ld16(lane_addr, out);      // grid_mlp output: 16 columns
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+        }
+
+        if (live && !in2) {
+            const float o0 = half_round(out[0]);
+            float sg;
+            if (density_act == 0) sg = expf(o0);
+            else { const float bx = beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / beta; }
+            sigma_out[row] = sg;
+        } else if (live) {
+            // sigma (network.py:112-115): the linear output is fp16 under autocast, the activation runs in fp32
+            const float o0 = half_round(out[0]);
+            float sg;
+            if (density_act == 0) sg = expf(o0);
+            else { const float bx = beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / beta; }
+            sigma_out[row] = sg;
+            // in2 = [feat(15), SH(dir)(16), (SH(light dir)(16)), 0]
+            __align__(16) __half rowbuf[LDIR ? 48 : 32];
+#pragma unroll
+            for (int i = 0; i < 15; i++) rowbuf[i] = __float2half_rn(out[i + 1]);
+            {
+                float dx = __ldg(dirs + (size_t)row * 3), dy = __ldg(dirs + (size_t)row * 3 + 1), dz = __ldg(dirs + (size_t)row * 3 + 2);
+                float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);          // renderer.py:544
+                dx *= inv; dy *= inv; dz *= inv;
+                inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);                // SHEncoder.forward, sphere_harmonics.py:81
+                const float x = dx * inv, y = dy * inv, z = dz * inv, zz = z * z;
+                constexpr int DEG = 4;
+#define SH_TERM(i, v, ddx, ddy, ddz) rowbuf[15 + i] = __float2half_rn(v);
+#include "sh_basis.inc"
+#undef SH_TERM
+            }
+            if (LDIR) {
+                float dx = __ldg(ldirs + (size_t)row * 3), dy = __ldg(ldirs + (size_t)row * 3 + 1), dz = __ldg(ldirs + (size_t)row * 3 + 2);
+                const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);    // SHEncoder.forward only (ldirs are not pre-normalised)
+                const float x = dx * inv, y = dy * inv, z = dz * inv, zz = z * z;
+                constexpr int DEG = 4;
+#define SH_TERM(i, v, ddx, ddy, ddz) rowbuf[31 + i] = __float2half_rn(v);
+#include "sh_basis.inc"
+#undef SH_TERM
+                rowbuf[47] = __float2half_rn(0.f);
+            } else {
+                rowbuf[31] = __float2half_rn(0.f);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(in2 + (size_t)row * ld2);
+            const uint4* src = reinterpret_cast<const uint4*>(rowbuf);
+#pragma unroll
+            for (int i = 0; i < (LDIR ? 6 : 4); i++) dst[i] = src[i];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kFwdTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward 1: [d sigma, d in2[:, :15]] -> grid_mlp backward -> table gradient
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kBwdTmemCols = 256;
+
+__global__ void __launch_bounds__(kTile)
+field_backward_density_kernel(const float* __restrict__ xyzs, const float* __restrict__ d_sigma, const float* __restrict__ sigma,
+                              const __half* __restrict__ d_in2, uint32_t ld2, const __half* __restrict__ enc, GridArgs g,
+                              MlpArgs p, uint32_t M, __half* __restrict__ grad_table, int density_act, float beta,
+                              uint32_t dz_off, uint32_t dz_bytes, uint32_t w_base, uint32_t ctrl_off) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t L = p.n_layers;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
+    LevelConst* s_lv = reinterpret_cast<LevelConst*>(smem + ctrl_off + 16);
+
+    uint32_t in_off[kMaxLayers], w_off[kMaxLayers], acc_col[kMaxLayers];
+    uint32_t work_cols = 0;
+    {
+        uint32_t o = 0, wo = w_base, col = 0;
+        for (uint32_t l = 0; l < L; l++) {
+            in_off[l] = o; o += kTile * p.dims[l] * 2;
+            w_off[l] = wo; wo += p.dims[l] * p.dims[l + 1] * 2;
+            work_cols = max(work_cols, p.dims[l]);
+        }
+        col = work_cols;
+        for (uint32_t l = 0; l < L; l++) { acc_col[l] = col; col += p.dims[l + 1]; }
+    }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kBwdTmemCols);
+    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
+    load_level_consts(s_lv, g);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t mbar_saddr = tc::smem_u32(mbar);
+
+    uint32_t phase = 0, iter = 0;
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
+        const uint32_t row = tile * kTile + t;
+        const bool live = row < M;
+        uint32_t cur = 0;
+        // saved activations of the forward pass
+        load_row_tile(smem + in_off[0], enc, p.dims[0], p.dims[0], row, M);
+        for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
+        // d out1 = [d sigma * d act / d out0, d feat(15)]
+        {
+            __align__(16) __half dz[16];
+            if (live) {
+                const float sg = __ldg(sigma + row);
+                float dact;
+                if (density_act == 0) dact = sg;                              // trunc_exp backward: g * exp(x) (activation.py:18-21)
+                else dact = 1.0f - expf(-beta * sg);                          // softplus' = sigmoid(beta x) = 1 - exp(-beta y)
+                dz[0] = __float2half_rn(__ldg(d_sigma + row) * dact);
+                const uint4* src = reinterpret_cast<const uint4*>(d_in2 + (size_t)row * ld2);
+                const uint4 a = __ldg(src), b = __ldg(src + 1);
+                const __half* ha = reinterpret_cast<const __half*>(&a);
+                const __half* hb = reinterpret_cast<const __half*>(&b);
+#pragma unroll
+                for (int i = 0; i < 8; i++) dz[1 + i] = ha[i];
+#pragma unroll
+                for (int i = 0; i < 7; i++) dz[9 + i] = hb[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) dz[i] = __float2half_rn(0.f);
+            }
+            uint8_t* dzt = smem + dz_off;
+            *reinterpret_cast<uint4*>(dzt + t * 16) = reinterpret_cast<const uint4*>(dz)[0];
+            *reinterpret_cast<uint4*>(dzt + kPanel + t * 16) = reinterpret_cast<const uint4*>(dz)[1];
+        }
+        tc::cp_async_wait_all();
+        tc::fence_async_smem();
+        __syncthreads();
+
+        for (int l = (int)L - 1; l >= 0; l--) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            const uint32_t dz_saddr = tc::smem_u32(smem + dz_off + cur * dz_bytes);
+            if (t == 0) {
+                tc::fence_after_sync();
+                const uint32_t in_saddr = tc::smem_u32(smem + in_off[l]);
+                const uint32_t idw = tc::instr_desc(kTile, N, true, true);
+                for (uint32_t ks = 0; ks < kTile / 16; ks++) {
+                    const uint64_t ad = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
+                    const uint64_t bd = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
+                    tc::mma_f16_ss(tmem + acc_col[l], ad, bd, idw, (iter > 0 || ks > 0) ? 1u : 0u);
+                }
+                const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
+                const uint32_t idh = tc::instr_desc(kTile, K, false, true);
+                for (uint32_t ks = 0; ks < N / 16; ks++) {
+                    const uint64_t ad = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
+                    const uint64_t bd = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
+                    tc::mma_f16_ss(tmem, ad, bd, idh, ks > 0);
+                }
+                tc::mma_commit(mbar_saddr);
+            }
+            tc::mbar_wait(mbar_saddr, phase);
+            phase ^= 1;
+            tc::fence_after_sync();
+            if (l > 0) {
+                uint8_t* nxt = smem + dz_off + (cur ^ 1) * dz_bytes;
+                const uint8_t* in_tile = smem + in_off[l];
+                for (uint32_t c0 = 0; c0 < K; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + c0, v);
+                    const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8) * kPanel + t * 16);
+                    const uint4 m1 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8 + 1) * kPanel + t * 16);
+                    const __half* h0 = reinterpret_cast<const __half*>(&m0);
+                    const __half* h1 = reinterpret_cast<const __half*>(&m1);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (!(__half2float(h0[i]) > 0.f)) v[i] = 0.f;
+                        if (!(__half2float(h1[i]) > 0.f)) v[8 + i] = 0.f;
+                    }
+                    uint4 lo, hi;
+                    pack16(v, lo, hi);
+                    *reinterpret_cast<uint4*>(nxt + (c0 / 8) * kPanel + t * 16) = lo;
+                    *reinterpret_cast<uint4*>(nxt + (c0 / 8 + 1) * kPanel + t * 16) = hi;
+                }
+                tc::fence_async_smem();
+            } else {
+                // ---- d enc of this thread's sample (TMEM lane) -> hash-table gradient, level by level ----
+                float x[3] = {2.f, 2.f, 2.f};
+                if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
+                for (uint32_t c0 = 0; c0 < K; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; j++) {
+                        const uint32_t level = c0 / 2 + j;
+                        if (level >= g.L) break;
+                        const LevelConst lv = s_lv[level];
+                        // the gradient reaches the encoder as fp16 (autocast), optionally through the annealing window
+                        float g0 = half_round(v[2 * j]), g1 = half_round(v[2 * j + 1]);
+                        if (g.feat_weights) {
+                            g0 = half_round(g0 * __ldg(g.feat_weights + 2 * level));
+                            g1 = half_round(g1 * __ldg(g.feat_weights + 2 * level + 1));
+                        }
+                        uint32_t base[3];
+                        float frac[3];
+                        const bool valid = live && locate3(x, lv.res, g.align_corners, g.interp, base, frac);
+                        float wg[8][2];
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; k++) {
+                            float w = 1;
+#pragma unroll
+                            for (uint32_t d = 0; d < 3; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
+                            wg[k][0] = valid ? w * g0 : 0.f;
+                            wg[k][1] = valid ? w * g1 : 0.f;
+                        }
+                        uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFF00u | lane;
+                        if (valid) { key0 = base[0] | (base[1] << 16); key1 = base[2]; }
+                        const uint32_t pk0 = __shfl_up_sync(0xffffffffu, key0, 1), pk1 = __shfl_up_sync(0xffffffffu, key1, 1);
+                        const bool head = (lane == 0) || (pk0 != key0) || (pk1 != key1);
+                        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+                        if (heads != 0xffffffffu) {
+                            const uint32_t above = heads & ~((2u << lane) - 1u);
+                            const uint32_t end = (lane == 31 || above == 0) ? 31u : (uint32_t)__ffs(above) - 2u;
+#pragma unroll
+                            for (uint32_t d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                                for (uint32_t k = 0; k < 8; k++) {
+                                    const float o0 = __shfl_down_sync(0xffffffffu, wg[k][0], d);
+                                    const float o1 = __shfl_down_sync(0xffffffffu, wg[k][1], d);
+                                    if (lane + d <= end) { wg[k][0] += o0; wg[k][1] += o1; }
+                                }
+                            }
+                        }
+                        if (valid && head) {
+                            __half* glvl = grad_table + (size_t)lv.offset * 2;
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; k += 2) {
+                                uint32_t q0[3], q1[3];
+#pragma unroll
+                                for (uint32_t d = 0; d < 3; d++) {
+                                    q0[d] = (k & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
+                                    q1[d] = ((k + 1) & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
+                                }
+                                scatter_pair<__half, 2>(glvl, entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q0),
+                                                        entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q1), wg[k], wg[k + 1]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+    if (iter > 0) {
+        tc::fence_after_sync();
+        for (uint32_t l = 0; l < L; l++) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(lane_addr + acc_col[l] + c0, v);
+                if (t < K) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) red_add_f32(p.dw[l] + (size_t)(c0 + i) * K + t, v[i]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kBwdTmemCols);
+}
+
+bool fill_args(MlpArgs& p, const void* const* weights, void* const* acts, float* const* dweights, const uint32_t* dims,
+               uint32_t n_layers) {
+    if (n_layers < 1 || n_layers > kMaxLayers) return false;
+    for (uint32_t l = 0; l <= n_layers; l++)
+        if (dims[l] == 0 || dims[l] % 16 != 0 || dims[l] > 128) return false;
+    p.n_layers = n_layers;
+    for (uint32_t l = 0; l < n_layers; l++) {
+        if (!weights[l] || !aligned(weights[l], 16)) return false;
+        p.w[l] = (const __half*)weights[l];
+        p.acts[l] = (acts && l + 1 < n_layers) ? (__half*)acts[l] : nullptr;
+        p.dw[l] = dweights ? dweights[l] : nullptr;
+    }
+    for (uint32_t l = 0; l <= n_layers; l++) p.dims[l] = dims[l];
+    return true;
+}
+
+}  // namespace
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, const float* ldirs, const void* table,
+                                         const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
+                                         uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,
+                                         const void* const* weights, const uint32_t* dims, uint32_t n_layers, uint32_t M,
+                                         int density_act, float beta, void* enc_out, void* const* acts_out, float* sigma_out,
+                                         void* in2, uint32_t ld2, ngp_stream_t stream) {
+    if (M == 0) return NGP_OK;
+    if (!xyzs || !table || !offsets || !weights || !dims || !sigma_out) return NGP_ERR_NULL;
+    if (in2 && !dirs) return NGP_ERR_NULL;   /* in2 == NULL: density only (NeRFNetwork.density) */
+    if (L == 0 || L > kMaxLevels || L % 4 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
+    MlpArgs p = {};
+    if (!fill_args(p, weights, acts_out, nullptr, dims, n_layers)) return NGP_ERR_UNSUPPORTED;
+    if (dims[0] != 2 * L || dims[n_layers] != 16) return NGP_ERR_UNSUPPORTED;
+    const uint32_t need2 = ldirs ? 48u : 32u;
+    if (in2 && (ld2 < need2 || ld2 % 8)) return NGP_ERR_BAD_ARG;
+    if (!aligned(table, 16) || (in2 && !aligned(in2, 16)) || (enc_out && !aligned(enc_out, 16))) return NGP_ERR_ALIGN;
+    GridArgs g = {(const __half*)table, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
+    uint32_t w_bytes = 0, max_k = 0;
+    for (uint32_t l = 0; l < n_layers; l++) { w_bytes += dims[l] * dims[l + 1] * 2; max_k = std::max(max_k, dims[l]); }
+    const uint32_t a_off = (w_bytes + 127) & ~127u;
+    const uint32_t ctrl_off = a_off + kTile * max_k * 2;
+    const uint32_t smem_bytes = ctrl_off + 16 + kMaxLevels * sizeof(LevelConst);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 4);
+#define NGP_LAUNCH_FWD(LD)                                                                                                \
+    {                                                                                                                     \
+        static thread_local uint32_t configured = 0;                                                                      \
+        if (smem_bytes > configured) {                                                                                    \
+            if (cudaFuncSetAttribute(field_forward_density_kernel<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)smem_bytes) != cudaSuccess) {                                                   \
+                set_last_cuda_error(cudaGetLastError());                                                                  \
+                return NGP_ERR_CUDA;                                                                                      \
+            }                                                                                                             \
+            configured = smem_bytes;                                                                                      \
+        }                                                                                                                 \
+        field_forward_density_kernel<LD><<<grid, kTile, smem_bytes, st>>>(xyzs, dirs, ldirs, g, p, M, (__half*)enc_out,   \
+                                                                          sigma_out, (__half*)in2, ld2, density_act, beta, \
+                                                                          a_off, ctrl_off);                               \
+    }
+    if (ldirs) NGP_LAUNCH_FWD(true) else NGP_LAUNCH_FWD(false)
+#undef NGP_LAUNCH_FWD
+    return finish_launch();
+}
+
+extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
+                                          uint32_t ld2, const void* enc, const void* table_unused, const int32_t* offsets,
+                                          const float* feat_weights, float bound, float S, uint32_t H, uint32_t L,
+                                          uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
+                                          const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
+                                          int density_act, float beta, void* grad_table, float* const* dweights,
+                                          ngp_stream_t stream) {
+    (void)table_unused;
+    if (M == 0) return NGP_OK;
+    if (!xyzs || !d_sigma || !sigma || !d_in2 || !enc || !offsets || !weights || !dims || !grad_table || !dweights) return NGP_ERR_NULL;
+    if (n_layers > 1 && !acts) return NGP_ERR_NULL;
+    if (L == 0 || L > kMaxLevels || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
+    MlpArgs p = {};
+    if (!fill_args(p, weights, (void* const*)acts, dweights, dims, n_layers)) return NGP_ERR_UNSUPPORTED;
+    if (dims[0] != 2 * L || dims[n_layers] != 16 || ld2 < 16 || ld2 % 8) return NGP_ERR_UNSUPPORTED;
+    if (!aligned(grad_table, 16) || !aligned(d_in2, 16) || !aligned(enc, 16)) return NGP_ERR_ALIGN;
+    for (uint32_t l = 0; l < n_layers; l++) {
+        if (!dweights[l]) return NGP_ERR_NULL;
+        if (l + 1 < n_layers && !acts[l]) return NGP_ERR_NULL;
+    }
+    GridArgs g = {nullptr, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
+    uint32_t w_bytes = 0, in_bytes = 0, max_n = 0, max_k = 0, acc_cols = 0;
+    for (uint32_t l = 0; l < n_layers; l++) {
+        w_bytes += dims[l] * dims[l + 1] * 2;
+        in_bytes += kTile * dims[l] * 2;
+        max_n = std::max(max_n, dims[l + 1]);
+        max_k = std::max(max_k, dims[l]);
+        acc_cols += dims[l + 1];
+    }
+    if (max_k + acc_cols > kBwdTmemCols) return NGP_ERR_UNSUPPORTED;
+    const uint32_t dz_bytes = kTile * std::max(max_n, max_k) * 2;
+    const uint32_t dz_off = in_bytes;
+    const uint32_t w_base = dz_off + 2 * dz_bytes;
+    const uint32_t ctrl_off = (w_base + w_bytes + 127) & ~127u;
+    const uint32_t last_in_off = in_bytes - kTile * dims[n_layers - 1] * 2;
+    const uint32_t smem_bytes = std::max<uint32_t>(ctrl_off + 16 + kMaxLevels * sizeof(LevelConst), last_in_off + 18 * kPanel);
+    if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
+    static thread_local uint32_t configured = 0;
+    if (smem_bytes > configured) {
+        if (cudaFuncSetAttribute(field_backward_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+            set_last_cuda_error(cudaGetLastError());
+            return NGP_ERR_CUDA;
+        }
+        configured = smem_bytes;
+    }
+    const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
+    field_backward_density_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>(
+        xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,
+        dz_off, dz_bytes, w_base, ctrl_off);
+    return finish_launch();
+}

@@ -11,51 +11,12 @@
 // [M, 64] activations round-tripping through HBM between them.
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "mlp_core.cuh"
 
 namespace ngp {
 namespace {
 
-constexpr uint32_t kTile = 128;          // samples per tile == UMMA M == threads per CTA
-constexpr uint32_t kPanel = kTile * 16;  // bytes of one 8-column panel of a 128-row tile
-constexpr uint32_t kMaxLayers = 4;
-
-struct MlpArgs {
-    const __half* w[kMaxLayers];   // [dims[l+1], dims[l]] row-major fp16
-    __half* acts[kMaxLayers];      // forward: hidden activations out; backward: hidden activations in
-    float* dw[kMaxLayers];         // backward: [dims[l+1], dims[l]] fp32, accumulated with atomics
-    uint32_t dims[kMaxLayers + 1];
-    uint32_t n_layers;
-};
-
-// weights -> shared memory in row-panel layout (R = N_l rows)
-__device__ __forceinline__ void load_weight_tile(uint8_t* dst, const __half* __restrict__ w, uint32_t N, uint32_t K) {
-    const uint32_t chunks = K / 8;
-    for (uint32_t i = threadIdx.x; i < N * chunks; i += blockDim.x) {
-        const uint32_t n = i / chunks, c = i - n * chunks;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * K + c * 8));
-        *reinterpret_cast<uint4*>(dst + (size_t)c * (N * 16) + n * 16) = v;
-    }
-}
-
-// one row of a [M, F] fp16 matrix -> this thread's row of a 128-row tile (cp.async, zero-fill past M)
-__device__ __forceinline__ void load_row_tile(uint8_t* tile, const __half* __restrict__ src, uint32_t ld, uint32_t F,
-                                              uint32_t row, uint32_t M) {
-    const uint32_t t = threadIdx.x;
-    if (row < M) {
-        const __half* p = src + (size_t)row * ld;
-        for (uint32_t c = 0; c < F / 8; c++) tc::cp_async16(tc::smem_u32(tile + c * kPanel + t * 16), p + c * 8);
-    } else {
-        for (uint32_t c = 0; c < F / 8; c++) *reinterpret_cast<uint4*>(tile + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
-    }
-}
-
-__device__ __forceinline__ void pack16(const float (&v)[16], uint4& lo, uint4& hi) {
-    __half2 h[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    lo = *reinterpret_cast<uint4*>(&h[0]);
-    hi = *reinterpret_cast<uint4*>(&h[4]);
-}
+using namespace mlpcore;
 
 // ---------------------------------------------------------------------------------------------------
 // forward
@@ -64,7 +25,7 @@ constexpr uint32_t kFwdTmemCols = 128;
 
 __global__ void __launch_bounds__(kTile)
 mlp_forward_kernel(const __half* __restrict__ x, uint32_t ldx, MlpArgs p, uint32_t M, __half* __restrict__ y, uint32_t ldy,
-                   uint32_t a_tile_off, uint32_t ctrl_off) {
+                   float* __restrict__ rgb_out, int head_act, uint32_t a_tile_off, uint32_t ctrl_off) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, warp = t >> 5;
     uint8_t* a_tile = smem + a_tile_off;
@@ -129,8 +90,23 @@ mlp_forward_kernel(const __half* __restrict__ x, uint32_t ldx, MlpArgs p, uint32
                         g[0] = lo; g[1] = hi;
                     }
                 } else if (row < M) {
-                    uint4* g = reinterpret_cast<uint4*>(y + (size_t)row * ldy + c0);
-                    g[0] = lo; g[1] = hi;
+                    if (head_act == 0) {
+                        uint4* g = reinterpret_cast<uint4*>(y + (size_t)row * ldy + c0);
+                        g[0] = lo; g[1] = hi;
+                    } else if (c0 == 0) {
+                        // colour head (network.py:131-138): fp16 linear output, `color - 5` in fp16, exp in fp32
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float o = __half2float(__float2half_rn(v[c]));
+                            float r;
+                            if (head_act == 2) r = __half2float(__float2half_rn(1.0f / (1.0f + expf(-o))));
+                            else {
+                                r = expf(__half2float(__float2half_rn(o - 5.0f)));
+                                if (head_act == 3) r = fminf(r, 5.0f);
+                            }
+                            rgb_out[(size_t)row * 3 + c] = r;
+                        }
+                    }
                 }
             }
             if (!last) tc::fence_async_smem();
@@ -149,7 +125,8 @@ constexpr uint32_t kBwdTmemCols = 256;
 
 __global__ void __launch_bounds__(kTile)
 mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* __restrict__ x, uint32_t ldx, MlpArgs p,
-                    uint32_t M, __half* __restrict__ dx, uint32_t lddx, uint32_t dz_off, uint32_t dz_bytes,
+                    uint32_t M, __half* __restrict__ dx, uint32_t lddx, const float* __restrict__ d_rgb,
+                    const float* __restrict__ rgb, int head_act, uint32_t dz_off, uint32_t dz_bytes,
                     uint32_t w_base, uint32_t ctrl_off) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, warp = t >> 5;
@@ -186,7 +163,29 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
         const uint32_t row = tile * kTile + t;
         uint32_t cur = 0;  // which dZ buffer holds dZ of the layer being processed
-        load_row_tile(smem + dz_off, dy, lddy, p.dims[L], row, M);
+        if (head_act == 0) {
+            load_row_tile(smem + dz_off, dy, lddy, p.dims[L], row, M);
+        } else {
+            // d out = d rgb * d act / d out from the activated colour (exp: rgb; clamped exp: rgb below the clamp;
+            // sigmoid: rgb (1 - rgb)); columns 3.. of the padded output carry no gradient
+            __align__(16) __half dz[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) dz[i] = __float2half_rn(0.f);
+            if (row < M) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float gc = __ldg(d_rgb + (size_t)row * 3 + c), r = __ldg(rgb + (size_t)row * 3 + c);
+                    float d;
+                    if (head_act == 2) d = gc * r * (1.0f - r);
+                    else if (head_act == 3) d = (r < 5.0f) ? gc * r : 0.f;
+                    else d = gc * r;
+                    dz[c] = __float2half_rn(d);
+                }
+            }
+            uint8_t* dzt = smem + dz_off;
+            for (uint32_t c = 0; c < p.dims[L] / 8; c++)
+                *reinterpret_cast<uint4*>(dzt + c * kPanel + t * 16) = (c < 2) ? reinterpret_cast<const uint4*>(dz)[c] : make_uint4(0, 0, 0, 0);
+        }
         load_row_tile(smem + in_off[0], x, ldx, p.dims[0], row, M);
         for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
         tc::cp_async_wait_all();
@@ -288,15 +287,15 @@ bool dims_ok(const uint32_t* dims, uint32_t n_layers) {
 
 using namespace ngp;
 
-extern "C" int ngp_mlp_forward(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
-                               uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy, void* const* acts_out,
-                               ngp_stream_t stream) {
+static int mlp_forward_impl(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
+                            uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy, void* const* acts_out,
+                            float* rgb_out, int head_act, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
-    if (!x || !weights || !dims || !y) return NGP_ERR_NULL;
+    if (!x || !weights || !dims) return NGP_ERR_NULL;
     if (act != NGP_ACT_RELU) return NGP_ERR_UNSUPPORTED;
     if (!dims_ok(dims, n_layers)) return NGP_ERR_UNSUPPORTED;
     if (ldx < dims[0] || ldy < dims[n_layers] || ldx % 8 || ldy % 8) return NGP_ERR_BAD_ARG;
-    if (!aligned(x, 16) || !aligned(y, 16)) return NGP_ERR_ALIGN;
+    if (!aligned(x, 16) || (y && !aligned(y, 16))) return NGP_ERR_ALIGN;
     MlpArgs p = {};
     p.n_layers = n_layers;
     uint32_t w_bytes = 0, max_k = 0;
@@ -322,20 +321,38 @@ extern "C" int ngp_mlp_forward(const void* x, uint32_t ldx, const void* const* w
     }
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 4);   // 4 CTAs/SM: 4 x 128 TMEM columns
-    mlp_forward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)x, ldx, p, M, (__half*)y, ldy, a_off, ctrl_off);
+    mlp_forward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)x, ldx, p, M, (__half*)y, ldy, rgb_out, head_act, a_off, ctrl_off);
     return finish_launch();
 }
 
-extern "C" int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
-                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
-                                void* dx, uint32_t lddx, float* const* dweights, ngp_stream_t stream) {
+extern "C" int ngp_mlp_forward(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
+                               uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy, void* const* acts_out,
+                               ngp_stream_t stream) {
+    if (M > 0 && !y) return NGP_ERR_NULL;
+    return mlp_forward_impl(x, ldx, weights, dims, n_layers, M, act, y, ldy, acts_out, nullptr, 0, stream);
+}
+
+extern "C" int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
+                                   uint32_t n_layers, uint32_t M, int act, int color_act, float* rgb_out,
+                                   void* const* acts_out, ngp_stream_t stream) {
+    if (M > 0 && !rgb_out) return NGP_ERR_NULL;
+    if (color_act < 1 || color_act > 3) return NGP_ERR_BAD_ARG;
+    return mlp_forward_impl(x, ldx, weights, dims, n_layers, M, act, nullptr, 16, acts_out, rgb_out, color_act, stream);
+}
+
+static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
+                             const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
+                             void* dx, uint32_t lddx, float* const* dweights, const float* d_rgb, const float* rgb,
+                             int head_act, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
-    if (!dy || !x || !weights || !dims || !dweights) return NGP_ERR_NULL;
+    if (!x || !weights || !dims || !dweights) return NGP_ERR_NULL;
+    if (head_act == 0 && !dy) return NGP_ERR_NULL;
+    if (head_act != 0 && (!d_rgb || !rgb)) return NGP_ERR_NULL;
     if (n_layers > 1 && !acts) return NGP_ERR_NULL;
     if (act != NGP_ACT_RELU) return NGP_ERR_UNSUPPORTED;
     if (!dims_ok(dims, n_layers)) return NGP_ERR_UNSUPPORTED;
     if (ldx < dims[0] || lddy < dims[n_layers] || ldx % 8 || lddy % 8 || (dx && (lddx < dims[0] || lddx % 8))) return NGP_ERR_BAD_ARG;
-    if (!aligned(x, 16) || !aligned(dy, 16) || (dx && !aligned(dx, 16))) return NGP_ERR_ALIGN;
+    if (!aligned(x, 16) || (dy && !aligned(dy, 16)) || (dx && !aligned(dx, 16))) return NGP_ERR_ALIGN;
     MlpArgs p = {};
     p.n_layers = n_layers;
     uint32_t w_bytes = 0, in_bytes = 0, max_n = 0, max_k = 0, acc_cols = 0;
@@ -373,6 +390,20 @@ extern "C" int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, ui
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
     mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
-                                                                          (__half*)dx, lddx, dz_off, dz_bytes, w_base, ctrl_off);
+                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off);
     return finish_launch();
+}
+
+extern "C" int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
+                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
+                                void* dx, uint32_t lddx, float* const* dweights, ngp_stream_t stream) {
+    return mlp_backward_impl(dy, lddy, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
+                                    const void* const* weights, const void* const* acts, const uint32_t* dims,
+                                    uint32_t n_layers, uint32_t M, int act, void* dx, uint32_t lddx, float* const* dweights,
+                                    ngp_stream_t stream) {
+    if (color_act < 1 || color_act > 3) return NGP_ERR_BAD_ARG;
+    return mlp_backward_impl(nullptr, 16, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, d_rgb, rgb, color_act, stream);
 }

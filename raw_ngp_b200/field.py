@@ -1,0 +1,127 @@
+"""Fused NeRF field: NeRFNetwork.forward / .density (nerf/network.py:74-156) in four kernels per training step
+(csrc/field.cu, csrc/mlp.cu) instead of ~60 PyTorch ops.  Used by raw_ngp_b200.nerf.NeRFNetwork when the configuration
+is eligible (fp16 table with F=2, ReLU MLPs, autocast, no gradient w.r.t. positions/directions); otherwise the network
+composes the individual operators exactly like the reference does."""
+import ctypes
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .ffmlp import NGP_ACT_RELU, _pad16, _ptr_array
+
+DENSITY_ACT = {"clamped_exp": 0, "softplus": 1}
+COLOR_ACT = {"exp": 1, "sigmoid": 2, "clamped_exp": 3}
+
+
+def _pad_weight(w, n, k):
+    wp = torch.zeros(n, k, dtype=torch.float16, device=w.device)
+    wp[:w.shape[0], :w.shape[1]] = w
+    return wp
+
+
+def _grid_scalars(enc):
+    return (float(np.log2(enc.per_level_scale)), int(enc.base_resolution), int(enc.num_levels), int(enc.gridtype_id),
+            int(bool(enc.align_corners)), int(enc.interp_id))
+
+
+def density_only(enc, grid_weights, xyzs, bound, density_act, beta, feat_weights=None):
+    """sigma [M] fp32 for NeRFNetwork.density (no gradient)."""
+    xyzs = xyzs.contiguous().float()
+    M = xyzs.shape[0]
+    dims = [w.shape[1] for w in grid_weights[:1]] + [w.shape[0] for w in grid_weights]
+    pdims = [_pad16(d) for d in dims]
+    w16 = [_pad_weight(w, pdims[i + 1], pdims[i]) for i, w in enumerate(grid_weights)]
+    sigma = torch.empty(M, dtype=torch.float32, device=xyzs.device)
+    S, H, L, gt, ac, ip = _grid_scalars(enc)
+    _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
+              _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16),
+              (ctypes.c_uint32 * len(pdims))(*pdims), len(w16), M, int(density_act), float(beta), None, None, _lib.ptr(sigma),
+              None, 0, _lib.stream())
+    return sigma
+
+
+class _fused_field(Function):
+    @staticmethod
+    def forward(ctx, xyzs, dirs, ldirs, table, feat_weights, cfg, *weights):
+        enc, bound, density_act, beta, color_act = cfg
+        n1 = len(weights) // 2
+        gw, vw = weights[:n1], weights[n1:]
+        xyzs = xyzs.contiguous().float()
+        dirs = dirs.contiguous().float()
+        ldirs = ldirs.contiguous().float() if ldirs is not None else None
+        M, dev = xyzs.shape[0], xyzs.device
+        d1 = [gw[0].shape[1]] + [w.shape[0] for w in gw]
+        d2 = [vw[0].shape[1]] + [w.shape[0] for w in vw]
+        p1, p2 = [_pad16(d) for d in d1], [_pad16(d) for d in d2]
+        w1 = [_pad_weight(w, p1[i + 1], p1[i]) for i, w in enumerate(gw)]
+        w2 = [_pad_weight(w, p2[i + 1], p2[i]) for i, w in enumerate(vw)]
+        keep = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward; this is the real signal)
+        f16 = dict(dtype=torch.float16, device=dev)
+        enc_buf = torch.empty(M, p1[0], **f16) if keep else None
+        acts1 = [torch.empty(M, p1[l + 1], **f16) if keep else None for l in range(len(w1) - 1)]
+        acts2 = [torch.empty(M, p2[l + 1], **f16) if keep else None for l in range(len(w2) - 1)]
+        in2 = torch.empty(M, p2[0], **f16)
+        sigma = torch.empty(M, dtype=torch.float32, device=dev)
+        rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        S, H, L, gt, ac, ip = _grid_scalars(enc)
+        st = _lib.stream()
+        c1 = (ctypes.c_uint32 * len(p1))(*p1)
+        c2 = (ctypes.c_uint32 * len(p2))(*p2)
+        _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table),
+                  _lib.ptr(enc.offsets), _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, len(w1), M,
+                  int(density_act), float(beta), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None, _lib.ptr(sigma),
+                  _lib.ptr(in2), p2[0], st)
+        _lib.call("ngp_mlp_forward_rgb", _lib.ptr(in2), p2[0], _ptr_array(w2), c2, len(w2), M, NGP_ACT_RELU, int(color_act),
+                  _lib.ptr(rgb), _ptr_array(acts2) if keep else None, st)
+        if keep:
+            ctx.save_for_backward(xyzs, enc_buf, in2, sigma, rgb, table, feat_weights if feat_weights is not None else xyzs.new_empty(0),
+                                  *acts1, *acts2, *w1, *w2)
+            ctx.meta = (enc, bound, density_act, beta, color_act, d1, d2, p1, p2, [w.dtype for w in weights],
+                        feat_weights is not None)
+        ctx.mark_non_differentiable()
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_rgb):
+        enc, bound, density_act, beta, color_act, d1, d2, p1, p2, wdt, has_fw = ctx.meta
+        sv = ctx.saved_tensors
+        xyzs, enc_buf, in2, sigma, rgb, table, fw = sv[:7]
+        n1, n2 = len(p1) - 1, len(p2) - 1
+        o = 7
+        acts1 = list(sv[o:o + n1 - 1]); o += n1 - 1
+        acts2 = list(sv[o:o + n2 - 1]); o += n2 - 1
+        w1 = list(sv[o:o + n1]); o += n1
+        w2 = list(sv[o:o + n2])
+        M, dev = xyzs.shape[0], xyzs.device
+        d_sigma = d_sigma.contiguous().float()
+        d_rgb = d_rgb.contiguous().float()
+        dw1 = [torch.zeros(p1[l + 1], p1[l], dtype=torch.float32, device=dev) for l in range(n1)]
+        dw2 = [torch.zeros(p2[l + 1], p2[l], dtype=torch.float32, device=dev) for l in range(n2)]
+        d_in2 = torch.empty(M, p2[0], dtype=torch.float16, device=dev)
+        sink = enc.grad_sink
+        if sink is not None:
+            if sink.shape != table.shape or sink.dtype != table.dtype:
+                raise RuntimeError("grad_sink must match the table")
+            gtable = sink
+        else:
+            gtable = torch.zeros_like(table)
+        S, H, L, gt, ac, ip = _grid_scalars(enc)
+        st = _lib.stream()
+        c1 = (ctypes.c_uint32 * len(p1))(*p1)
+        c2 = (ctypes.c_uint32 * len(p2))(*p2)
+        _lib.call("ngp_mlp_backward_rgb", _lib.ptr(d_rgb), _lib.ptr(rgb), int(color_act), _lib.ptr(in2), p2[0], _ptr_array(w2),
+                  _ptr_array(acts2), c2, n2, M, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), st)
+        _lib.call("ngp_field_backward_density", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_in2), p2[0],
+                  _lib.ptr(enc_buf), None, _lib.ptr(enc.offsets), _lib.ptr(fw) if has_fw else None, float(bound), S, H, L, gt, ac, ip,
+                  _ptr_array(w1), _ptr_array(acts1), c1, n1, M, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), st)
+        gw = [dw1[l][:d1[l + 1], :d1[l]].to(wdt[l]) for l in range(n1)]
+        vw = [dw2[l][:d2[l + 1], :d2[l]].to(wdt[n1 + l]) for l in range(n2)]
+        return (None, None, None, None if sink is not None else gtable, None, None, *gw, *vw)
+
+
+def fused_field(xyzs, dirs, ldirs, enc, grid_weights, view_weights, bound, density_act, beta, color_act, feat_weights=None):
+    """Returns sigma [M] fp32, rgb [M,3] fp32."""
+    cfg = (enc, bound, density_act, beta, color_act)
+    return _fused_field.apply(xyzs, dirs, ldirs, enc.embeddings, feat_weights, cfg, *grid_weights, *view_weights)

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from ..activation import trunc_exp
 from ..encoding import get_encoder
 from ..ffmlp import fused_mlp
+from .. import field as _field
 from .renderer import NeRFRenderer
 
 
@@ -75,6 +76,28 @@ class NeRFNetwork(NeRFRenderer):
         alpha = (self.annealing - start) / (end - start) * L
         return (1 - (alpha - k).clamp_(min=0, max=1).mul_(np.pi).cos_()) / 2
 
+    # ---- fused path (csrc/field.cu): same maths as the op-by-op path below, four kernels instead of ~60 ops ----------
+    FUSED = True
+
+    def _fused_eligible(self, *tensors):
+        enc = self.grid_encoder
+        return (self.FUSED and enc.embeddings.is_cuda and enc.embeddings.dtype == torch.float16 and enc.level_dim == 2
+                and enc.input_dim == 3 and enc.num_levels % 8 == 0 and self.opt.internal_activation == "relu"
+                and self.opt.density_activation in ("clamped_exp", "softplus")
+                and self.opt.color_activation in _field.COLOR_ACT and self.opt.pose_opt in ("none", "barf")
+                and torch.is_autocast_enabled("cuda") and self.grid_mlp.num_layers == 3 and self.view_mlp.num_layers == 3
+                and not any(t is not None and t.requires_grad for t in tensors))
+
+    def _feat_weights(self, device):
+        if self.opt.pose_opt != "barf":
+            return None
+        w = self._annealing_window(self.grid_mlp.dim_out, device).repeat_interleave(self.level_dim)
+        w[0:2] = 1
+        return w.contiguous()
+
+    def _density_act(self):
+        return _field.DENSITY_ACT["clamped_exp" if self.opt.density_activation == "clamped_exp" else "softplus"]
+
     def common_forward(self, x):
         f = self.grid_encoder(x, bound=self.bound)
         if self.opt.pose_opt == "baangp":      # network.py:77-97
@@ -103,6 +126,12 @@ class NeRFNetwork(NeRFRenderer):
 
     def forward(self, x, d, ld=None, **kwargs):
         # x [N, 3] in [-bound, bound], d [N, 3] unit view directions, ld [N, 3] unit light directions (rfield)
+        if x.dim() == 2 and self._fused_eligible(x, d, ld) and (ld is not None) == bool(self.opt.rfield):
+            sigma, color = _field.fused_field(
+                x, d, ld if self.opt.rfield else None, self.grid_encoder, [l.weight for l in self.grid_mlp.net],
+                [l.weight for l in self.view_mlp.net], self.bound, self._density_act(), self.opt.beta,
+                _field.COLOR_ACT[self.opt.color_activation], self._feat_weights(x.device))
+            return {"sigma": sigma, "color": color}
         sigma, feat = self.common_forward(x)
         d = self.view_encoder(d)
         if self.opt.rfield:
@@ -119,6 +148,9 @@ class NeRFNetwork(NeRFRenderer):
         return {"sigma": sigma, "color": color}
 
     def density(self, x, proposal=-1):
+        if x.dim() == 2 and not torch.is_grad_enabled() and self._fused_eligible(x):
+            return {"sigma": _field.density_only(self.grid_encoder, [l.weight for l in self.grid_mlp.net], x, self.bound,
+                                                 self._density_act(), self.opt.beta, self._feat_weights(x.device))}
         sigma, _ = self.common_forward(x)
         return {"sigma": sigma}
 
