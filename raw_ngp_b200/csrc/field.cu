@@ -77,14 +77,24 @@ __device__ __forceinline__ float half_round(float v) { return __half2float(__flo
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kFwdTmemCols = 128;
 
+// 512 threads per CTA: thread (row, grp) with row = (warp % 4) * 32 + lane (the TMEM lane quadrant a warp may read) and
+// grp = warp / 4.  The encode phase gives each thread 4 of its sample's 16 levels (32 gathers in flight, one 16-byte
+// chunk of the A tile), hidden-layer epilogues give each group 16 of the 64 columns; only group 0 runs the last
+// epilogue.  A single group of 128 threads left the gather phase latency bound (25 % of the standalone encoder's
+// memory-level parallelism).
+constexpr uint32_t kFieldThreads = 512;
+constexpr uint32_t kGroups = kFieldThreads / kTile;
+
 template <bool LDIR>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kFieldThreads, 2)
 field_forward_density_kernel(const float* __restrict__ xyzs, const float* __restrict__ dirs, const float* __restrict__ ldirs,
                              GridArgs g, MlpArgs p, uint32_t M, __half* __restrict__ enc_out, float* __restrict__ sigma_out,
                              __half* __restrict__ in2, uint32_t ld2, int density_act, float beta, uint32_t a_tile_off,
                              uint32_t ctrl_off) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t t = threadIdx.x, warp = t >> 5;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t t = (warp & 3u) * 32u + (threadIdx.x & 31u);   // sample row inside the tile == TMEM lane
+    const uint32_t grp = warp >> 2;
     uint8_t* a_tile = smem + a_tile_off;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
@@ -96,7 +106,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
         for (uint32_t l = 0; l < p.n_layers; l++) { w_off[l] = o; o += p.dims[l] * p.dims[l + 1] * 2; }
     }
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kFwdTmemCols);
-    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    if (threadIdx.x == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
     for (uint32_t l = 0; l < p.n_layers; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
     load_level_consts(s_lv, g);
     tc::fence_async_smem();
@@ -104,7 +114,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t a_saddr = tc::smem_u32(a_tile), mbar_saddr = tc::smem_u32(mbar);
     const uint32_t F = p.dims[0];  // = 2 * L
 
@@ -116,7 +126,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
         // ---- hash-grid encode of this thread's sample, 4 levels (8 features = one 16-byte chunk) at a time ----
         float x[3] = {2.f, 2.f, 2.f};
         if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
-        for (uint32_t lg = 0; lg < g.L; lg += 4) {
+        for (uint32_t lg = grp * 4; lg < g.L; lg += kGroups * 4) {
             __align__(16) __half2 feat[4];
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
@@ -163,7 +173,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
         float out[16];
         for (uint32_t l = 0; l < p.n_layers; l++) {
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
-            if (t == 0) {
+            if (threadIdx.x == 0) {
                 tc::fence_after_sync();
                 const uint32_t idesc = tc::instr_desc(kTile, N, false, false);
                 const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
@@ -179,7 +189,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
             tc::fence_after_sync();
             const bool last = (l + 1 == p.n_layers);
             if (!last) {
-                for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                for (uint32_t c0 = grp * 16; c0 < N; c0 += kGroups * 16) {
                     float v[16];
                     tc::tmem_ld16(lane_addr + c0, v);
 #pragma unroll
@@ -194,13 +204,14 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
                     }
                 }
                 tc::fence_async_smem();
-            } else {
-                tc::tmem_ld16(lane_addr, out);      // grid_mlp output: 16 columns
+            } else if (grp == 0) {
+                tc::tmem_ld16(lane_addr, out);      // grid_mlp output: 16 columns (warp-uniform branch)
             }
             tc::fence_before_sync();
             __syncthreads();
         }
 
+        if (grp != 0) continue;                     // the last epilogue is small: group 0 only
         if (live && !in2) {
             const float o0 = half_round(out[0]);
             float sg;
@@ -520,7 +531,7 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
             }                                                                                                             \
             configured = smem_bytes;                                                                                      \
         }                                                                                                                 \
-        field_forward_density_kernel<LD><<<grid, kTile, smem_bytes, st>>>(xyzs, dirs, ldirs, g, p, M, (__half*)enc_out,   \
+        field_forward_density_kernel<LD><<<grid, kFieldThreads, smem_bytes, st>>>(xyzs, dirs, ldirs, g, p, M, (__half*)enc_out,   \
                                                                           sigma_out, (__half*)in2, ld2, density_act, beta, \
                                                                           a_off, ctrl_off);                               \
     }
