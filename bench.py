@@ -6,8 +6,8 @@
 ours:       BASELINE.json configs[1] -- synthetic NeRF training step (bound 1, cascade 1, grid 128^3, 4096 rays per
             GPU, max_steps 1024, fp16 hash table, 64-wide MLPs) through raw_ngp_b200 (libngp_b200.so).  One JSON line:
             value = training rays/s over all ranks (device-timed, inputs resident in HBM); e2e = the same step fed
-            from pinned host buffers with the loss read back each step; roofline = the dominant kernel of the step
-            timed alone on the step's own sample batch; grid_encode = the configs[0] micro-benchmark (2^18 points);
+            from pinned host buffers with the loss read back each step; roofline = the slowest kernel of the step,
+            timed with CUDA events around its launches inside the step; grid_encode = the configs[0] micro-benchmark (2^18 points);
             cpu_baseline = the PyTorch-on-CPU port of the same step (oracle/cpu_pipeline.py) on a bounded ray sample.
 reference:  the same step in the CPU port (the reference has no CPU path of its own; kind "port"), rank 0 only.
 """
@@ -236,7 +236,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from raw_ngp_b200 import _lib
-    from raw_ngp_b200.trainer import TrainStep
+    from raw_ngp_b200.trainer import FusedTrainStep
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (ours) needs a CUDA device: the hot path has no CPU fallback")
     _lib.load()
@@ -251,7 +251,7 @@ def run_ours(args):
     hbm_peak, peak_src = _peaks()
 
     model, o_cpu, d_cpu, tgt_cpu = build_scene(device, rank)
-    step = TrainStep(model, lr=1e-2, table_dtype=torch.float16, loss_scale=128.0, update_extra_interval=16)
+    step = FusedTrainStep(model, RAYS_PER_GPU, lr=1e-2, loss_scale=128.0, update_extra_interval=16)
     o, d, tgt = o_cpu.to(device), d_cpu.to(device), tgt_cpu.to(device)
     # the occupancy grid of the synthetic scene is fixed (random-init weights would empty it): update_extra_state is
     # exercised once per 16 steps on a scratch copy so its cost is inside the timed region without changing M
@@ -284,10 +284,11 @@ def run_ours(args):
         loss = one_step(o, d, tgt)
     e1.record()
     barrier()
-    launches = _lib.launch_count - l0
+    launches = _lib.launch_count - l0 + K * step.graph_kernels   # eager C-ABI calls + kernels replayed from the CUDA graph
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     M = step.last_num_points
+    final_loss = float(loss.item())
 
     # ---------------- end to end: pinned host inputs, loss read back ----------------
     o_pin, d_pin, t_pin = o_cpu.pin_memory(), d_cpu.pin_memory(), tgt_cpu.pin_memory()
@@ -296,10 +297,7 @@ def run_ours(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(K):
-        ro = o_pin.to(device, non_blocking=True)
-        rd = d_pin.to(device, non_blocking=True)
-        tg = t_pin.to(device, non_blocking=True)
-        loss = one_step(ro, rd, tg)
+        loss = one_step(o_pin, d_pin, t_pin)            # pinned host -> static device buffers (async H2D) inside step()
         loss_host.copy_(loss.reshape(1), non_blocking=False)
     f1.record()
     barrier()
@@ -311,36 +309,26 @@ def run_ours(args):
     ms, ms_e2e = t.tolist()
 
     if rank == 0:
-        # ---------------- roofline of the dominant kernel, on the step's own sample batch ----------------
-        import numpy as np
-        from raw_ngp_b200 import raymarching
-        enc = model.grid_encoder
-        with torch.no_grad():
-            nears, fars = __import__("raw_ngp_b200.nerf", fromlist=["near_far_from_aabb"]).near_far_from_aabb(o, d, model.aabb_train, 0.05)
-            xyzs, dirs, ts_, rays_, _ = raymarching.march_rays_train(o, d, None, 1.0, False, model.density_bitfield, 1, 128,
-                                                                     nears, fars, True, 0, 1024)
-        Mk = xyzs.shape[0]
-        x01 = ((xyzs + 1) / 2).contiguous()
-        gradk = (torch.randn(Mk, 32, device=device) * 1e-3).half()
-        S = float(np.log2(enc.per_level_scale))
-
-        def k_bwd():
-            _lib.call("ngp_grid_encode_backward", gradk.data_ptr(), x01.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(),
-                      step.table_grad.data_ptr(), Mk, 3, 2, 16, 16, S, 16, None, 0, 0, 0, _lib.NGP_F16, 0, _lib.stream())
-        outk = torch.empty(Mk, 32, device=device, dtype=torch.float16)
-
-        def k_fwd():
-            _lib.call("ngp_grid_encode_forward", x01.data_ptr(), enc.embeddings.data_ptr(), enc.offsets.data_ptr(), outk.data_ptr(),
-                      Mk, 3, 2, 16, 16, S, 16, None, 0, 0, 0, _lib.NGP_F16, 1, _lib.stream())
-        t_bwd, t_fwd = time_kernel(k_bwd), time_kernel(k_fwd)
-        step.table_grad.zero_()
-        bytes_pt = 12 + 256 * 2 + 32 * 2
-        dom, t_dom = ("grid_backward_kernel", t_bwd) if t_bwd >= t_fwd else ("grid_forward_kernel", t_fwd)
-        achieved = bytes_pt * Mk / (t_dom * 1e-3) / 1e9
+        # ---------------- roofline of the dominant kernel, timed live inside the step (CUDA events per launch) --------
+        kt = step.profile_kernels(iters=10)
+        # algorithmic bytes per sample; the 512 B of corner payload / table-gradient reductions are
+        # L2 traffic by design, everything else is compulsory HBM traffic
+        per_sample = {
+            "ngp_field_forward_density": 12 + 12 + 512 + 64 + 256 + 4 + 64,
+            "ngp_field_backward_density": 12 + 4 + 4 + 32 + 64 + 256 + 512,
+            "ngp_mlp_forward_rgb": 64 + 256 + 12,
+            "ngp_mlp_backward_rgb": 12 + 12 + 64 + 256 + 64,
+            "ngp_march_rays_train_write": 4 + 32,
+            "ngp_composite_train_mse": 2 * 24 + 16,
+        }
+        dom = max((k for k in kt if k in per_sample), key=lambda k: kt[k])
+        t_dom = kt[dom]
+        achieved = per_sample[dom] * M / (t_dom * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else peak_src,
-                    "algorithmic_bytes_per_launch": bytes_pt * Mk, "ms_per_launch": t_dom, "points_per_launch": Mk,
-                    "other": {"grid_forward_ms": t_fwd, "grid_backward_ms": t_bwd}}
+                    "algorithmic_bytes_per_sample": per_sample[dom], "algorithmic_bytes_per_launch": per_sample[dom] * M,
+                    "ms_per_launch": t_dom, "samples_per_launch": M,
+                    "step_kernels_ms": {k: round(v, 5) for k, v in kt.items()}}
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             tj = json.load(open(prof))
@@ -364,7 +352,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(o_pin.numel() * 4 + d_pin.numel() * 4 + t_pin.numel() * 4), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "grid_encode": micro,
-            "final_loss": float(loss.item()),
+            "final_loss": final_loss,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NGP_B200_ABI_VERSION 1
+#define NGP_B200_ABI_VERSION 2
 
 typedef void* ngp_stream_t; /* cudaStream_t */
 
@@ -180,13 +180,26 @@ int ngp_march_rays_train_count(const float* rays_o, const float* rays_d, const u
 /* Pass 2 of march_rays_train              raymarching.cu:337-508 with xyzs != nullptr
  * (raymarching/raymarching.py:311).  xyzs/dirs [M,3], ts [M,2], ldirs [M,3] or NULL (with rays_ldir).
  * t_scratch: the workspace filled by ngp_march_rays_train_count (samples are then written in parallel from their
- * stored t, no second march) or NULL (re-march like the reference). */
+ * stored t, no second march) or NULL (re-march like the reference; nears/fars/noises are only read then).
+ * m_dev: NULL or device int32: rows available = min(M, *m_dev) (requires t_scratch). */
 int ngp_march_rays_train_write(const float* rays_o, const float* rays_d, const float* rays_ldir,
                                const uint8_t* grid, float bound, int contract, float dt_gamma,
                                uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                const float* nears, const float* fars, const float* noises,
-                               const int32_t* rays, uint32_t M, const float* t_scratch, float* xyzs,
-                               float* dirs, float* ts, float* ldirs, ngp_stream_t stream);
+                               const int32_t* rays, uint32_t M, const int32_t* m_dev, const float* t_scratch,
+                               float* xyzs, float* dirs, float* ts, float* ldirs, ngp_stream_t stream);
+
+/* Pass 1 of march_rays_train with the renderer's differentiable near/far slab test (nerf/renderer.py:139-158,
+ * torch semantics: (aabb - o) / (d + 1e-15), miss -> 1e9, near clamped to min_near) evaluated in the same kernel,
+ * and a capacity: counter (int32[3], zero-filled once) receives [0] = total samples, [2] = samples of the longest
+ * ray-ordered prefix whose rows fit in `cap` (what later stages use as the device-side M).  nears_out/fars_out
+ * [N] or NULL.  t_scratch is required (warp-cooperative march).  No host synchronisation is needed between this
+ * call and ngp_march_rays_train_write(..., M = cap, m_dev = counter + 2, ...). */
+int ngp_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
+                                    const uint8_t* grid, float bound, int contract, float dt_gamma,
+                                    uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* noises,
+                                    uint32_t cap, float* nears_out, float* fars_out, int32_t* rays,
+                                    int32_t* counter, float* t_scratch, ngp_stream_t stream);
 
 /* replaces composite_rays_train_forward   raymarching/src/raymarching.h:15, raymarching.cu:519-608
  * weights [M] must be zero-filled by the caller (raymarching/raymarching.py:356). */
@@ -204,6 +217,18 @@ int ngp_composite_rays_train_backward(const float* grad_weights, const float* gr
                                       const float* depth, const float* image, uint32_t M, uint32_t N,
                                       float T_thresh, float* grad_sigmas, float* grad_rgbs,
                                       ngp_stream_t stream);
+
+/* composite_rays_train forward + background blend + MSE loss + composite_rays_train backward for one training step
+ * (raymarching.cu:519-723, nerf/renderer.py:553,672, nerf/train_utils.py:540-541) in one launch, one warp per ray:
+ *   image = composite + (1 - weights_sum) * bg_color ;  loss = mean_n mean_c (image - target)^2
+ *   grad_sigmas / grad_rgbs = d (loss_scale * loss) / d sigmas, rgbs   (every row of a ray that fits is written)
+ * target [N,3]; image_out [N,3] or NULL; ray_loss [N] scratch; loss_out [1] (unscaled loss, summed in a fixed
+ * order by the last block); ticket: int32[1] zero-filled once.  m_dev as in the field kernels. */
+int ngp_composite_train_mse(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
+                            uint32_t M, const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color,
+                            const float* target, float loss_scale, float* image_out, float* ray_loss,
+                            float* loss_out, int32_t* ticket, float* grad_sigmas, float* grad_rgbs,
+                            ngp_stream_t stream);
 
 /* Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329, which used
  * torch_scatter.segment_csr): dL/drays_o[n] = sum_seg dL/dxyz ; dL/drays_d[n] = sum_seg (dL/dxyz * t + dL/ddirs).
@@ -294,6 +319,9 @@ int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx,
  *   ngp_mlp_backward_rgb      : d rgb -> view_mlp backward -> d in2
  *   ngp_field_backward_density: [d sigma, d in2[:, :15]] -> grid_mlp backward -> hash-table gradient (accumulated)
  * Table fp16 with F = 2, D = 3; MLP dims as ngp_mlp_forward (dims[0] = 2L, dims[n] = 16).
+ * m_dev (all four): NULL, or a device int32 holding the live sample count; the kernels then process
+ * min(M, *m_dev) rows, M being the capacity of the buffers.  This is what lets a whole training step run without the
+ * reference's step_counter.item() host sync (raymarching/raymarching.py:303) and be captured in a CUDA graph.
  * ---------------------------------------------------------------------------------------- */
 
 enum ngp_density_activation { NGP_DENSITY_EXP = 0, NGP_DENSITY_SOFTPLUS = 1 };           /* network.py:112-115 */
@@ -307,8 +335,8 @@ int ngp_field_forward_density(const float* xyzs, const float* dirs, const float*
                               const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
                               uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,
                               const void* const* weights, const uint32_t* dims, uint32_t n_layers, uint32_t M,
-                              int density_act, float beta, void* enc_out, void* const* acts_out, float* sigma_out,
-                              void* in2, uint32_t ld2, ngp_stream_t stream);
+                              const int32_t* m_dev, int density_act, float beta, void* enc_out, void* const* acts_out,
+                              float* sigma_out, void* in2, uint32_t ld2, ngp_stream_t stream);
 
 /* d_sigma, sigma [M] fp32; d_in2 [M, ld2] fp16 (columns 0..14 are used); enc / acts as saved by the forward;
  * grad_table [sO, 2] fp16 is ACCUMULATED into; dweights[l] fp32 accumulated with atomics. */
@@ -317,19 +345,19 @@ int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const fl
                                const float* feat_weights, float bound, float S, uint32_t H, uint32_t L,
                                uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
-                               int density_act, float beta, void* grad_table, float* const* dweights,
-                               ngp_stream_t stream);
+                               const int32_t* m_dev, int density_act, float beta, void* grad_table,
+                               float* const* dweights, ngp_stream_t stream);
 
 /* ngp_mlp_forward whose last epilogue applies the colour activation to output columns 0..2 and writes rgb_out [M,3] fp32 */
 int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
-                        uint32_t n_layers, uint32_t M, int act, int color_act, float* rgb_out,
-                        void* const* acts_out, ngp_stream_t stream);
+                        uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, int color_act,
+                        float* rgb_out, void* const* acts_out, ngp_stream_t stream);
 
 /* ngp_mlp_backward whose incoming gradient is computed from d_rgb [M,3] fp32 and the activated rgb [M,3] fp32 */
 int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
                          const void* const* weights, const void* const* acts, const uint32_t* dims,
-                         uint32_t n_layers, uint32_t M, int act, void* dx, uint32_t lddx, float* const* dweights,
-                         ngp_stream_t stream);
+                         uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
+                         float* const* dweights, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (reference: torch.optim.Adam, main.py:245;

@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(kFieldThreads, 2)
 field_forward_density_kernel(const float* __restrict__ xyzs, const float* __restrict__ dirs, const float* __restrict__ ldirs,
                              GridArgs g, MlpArgs p, uint32_t M, __half* __restrict__ enc_out, float* __restrict__ sigma_out,
                              __half* __restrict__ in2, uint32_t ld2, int density_act, float beta, uint32_t a_tile_off,
-                             uint32_t ctrl_off) {
+                             uint32_t ctrl_off, const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));   // sample count produced on the device (no host sync)
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t t = (warp & 3u) * 32u + (threadIdx.x & 31u);   // sample row inside the tile == TMEM lane
     const uint32_t grp = warp >> 2;
@@ -271,8 +272,10 @@ __global__ void __launch_bounds__(kTile)
 field_backward_density_kernel(const float* __restrict__ xyzs, const float* __restrict__ d_sigma, const float* __restrict__ sigma,
                               const __half* __restrict__ d_in2, uint32_t ld2, const __half* __restrict__ enc, GridArgs g,
                               MlpArgs p, uint32_t M, __half* __restrict__ grad_table, int density_act, float beta,
-                              uint32_t dz_off, uint32_t dz_bytes, uint32_t w_base, uint32_t ctrl_off) {
+                              uint32_t dz_off, uint32_t dz_bytes, uint32_t w_base, uint32_t ctrl_off,
+                              const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
     const uint32_t L = p.n_layers;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
@@ -500,7 +503,7 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
                                          const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
                                          uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,
                                          const void* const* weights, const uint32_t* dims, uint32_t n_layers, uint32_t M,
-                                         int density_act, float beta, void* enc_out, void* const* acts_out, float* sigma_out,
+                                         const int32_t* m_dev, int density_act, float beta, void* enc_out, void* const* acts_out, float* sigma_out,
                                          void* in2, uint32_t ld2, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     if (!xyzs || !table || !offsets || !weights || !dims || !sigma_out) return NGP_ERR_NULL;
@@ -533,7 +536,7 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
         }                                                                                                                 \
         field_forward_density_kernel<LD><<<grid, kFieldThreads, smem_bytes, st>>>(xyzs, dirs, ldirs, g, p, M, (__half*)enc_out,   \
                                                                           sigma_out, (__half*)in2, ld2, density_act, beta, \
-                                                                          a_off, ctrl_off);                               \
+                                                                          a_off, ctrl_off, m_dev);                        \
     }
     if (ldirs) NGP_LAUNCH_FWD(true) else NGP_LAUNCH_FWD(false)
 #undef NGP_LAUNCH_FWD
@@ -545,7 +548,7 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
                                           const float* feat_weights, float bound, float S, uint32_t H, uint32_t L,
                                           uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                           const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
-                                          int density_act, float beta, void* grad_table, float* const* dweights,
+                                          const int32_t* m_dev, int density_act, float beta, void* grad_table, float* const* dweights,
                                           ngp_stream_t stream) {
     (void)table_unused;
     if (M == 0) return NGP_OK;
@@ -588,6 +591,6 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
     field_backward_density_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>(
         xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,
-        dz_off, dz_bytes, w_base, ctrl_off);
+        dz_off, dz_bytes, w_base, ctrl_off, m_dev);
     return finish_launch();
 }

@@ -25,9 +25,11 @@ constexpr uint32_t kFwdTmemCols = 128;
 
 __global__ void __launch_bounds__(kTile)
 mlp_forward_kernel(const __half* __restrict__ x, uint32_t ldx, MlpArgs p, uint32_t M, __half* __restrict__ y, uint32_t ldy,
-                   float* __restrict__ rgb_out, int head_act, uint32_t a_tile_off, uint32_t ctrl_off) {
+                   float* __restrict__ rgb_out, int head_act, uint32_t a_tile_off, uint32_t ctrl_off,
+                   const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, warp = t >> 5;
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));   // sample count produced on the device (no host sync)
     uint8_t* a_tile = smem + a_tile_off;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
@@ -127,10 +129,11 @@ __global__ void __launch_bounds__(kTile)
 mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* __restrict__ x, uint32_t ldx, MlpArgs p,
                     uint32_t M, __half* __restrict__ dx, uint32_t lddx, const float* __restrict__ d_rgb,
                     const float* __restrict__ rgb, int head_act, uint32_t dz_off, uint32_t dz_bytes,
-                    uint32_t w_base, uint32_t ctrl_off) {
+                    uint32_t w_base, uint32_t ctrl_off, const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, warp = t >> 5;
     const uint32_t L = p.n_layers;
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
 
@@ -289,7 +292,7 @@ using namespace ngp;
 
 static int mlp_forward_impl(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
                             uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy, void* const* acts_out,
-                            float* rgb_out, int head_act, ngp_stream_t stream) {
+                            float* rgb_out, int head_act, const int32_t* m_dev, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     if (!x || !weights || !dims) return NGP_ERR_NULL;
     if (act != NGP_ACT_RELU) return NGP_ERR_UNSUPPORTED;
@@ -321,7 +324,7 @@ static int mlp_forward_impl(const void* x, uint32_t ldx, const void* const* weig
     }
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 4);   // 4 CTAs/SM: 4 x 128 TMEM columns
-    mlp_forward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)x, ldx, p, M, (__half*)y, ldy, rgb_out, head_act, a_off, ctrl_off);
+    mlp_forward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)x, ldx, p, M, (__half*)y, ldy, rgb_out, head_act, a_off, ctrl_off, m_dev);
     return finish_launch();
 }
 
@@ -329,21 +332,21 @@ extern "C" int ngp_mlp_forward(const void* x, uint32_t ldx, const void* const* w
                                uint32_t n_layers, uint32_t M, int act, void* y, uint32_t ldy, void* const* acts_out,
                                ngp_stream_t stream) {
     if (M > 0 && !y) return NGP_ERR_NULL;
-    return mlp_forward_impl(x, ldx, weights, dims, n_layers, M, act, y, ldy, acts_out, nullptr, 0, stream);
+    return mlp_forward_impl(x, ldx, weights, dims, n_layers, M, act, y, ldy, acts_out, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
-                                   uint32_t n_layers, uint32_t M, int act, int color_act, float* rgb_out,
-                                   void* const* acts_out, ngp_stream_t stream) {
+                                   uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, int color_act,
+                                   float* rgb_out, void* const* acts_out, ngp_stream_t stream) {
     if (M > 0 && !rgb_out) return NGP_ERR_NULL;
     if (color_act < 1 || color_act > 3) return NGP_ERR_BAD_ARG;
-    return mlp_forward_impl(x, ldx, weights, dims, n_layers, M, act, nullptr, 16, acts_out, rgb_out, color_act, stream);
+    return mlp_forward_impl(x, ldx, weights, dims, n_layers, M, act, nullptr, 16, acts_out, rgb_out, color_act, m_dev, stream);
 }
 
 static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
                              const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
                              void* dx, uint32_t lddx, float* const* dweights, const float* d_rgb, const float* rgb,
-                             int head_act, ngp_stream_t stream) {
+                             int head_act, const int32_t* m_dev, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     if (!x || !weights || !dims || !dweights) return NGP_ERR_NULL;
     if (head_act == 0 && !dy) return NGP_ERR_NULL;
@@ -390,20 +393,20 @@ static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint3
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
     mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
-                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off);
+                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off, m_dev);
     return finish_launch();
 }
 
 extern "C" int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
                                 const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
                                 void* dx, uint32_t lddx, float* const* dweights, ngp_stream_t stream) {
-    return mlp_backward_impl(dy, lddy, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, nullptr, nullptr, 0, stream);
+    return mlp_backward_impl(dy, lddy, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, nullptr, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
                                     const void* const* weights, const void* const* acts, const uint32_t* dims,
-                                    uint32_t n_layers, uint32_t M, int act, void* dx, uint32_t lddx, float* const* dweights,
-                                    ngp_stream_t stream) {
+                                    uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
+                                    float* const* dweights, ngp_stream_t stream) {
     if (color_act < 1 || color_act > 3) return NGP_ERR_BAD_ARG;
-    return mlp_backward_impl(nullptr, 16, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, d_rgb, rgb, color_act, stream);
+    return mlp_backward_impl(nullptr, 16, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, d_rgb, rgb, color_act, m_dev, stream);
 }

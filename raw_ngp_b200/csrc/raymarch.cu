@@ -356,11 +356,35 @@ __device__ __forceinline__ float voxel_exit(const MarchParams& p, const Ray& r, 
     return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
 }
 
+// The differentiable slab test the renderer actually uses (nerf/renderer.py:139-158, torch ops in fp32):
+// (aabb - o) / (d + 1e-15), near = max over axes of the smaller root, far = min of the larger, miss -> 1e9 for both,
+// near clamped to min_near.
+__device__ __forceinline__ void near_far_torch(const Ray& r, const float* __restrict__ aabb, float min_near, float& near, float& far) {
+    const float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+    near = -INFINITY; far = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float den = __fadd_rn(d[a], 1e-15f);
+        const float t0 = __fdiv_rn(__fsub_rn(__ldg(aabb + a), o[a]), den);
+        const float t1 = __fdiv_rn(__fsub_rn(__ldg(aabb + 3 + a), o[a]), den);
+        const float lo = (t0 < t1) ? t0 : t1, hi = (t0 > t1) ? t0 : t1;
+        near = fmaxf(near, lo);
+        far = fminf(far, hi);
+    }
+    if (far < near) { near = 1e9f; far = 1e9f; }
+    near = fmaxf(near, min_near);
+}
+
+// NF: near/far are computed here from the AABB (and written to nears/fars when those are non-null) instead of read.
+// cap != 0: counter[2] receives the number of samples of the longest ray-ordered prefix that fits in `cap` rows.
+template <bool NF>
 __global__ void __launch_bounds__(kCoopWarps * 32)
 march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
                               float bound, bool contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                               const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
-                              int* __restrict__ rays, int* __restrict__ counter, float* __restrict__ t_scratch) {
+                              int* __restrict__ rays, int* __restrict__ counter, float* __restrict__ t_scratch,
+                              const float* __restrict__ aabb, float min_near, float* __restrict__ nears_out,
+                              float* __restrict__ fars_out, uint32_t cap) {
     __shared__ float s_u[kCoopWarps][kWin];
     __shared__ uint16_t s_next[kCoopWarps][kWin];   // bit 15: keep, low bits: next lattice index (kWin = leaves the window)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -368,8 +392,14 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
     if (n < N) {
         const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
         const Ray r = load_ray(rays_o, rays_d, n, false);
-        const float far = __ldg(fars + n);
-        float t = __ldg(nears + n);
+        float far, t;
+        if (NF) {
+            near_far_torch(r, aabb, min_near, t, far);
+            if (lane == 0 && nears_out) { nears_out[n] = t; fars_out[n] = far; }
+        } else {
+            far = __ldg(fars + n);
+            t = __ldg(nears + n);
+        }
         t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
         float* u = s_u[warp];
         uint16_t* nx = s_next[warp];
@@ -453,7 +483,7 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x >= 32) return;
-    uint32_t carry = 0;
+    uint32_t carry = 0, fit = 0;
     for (uint32_t base = 0; base < N; base += 32) {
         const uint32_t i = base + lane;
         const uint32_t c = (i < N) ? (uint32_t)__ldcg(rays + (size_t)i * 2 + 1) : 0u;
@@ -464,9 +494,15 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
             if (lane >= (uint32_t)s) incl += v;
         }
         if (i < N) rays[(size_t)i * 2] = (int)(carry + incl - c);
+        if (i < N && carry + incl <= cap) fit = max(fit, carry + incl);
         carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) { counter[0] = (int)carry; counter[1] = 0; }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) fit = max(fit, __shfl_xor_sync(0xffffffffu, fit, s));
+    if (lane == 0) {
+        counter[0] = (int)carry; counter[1] = 0;
+        if (cap) counter[2] = (int)fit;
+    }
 }
 
 // Pass 2 from the stored sample t's: one warp per ray, samples written in parallel (coalesced).
@@ -475,11 +511,12 @@ __global__ void __launch_bounds__(kCoopWarps * 32)
 march_train_write_coop_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ rays_ldir,
                               const uint8_t* __restrict__ grid, float bound, bool contract, float dt_gamma, uint32_t max_steps,
                               uint32_t N, uint32_t C, uint32_t H, const int* __restrict__ rays, uint32_t M,
-                              const float* __restrict__ t_scratch, float* __restrict__ xyzs, float* __restrict__ dirs,
-                              float* __restrict__ ts, float* __restrict__ ldirs) {
+                              const int* __restrict__ m_dev, const float* __restrict__ t_scratch, float* __restrict__ xyzs,
+                              float* __restrict__ dirs, float* __restrict__ ts, float* __restrict__ ldirs) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n = blockIdx.x * kCoopWarps + warp;
     if (n >= N) return;
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
     if (count == 0 || offset + count > M) return;
     const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
@@ -629,6 +666,124 @@ composite_train_bwd_kernel(const float* __restrict__ grad_weights, const float* 
         r0 = __shfl_sync(0xffffffffu, pr, 31); g0 = __shfl_sync(0xffffffffu, pg, 31); b0 = __shfl_sync(0xffffffffu, pb, 31);
         ws0 = __shfl_sync(0xffffffffu, pw, 31); d0 = __shfl_sync(0xffffffffu, pd, 31);
     }
+}
+
+
+// Training composite + MSE loss + its backward in one pass per ray (one warp per ray):
+//   image = composite + (1 - weights_sum) * bg            (renderer.py:553,672)
+//   loss  = mean_rays mean_c (image - target)^2           (train_utils.py:540-541)
+//   d image = loss_scale * 2 (image - target) / (3 N),  d weights_sum = -bg * sum_c d image_c
+// followed by the backward recurrences of raymarching.cu:623-712 on the same samples (still in L1/L2).
+// Every sample row < M of a ray that fits gets a gradient (zero past the early stop), so no memset is needed.
+// The last block sums the per-ray losses in a fixed order (deterministic) into loss_out[0].
+__global__ void __launch_bounds__(kCompThreads)
+composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ts,
+                           const int* __restrict__ rays, uint32_t M, const int* __restrict__ m_dev, uint32_t N, float T_thresh,
+                           float bg, const float* __restrict__ target, float loss_scale, float* __restrict__ image_out,
+                           float* __restrict__ ray_loss, float* __restrict__ loss_out, int* __restrict__ ticket,
+                           float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
+    if (n < N) {
+        const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+        const bool has = count != 0 && offset + count <= M;
+        float r = 0, g = 0, b = 0, ws = 0, d = 0;
+        if (has) {
+            float T = 1.0f;
+            for (uint32_t base = 0; base < count; base += 32) {
+                const uint32_t k = base + lane;
+                const bool valid = k < count;
+                const size_t i = (size_t)offset + k;
+                float alpha = 0.f, tk = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+                if (valid) {
+                    const float2 tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
+                    tk = tt.x;
+                    alpha = 1.0f - __expf(-__ldg(sigmas + i) * tt.y);
+                    cr = __ldg(rgbs + i * 3); cg = __ldg(rgbs + i * 3 + 1); cb = __ldg(rgbs + i * 3 + 2);
+                }
+                const float incl = warp_incl_prod(1.0f - alpha, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                const float T_before = T * excl, T_after = T * incl;
+                const uint32_t dead = __ballot_sync(0xffffffffu, valid && T_after < T_thresh);
+                const uint32_t last_live = dead ? (uint32_t)(__ffs(dead) - 1) : 31u;
+                if (valid && lane <= last_live) {
+                    const float w = alpha * T_before;
+                    r += w * cr; g += w * cg; b += w * cb; ws += w; d += w * tk;
+                }
+                if (dead) break;
+                T = __shfl_sync(0xffffffffu, T_after, 31);
+            }
+            r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+        }
+        const float ir = r + (1.0f - ws) * bg, ig = g + (1.0f - ws) * bg, ib = b + (1.0f - ws) * bg;
+        const float er = ir - __ldg(target + (size_t)n * 3), eg = ig - __ldg(target + (size_t)n * 3 + 1), eb = ib - __ldg(target + (size_t)n * 3 + 2);
+        if (lane == 0) {
+            if (image_out) { image_out[(size_t)n * 3] = ir; image_out[(size_t)n * 3 + 1] = ig; image_out[(size_t)n * 3 + 2] = ib; }
+            ray_loss[n] = (er * er + eg * eg + eb * eb) * (1.0f / 3.0f);
+        }
+        if (has) {
+            const float gs = loss_scale * 2.0f / (3.0f * (float)N);
+            const float gi_r = gs * er, gi_g = gs * eg, gi_b = gs * eb;
+            const float g_ws = -bg * (gi_r + gi_g + gi_b);
+            float T = 1.0f, r0 = 0, g0 = 0, b0 = 0, ws0 = 0;
+            uint32_t base = 0;
+            for (; base < count; base += 32) {
+                const uint32_t k = base + lane;
+                const bool valid = k < count;
+                const size_t i = (size_t)offset + k;
+                float alpha = 0.f, dtk = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+                if (valid) {
+                    const float2 tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
+                    dtk = tt.y;
+                    alpha = 1.0f - __expf(-__ldg(sigmas + i) * dtk);
+                    cr = __ldg(rgbs + i * 3); cg = __ldg(rgbs + i * 3 + 1); cb = __ldg(rgbs + i * 3 + 2);
+                }
+                const float incl = warp_incl_prod(1.0f - alpha, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                const float T_before = T * excl, T_after = T * incl;
+                const uint32_t dead = __ballot_sync(0xffffffffu, valid && T_after < T_thresh);
+                const uint32_t last_live = dead ? (uint32_t)(__ffs(dead) - 1) : 31u;
+                const bool live = valid && lane <= last_live;
+                const float w = live ? alpha * T_before : 0.f;
+                const float pr = r0 + warp_incl_sum(w * cr, lane);
+                const float pg = g0 + warp_incl_sum(w * cg, lane);
+                const float pb = b0 + warp_incl_sum(w * cb, lane);
+                const float pw = ws0 + warp_incl_sum(w, lane);
+                if (valid) {
+                    float gsig = 0.f;
+                    if (live)
+                        gsig = dtk * (gi_r * (T_after * cr - (r - pr)) + gi_g * (T_after * cg - (g - pg)) +
+                                      gi_b * (T_after * cb - (b - pb)) + g_ws * (T_after - (ws - pw)));
+                    grad_rgbs[i * 3] = gi_r * w; grad_rgbs[i * 3 + 1] = gi_g * w; grad_rgbs[i * 3 + 2] = gi_b * w;
+                    grad_sigmas[i] = gsig;
+                }
+                if (dead) { base += 32; break; }
+                T = __shfl_sync(0xffffffffu, T_after, 31);
+                r0 = __shfl_sync(0xffffffffu, pr, 31); g0 = __shfl_sync(0xffffffffu, pg, 31); b0 = __shfl_sync(0xffffffffu, pb, 31);
+                ws0 = __shfl_sync(0xffffffffu, pw, 31);
+            }
+            for (uint32_t k = base + lane; k < count; k += 32) {   // samples after the early stop carry no gradient
+                const size_t i = (size_t)offset + k;
+                grad_rgbs[i * 3] = 0.f; grad_rgbs[i * 3 + 1] = 0.f; grad_rgbs[i * 3 + 2] = 0.f;
+                grad_sigmas[i] = 0.f;
+            }
+        }
+    }
+    // last block: deterministic mean of the per-ray losses
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    float acc = 0.f;
+    for (uint32_t i = lane; i < N; i += 32) acc += __ldcg(ray_loss + i);
+    acc = warp_sum(acc);
+    if (lane == 0) { loss_out[0] = acc / (float)N; *ticket = 0; }
 }
 
 // Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329); one warp per ray.
@@ -833,11 +988,28 @@ extern "C" int ngp_march_rays_train_count(const float* rays_o, const float* rays
     if (!rays_o || !rays_d || !grid || !nears || !fars || !noises || !rays) return NGP_ERR_NULL;
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
     if (t_scratch)
-        march_train_count_coop_kernel<<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
-            rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, t_scratch);
+        march_train_count_coop_kernel<false><<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, t_scratch,
+            nullptr, 0.f, nullptr, nullptr, 0u);
     else
         march_train_count_kernel<<<div_up(N, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
             rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter);
+    return finish_launch();
+}
+
+extern "C" int ngp_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
+                                               const uint8_t* grid, float bound, int contract, float dt_gamma,
+                                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* noises,
+                                               uint32_t cap, float* nears_out, float* fars_out, int32_t* rays,
+                                               int32_t* counter, float* t_scratch, ngp_stream_t stream) {
+    if (!counter) return NGP_ERR_NULL;
+    if (N == 0) return NGP_OK;
+    if (!rays_o || !rays_d || !aabb || !grid || !noises || !rays || !t_scratch) return NGP_ERR_NULL;
+    if ((nears_out != nullptr) != (fars_out != nullptr)) return NGP_ERR_NULL;
+    if (max_steps == 0 || H == 0 || C == 0 || H > 1024 || cap == 0) return NGP_ERR_BAD_ARG;
+    march_train_count_coop_kernel<true><<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nullptr, nullptr, noises, rays, counter,
+        t_scratch, aabb, min_near, nears_out, fars_out, cap);
     return finish_launch();
 }
 
@@ -845,10 +1017,11 @@ extern "C" int ngp_march_rays_train_write(const float* rays_o, const float* rays
                                           const uint8_t* grid, float bound, int contract, float dt_gamma,
                                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears,
                                           const float* fars, const float* noises, const int32_t* rays, uint32_t M,
-                                          const float* t_scratch, float* xyzs, float* dirs, float* ts, float* ldirs,
-                                          ngp_stream_t stream) {
+                                          const int32_t* m_dev, const float* t_scratch, float* xyzs, float* dirs, float* ts,
+                                          float* ldirs, ngp_stream_t stream) {
     if (N == 0 || M == 0) return NGP_OK;
-    if (!rays_o || !rays_d || !grid || !nears || !fars || !noises || !rays || !xyzs || !dirs || !ts) return NGP_ERR_NULL;
+    if (!rays_o || !rays_d || !grid || !rays || !xyzs || !dirs || !ts) return NGP_ERR_NULL;
+    if (!t_scratch && (!nears || !fars || !noises || m_dev)) return NGP_ERR_NULL;
     if ((rays_ldir != nullptr) != (ldirs != nullptr)) return NGP_ERR_NULL;
     if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
@@ -856,10 +1029,10 @@ extern "C" int ngp_march_rays_train_write(const float* rays_o, const float* rays
         const uint32_t cb = div_up(N, kCoopWarps);
         if (rays_ldir)
             march_train_write_coop_kernel<true><<<cb, kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
-                rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, rays, M, t_scratch, xyzs, dirs, ts, ldirs);
+                rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, rays, M, m_dev, t_scratch, xyzs, dirs, ts, ldirs);
         else
             march_train_write_coop_kernel<false><<<cb, kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
-                rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, rays, M, t_scratch, xyzs, dirs, ts, ldirs);
+                rays_o, rays_d, rays_ldir, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, rays, M, m_dev, t_scratch, xyzs, dirs, ts, ldirs);
         return finish_launch();
     }
     const uint32_t blocks = div_up(N, kMarchThreads);
@@ -899,6 +1072,20 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights, cons
     composite_train_bwd_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
         grad_weights, grad_weights_sum, grad_depth, grad_image, sigmas, rgbs, ts, rays, weights_sum, depth, image, M, N,
         T_thresh, grad_sigmas, grad_rgbs);
+    return finish_launch();
+}
+
+extern "C" int ngp_composite_train_mse(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays, uint32_t M,
+                                       const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color, const float* target,
+                                       float loss_scale, float* image_out, float* ray_loss, float* loss_out, int32_t* ticket,
+                                       float* grad_sigmas, float* grad_rgbs, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays || !target || !ray_loss || !loss_out || !ticket) return NGP_ERR_NULL;
+    if (M > 0 && (!sigmas || !rgbs || !ts || !grad_sigmas || !grad_rgbs)) return NGP_ERR_NULL;
+    if (M > 0 && !aligned(ts, 8)) return NGP_ERR_ALIGN;
+    composite_train_mse_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, ts, rays, M, m_dev, N, T_thresh, bg_color, target, loss_scale, image_out, ray_loss, loss_out, ticket,
+        grad_sigmas, grad_rgbs);
     return finish_launch();
 }
 

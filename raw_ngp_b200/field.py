@@ -37,7 +37,7 @@ def density_only(enc, grid_weights, xyzs, bound, density_act, beta, feat_weights
     S, H, L, gt, ac, ip = _grid_scalars(enc)
     _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
               _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16),
-              (ctypes.c_uint32 * len(pdims))(*pdims), len(w16), M, int(density_act), float(beta), None, None, _lib.ptr(sigma),
+              (ctypes.c_uint32 * len(pdims))(*pdims), len(w16), M, None, int(density_act), float(beta), None, None, _lib.ptr(sigma),
               None, 0, _lib.stream())
     return sigma
 
@@ -71,9 +71,9 @@ class _fused_field(Function):
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
         _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table),
                   _lib.ptr(enc.offsets), _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, len(w1), M,
-                  int(density_act), float(beta), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None, _lib.ptr(sigma),
+                  None, int(density_act), float(beta), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None, _lib.ptr(sigma),
                   _lib.ptr(in2), p2[0], st)
-        _lib.call("ngp_mlp_forward_rgb", _lib.ptr(in2), p2[0], _ptr_array(w2), c2, len(w2), M, NGP_ACT_RELU, int(color_act),
+        _lib.call("ngp_mlp_forward_rgb", _lib.ptr(in2), p2[0], _ptr_array(w2), c2, len(w2), M, None, NGP_ACT_RELU, int(color_act),
                   _lib.ptr(rgb), _ptr_array(acts2) if keep else None, st)
         if keep:
             ctx.save_for_backward(xyzs, enc_buf, in2, sigma, rgb, table, feat_weights if feat_weights is not None else xyzs.new_empty(0),
@@ -112,10 +112,10 @@ class _fused_field(Function):
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
         _lib.call("ngp_mlp_backward_rgb", _lib.ptr(d_rgb), _lib.ptr(rgb), int(color_act), _lib.ptr(in2), p2[0], _ptr_array(w2),
-                  _ptr_array(acts2), c2, n2, M, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), st)
+                  _ptr_array(acts2), c2, n2, M, None, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), st)
         _lib.call("ngp_field_backward_density", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_in2), p2[0],
                   _lib.ptr(enc_buf), None, _lib.ptr(enc.offsets), _lib.ptr(fw) if has_fw else None, float(bound), S, H, L, gt, ac, ip,
-                  _ptr_array(w1), _ptr_array(acts1), c1, n1, M, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), st)
+                  _ptr_array(w1), _ptr_array(acts1), c1, n1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), st)
         gw = [dw1[l][:d1[l + 1], :d1[l]].to(wdt[l]) for l in range(n1)]
         vw = [dw2[l][:d2[l + 1], :d2[l]].to(wdt[n1 + l]) for l in range(n2)]
         return (None, None, None, None if sink is not None else gtable, None, None, *gw, *vw)

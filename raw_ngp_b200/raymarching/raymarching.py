@@ -193,8 +193,8 @@ class _march_rays_train(Function):
         ldirs = torch.empty(M, 3, dtype=torch.float32, device=dev) if rays_ldir is not None else None
         _lib.call("ngp_march_rays_train_write", _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(rays_ldir),
                   _lib.ptr(density_bitfield), float(bound), int(bool(contract)), float(dt_gamma), int(max_steps), N,
-                  int(C), int(H), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(noises), _lib.ptr(rays), M, _lib.ptr(scratch),
-                  _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ts), _lib.ptr(ldirs), st)
+                  int(C), int(H), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(noises), _lib.ptr(rays), M, None,
+                  _lib.ptr(scratch), _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ts), _lib.ptr(ldirs), st)
 
         ctx.save_for_backward(rays, ts)
         ctx.mark_non_differentiable(rays)

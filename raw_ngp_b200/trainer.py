@@ -123,3 +123,244 @@ class TrainStep:
                     self.loss_scale *= 2.0
         self.global_step += 1
         return loss.detach()
+
+
+class FusedTrainStep:
+    """The same training step as TrainStep with nothing left on the host: ~10 kernels, no synchronisation, replayed as
+    a CUDA graph.
+
+    What the reference does per step and where it went:
+      * near_far_from_aabb (renderer.py:139-158, ~10 torch kernels)      -> inside the marching kernel
+      * march pass 1, step_counter.item() HOST SYNC, allocation, pass 2   -> the sample count stays on the device
+        (raymarching.py:301-311)                                             (m_dev), buffers have a fixed capacity
+      * dirs normalisation, encoder, MLPs, activations (~60 kernels)      -> ngp_field_forward_density + ngp_mlp_forward_rgb
+      * composite fwd, bg blend, MSE, autograd of all that, composite bwd -> ngp_composite_train_mse
+      * MLP / encoder backward incl. zeros_like(embeddings)               -> ngp_mlp_backward_rgb + ngp_field_backward_density
+      * GradScaler.unscale_/inf check/Adam/zero_grad                      -> ngp_check_finite + ngp_fused_adam
+    Numerically it is the autograd path of TrainStep (same kernels for march / field / MLP / Adam, same loss); the
+    equality is tested in tests/test_gpu_trainstep.py.  Eligibility = the fused-field conditions of NeRFNetwork plus an
+    MSE loss and a scalar background."""
+
+    def __init__(self, model, n_rays, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, loss_scale=128.0, max_samples=None,
+                 process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True):
+        import ctypes
+        from . import field as _field
+        from .ffmlp import _pad16
+        self._ct = ctypes
+        self.model, self.N = model, int(n_rays)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        enc = model.grid_encoder
+        dev = model.density_grid.device
+        self.dev = dev
+        opt = model.opt
+        if not (enc.level_dim == 2 and enc.input_dim == 3 and enc.num_levels % 4 == 0 and opt.internal_activation == "relu"
+                and opt.density_activation in ("clamped_exp", "softplus") and opt.color_activation in _field.COLOR_ACT
+                and opt.pose_opt in ("none", "barf") and model.grid_mlp.num_layers == 3 and model.view_mlp.num_layers == 3):
+            raise RuntimeError("FusedTrainStep: configuration outside the fused field path; use TrainStep")
+        self.rfield = bool(opt.rfield)
+        self.perturb = perturb
+        self.bg_color = float(bg_color)
+        self.loss_scale = float(loss_scale)
+        self.update_extra_interval = update_extra_interval
+        self.global_step = 0
+        N = self.N
+        self.cap = int(max_samples) if max_samples else N * int(opt.max_steps)
+
+        # ---- parameters: fp32 master + fp16 working copy + fp32/fp16 gradient buffers -------------------------------
+        self.table_master = enc.embeddings.data.float().contiguous()
+        enc.embeddings.data = self.table_master.half()
+        self.table_grad = torch.zeros_like(enc.embeddings.data)
+        enc.grad_sink = self.table_grad
+        layers = [l for l in model.grid_mlp.net] + [l for l in model.view_mlp.net]
+        self.d1 = [model.grid_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.grid_mlp.net]
+        self.d2 = [model.view_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.view_mlp.net]
+        self.p1, self.p2 = [_pad16(d) for d in self.d1], [_pad16(d) for d in self.d2]
+        shapes = [(self.p1[i + 1], self.p1[i]) for i in range(3)] + [(self.p2[i + 1], self.p2[i]) for i in range(3)]
+        n_w = sum(a * b for a, b in shapes)
+        self.w_master = torch.zeros(n_w, device=dev, dtype=torch.float32)
+        self.w_grad = torch.zeros(n_w, device=dev, dtype=torch.float32)
+        self.w_lp = torch.zeros(n_w, device=dev, dtype=torch.float16)
+        self._w_master_views, self._w_lp_views, self._w_grad_views = [], [], []
+        o = 0
+        for lin, (n, k) in zip(layers, shapes):
+            mv = self.w_master[o:o + n * k].view(n, k)
+            mv[:lin.weight.shape[0], :lin.weight.shape[1]].copy_(lin.weight.data)
+            lin.weight.data = mv[:lin.weight.shape[0], :lin.weight.shape[1]]      # the module keeps seeing the trained weights
+            self._w_master_views.append(mv)
+            self._w_lp_views.append(self.w_lp[o:o + n * k].view(n, k))
+            self._w_grad_views.append(self.w_grad[o:o + n * k].view(n, k))
+            o += n * k
+        self.w_lp.copy_(self.w_master)
+
+        self.opt = FusedAdam(lr=lr, betas=betas, eps=eps)
+        self.opt.add_group(self.table_master, self.table_grad, enc.embeddings.data)
+        self.opt.add_group(self.w_master, self.w_grad, self.w_lp)
+        self.inv_scale = torch.full((1,), parallel.unscale_factor(self.loss_scale, self.world), device=dev, dtype=torch.float32)
+        self.found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
+
+        # ---- static buffers --------------------------------------------------------------------------------------------
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        cap = self.cap
+        self.rays_o, self.rays_d, self.target = torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32)
+        self.rays_ldir = torch.zeros(N, 3, **f32) if self.rfield else None
+        self.noises = torch.zeros(N, **f32)
+        self.rays = torch.zeros(N, 2, device=dev, dtype=torch.int32)
+        self.counter = torch.zeros(4, device=dev, dtype=torch.int32)
+        self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.t_scratch = torch.empty(N * int(opt.max_steps), **f32)
+        self.xyzs, self.dirs, self.ts = torch.empty(cap, 3, **f32), torch.empty(cap, 3, **f32), torch.empty(cap, 2, **f32)
+        self.ldirs = torch.empty(cap, 3, **f32) if self.rfield else None
+        self.enc_buf = torch.empty(cap, self.p1[0], **f16)
+        self.acts1 = [torch.empty(cap, self.p1[l + 1], **f16) for l in range(2)]
+        self.acts2 = [torch.empty(cap, self.p2[l + 1], **f16) for l in range(2)]
+        self.in2, self.d_in2 = torch.empty(cap, self.p2[0], **f16), torch.empty(cap, self.p2[0], **f16)
+        self.sigma, self.rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
+        self.d_sigma, self.d_rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
+        self.image, self.ray_loss, self.loss = torch.zeros(N, 3, **f32), torch.zeros(N, **f32), torch.zeros(1, **f32)
+        self.feat_weights = torch.ones(2 * enc.num_levels, **f32) if opt.pose_opt == "barf" else None
+        self._density_act = model._density_act()
+        self._color_act = _field.COLOR_ACT[opt.color_activation]
+        self._grid_scalars = _field._grid_scalars(enc)
+        self.use_graph = use_graph
+        self._graph = None
+        self.graph_kernels = 0
+        self._m_dev = self.counter.data_ptr() + 8   # counter[2]: samples of the rays that fit in `cap`
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _ptrs(self, tensors):
+        arr = (self._ct.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = t.data_ptr()
+        return arr
+
+    def _launch_forward_backward(self):
+        """march -> field -> composite+loss -> backward, all on the current stream (graph-capturable)."""
+        m, opt, N, cap, ct = self.model, self.model.opt, self.N, self.cap, self._ct
+        st = _lib.stream()
+        P = _lib.ptr
+        if self.perturb:
+            self.noises.uniform_()
+        aabb = m.aabb_train
+        _lib.call("ngp_march_rays_train_count_aabb", P(self.rays_o), P(self.rays_d), P(aabb), float(m.min_near),
+                  P(m.density_bitfield), float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma), int(opt.max_steps),
+                  N, int(m.cascade), int(m.grid_size), P(self.noises), cap, None, None, P(self.rays), P(self.counter),
+                  P(self.t_scratch), st)
+        _lib.call("ngp_march_rays_train_write", P(self.rays_o), P(self.rays_d), P(self.rays_ldir), P(m.density_bitfield),
+                  float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma), int(opt.max_steps), N, int(m.cascade),
+                  int(m.grid_size), None, None, None, P(self.rays), cap, self._m_dev, P(self.t_scratch), P(self.xyzs),
+                  P(self.dirs), P(self.ts), P(self.ldirs), st)
+        S, H, L, gt, ac, ip = self._grid_scalars
+        enc = m.grid_encoder
+        c1 = (ct.c_uint32 * 4)(*self.p1)
+        c2 = (ct.c_uint32 * 4)(*self.p2)
+        w1, w2 = self._ptrs(self._w_lp_views[:3]), self._ptrs(self._w_lp_views[3:])
+        a1, a2 = self._ptrs(self.acts1), self._ptrs(self.acts2)
+        _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
+                  P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, 3, cap, self._m_dev, self._density_act,
+                  float(opt.beta), P(self.enc_buf), a1, P(self.sigma), P(self.in2), self.p2[0], st)
+        _lib.call("ngp_mlp_forward_rgb", P(self.in2), self.p2[0], w2, c2, 3, cap, self._m_dev, 1, self._color_act, P(self.rgb), a2, st)
+        _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
+                  float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
+                  P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), st)
+        _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), self.p2[0], w2, a2, c2, 3, cap,
+                  self._m_dev, 1, P(self.d_in2), self.p2[0], self._ptrs(self._w_grad_views[3:]), st)
+        _lib.call("ngp_field_backward_density", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), self.p2[0],
+                  P(self.enc_buf), None, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap,
+                  self._m_dev, self._density_act, float(opt.beta), P(self.table_grad), self._ptrs(self._w_grad_views[:3]), st)
+
+    def _launch_check(self):
+        st = _lib.stream()
+        self.found_inf.zero_()
+        _lib.call("ngp_check_finite", _lib.ptr(self.table_grad), _lib.NGP_F16, self.table_grad.numel(), _lib.ptr(self.found_inf), st)
+        _lib.call("ngp_check_finite", _lib.ptr(self.w_grad), _lib.NGP_F32, self.w_grad.numel(), _lib.ptr(self.found_inf), st)
+
+    def _capture(self):
+        # one eager pass first: sets the dynamic shared-memory attributes and warms the allocator outside the capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._launch_forward_backward()
+            self._launch_check()
+            self.table_grad.zero_()
+            self.w_grad.zero_()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph_fb, self._graph_chk = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        c0 = _lib.launch_count
+        with torch.cuda.graph(self._graph_fb):
+            self._launch_forward_backward()
+        with torch.cuda.graph(self._graph_chk):
+            self._launch_check()
+        self.graph_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0) + 1   # + uniform_ + found_inf.zero_
+        self.table_grad.zero_()
+        self.w_grad.zero_()
+
+    def profile_kernels(self, iters=10):
+        """Average device time (ms, CUDA events on the launching stream) of every kernel of the step, launched eagerly in
+        step order on the current inputs (these are real optimisation steps: the model trains `iters` steps).  Returns {entry point: ms}."""
+        names, events = [], []
+        real_call = _lib.call
+
+        def timed_call(name, *args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            real_call(name, *args)
+            e1.record()
+            names.append(name)
+            events.append((e0, e1))
+
+        try:
+            _lib.call = timed_call
+            for _ in range(iters):
+                self._launch_forward_backward()
+                self._launch_check()
+                self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+        finally:
+            _lib.call = real_call
+        torch.cuda.synchronize()
+        out = {}
+        for n, (e0, e1) in zip(names, events):
+            out.setdefault(n, []).append(e0.elapsed_time(e1))
+        return {n: sum(v) / iters for n, v in out.items()}
+
+    def set_rays(self, rays_o, rays_d, target_rgb, rays_ldir=None):
+        """Copies the step's inputs into the static buffers (pinned host tensors are copied asynchronously)."""
+        for dst, src in ((self.rays_o, rays_o), (self.rays_d, rays_d), (self.target, target_rgb), (self.rays_ldir, rays_ldir)):
+            if dst is None or src is None or (src.is_cuda and src.data_ptr() == dst.data_ptr()):
+                continue
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
+    @property
+    def last_num_points(self):
+        return int(self.counter[0].item())
+
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True):
+        """One optimisation step; returns the (unscaled) loss as a 1-element device tensor (overwritten by the next step)."""
+        model = self.model
+        if update_grid and self.global_step % self.update_extra_interval == 0:
+            model.update_extra_state()
+        if rays_o is not None:
+            self.set_rays(rays_o, rays_d, target_rgb, rays_ldir)
+        if self.feat_weights is not None:
+            self.feat_weights.copy_(model._feat_weights(self.dev))
+        if self.use_graph:
+            sig = (model.density_bitfield.data_ptr(), model.aabb_train.data_ptr(), model.grid_encoder.embeddings.data_ptr())
+            if self._graph != sig:      # first step, or a captured buffer was re-allocated (update_aabb, load_state_dict)
+                self._capture()
+                self._graph = sig
+            self._graph_fb.replay()
+        else:
+            self._launch_forward_backward()
+        if self.world > 1:
+            parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
+        if self.use_graph:
+            self._graph_chk.replay()
+        else:
+            self._launch_check()
+        if self.world > 1:
+            dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
+        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+        self.global_step += 1
+        return self.loss

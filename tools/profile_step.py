@@ -9,13 +9,16 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from raw_ngp_b200.trainer import TrainStep  # noqa: E402
+from raw_ngp_b200.trainer import FusedTrainStep, TrainStep  # noqa: E402
 
 
 def main():
     dev = torch.device("cuda:0")
     model, o, d, tgt = bench.build_scene(dev, 0)
-    step = TrainStep(model, table_dtype=torch.float16)
+    if "--autograd" in sys.argv:
+        step = TrainStep(model, table_dtype=torch.float16)
+    else:
+        step = FusedTrainStep(model, bench.RAYS_PER_GPU)
     o, d, tgt = o.to(dev), d.to(dev), tgt.to(dev)
     for _ in range(5):
         step.step(o, d, tgt, update_grid=False)
@@ -34,7 +37,10 @@ def main():
         for _ in range(4):
             step.step(o, d, tgt, update_grid=False)
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+    if isinstance(step, FusedTrainStep):
+        for k, v in step.profile_kernels(10).items():
+            print(f"{k:40s} {v * 1e3:9.1f} us")
 
 
 if __name__ == "__main__":
