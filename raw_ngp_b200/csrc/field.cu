@@ -146,17 +146,18 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
                         for (uint32_t d = 0; d < 3; d++) q[d] = (k & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
                         load_row<__half, 2>(lvl + (size_t)entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q) * 2, val[k]);
                     }
-                    // same half-precision accumulation as grid_forward_kernel with NGP_GRID_REF_ROUNDING
-                    __half a0 = __float2half_rn(0.f), a1 = a0;
+                    // Half-precision accumulation of the reference (at::Half results += w * value, gridencoder.cu:168,191):
+                    // each product is rounded to fp16 and added in fp16.  HADD2 rounds the exact sum once, which equals
+                    // the reference's fp32 add + fp16 rounding (24 >= 2 * 11 + 2 significand bits: no double rounding).
+                    __half2 acc = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
                     for (uint32_t k = 0; k < 8; k++) {
                         float w = 1;
 #pragma unroll
                         for (uint32_t d = 0; d < 3; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
-                        a0 = __float2half_rn(__half2float(a0) + __half2float(__float2half_rn(w * val[k][0])));
-                        a1 = __float2half_rn(__half2float(a1) + __half2float(__float2half_rn(w * val[k][1])));
+                        acc = __hadd2(acc, __floats2half2_rn(w * val[k][0], w * val[k][1]));
                     }
-                    f0 = __half2float(a0); f1 = __half2float(a1);
+                    f0 = __low2float(acc); f1 = __high2float(acc);
                     if (g.feat_weights) {
                         f0 *= __ldg(g.feat_weights + 2 * level);
                         f1 *= __ldg(g.feat_weights + 2 * level + 1);
@@ -267,8 +268,32 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
 // backward 1: [d sigma, d in2[:, :15]] -> grid_mlp backward -> table gradient
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kBwdTmemCols = 256;
+constexpr uint32_t kBwdThreads = 512;
+constexpr uint32_t kBwdGroups = kBwdThreads / kTile;
 
-__global__ void __launch_bounds__(kTile)
+// Two table rows that share a 16-byte block (4 rows of an fp16 F=2 table): one red.global.add.noftz.v4.f16x2 for both.
+__device__ __forceinline__ void scatter_pair_h2(__half* glvl, uint32_t row0, uint32_t row1, uint32_t p0, uint32_t p1) {
+    if ((row0 >> 2) == (row1 >> 2)) {
+        const uint32_t a = row0 & 3u, b = row1 & 3u;
+        if (a == b) {   // both corners clamp to the same row (level border)
+            const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&p0), *reinterpret_cast<const __half2*>(&p1));
+            p0 = *reinterpret_cast<const uint32_t*>(&sum);
+            p1 = 0u;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4; s4++) w[s4] = (s4 == a ? p0 : 0u) | ((s4 == b && a != b) ? p1 : 0u);
+        red_add_v4_h2(glvl + (size_t)(row0 >> 2) * 8, w[0], w[1], w[2], w[3]);
+    } else {
+        red_add_h2(glvl + (size_t)row0 * 2, p0);
+        red_add_h2(glvl + (size_t)row1 * 2, p1);
+    }
+}
+
+// 512 threads per CTA, thread (row, grp) as in the forward kernel: row = (warp % 4) * 32 + lane is the sample (TMEM lane),
+// grp = warp / 4 splits the column work: saved-activation loads, the 64 columns of the hidden-layer epilogues and -- the
+// expensive part -- the 16 levels of the table-gradient scatter (4 levels per group).
+__global__ void __launch_bounds__(kBwdThreads, 2)
 field_backward_density_kernel(const float* __restrict__ xyzs, const float* __restrict__ d_sigma, const float* __restrict__ sigma,
                               const __half* __restrict__ d_in2, uint32_t ld2, const __half* __restrict__ enc, GridArgs g,
                               MlpArgs p, uint32_t M, __half* __restrict__ grad_table, int density_act, float beta,
@@ -276,7 +301,9 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                               const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t t = (warp & 3u) * 32u + lane;     // sample row inside the tile == TMEM lane
+    const uint32_t grp = warp >> 2;
     const uint32_t L = p.n_layers;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
@@ -295,7 +322,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
         for (uint32_t l = 0; l < L; l++) { acc_col[l] = col; col += p.dims[l + 1]; }
     }
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kBwdTmemCols);
-    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    if (threadIdx.x == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
     for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
     load_level_consts(s_lv, g);
     tc::fence_async_smem();
@@ -303,7 +330,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t mbar_saddr = tc::smem_u32(mbar);
 
     uint32_t phase = 0, iter = 0;
@@ -312,11 +339,17 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
         const uint32_t row = tile * kTile + t;
         const bool live = row < M;
         uint32_t cur = 0;
-        // saved activations of the forward pass
-        load_row_tile(smem + in_off[0], enc, p.dims[0], p.dims[0], row, M);
-        for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
+        // saved activations of the forward pass: 16-byte chunk c of the row goes to group c % 4
+        for (uint32_t l = 0; l < L; l++) {
+            const __half* src = (l == 0) ? enc : p.acts[l - 1];
+            uint8_t* tile_s = smem + in_off[l];
+            for (uint32_t c = grp; c < p.dims[l] / 8; c += kBwdGroups) {
+                if (live) tc::cp_async16(tc::smem_u32(tile_s + c * kPanel + t * 16), src + (size_t)row * p.dims[l] + c * 8);
+                else *reinterpret_cast<uint4*>(tile_s + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
         // d out1 = [d sigma * d act / d out0, d feat(15)]
-        {
+        if (grp == 0) {
             __align__(16) __half dz[16];
             if (live) {
                 const float sg = __ldg(sigma + row);
@@ -347,7 +380,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
         for (int l = (int)L - 1; l >= 0; l--) {
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
             const uint32_t dz_saddr = tc::smem_u32(smem + dz_off + cur * dz_bytes);
-            if (t == 0) {
+            if (threadIdx.x == 0) {
                 tc::fence_after_sync();
                 const uint32_t in_saddr = tc::smem_u32(smem + in_off[l]);
                 const uint32_t idw = tc::instr_desc(kTile, N, true, true);
@@ -371,7 +404,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
             if (l > 0) {
                 uint8_t* nxt = smem + dz_off + (cur ^ 1) * dz_bytes;
                 const uint8_t* in_tile = smem + in_off[l];
-                for (uint32_t c0 = 0; c0 < K; c0 += 16) {
+                for (uint32_t c0 = grp * 16; c0 < K; c0 += kBwdGroups * 16) {
                     float v[16];
                     tc::tmem_ld16(lane_addr + c0, v);
                     const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8) * kPanel + t * 16);
@@ -390,35 +423,39 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                 }
                 tc::fence_async_smem();
             } else {
-                // ---- d enc of this thread's sample (TMEM lane) -> hash-table gradient, level by level ----
+                // ---- d enc of this thread's sample (TMEM lane) -> hash-table gradient; this group's 4 levels per pass ----
                 float x[3] = {2.f, 2.f, 2.f};
                 if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
-                for (uint32_t c0 = 0; c0 < K; c0 += 16) {
-                    float v[16];
-                    tc::tmem_ld16(lane_addr + c0, v);
+                for (uint32_t c0 = grp * 8; c0 < K; c0 += kBwdGroups * 8) {
+                    float v[8];
+                    tc::tmem_ld8(lane_addr + c0, v);
 #pragma unroll
-                    for (uint32_t j = 0; j < 8; j++) {
+                    for (uint32_t j = 0; j < 4; j++) {
                         const uint32_t level = c0 / 2 + j;
-                        if (level >= g.L) break;
                         const LevelConst lv = s_lv[level];
                         // the gradient reaches the encoder as fp16 (autocast), optionally through the annealing window
-                        float g0 = half_round(v[2 * j]), g1 = half_round(v[2 * j + 1]);
+                        __half2 gh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
                         if (g.feat_weights) {
-                            g0 = half_round(g0 * __ldg(g.feat_weights + 2 * level));
-                            g1 = half_round(g1 * __ldg(g.feat_weights + 2 * level + 1));
+                            const float2 gf = __half22float2(gh);
+                            gh = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
                         }
+                        const float2 gf = __half22float2(gh);
                         uint32_t base[3];
                         float frac[3];
                         const bool valid = live && locate3(x, lv.res, g.align_corners, g.interp, base, frac);
-                        float wg[8][2];
+                        // weighted contributions of the 8 corners, packed (channel 0, channel 1) in fp16: the table gradient
+                        // is fp16 and is accumulated by fp16 reductions either way (the reference issues one fp16x2 atomic
+                        // per corner and sample, gridencoder.cu:334-340)
+                        uint32_t wg[8];
 #pragma unroll
                         for (uint32_t k = 0; k < 8; k++) {
                             float w = 1;
 #pragma unroll
                             for (uint32_t d = 0; d < 3; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
-                            wg[k][0] = valid ? w * g0 : 0.f;
-                            wg[k][1] = valid ? w * g1 : 0.f;
+                            wg[k] = valid ? pack_h2(w * gf.x, w * gf.y) : 0u;
                         }
+                        // warp aggregation: consecutive samples of a ray that sit in the same cell are summed with a
+                        // segmented shuffle reduction and only the first lane of the run issues reductions
                         uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFF00u | lane;
                         if (valid) { key0 = base[0] | (base[1] << 16); key1 = base[2]; }
                         const uint32_t pk0 = __shfl_up_sync(0xffffffffu, key0, 1), pk1 = __shfl_up_sync(0xffffffffu, key1, 1);
@@ -429,11 +466,14 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                             const uint32_t end = (lane == 31 || above == 0) ? 31u : (uint32_t)__ffs(above) - 2u;
 #pragma unroll
                             for (uint32_t d = 1; d < 32; d <<= 1) {
+                                const bool take = lane + d <= end;
 #pragma unroll
                                 for (uint32_t k = 0; k < 8; k++) {
-                                    const float o0 = __shfl_down_sync(0xffffffffu, wg[k][0], d);
-                                    const float o1 = __shfl_down_sync(0xffffffffu, wg[k][1], d);
-                                    if (lane + d <= end) { wg[k][0] += o0; wg[k][1] += o1; }
+                                    const uint32_t o = __shfl_down_sync(0xffffffffu, wg[k], d);
+                                    if (take) {
+                                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&wg[k]), *reinterpret_cast<const __half2*>(&o));
+                                        wg[k] = *reinterpret_cast<const uint32_t*>(&sum);
+                                    }
                                 }
                             }
                         }
@@ -447,8 +487,8 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                                     q0[d] = (k & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
                                     q1[d] = ((k + 1) & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
                                 }
-                                scatter_pair<__half, 2>(glvl, entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q0),
-                                                        entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q1), wg[k], wg[k + 1]);
+                                scatter_pair_h2(glvl, entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q0),
+                                                entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q1), wg[k], wg[k + 1]);
                             }
                         }
                     }
@@ -463,7 +503,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
         tc::fence_after_sync();
         for (uint32_t l = 0; l < L; l++) {
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
-            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+            for (uint32_t c0 = grp * 16; c0 < N; c0 += kBwdGroups * 16) {
                 float v[16];
                 tc::tmem_ld16(lane_addr + acc_col[l] + c0, v);
                 if (t < K) {
@@ -554,7 +594,7 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     if (M == 0) return NGP_OK;
     if (!xyzs || !d_sigma || !sigma || !d_in2 || !enc || !offsets || !weights || !dims || !grad_table || !dweights) return NGP_ERR_NULL;
     if (n_layers > 1 && !acts) return NGP_ERR_NULL;
-    if (L == 0 || L > kMaxLevels || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
+    if (L == 0 || L > kMaxLevels || L % 4 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
     MlpArgs p = {};
     if (!fill_args(p, weights, (void* const*)acts, dweights, dims, n_layers)) return NGP_ERR_UNSUPPORTED;
     if (dims[0] != 2 * L || dims[n_layers] != 16 || ld2 < 16 || ld2 % 8) return NGP_ERR_UNSUPPORTED;
@@ -589,7 +629,7 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
         configured = smem_bytes;
     }
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
-    field_backward_density_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>(
+    field_backward_density_kernel<<<grid, kBwdThreads, smem_bytes, (cudaStream_t)stream>>>(
         xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,
         dz_off, dz_bytes, w_base, ctrl_off, m_dev);
     return finish_launch();
