@@ -32,15 +32,79 @@ struct GridArgs {
     bool align_corners;
 };
 
-struct LevelConst { uint32_t res, hashmap_size, offset; };
+// Per-level constants, computed once per CTA into shared memory.  The index map of gridencoder.cu:61-79 (accumulate
+// dense strides while stride <= hashmap_size, hash if the stride product exceeds the level's size, then wrap) is resolved
+// per LEVEL here, so the per-corner work is two integer ops:
+//   mode 0 (dense, never wraps):      row = x + y*cy + z*cz
+//   mode 1 (hashed, power-of-two T):  row = (x ^ y*cy ^ z*cz) & mask         (cy, cz = the hash primes)
+//   mode 2 (anything else: tiled grids that wrap, non power-of-two hash sizes): the generic entry_index()
+struct LevelConst { uint32_t res, hashmap_size, offset, cy, cz, mask, mode, pad; };
 
 __device__ __forceinline__ void load_level_consts(LevelConst* s_lv, const GridArgs& g) {
     for (uint32_t l = threadIdx.x; l < g.L; l += blockDim.x) {
         const uint32_t off = (uint32_t)__ldg(g.offsets + l);
-        s_lv[l].res = level_resolution(l, g.S, g.H);
-        s_lv[l].offset = off;
-        s_lv[l].hashmap_size = (uint32_t)__ldg(g.offsets + l + 1) - off;
+        const uint32_t hs = (uint32_t)__ldg(g.offsets + l + 1) - off;
+        const uint32_t res = level_resolution(l, g.S, g.H);
+        LevelConst lv;
+        lv.res = res; lv.offset = off; lv.hashmap_size = hs; lv.pad = 0;
+        uint32_t stride = 1, c[3] = {0, 0, 0};
+        bool all = true;
+        for (uint32_t d = 0; d < 3; d++) {
+            if (stride <= hs) { c[d] = stride; stride *= res; } else all = false;
+        }
+        const bool hashed = g.gridtype == 0 && stride > hs;
+        if (hashed) {
+            lv.cy = 2654435761u; lv.cz = 805459861u; lv.mask = hs - 1;
+            lv.mode = ((hs & (hs - 1)) == 0) ? 1u : 2u;
+        } else {
+            lv.cy = c[1]; lv.cz = c[2]; lv.mask = 0xFFFFFFFFu;
+            // all three strides accumulated and res^3 <= hs: the largest row is res^3 - 1 < hs, no wrap
+            lv.mode = (all && stride <= hs) ? 0u : 2u;
+        }
+        s_lv[l] = lv;
     }
+}
+
+// rows of the 8 corners of cell `base` (corner k: bit 0 = +x, bit 1 = +y, bit 2 = +z; +1 clamped to res-1); modes 0 and 1
+__device__ __forceinline__ void corner_rows(const LevelConst& lv, const uint32_t (&base)[3], uint32_t (&rows)[8]) {
+    const uint32_t x1 = min(base[0] + 1, lv.res - 1), y1 = min(base[1] + 1, lv.res - 1), z1 = min(base[2] + 1, lv.res - 1);
+    const uint32_t ya = base[1] * lv.cy, yb = y1 * lv.cy, za = base[2] * lv.cz, zb = z1 * lv.cz;
+    if (lv.mode == 0) {
+        rows[0] = base[0] + ya + za; rows[1] = x1 + ya + za; rows[2] = base[0] + yb + za; rows[3] = x1 + yb + za;
+        rows[4] = base[0] + ya + zb; rows[5] = x1 + ya + zb; rows[6] = base[0] + yb + zb; rows[7] = x1 + yb + zb;
+    } else {
+        rows[0] = (base[0] ^ ya ^ za) & lv.mask; rows[1] = (x1 ^ ya ^ za) & lv.mask;
+        rows[2] = (base[0] ^ yb ^ za) & lv.mask; rows[3] = (x1 ^ yb ^ za) & lv.mask;
+        rows[4] = (base[0] ^ ya ^ zb) & lv.mask; rows[5] = (x1 ^ ya ^ zb) & lv.mask;
+        rows[6] = (base[0] ^ yb ^ zb) & lv.mask; rows[7] = (x1 ^ yb ^ zb) & lv.mask;
+    }
+}
+// the same through the generic index map (mode 2 levels)
+__device__ __noinline__ void corner_rows_generic(uint32_t gridtype, uint32_t hashmap_size, uint32_t res, uint32_t bx, uint32_t by,
+                                                 uint32_t bz, uint32_t* rows) {
+    const uint32_t x1 = min(bx + 1, res - 1), y1 = min(by + 1, res - 1), z1 = min(bz + 1, res - 1);
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t q[3] = {(k & 1u) ? x1 : bx, (k & 2u) ? y1 : by, (k & 4u) ? z1 : bz};
+        rows[k] = entry_index<3>(gridtype, hashmap_size, res, q);
+    }
+}
+
+// trilinear weights in the reference's evaluation order ((1 * wx) * wy) * wz  (gridencoder.cu:172-186)
+__device__ __forceinline__ void corner_weights(const float (&frac)[3], float (&w)[8]) {
+    const float x0 = 1 - frac[0], y0 = 1 - frac[1], z0 = 1 - frac[2];
+    const float xy[4] = {x0 * y0, frac[0] * y0, x0 * frac[1], frac[0] * frac[1]};
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) { w[k] = xy[k] * z0; w[k + 4] = xy[k] * frac[2]; }
+}
+
+// tcgen05.mma operand descriptors of one layer, built once per CTA (they do not change from tile to tile)
+struct MmaStep { uint64_t a, b; };
+constexpr uint32_t kMaxKSteps = 8;    // K <= 128
+struct MmaPlan { MmaStep step[kMaxKSteps]; uint32_t idesc, n_steps, d_col, pad; };
+
+__device__ __forceinline__ void issue_plan(uint32_t tmem, const MmaPlan& pl, bool accumulate_first) {
+    for (uint32_t ks = 0; ks < pl.n_steps; ks++)
+        tc::mma_f16_ss(tmem + pl.d_col, pl.step[ks].a, pl.step[ks].b, pl.idesc, (accumulate_first || ks > 0) ? 1u : 0u);
 }
 
 // position in [0,1]^3 the way GridEncoder.forward computes it: (x + bound) / (2*bound), the division by a host
@@ -76,14 +140,69 @@ __device__ __forceinline__ float half_round(float v) { return __half2float(__flo
 // forward 1: encode -> grid_mlp -> sigma, in2
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kFwdTmemCols = 128;
+constexpr uint32_t kCtrlLevels = 16;                                          // byte offset of the LevelConst table in the control block
+constexpr uint32_t kCtrlPlans = kCtrlLevels + kMaxLevels * sizeof(LevelConst);  // byte offset of the MMA plans
 
 // 512 threads per CTA: thread (row, grp) with row = (warp % 4) * 32 + lane (the TMEM lane quadrant a warp may read) and
-// grp = warp / 4.  The encode phase gives each thread 4 of its sample's 16 levels (32 gathers in flight, one 16-byte
-// chunk of the A tile), hidden-layer epilogues give each group 16 of the 64 columns; only group 0 runs the last
-// epilogue.  A single group of 128 threads left the gather phase latency bound (25 % of the standalone encoder's
-// memory-level parallelism).
+// grp = warp / 4.  In the encode phase group g takes levels g, g+4, g+8, ... of its sample (coarse and fine levels
+// interleaved, so the four groups finish together); hidden-layer epilogues give each group 16 of the 64 columns; only
+// group 0 runs the last epilogue while the other groups already gather the next tile.
 constexpr uint32_t kFieldThreads = 512;
 constexpr uint32_t kGroups = kFieldThreads / kTile;
+
+// One level of one sample: 8 gathers + half-precision interpolation (bit-identical to grid_forward_kernel with
+// NGP_GRID_REF_ROUNDING).  Branch-free: a point outside [0,1]^3 (or a dead row) is clamped into the box so that its
+// loads stay in bounds and the result is zeroed at the end; all gathers of a batch of levels are issued before the first
+// one is consumed, and only the three interpolation fractions are kept live across the loads.
+struct LevelGather {
+    uint32_t v[8];      // raw half2 rows
+    float frac[3];
+};
+__device__ __forceinline__ void gather_issue(LevelGather& q, const GridArgs& g, const LevelConst& lv, const float (&xc)[3]) {
+    uint32_t base[3];
+    locate3(xc, lv.res, g.align_corners, g.interp, base, q.frac);
+    uint32_t rows[8];
+    corner_rows(lv, base, rows);
+    const uint32_t* __restrict__ lvl = reinterpret_cast<const uint32_t*>(g.table) + lv.offset;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) q.v[k] = __ldg(lvl + rows[k]);
+}
+__device__ __forceinline__ __half2 gather_finish(const LevelGather& q, const GridArgs& g, uint32_t level, bool inside) {
+    // Half-precision accumulation of the reference (at::Half results += w * value, gridencoder.cu:168,191): each product
+    // is rounded to fp16 and added in fp16.  HADD2 rounds the exact sum once, which equals the reference's fp32 add +
+    // fp16 rounding (24 >= 2 * 11 + 2 significand bits: no double rounding).
+    float w[8];
+    corner_weights(q.frac, w);
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q.v[k]));
+        acc = __hadd2(acc, __floats2half2_rn(w[k] * f.x, w[k] * f.y));
+    }
+    if (g.feat_weights) {
+        const float2 f = __half22float2(acc);
+        acc = __floats2half2_rn(f.x * __ldg(g.feat_weights + 2 * level), f.y * __ldg(g.feat_weights + 2 * level + 1));
+    }
+    return inside ? acc : __floats2half2_rn(0.f, 0.f);
+}
+
+// a whole level through the generic index map (tiled grids that wrap, non power-of-two hash sizes): out of line, so
+// that the common path above carries no call and keeps its gathers in registers
+__device__ __noinline__ uint32_t gather_level_generic(const __half* table, const float* feat_weights, uint32_t gridtype,
+                                                      bool align_corners, uint32_t interp, uint32_t res, uint32_t hashmap_size,
+                                                      uint32_t offset, float x0, float x1, float x2, uint32_t level, bool inside) {
+    const float xc[3] = {x0, x1, x2};
+    uint32_t base[3], rows[8];
+    LevelGather q;
+    locate3(xc, res, align_corners, interp, base, q.frac);
+    corner_rows_generic(gridtype, hashmap_size, res, base[0], base[1], base[2], rows);
+    const uint32_t* lvl = reinterpret_cast<const uint32_t*>(table) + offset;
+    for (uint32_t k = 0; k < 8; k++) q.v[k] = __ldg(lvl + rows[k]);
+    GridArgs g = {};
+    g.feat_weights = feat_weights;
+    const __half2 r = gather_finish(q, g, level, inside);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 template <bool LDIR>
 __global__ void __launch_bounds__(kFieldThreads, 2)
@@ -99,16 +218,29 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
     uint8_t* a_tile = smem + a_tile_off;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
-    LevelConst* s_lv = reinterpret_cast<LevelConst*>(smem + ctrl_off + 16);
+    LevelConst* s_lv = reinterpret_cast<LevelConst*>(smem + ctrl_off + kCtrlLevels);
+    MmaPlan* plans = reinterpret_cast<MmaPlan*>(smem + ctrl_off + kCtrlPlans);
 
-    uint32_t w_off[kMaxLayers];
-    {
-        uint32_t o = 0;
-        for (uint32_t l = 0; l < p.n_layers; l++) { w_off[l] = o; o += p.dims[l] * p.dims[l + 1] * 2; }
-    }
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kFwdTmemCols);
     if (threadIdx.x == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
-    for (uint32_t l = 0; l < p.n_layers; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
+    {
+        uint32_t o = 0;
+        for (uint32_t l = 0; l < p.n_layers; l++) {
+            const uint32_t K = p.dims[l], N = p.dims[l + 1];
+            load_weight_tile(smem + o, p.w[l], N, K);
+            if (threadIdx.x == l) {     // Y = A [128 x K] (K-major) * W_l^T: one tcgen05.mma per 16 columns of K
+                MmaPlan& pl = plans[l];
+                const uint32_t a_saddr = tc::smem_u32(a_tile), w_saddr = tc::smem_u32(smem + o);
+                pl.idesc = tc::instr_desc(kTile, N, false, false);
+                pl.n_steps = K / 16; pl.d_col = 0; pl.pad = 0;
+                for (uint32_t ks = 0; ks < K / 16; ks++) {
+                    pl.step[ks].a = tc::smem_desc(a_saddr + ks * 2 * kPanel, kPanel, 128);
+                    pl.step[ks].b = tc::smem_desc(w_saddr + ks * 2 * (N * 16), N * 16, 128);
+                }
+            }
+            o += K * N * 2;
+        }
+    }
     load_level_consts(s_lv, g);
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -116,7 +248,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16);
-    const uint32_t a_saddr = tc::smem_u32(a_tile), mbar_saddr = tc::smem_u32(mbar);
+    const uint32_t mbar_saddr = tc::smem_u32(mbar);
     const uint32_t F = p.dims[0];  // = 2 * L
 
     uint32_t phase = 0;
@@ -124,109 +256,91 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t row = tile * kTile + t;
         const bool live = row < M;
-        // ---- hash-grid encode of this thread's sample, 4 levels (8 features = one 16-byte chunk) at a time ----
+        // ---- hash-grid encode: this thread's levels of its sample, two levels (16 gathers) in flight at a time ----
         float x[3] = {2.f, 2.f, 2.f};
         if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
-        for (uint32_t lg = grp * 4; lg < g.L; lg += kGroups * 4) {
-            __align__(16) __half2 feat[4];
-#pragma unroll
-            for (uint32_t j = 0; j < 4; j++) {
-                const uint32_t level = lg + j;
-                const LevelConst lv = s_lv[level];
-                uint32_t base[3];
-                float frac[3];
-                float f0 = 0.f, f1 = 0.f;
-                if (live && locate3(x, lv.res, g.align_corners, g.interp, base, frac)) {
-                    const __half* __restrict__ lvl = g.table + (size_t)lv.offset * 2;
-                    float val[8][2];
-#pragma unroll
-                    for (uint32_t k = 0; k < 8; k++) {
-                        uint32_t q[3];
-#pragma unroll
-                        for (uint32_t d = 0; d < 3; d++) q[d] = (k & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
-                        load_row<__half, 2>(lvl + (size_t)entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q) * 2, val[k]);
-                    }
-                    // Half-precision accumulation of the reference (at::Half results += w * value, gridencoder.cu:168,191):
-                    // each product is rounded to fp16 and added in fp16.  HADD2 rounds the exact sum once, which equals
-                    // the reference's fp32 add + fp16 rounding (24 >= 2 * 11 + 2 significand bits: no double rounding).
-                    __half2 acc = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-                    for (uint32_t k = 0; k < 8; k++) {
-                        float w = 1;
-#pragma unroll
-                        for (uint32_t d = 0; d < 3; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
-                        acc = __hadd2(acc, __floats2half2_rn(w * val[k][0], w * val[k][1]));
-                    }
-                    f0 = __low2float(acc); f1 = __high2float(acc);
-                    if (g.feat_weights) {
-                        f0 *= __ldg(g.feat_weights + 2 * level);
-                        f1 *= __ldg(g.feat_weights + 2 * level + 1);
-                    }
-                }
-                feat[j] = __floats2half2_rn(f0, f1);
+        const bool inside = x[0] >= 0 && x[0] <= 1 && x[1] >= 0 && x[1] <= 1 && x[2] >= 0 && x[2] <= 1;
+        const float xc[3] = {fminf(fmaxf(x[0], 0.f), 1.f), fminf(fmaxf(x[1], 0.f), 1.f), fminf(fmaxf(x[2], 0.f), 1.f)};
+        for (uint32_t level = grp; level < g.L; level += 2 * kGroups) {
+            __half2 f0, f1;
+            if (s_lv[level].mode == 2 || s_lv[level + kGroups].mode == 2) {      // warp-uniform, rare
+                const uint32_t la = level, lb = level + kGroups;
+                const uint32_t ra = gather_level_generic(g.table, g.feat_weights, g.gridtype, g.align_corners, g.interp, s_lv[la].res,
+                                                         s_lv[la].hashmap_size, s_lv[la].offset, xc[0], xc[1], xc[2], la, inside);
+                const uint32_t rb = gather_level_generic(g.table, g.feat_weights, g.gridtype, g.align_corners, g.interp, s_lv[lb].res,
+                                                         s_lv[lb].hashmap_size, s_lv[lb].offset, xc[0], xc[1], xc[2], lb, inside);
+                f0 = *reinterpret_cast<const __half2*>(&ra); f1 = *reinterpret_cast<const __half2*>(&rb);
+            } else {
+                LevelGather q0, q1;
+                gather_issue(q0, g, s_lv[level], xc);
+                gather_issue(q1, g, s_lv[level + kGroups], xc);          // L % 8 == 0
+                f0 = gather_finish(q0, g, level, inside); f1 = gather_finish(q1, g, level + kGroups, inside);
             }
-            const uint4 chunk = *reinterpret_cast<uint4*>(feat);
-            *reinterpret_cast<uint4*>(a_tile + (lg / 4) * kPanel + t * 16) = chunk;
-            if (live && enc_out) *reinterpret_cast<uint4*>(enc_out + (size_t)row * F + lg * 2) = chunk;
+            // features 2l, 2l+1 of row t: panel l / 4, byte (l % 4) * 4 of the row's 16-byte chunk
+            *reinterpret_cast<__half2*>(a_tile + (level / 4) * kPanel + t * 16 + (level % 4) * 4) = f0;
+            *reinterpret_cast<__half2*>(a_tile + ((level + kGroups) / 4) * kPanel + t * 16 + ((level + kGroups) % 4) * 4) = f1;
         }
         tc::fence_async_smem();
+        tc::fence_before_sync();
         __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::fence_after_sync();
+            issue_plan(tmem, plans[0], false);
+            tc::mma_commit(mbar_saddr);
+        }
+        if (enc_out && live) {      // saved for the backward pass: chunk grp, grp + 4, ... of the row, read back from the tile
+            for (uint32_t c = grp; c < F / 8; c += kGroups)
+                *reinterpret_cast<uint4*>(enc_out + (size_t)row * F + c * 8) = *reinterpret_cast<const uint4*>(a_tile + c * kPanel + t * 16);
+        }
 
         float out[16];
         for (uint32_t l = 0; l < p.n_layers; l++) {
-            const uint32_t K = p.dims[l], N = p.dims[l + 1];
-            if (threadIdx.x == 0) {
-                tc::fence_after_sync();
-                const uint32_t idesc = tc::instr_desc(kTile, N, false, false);
-                const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
-                for (uint32_t ks = 0; ks < K / 16; ks++) {
-                    const uint64_t ad = tc::smem_desc(a_saddr + ks * 2 * kPanel, kPanel, 128);
-                    const uint64_t bd = tc::smem_desc(w_saddr + ks * 2 * (N * 16), N * 16, 128);
-                    tc::mma_f16_ss(tmem, ad, bd, idesc, ks > 0);
-                }
-                tc::mma_commit(mbar_saddr);
-            }
+            const uint32_t N = p.dims[l + 1];
             tc::mbar_wait(mbar_saddr, phase);
             phase ^= 1;
             tc::fence_after_sync();
-            const bool last = (l + 1 == p.n_layers);
-            if (!last) {
-                for (uint32_t c0 = grp * 16; c0 < N; c0 += kGroups * 16) {
+            if (l + 1 < p.n_layers) {
+                // hidden width <= 64: one 16-column slice per group (groups past N only take part in the barrier)
+                const uint32_t c0 = grp * 16;
+                const bool mine = c0 < N;
+                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+                if (mine) {
                     float v[16];
                     tc::tmem_ld16(lane_addr + c0, v);
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
-                    uint4 lo, hi;
                     pack16(v, lo, hi);
                     *reinterpret_cast<uint4*>(a_tile + (c0 / 8) * kPanel + t * 16) = lo;
                     *reinterpret_cast<uint4*>(a_tile + (c0 / 8 + 1) * kPanel + t * 16) = hi;
-                    if (p.acts[l] && live) {
-                        uint4* gp = reinterpret_cast<uint4*>(p.acts[l] + (size_t)row * N + c0);
-                        gp[0] = lo; gp[1] = hi;
-                    }
+                    tc::fence_async_smem();
                 }
-                tc::fence_async_smem();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    tc::fence_after_sync();
+                    issue_plan(tmem, plans[l + 1], false);
+                    tc::mma_commit(mbar_saddr);
+                }
+                if (mine && p.acts[l] && live) {    // the hidden activations stream out while the next layer's MMA runs
+                    uint4* gp = reinterpret_cast<uint4*>(p.acts[l] + (size_t)row * N + c0);
+                    gp[0] = lo; gp[1] = hi;
+                }
             } else if (grp == 0) {
                 tc::tmem_ld16(lane_addr, out);      // grid_mlp output: 16 columns (warp-uniform branch)
+                tc::fence_before_sync();
             }
-            tc::fence_before_sync();
-            __syncthreads();
         }
 
         if (grp != 0) continue;                     // the last epilogue is small: group 0 only
-        if (live && !in2) {
-            const float o0 = half_round(out[0]);
-            float sg;
-            if (density_act == 0) sg = expf(o0);
-            else { const float bx = beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / beta; }
-            sigma_out[row] = sg;
-        } else if (live) {
+        if (live) {
             // sigma (network.py:112-115): the linear output is fp16 under autocast, the activation runs in fp32
             const float o0 = half_round(out[0]);
             float sg;
             if (density_act == 0) sg = expf(o0);
             else { const float bx = beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / beta; }
             sigma_out[row] = sg;
+        }
+        if (live && in2) {
             // in2 = [feat(15), SH(dir)(16), (SH(light dir)(16)), 0]
             __align__(16) __half rowbuf[LDIR ? 48 : 32];
 #pragma unroll
@@ -260,6 +374,7 @@ field_forward_density_kernel(const float* __restrict__ xyzs, const float* __rest
             for (int i = 0; i < (LDIR ? 6 : 4); i++) dst[i] = src[i];
         }
     }
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, kFwdTmemCols);
 }
@@ -307,7 +422,8 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
     const uint32_t L = p.n_layers;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctrl_off + 8);
-    LevelConst* s_lv = reinterpret_cast<LevelConst*>(smem + ctrl_off + 16);
+    LevelConst* s_lv = reinterpret_cast<LevelConst*>(smem + ctrl_off + kCtrlLevels);
+    MmaPlan* plans = reinterpret_cast<MmaPlan*>(smem + ctrl_off + kCtrlPlans);    // [2 l] = dW of layer l, [2 l + 1] = dH
 
     uint32_t in_off[kMaxLayers], w_off[kMaxLayers], acc_col[kMaxLayers];
     uint32_t work_cols = 0;
@@ -324,6 +440,26 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kBwdTmemCols);
     if (threadIdx.x == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
     for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
+    if (threadIdx.x < L) {
+        const uint32_t l = threadIdx.x, K = p.dims[l], N = p.dims[l + 1];
+        // dZ of layer l sits in the ping-pong buffer (L - 1 - l) & 1
+        const uint32_t dz_saddr = tc::smem_u32(smem + dz_off + ((L - 1 - l) & 1u) * dz_bytes);
+        const uint32_t in_saddr = tc::smem_u32(smem + in_off[l]), w_saddr = tc::smem_u32(smem + w_off[l]);
+        MmaPlan& dw = plans[2 * l];      // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]  (both MN-major views of row tiles)
+        dw.idesc = tc::instr_desc(kTile, N, true, true);
+        dw.n_steps = kTile / 16; dw.d_col = acc_col[l]; dw.pad = 0;
+        for (uint32_t ks = 0; ks < kTile / 16; ks++) {
+            dw.step[ks].a = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
+            dw.step[ks].b = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
+        }
+        MmaPlan& dh = plans[2 * l + 1];  // dH [128 x K] = dZ_l [128 x N] * W_l [N x K]  (A K-major, B = MN-major view of the weights)
+        dh.idesc = tc::instr_desc(kTile, K, false, true);
+        dh.n_steps = N / 16; dh.d_col = 0; dh.pad = 0;
+        for (uint32_t ks = 0; ks < N / 16; ks++) {
+            dh.step[ks].a = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
+            dh.step[ks].b = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
+        }
+    }
     load_level_consts(s_lv, g);
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -379,23 +515,10 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
 
         for (int l = (int)L - 1; l >= 0; l--) {
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
-            const uint32_t dz_saddr = tc::smem_u32(smem + dz_off + cur * dz_bytes);
             if (threadIdx.x == 0) {
                 tc::fence_after_sync();
-                const uint32_t in_saddr = tc::smem_u32(smem + in_off[l]);
-                const uint32_t idw = tc::instr_desc(kTile, N, true, true);
-                for (uint32_t ks = 0; ks < kTile / 16; ks++) {
-                    const uint64_t ad = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
-                    const uint64_t bd = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
-                    tc::mma_f16_ss(tmem + acc_col[l], ad, bd, idw, (iter > 0 || ks > 0) ? 1u : 0u);
-                }
-                const uint32_t w_saddr = tc::smem_u32(smem + w_off[l]);
-                const uint32_t idh = tc::instr_desc(kTile, K, false, true);
-                for (uint32_t ks = 0; ks < N / 16; ks++) {
-                    const uint64_t ad = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
-                    const uint64_t bd = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
-                    tc::mma_f16_ss(tmem, ad, bd, idh, ks > 0);
-                }
+                issue_plan(tmem, plans[2 * l], iter > 0);
+                issue_plan(tmem, plans[2 * l + 1], false);
                 tc::mma_commit(mbar_saddr);
             }
             tc::mbar_wait(mbar_saddr, phase);
@@ -426,71 +549,60 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                 // ---- d enc of this thread's sample (TMEM lane) -> hash-table gradient; this group's 4 levels per pass ----
                 float x[3] = {2.f, 2.f, 2.f};
                 if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
-                for (uint32_t c0 = grp * 8; c0 < K; c0 += kBwdGroups * 8) {
-                    float v[8];
-                    tc::tmem_ld8(lane_addr + c0, v);
-#pragma unroll
-                    for (uint32_t j = 0; j < 4; j++) {
-                        const uint32_t level = c0 / 2 + j;
-                        const LevelConst lv = s_lv[level];
-                        // the gradient reaches the encoder as fp16 (autocast), optionally through the annealing window
-                        __half2 gh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                        if (g.feat_weights) {
-                            const float2 gf = __half22float2(gh);
-                            gh = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
-                        }
+                for (uint32_t level = grp; level < g.L; level += kBwdGroups) {     // levels interleaved across the groups
+                    float v[2];
+                    tc::tmem_ld2(lane_addr + 2 * level, v);
+                    const LevelConst lv = s_lv[level];
+                    // the gradient reaches the encoder as fp16 (autocast), optionally through the annealing window
+                    __half2 gh = __floats2half2_rn(v[0], v[1]);
+                    if (g.feat_weights) {
                         const float2 gf = __half22float2(gh);
-                        uint32_t base[3];
-                        float frac[3];
-                        const bool valid = live && locate3(x, lv.res, g.align_corners, g.interp, base, frac);
-                        // weighted contributions of the 8 corners, packed (channel 0, channel 1) in fp16: the table gradient
-                        // is fp16 and is accumulated by fp16 reductions either way (the reference issues one fp16x2 atomic
-                        // per corner and sample, gridencoder.cu:334-340)
-                        uint32_t wg[8];
+                        gh = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
+                    }
+                    const float2 gf = __half22float2(gh);
+                    uint32_t base[3];
+                    float frac[3];
+                    const bool valid = live && locate3(x, lv.res, g.align_corners, g.interp, base, frac);
+                    // weighted contributions of the 8 corners, packed (channel 0, channel 1) in fp16: the table gradient is
+                    // fp16 and is accumulated by fp16 reductions either way (the reference issues one fp16x2 atomic per
+                    // corner and sample, gridencoder.cu:334-340)
+                    uint32_t wg[8];
+                    {
+                        float w[8];
+                        corner_weights(frac, w);
 #pragma unroll
-                        for (uint32_t k = 0; k < 8; k++) {
-                            float w = 1;
+                        for (uint32_t k = 0; k < 8; k++) wg[k] = valid ? pack_h2(w[k] * gf.x, w[k] * gf.y) : 0u;
+                    }
+                    // warp aggregation: consecutive samples of a ray that sit in the same cell are summed with a segmented
+                    // shuffle reduction (as many rounds as the longest run needs) and only run heads issue reductions
+                    uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFF00u | lane;
+                    if (valid) { key0 = base[0] | (base[1] << 16); key1 = base[2]; }
+                    const uint32_t pk0 = __shfl_up_sync(0xffffffffu, key0, 1), pk1 = __shfl_up_sync(0xffffffffu, key1, 1);
+                    const bool head = (lane == 0) || (pk0 != key0) || (pk1 != key1);
+                    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+                    if (heads != 0xffffffffu) {
+                        const uint32_t above = heads & ~((2u << lane) - 1u);
+                        const uint32_t end = (lane == 31 || above == 0) ? 31u : (uint32_t)__ffs(above) - 2u;
+                        const uint32_t longest = __reduce_max_sync(0xffffffffu, head ? end - lane + 1u : 0u);
+                        for (uint32_t d = 1; d < longest; d <<= 1) {
+                            const bool take = lane + d <= end;
 #pragma unroll
-                            for (uint32_t d = 0; d < 3; d++) w *= (k & (1u << d)) ? frac[d] : 1 - frac[d];
-                            wg[k] = valid ? pack_h2(w * gf.x, w * gf.y) : 0u;
-                        }
-                        // warp aggregation: consecutive samples of a ray that sit in the same cell are summed with a
-                        // segmented shuffle reduction and only the first lane of the run issues reductions
-                        uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFF00u | lane;
-                        if (valid) { key0 = base[0] | (base[1] << 16); key1 = base[2]; }
-                        const uint32_t pk0 = __shfl_up_sync(0xffffffffu, key0, 1), pk1 = __shfl_up_sync(0xffffffffu, key1, 1);
-                        const bool head = (lane == 0) || (pk0 != key0) || (pk1 != key1);
-                        const uint32_t heads = __ballot_sync(0xffffffffu, head);
-                        if (heads != 0xffffffffu) {
-                            const uint32_t above = heads & ~((2u << lane) - 1u);
-                            const uint32_t end = (lane == 31 || above == 0) ? 31u : (uint32_t)__ffs(above) - 2u;
-#pragma unroll
-                            for (uint32_t d = 1; d < 32; d <<= 1) {
-                                const bool take = lane + d <= end;
-#pragma unroll
-                                for (uint32_t k = 0; k < 8; k++) {
-                                    const uint32_t o = __shfl_down_sync(0xffffffffu, wg[k], d);
-                                    if (take) {
-                                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&wg[k]), *reinterpret_cast<const __half2*>(&o));
-                                        wg[k] = *reinterpret_cast<const uint32_t*>(&sum);
-                                    }
+                            for (uint32_t k = 0; k < 8; k++) {
+                                const uint32_t o = __shfl_down_sync(0xffffffffu, wg[k], d);
+                                if (take) {
+                                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&wg[k]), *reinterpret_cast<const __half2*>(&o));
+                                    wg[k] = *reinterpret_cast<const uint32_t*>(&sum);
                                 }
                             }
                         }
-                        if (valid && head) {
-                            __half* glvl = grad_table + (size_t)lv.offset * 2;
+                    }
+                    if (valid && head) {
+                        uint32_t rows[8];
+                        if (lv.mode == 2) corner_rows_generic(g.gridtype, lv.hashmap_size, lv.res, base[0], base[1], base[2], rows);
+                        else corner_rows(lv, base, rows);
+                        __half* glvl = grad_table + (size_t)lv.offset * 2;
 #pragma unroll
-                            for (uint32_t k = 0; k < 8; k += 2) {
-                                uint32_t q0[3], q1[3];
-#pragma unroll
-                                for (uint32_t d = 0; d < 3; d++) {
-                                    q0[d] = (k & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
-                                    q1[d] = ((k + 1) & (1u << d)) ? min(base[d] + 1, lv.res - 1) : base[d];
-                                }
-                                scatter_pair_h2(glvl, entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q0),
-                                                entry_index<3>(g.gridtype, lv.hashmap_size, lv.res, q1), wg[k], wg[k + 1]);
-                            }
-                        }
+                        for (uint32_t k = 0; k < 8; k += 2) scatter_pair_h2(glvl, rows[k], rows[k + 1], wg[k], wg[k + 1]);
                     }
                 }
             }
@@ -548,10 +660,12 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
     if (M == 0) return NGP_OK;
     if (!xyzs || !table || !offsets || !weights || !dims || !sigma_out) return NGP_ERR_NULL;
     if (in2 && !dirs) return NGP_ERR_NULL;   /* in2 == NULL: density only (NeRFNetwork.density) */
-    if (L == 0 || L > kMaxLevels || L % 4 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
+    if (L == 0 || L > kMaxLevels || L % 8 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
     MlpArgs p = {};
     if (!fill_args(p, weights, acts_out, nullptr, dims, n_layers)) return NGP_ERR_UNSUPPORTED;
     if (dims[0] != 2 * L || dims[n_layers] != 16) return NGP_ERR_UNSUPPORTED;
+    for (uint32_t l = 1; l < n_layers; l++)
+        if (dims[l] > kGroups * 16) return NGP_ERR_UNSUPPORTED;     /* hidden width <= 64 (network.py:49) */
     const uint32_t need2 = ldirs ? 48u : 32u;
     if (in2 && (ld2 < need2 || ld2 % 8)) return NGP_ERR_BAD_ARG;
     if (!aligned(table, 16) || (in2 && !aligned(in2, 16)) || (enc_out && !aligned(enc_out, 16))) return NGP_ERR_ALIGN;
@@ -560,9 +674,9 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
     for (uint32_t l = 0; l < n_layers; l++) { w_bytes += dims[l] * dims[l + 1] * 2; max_k = std::max(max_k, dims[l]); }
     const uint32_t a_off = (w_bytes + 127) & ~127u;
     const uint32_t ctrl_off = a_off + kTile * max_k * 2;
-    const uint32_t smem_bytes = ctrl_off + 16 + kMaxLevels * sizeof(LevelConst);
+    const uint32_t smem_bytes = ctrl_off + kCtrlPlans + kMaxLayers * sizeof(MmaPlan);
     cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 4);
+    const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
 #define NGP_LAUNCH_FWD(LD)                                                                                                \
     {                                                                                                                     \
         static thread_local uint32_t configured = 0;                                                                      \
@@ -618,7 +732,7 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     const uint32_t w_base = dz_off + 2 * dz_bytes;
     const uint32_t ctrl_off = (w_base + w_bytes + 127) & ~127u;
     const uint32_t last_in_off = in_bytes - kTile * dims[n_layers - 1] * 2;
-    const uint32_t smem_bytes = std::max<uint32_t>(ctrl_off + 16 + kMaxLevels * sizeof(LevelConst), last_in_off + 18 * kPanel);
+    const uint32_t smem_bytes = std::max<uint32_t>(ctrl_off + kCtrlPlans + 2 * kMaxLayers * sizeof(MmaPlan), last_in_off + 18 * kPanel);
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
     static thread_local uint32_t configured = 0;
     if (smem_bytes > configured) {

@@ -95,6 +95,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// 2 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
+    uint32_t r0, r1;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1);
+}
+
 // 8 consecutive fp32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
