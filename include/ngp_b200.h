@@ -346,7 +346,7 @@ int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const fl
                                uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
                                const int32_t* m_dev, int density_act, float beta, void* grad_table,
-                               float* const* dweights, ngp_stream_t stream);
+                               float* const* dweights, int tiled, ngp_stream_t stream);
 
 /* ngp_mlp_forward whose last epilogue applies the colour activation to output columns 0..2 and writes rgb_out [M,3] fp32 */
 int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
@@ -357,7 +357,23 @@ int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights,
 int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
                          const void* const* weights, const void* const* acts, const uint32_t* dims,
                          uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
-                         float* const* dweights, ngp_stream_t stream);
+                         float* const* dweights, int tiled, ngp_stream_t stream);
+
+/* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
+ * shared-memory tiles while two groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.
+ * grid_dims = {2L, h, h, 16}, view_dims = {32 (48 with ldirs), h2, h2, 16}, all multiples of 16 and <= 128.
+ * Outputs sigma_out [M], rgb_out [M,3] fp32.  Saved for the backward kernels (each may be NULL), all in the TILE-PANEL
+ * layout [ceil(M/128)][width / 8][128][8] fp16 (the shared-memory image of a 128-row tile; buffers hold whole tiles):
+ * enc_out (width 2L), grid_acts_out[0..1] (h), in2_out (32/48), view_acts_out[0..1] (h2).  Pass tiled = 1 to
+ * ngp_mlp_backward_rgb / ngp_field_backward_density to consume them (x = in2, dx = d_in2 are tiled as well). */
+int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ldirs, const void* table,
+                           const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
+                           uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,
+                           const void* const* grid_weights, const uint32_t* grid_dims,
+                           const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
+                           const int32_t* m_dev, int density_act, float beta, int color_act, void* enc_out,
+                           void* const* grid_acts_out, void* in2_out, void* const* view_acts_out,
+                           float* sigma_out, float* rgb_out, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (reference: torch.optim.Adam, main.py:245;

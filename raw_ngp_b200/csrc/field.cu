@@ -10,131 +10,14 @@
 // Every elementwise op the reference runs as its own PyTorch kernel between these stages (input scaling, direction
 // normalisation, slicing, cat, casts, exp/clamp and all their autograd mirrors) happens in registers here.
 // Rounding points follow the autocast pipeline of the reference (fp16 linear outputs, fp32 exp, fp16 features).
-#include "common.cuh"
-#include "grid_core.cuh"
-#include "mlp_core.cuh"
-#include "tcgen05.cuh"
+#include "field_core.cuh"
 
 namespace ngp {
 namespace {
 
 using namespace mlpcore;
 using namespace gridcore;
-
-constexpr uint32_t kMaxLevels = 32;
-
-struct GridArgs {
-    const __half* table;        // [sO, 2] fp16
-    const int* offsets;         // [L+1]
-    const float* feat_weights;  // [2L] or nullptr (BARF annealing window, network.py:99-109)
-    float S, bound;
-    uint32_t H, L, gridtype, interp;
-    bool align_corners;
-};
-
-// Per-level constants, computed once per CTA into shared memory.  The index map of gridencoder.cu:61-79 (accumulate
-// dense strides while stride <= hashmap_size, hash if the stride product exceeds the level's size, then wrap) is resolved
-// per LEVEL here, so the per-corner work is two integer ops:
-//   mode 0 (dense, never wraps):      row = x + y*cy + z*cz
-//   mode 1 (hashed, power-of-two T):  row = (x ^ y*cy ^ z*cz) & mask         (cy, cz = the hash primes)
-//   mode 2 (anything else: tiled grids that wrap, non power-of-two hash sizes): the generic entry_index()
-struct LevelConst { uint32_t res, hashmap_size, offset, cy, cz, mask, mode, pad; };
-
-__device__ __forceinline__ void load_level_consts(LevelConst* s_lv, const GridArgs& g) {
-    for (uint32_t l = threadIdx.x; l < g.L; l += blockDim.x) {
-        const uint32_t off = (uint32_t)__ldg(g.offsets + l);
-        const uint32_t hs = (uint32_t)__ldg(g.offsets + l + 1) - off;
-        const uint32_t res = level_resolution(l, g.S, g.H);
-        LevelConst lv;
-        lv.res = res; lv.offset = off; lv.hashmap_size = hs; lv.pad = 0;
-        uint32_t stride = 1, c[3] = {0, 0, 0};
-        bool all = true;
-        for (uint32_t d = 0; d < 3; d++) {
-            if (stride <= hs) { c[d] = stride; stride *= res; } else all = false;
-        }
-        const bool hashed = g.gridtype == 0 && stride > hs;
-        if (hashed) {
-            lv.cy = 2654435761u; lv.cz = 805459861u; lv.mask = hs - 1;
-            lv.mode = ((hs & (hs - 1)) == 0) ? 1u : 2u;
-        } else {
-            lv.cy = c[1]; lv.cz = c[2]; lv.mask = 0xFFFFFFFFu;
-            // all three strides accumulated and res^3 <= hs: the largest row is res^3 - 1 < hs, no wrap
-            lv.mode = (all && stride <= hs) ? 0u : 2u;
-        }
-        s_lv[l] = lv;
-    }
-}
-
-// rows of the 8 corners of cell `base` (corner k: bit 0 = +x, bit 1 = +y, bit 2 = +z; +1 clamped to res-1); modes 0 and 1
-__device__ __forceinline__ void corner_rows(const LevelConst& lv, const uint32_t (&base)[3], uint32_t (&rows)[8]) {
-    const uint32_t x1 = min(base[0] + 1, lv.res - 1), y1 = min(base[1] + 1, lv.res - 1), z1 = min(base[2] + 1, lv.res - 1);
-    const uint32_t ya = base[1] * lv.cy, yb = y1 * lv.cy, za = base[2] * lv.cz, zb = z1 * lv.cz;
-    if (lv.mode == 0) {
-        rows[0] = base[0] + ya + za; rows[1] = x1 + ya + za; rows[2] = base[0] + yb + za; rows[3] = x1 + yb + za;
-        rows[4] = base[0] + ya + zb; rows[5] = x1 + ya + zb; rows[6] = base[0] + yb + zb; rows[7] = x1 + yb + zb;
-    } else {
-        rows[0] = (base[0] ^ ya ^ za) & lv.mask; rows[1] = (x1 ^ ya ^ za) & lv.mask;
-        rows[2] = (base[0] ^ yb ^ za) & lv.mask; rows[3] = (x1 ^ yb ^ za) & lv.mask;
-        rows[4] = (base[0] ^ ya ^ zb) & lv.mask; rows[5] = (x1 ^ ya ^ zb) & lv.mask;
-        rows[6] = (base[0] ^ yb ^ zb) & lv.mask; rows[7] = (x1 ^ yb ^ zb) & lv.mask;
-    }
-}
-// the same through the generic index map (mode 2 levels)
-__device__ __noinline__ void corner_rows_generic(uint32_t gridtype, uint32_t hashmap_size, uint32_t res, uint32_t bx, uint32_t by,
-                                                 uint32_t bz, uint32_t* rows) {
-    const uint32_t x1 = min(bx + 1, res - 1), y1 = min(by + 1, res - 1), z1 = min(bz + 1, res - 1);
-    for (uint32_t k = 0; k < 8; k++) {
-        const uint32_t q[3] = {(k & 1u) ? x1 : bx, (k & 2u) ? y1 : by, (k & 4u) ? z1 : bz};
-        rows[k] = entry_index<3>(gridtype, hashmap_size, res, q);
-    }
-}
-
-// trilinear weights in the reference's evaluation order ((1 * wx) * wy) * wz  (gridencoder.cu:172-186)
-__device__ __forceinline__ void corner_weights(const float (&frac)[3], float (&w)[8]) {
-    const float x0 = 1 - frac[0], y0 = 1 - frac[1], z0 = 1 - frac[2];
-    const float xy[4] = {x0 * y0, frac[0] * y0, x0 * frac[1], frac[0] * frac[1]};
-#pragma unroll
-    for (uint32_t k = 0; k < 4; k++) { w[k] = xy[k] * z0; w[k + 4] = xy[k] * frac[2]; }
-}
-
-// tcgen05.mma operand descriptors of one layer, built once per CTA (they do not change from tile to tile)
-struct MmaStep { uint64_t a, b; };
-constexpr uint32_t kMaxKSteps = 8;    // K <= 128
-struct MmaPlan { MmaStep step[kMaxKSteps]; uint32_t idesc, n_steps, d_col, pad; };
-
-__device__ __forceinline__ void issue_plan(uint32_t tmem, const MmaPlan& pl, bool accumulate_first) {
-    for (uint32_t ks = 0; ks < pl.n_steps; ks++)
-        tc::mma_f16_ss(tmem + pl.d_col, pl.step[ks].a, pl.step[ks].b, pl.idesc, (accumulate_first || ks > 0) ? 1u : 0u);
-}
-
-// position in [0,1]^3 the way GridEncoder.forward computes it: (x + bound) / (2*bound), the division by a host
-// scalar being a multiplication by its fp32 reciprocal in torch (grid.py:160).
-__device__ __forceinline__ void unit_cube(const float* __restrict__ xyz, float bound, float (&x)[3]) {
-    const float inv = __fdiv_rn(1.0f, 2.0f * bound);
-#pragma unroll
-    for (int d = 0; d < 3; d++) x[d] = __fmul_rn(__fadd_rn(__ldg(xyz + d), bound), inv);
-}
-
-__device__ __forceinline__ bool locate3(const float (&x)[3], uint32_t res, bool align_corners, uint32_t interp,
-                                        uint32_t (&base)[3], float (&frac)[3]) {
-    if (x[0] < 0 || x[0] > 1 || x[1] < 0 || x[1] > 1 || x[2] < 0 || x[2] > 1) return false;
-#pragma unroll
-    for (uint32_t d = 0; d < 3; d++) {
-        float p;
-        if (align_corners) {
-            p = x[d] * (float)(res - 1);
-            base[d] = min((uint32_t)floorf(p), res - 2);
-        } else {
-            p = fminf(fmaxf(x[d] * (float)res - 0.5f, 0.0f), (float)(res - 1));
-            base[d] = (uint32_t)floorf(p);
-        }
-        p -= (float)base[d];
-        frac[d] = (interp == 1) ? smoothstep_f(p) : p;
-    }
-    return true;
-}
-
-__device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
+using namespace fieldcore;
 
 // ---------------------------------------------------------------------------------------------------
 // forward 1: encode -> grid_mlp -> sigma, in2
@@ -150,59 +33,6 @@ constexpr uint32_t kCtrlPlans = kCtrlLevels + kMaxLevels * sizeof(LevelConst);  
 constexpr uint32_t kFieldThreads = 512;
 constexpr uint32_t kGroups = kFieldThreads / kTile;
 
-// One level of one sample: 8 gathers + half-precision interpolation (bit-identical to grid_forward_kernel with
-// NGP_GRID_REF_ROUNDING).  Branch-free: a point outside [0,1]^3 (or a dead row) is clamped into the box so that its
-// loads stay in bounds and the result is zeroed at the end; all gathers of a batch of levels are issued before the first
-// one is consumed, and only the three interpolation fractions are kept live across the loads.
-struct LevelGather {
-    uint32_t v[8];      // raw half2 rows
-    float frac[3];
-};
-__device__ __forceinline__ void gather_issue(LevelGather& q, const GridArgs& g, const LevelConst& lv, const float (&xc)[3]) {
-    uint32_t base[3];
-    locate3(xc, lv.res, g.align_corners, g.interp, base, q.frac);
-    uint32_t rows[8];
-    corner_rows(lv, base, rows);
-    const uint32_t* __restrict__ lvl = reinterpret_cast<const uint32_t*>(g.table) + lv.offset;
-#pragma unroll
-    for (uint32_t k = 0; k < 8; k++) q.v[k] = __ldg(lvl + rows[k]);
-}
-__device__ __forceinline__ __half2 gather_finish(const LevelGather& q, const GridArgs& g, uint32_t level, bool inside) {
-    // Half-precision accumulation of the reference (at::Half results += w * value, gridencoder.cu:168,191): each product
-    // is rounded to fp16 and added in fp16.  HADD2 rounds the exact sum once, which equals the reference's fp32 add +
-    // fp16 rounding (24 >= 2 * 11 + 2 significand bits: no double rounding).
-    float w[8];
-    corner_weights(q.frac, w);
-    __half2 acc = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-    for (uint32_t k = 0; k < 8; k++) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q.v[k]));
-        acc = __hadd2(acc, __floats2half2_rn(w[k] * f.x, w[k] * f.y));
-    }
-    if (g.feat_weights) {
-        const float2 f = __half22float2(acc);
-        acc = __floats2half2_rn(f.x * __ldg(g.feat_weights + 2 * level), f.y * __ldg(g.feat_weights + 2 * level + 1));
-    }
-    return inside ? acc : __floats2half2_rn(0.f, 0.f);
-}
-
-// a whole level through the generic index map (tiled grids that wrap, non power-of-two hash sizes): out of line, so
-// that the common path above carries no call and keeps its gathers in registers
-__device__ __noinline__ uint32_t gather_level_generic(const __half* table, const float* feat_weights, uint32_t gridtype,
-                                                      bool align_corners, uint32_t interp, uint32_t res, uint32_t hashmap_size,
-                                                      uint32_t offset, float x0, float x1, float x2, uint32_t level, bool inside) {
-    const float xc[3] = {x0, x1, x2};
-    uint32_t base[3], rows[8];
-    LevelGather q;
-    locate3(xc, res, align_corners, interp, base, q.frac);
-    corner_rows_generic(gridtype, hashmap_size, res, base[0], base[1], base[2], rows);
-    const uint32_t* lvl = reinterpret_cast<const uint32_t*>(table) + offset;
-    for (uint32_t k = 0; k < 8; k++) q.v[k] = __ldg(lvl + rows[k]);
-    GridArgs g = {};
-    g.feat_weights = feat_weights;
-    const __half2 r = gather_finish(q, g, level, inside);
-    return *reinterpret_cast<const uint32_t*>(&r);
-}
 
 template <bool LDIR>
 __global__ void __launch_bounds__(kFieldThreads, 2)
@@ -413,7 +243,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                               const __half* __restrict__ d_in2, uint32_t ld2, const __half* __restrict__ enc, GridArgs g,
                               MlpArgs p, uint32_t M, __half* __restrict__ grad_table, int density_act, float beta,
                               uint32_t dz_off, uint32_t dz_bytes, uint32_t w_base, uint32_t ctrl_off,
-                              const int* __restrict__ m_dev) {
+                              const int* __restrict__ m_dev, bool tiled) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -479,8 +309,11 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
         for (uint32_t l = 0; l < L; l++) {
             const __half* src = (l == 0) ? enc : p.acts[l - 1];
             uint8_t* tile_s = smem + in_off[l];
+            // tiled: the saved tile is the shared-memory image itself ([column / 8][row][8 halves]): 512 contiguous bytes per warp
+            const __half* src_tile = src + (size_t)tile * (p.dims[l] * kTile);
             for (uint32_t c = grp; c < p.dims[l] / 8; c += kBwdGroups) {
-                if (live) tc::cp_async16(tc::smem_u32(tile_s + c * kPanel + t * 16), src + (size_t)row * p.dims[l] + c * 8);
+                if (live) tc::cp_async16(tc::smem_u32(tile_s + c * kPanel + t * 16),
+                                         tiled ? src_tile + (c * kTile + t) * 8 : src + (size_t)row * p.dims[l] + c * 8);
                 else *reinterpret_cast<uint4*>(tile_s + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
             }
         }
@@ -493,8 +326,9 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                 if (density_act == 0) dact = sg;                              // trunc_exp backward: g * exp(x) (activation.py:18-21)
                 else dact = 1.0f - expf(-beta * sg);                          // softplus' = sigmoid(beta x) = 1 - exp(-beta y)
                 dz[0] = __float2half_rn(__ldg(d_sigma + row) * dact);
-                const uint4* src = reinterpret_cast<const uint4*>(d_in2 + (size_t)row * ld2);
-                const uint4 a = __ldg(src), b = __ldg(src + 1);
+                const __half* d_tile = d_in2 + (size_t)tile * (ld2 * kTile);
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(tiled ? d_tile + t * 8 : d_in2 + (size_t)row * ld2));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(tiled ? d_tile + (kTile + t) * 8 : d_in2 + (size_t)row * ld2 + 8));
                 const __half* ha = reinterpret_cast<const __half*>(&a);
                 const __half* hb = reinterpret_cast<const __half*>(&b);
 #pragma unroll
@@ -703,7 +537,7 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
                                           uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                           const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
                                           const int32_t* m_dev, int density_act, float beta, void* grad_table, float* const* dweights,
-                                          ngp_stream_t stream) {
+                                          int tiled, ngp_stream_t stream) {
     (void)table_unused;
     if (M == 0) return NGP_OK;
     if (!xyzs || !d_sigma || !sigma || !d_in2 || !enc || !offsets || !weights || !dims || !grad_table || !dweights) return NGP_ERR_NULL;
@@ -745,6 +579,6 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
     field_backward_density_kernel<<<grid, kBwdThreads, smem_bytes, (cudaStream_t)stream>>>(
         xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,
-        dz_off, dz_bytes, w_base, ctrl_off, m_dev);
+        dz_off, dz_bytes, w_base, ctrl_off, m_dev, tiled != 0);
     return finish_launch();
 }

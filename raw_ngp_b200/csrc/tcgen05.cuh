@@ -54,6 +54,23 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar_saddr, uint32_t count) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar_saddr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_saddr) : "memory");
+}
+// expect `bytes` of async (bulk copy) traffic and arrive once
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar_saddr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_saddr), "r"(bytes) : "memory");
+}
+// named barrier among `count` threads (count a multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// bulk async copy global -> shared (the TMA engine, no tensor map: 1-D, 16-byte granular), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t mbar_saddr) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_saddr), "l"(src), "r"(bytes), "r"(mbar_saddr) : "memory");
+}
+
 // Bounded wait: a mis-programmed pipeline traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t mbar_saddr, uint32_t parity) {
     uint32_t done = 0;

@@ -1,5 +1,5 @@
-"""Fused NeRF field: NeRFNetwork.forward / .density (nerf/network.py:74-156) in four kernels per training step
-(csrc/field.cu, csrc/mlp.cu) instead of ~60 PyTorch ops.  Used by raw_ngp_b200.nerf.NeRFNetwork when the configuration
+"""Fused NeRF field: NeRFNetwork.forward / .density (nerf/network.py:74-156) in three kernels per training step
+(csrc/field_ws.cu forward, csrc/mlp.cu + csrc/field.cu backward) instead of ~60 PyTorch ops.  Used by raw_ngp_b200.nerf.NeRFNetwork when the configuration
 is eligible (fp16 table with F=2, ReLU MLPs, autocast, no gradient w.r.t. positions/directions); otherwise the network
 composes the individual operators exactly like the reference does."""
 import ctypes
@@ -59,22 +59,21 @@ class _fused_field(Function):
         w2 = [_pad_weight(w, p2[i + 1], p2[i]) for i, w in enumerate(vw)]
         keep = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward; this is the real signal)
         f16 = dict(dtype=torch.float16, device=dev)
-        enc_buf = torch.empty(M, p1[0], **f16) if keep else None
-        acts1 = [torch.empty(M, p1[l + 1], **f16) if keep else None for l in range(len(w1) - 1)]
-        acts2 = [torch.empty(M, p2[l + 1], **f16) if keep else None for l in range(len(w2) - 1)]
-        in2 = torch.empty(M, p2[0], **f16)
+        Mt = (M + 127) // 128 * 128          # saved activations use the tile-panel layout: whole 128-row tiles
+        enc_buf = torch.empty(Mt, p1[0], **f16) if keep else None
+        acts1 = [torch.empty(Mt, p1[l + 1], **f16) if keep else None for l in range(len(w1) - 1)]
+        acts2 = [torch.empty(Mt, p2[l + 1], **f16) if keep else None for l in range(len(w2) - 1)]
+        in2 = torch.empty(Mt, p2[0], **f16) if keep else None
         sigma = torch.empty(M, dtype=torch.float32, device=dev)
         rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
         S, H, L, gt, ac, ip = _grid_scalars(enc)
         st = _lib.stream()
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
-        _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table),
-                  _lib.ptr(enc.offsets), _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, len(w1), M,
-                  None, int(density_act), float(beta), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None, _lib.ptr(sigma),
-                  _lib.ptr(in2), p2[0], st)
-        _lib.call("ngp_mlp_forward_rgb", _lib.ptr(in2), p2[0], _ptr_array(w2), c2, len(w2), M, None, NGP_ACT_RELU, int(color_act),
-                  _lib.ptr(rgb), _ptr_array(acts2) if keep else None, st)
+        _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table), _lib.ptr(enc.offsets),
+                  _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
+                  int(density_act), float(beta), int(color_act), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None,
+                  _lib.ptr(in2), _ptr_array(acts2) if keep else None, _lib.ptr(sigma), _lib.ptr(rgb), st)
         if keep:
             ctx.save_for_backward(xyzs, enc_buf, in2, sigma, rgb, table, feat_weights if feat_weights is not None else xyzs.new_empty(0),
                                   *acts1, *acts2, *w1, *w2)
@@ -99,7 +98,7 @@ class _fused_field(Function):
         d_rgb = d_rgb.contiguous().float()
         dw1 = [torch.zeros(p1[l + 1], p1[l], dtype=torch.float32, device=dev) for l in range(n1)]
         dw2 = [torch.zeros(p2[l + 1], p2[l], dtype=torch.float32, device=dev) for l in range(n2)]
-        d_in2 = torch.empty(M, p2[0], dtype=torch.float16, device=dev)
+        d_in2 = torch.empty(in2.shape[0], p2[0], dtype=torch.float16, device=dev)
         sink = enc.grad_sink
         if sink is not None:
             if sink.shape != table.shape or sink.dtype != table.dtype:
@@ -112,10 +111,10 @@ class _fused_field(Function):
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
         _lib.call("ngp_mlp_backward_rgb", _lib.ptr(d_rgb), _lib.ptr(rgb), int(color_act), _lib.ptr(in2), p2[0], _ptr_array(w2),
-                  _ptr_array(acts2), c2, n2, M, None, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), st)
+                  _ptr_array(acts2), c2, n2, M, None, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), 1, st)
         _lib.call("ngp_field_backward_density", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_in2), p2[0],
                   _lib.ptr(enc_buf), None, _lib.ptr(enc.offsets), _lib.ptr(fw) if has_fw else None, float(bound), S, H, L, gt, ac, ip,
-                  _ptr_array(w1), _ptr_array(acts1), c1, n1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), st)
+                  _ptr_array(w1), _ptr_array(acts1), c1, n1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), 1, st)
         gw = [dw1[l][:d1[l + 1], :d1[l]].to(wdt[l]) for l in range(n1)]
         vw = [dw2[l][:d2[l + 1], :d2[l]].to(wdt[n1 + l]) for l in range(n2)]
         return (None, None, None, None if sink is not None else gtable, None, None, *gw, *vw)

@@ -166,6 +166,7 @@ class FusedTrainStep:
         self.global_step = 0
         N = self.N
         self.cap = int(max_samples) if max_samples else N * int(opt.max_steps)
+        cap_t = (self.cap + 127) // 128 * 128      # saved activations are stored as whole 128-row tiles
 
         # ---- parameters: fp32 master + fp16 working copy + fp32/fp16 gradient buffers -------------------------------
         self.table_master = enc.embeddings.data.float().contiguous()
@@ -212,10 +213,10 @@ class FusedTrainStep:
         self.t_scratch = torch.empty(N * int(opt.max_steps), **f32)
         self.xyzs, self.dirs, self.ts = torch.empty(cap, 3, **f32), torch.empty(cap, 3, **f32), torch.empty(cap, 2, **f32)
         self.ldirs = torch.empty(cap, 3, **f32) if self.rfield else None
-        self.enc_buf = torch.empty(cap, self.p1[0], **f16)
-        self.acts1 = [torch.empty(cap, self.p1[l + 1], **f16) for l in range(2)]
-        self.acts2 = [torch.empty(cap, self.p2[l + 1], **f16) for l in range(2)]
-        self.in2, self.d_in2 = torch.empty(cap, self.p2[0], **f16), torch.empty(cap, self.p2[0], **f16)
+        self.enc_buf = torch.empty(cap_t, self.p1[0], **f16)
+        self.acts1 = [torch.empty(cap_t, self.p1[l + 1], **f16) for l in range(2)]
+        self.acts2 = [torch.empty(cap_t, self.p2[l + 1], **f16) for l in range(2)]
+        self.in2, self.d_in2 = torch.empty(cap_t, self.p2[0], **f16), torch.empty(cap_t, self.p2[0], **f16)
         self.sigma, self.rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.d_sigma, self.d_rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.image, self.ray_loss, self.loss = torch.zeros(N, 3, **f32), torch.zeros(N, **f32), torch.zeros(1, **f32)
@@ -257,18 +258,17 @@ class FusedTrainStep:
         c2 = (ct.c_uint32 * 4)(*self.p2)
         w1, w2 = self._ptrs(self._w_lp_views[:3]), self._ptrs(self._w_lp_views[3:])
         a1, a2 = self._ptrs(self.acts1), self._ptrs(self.acts2)
-        _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
-                  P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, 3, cap, self._m_dev, self._density_act,
-                  float(opt.beta), P(self.enc_buf), a1, P(self.sigma), P(self.in2), self.p2[0], st)
-        _lib.call("ngp_mlp_forward_rgb", P(self.in2), self.p2[0], w2, c2, 3, cap, self._m_dev, 1, self._color_act, P(self.rgb), a2, st)
+        _lib.call("ngp_field_forward_full", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
+                  P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap, self._m_dev, self._density_act,
+                  float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), st)
         _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
                   float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
                   P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), st)
         _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), self.p2[0], w2, a2, c2, 3, cap,
-                  self._m_dev, 1, P(self.d_in2), self.p2[0], self._ptrs(self._w_grad_views[3:]), st)
+                  self._m_dev, 1, P(self.d_in2), self.p2[0], self._ptrs(self._w_grad_views[3:]), 1, st)
         _lib.call("ngp_field_backward_density", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), self.p2[0],
                   P(self.enc_buf), None, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap,
-                  self._m_dev, self._density_act, float(opt.beta), P(self.table_grad), self._ptrs(self._w_grad_views[:3]), st)
+                  self._m_dev, self._density_act, float(opt.beta), P(self.table_grad), self._ptrs(self._w_grad_views[:3]), 1, st)
 
     def _launch_check(self):
         st = _lib.stream()
