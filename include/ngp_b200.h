@@ -359,6 +359,17 @@ int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, co
                          uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
                          float* const* dweights, int tiled, ngp_stream_t stream);
 
+/* ngp_field_backward_density as a warp-specialised persistent kernel (csrc/field_bwd_ws.cu): one MLP group runs the
+ * grid_mlp backward on the tensor cores (saved tiles fetched with bulk async copies, double buffered) and hands d enc to
+ * 16 scatter warps through a shared-memory ring.  Inputs in the tile-panel layout of ngp_field_forward_full: d_in2
+ * (width ld2), enc, acts[0..1]; three layers, dims = {2L, h, h, 16}.  grad_table / dweights are accumulated into. */
+int ngp_field_backward_ws(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
+                          uint32_t ld2, const void* enc, const int32_t* offsets, const float* feat_weights,
+                          float bound, float S, uint32_t H, uint32_t L, uint32_t gridtype, int align_corners,
+                          uint32_t interp, const void* const* weights, const void* const* acts,
+                          const uint32_t* dims, uint32_t M, const int32_t* m_dev, int density_act, float beta,
+                          void* grad_table, float* const* dweights, ngp_stream_t stream);
+
 /* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
  * shared-memory tiles while two groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.
  * grid_dims = {2L, h, h, 16}, view_dims = {32 (48 with ldirs), h2, h2, 16}, all multiples of 16 and <= 128.

@@ -216,25 +216,6 @@ constexpr uint32_t kBwdTmemCols = 256;
 constexpr uint32_t kBwdThreads = 512;
 constexpr uint32_t kBwdGroups = kBwdThreads / kTile;
 
-// Two table rows that share a 16-byte block (4 rows of an fp16 F=2 table): one red.global.add.noftz.v4.f16x2 for both.
-__device__ __forceinline__ void scatter_pair_h2(__half* glvl, uint32_t row0, uint32_t row1, uint32_t p0, uint32_t p1) {
-    if ((row0 >> 2) == (row1 >> 2)) {
-        const uint32_t a = row0 & 3u, b = row1 & 3u;
-        if (a == b) {   // both corners clamp to the same row (level border)
-            const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&p0), *reinterpret_cast<const __half2*>(&p1));
-            p0 = *reinterpret_cast<const uint32_t*>(&sum);
-            p1 = 0u;
-        }
-        uint32_t w[4];
-#pragma unroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) w[s4] = (s4 == a ? p0 : 0u) | ((s4 == b && a != b) ? p1 : 0u);
-        red_add_v4_h2(glvl + (size_t)(row0 >> 2) * 8, w[0], w[1], w[2], w[3]);
-    } else {
-        red_add_h2(glvl + (size_t)row0 * 2, p0);
-        red_add_h2(glvl + (size_t)row1 * 2, p1);
-    }
-}
-
 // 512 threads per CTA, thread (row, grp) as in the forward kernel: row = (warp % 4) * 32 + lane is the sample (TMEM lane),
 // grp = warp / 4 splits the column work: saved-activation loads, the 64 columns of the hidden-layer epilogues and -- the
 // expensive part -- the 16 levels of the table-gradient scatter (4 levels per group).
@@ -386,58 +367,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                 for (uint32_t level = grp; level < g.L; level += kBwdGroups) {     // levels interleaved across the groups
                     float v[2];
                     tc::tmem_ld2(lane_addr + 2 * level, v);
-                    const LevelConst lv = s_lv[level];
-                    // the gradient reaches the encoder as fp16 (autocast), optionally through the annealing window
-                    __half2 gh = __floats2half2_rn(v[0], v[1]);
-                    if (g.feat_weights) {
-                        const float2 gf = __half22float2(gh);
-                        gh = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
-                    }
-                    const float2 gf = __half22float2(gh);
-                    uint32_t base[3];
-                    float frac[3];
-                    const bool valid = live && locate3(x, lv.res, g.align_corners, g.interp, base, frac);
-                    // weighted contributions of the 8 corners, packed (channel 0, channel 1) in fp16: the table gradient is
-                    // fp16 and is accumulated by fp16 reductions either way (the reference issues one fp16x2 atomic per
-                    // corner and sample, gridencoder.cu:334-340)
-                    uint32_t wg[8];
-                    {
-                        float w[8];
-                        corner_weights(frac, w);
-#pragma unroll
-                        for (uint32_t k = 0; k < 8; k++) wg[k] = valid ? pack_h2(w[k] * gf.x, w[k] * gf.y) : 0u;
-                    }
-                    // warp aggregation: consecutive samples of a ray that sit in the same cell are summed with a segmented
-                    // shuffle reduction (as many rounds as the longest run needs) and only run heads issue reductions
-                    uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFF00u | lane;
-                    if (valid) { key0 = base[0] | (base[1] << 16); key1 = base[2]; }
-                    const uint32_t pk0 = __shfl_up_sync(0xffffffffu, key0, 1), pk1 = __shfl_up_sync(0xffffffffu, key1, 1);
-                    const bool head = (lane == 0) || (pk0 != key0) || (pk1 != key1);
-                    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-                    if (heads != 0xffffffffu) {
-                        const uint32_t above = heads & ~((2u << lane) - 1u);
-                        const uint32_t end = (lane == 31 || above == 0) ? 31u : (uint32_t)__ffs(above) - 2u;
-                        const uint32_t longest = __reduce_max_sync(0xffffffffu, head ? end - lane + 1u : 0u);
-                        for (uint32_t d = 1; d < longest; d <<= 1) {
-                            const bool take = lane + d <= end;
-#pragma unroll
-                            for (uint32_t k = 0; k < 8; k++) {
-                                const uint32_t o = __shfl_down_sync(0xffffffffu, wg[k], d);
-                                if (take) {
-                                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&wg[k]), *reinterpret_cast<const __half2*>(&o));
-                                    wg[k] = *reinterpret_cast<const uint32_t*>(&sum);
-                                }
-                            }
-                        }
-                    }
-                    if (valid && head) {
-                        uint32_t rows[8];
-                        if (lv.mode == 2) corner_rows_generic(g.gridtype, lv.hashmap_size, lv.res, base[0], base[1], base[2], rows);
-                        else corner_rows(lv, base, rows);
-                        __half* glvl = grad_table + (size_t)lv.offset * 2;
-#pragma unroll
-                        for (uint32_t k = 0; k < 8; k += 2) scatter_pair_h2(glvl, rows[k], rows[k + 1], wg[k], wg[k + 1]);
-                    }
+                    scatter_level(g, s_lv[level], level, x, live, __floats2half2_rn(v[0], v[1]), grad_table, lane);
                 }
             }
             tc::fence_before_sync();

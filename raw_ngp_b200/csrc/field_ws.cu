@@ -3,12 +3,12 @@
 //     xyz --gather warps--> hash-grid features --> [A0 ring in shared memory] --MLP warps--> grid_mlp -> sigma, feat
 //                                                                                   SH(dir) -> view_mlp -> colour -> rgb
 //
-// One CTA per SM, 24 warps:
+// One CTA per SM, 28 warps:
 //   * warps 0-15 (512 threads) only gather: thread (row, g) encodes levels g, g+4, g+8, g+12 of its sample with two levels
 //     (16 table rows) in flight, writes the fp16 features into stage s of a 3-deep ring of 128 x 2L tiles and arrives on
 //     full[s].  The gathers are bound by the SM's L1-miss path into the L2-resident table, so these warps never wait for
 //     anything else: the ring decouples them from the tensor-core chain.
-//   * warps 16-19 and 20-23 are two MLP groups that take tiles alternately.  A group waits for full[s], then runs the six
+//   * warps 16-27 are three MLP groups (4 warps each) that take tiles in turn.  A group waits for full[s], then runs the six
 //     layers of grid_mlp and view_mlp as tcgen05.mma (M = 128, accumulators in the group's 128 TMEM columns), with the
 //     fp16 activations going TMEM -> registers -> shared memory between layers; tcgen05.commit on empty[s] hands the ring
 //     stage back to the gather warps as soon as the first layer has consumed it.
@@ -28,11 +28,11 @@ using namespace fieldcore;
 
 constexpr uint32_t kGatherThreads = 512;
 constexpr uint32_t kGatherGroups = kGatherThreads / kTile;
-constexpr uint32_t kMlpGroups = 2;
+constexpr uint32_t kMlpGroups = 3;
 constexpr uint32_t kWsThreads = kGatherThreads + kMlpGroups * kTile;     // 768
 constexpr uint32_t kStages = 3;
 constexpr uint32_t kGroupTmemCols = 128;
-constexpr uint32_t kWsTmemCols = kMlpGroups * kGroupTmemCols;
+constexpr uint32_t kWsTmemCols = 512;
 constexpr uint32_t kWsLayers = 6;
 
 // control block (byte offsets from ctrl_off)

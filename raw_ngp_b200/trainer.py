@@ -266,9 +266,9 @@ class FusedTrainStep:
                   P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), st)
         _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), self.p2[0], w2, a2, c2, 3, cap,
                   self._m_dev, 1, P(self.d_in2), self.p2[0], self._ptrs(self._w_grad_views[3:]), 1, st)
-        _lib.call("ngp_field_backward_density", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), self.p2[0],
-                  P(self.enc_buf), None, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap,
-                  self._m_dev, self._density_act, float(opt.beta), P(self.table_grad), self._ptrs(self._w_grad_views[:3]), 1, st)
+        _lib.call("ngp_field_backward_ws", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), self.p2[0],
+                  P(self.enc_buf), P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, cap,
+                  self._m_dev, self._density_act, float(opt.beta), P(self.table_grad), self._ptrs(self._w_grad_views[:3]), st)
 
     def _launch_check(self):
         st = _lib.stream()
