@@ -3,8 +3,8 @@
 //     [d sigma, d in2[:, :15]] --MLP warps--> grid_mlp backward (tcgen05: dW in TMEM, dH chain) --> d enc tile
 //                                                                  [ring in shared memory] --scatter warps--> table gradient
 //
-// One CTA per SM, 20 warps:
-//   * warps 16-19 (the MLP group) own the tensor-core chain of a tile: the saved activations (enc, h1, h2 in the tile-panel
+// One CTA per SM, 24 warps:
+//   * warps 16-19 and 20-23 (two MLP groups, alternating tiles) own the tensor-core chain of a tile: the saved activations (enc, h1, h2 in the tile-panel
 //     layout written by field_ws.cu) arrive by BULK ASYNC COPIES (cp.async.bulk, one per tensor and tile, mbarrier
 //     complete_tx) into a double-buffered set of shared-memory tiles, so the next tile streams in while this one is being
 //     processed.  Per layer: dW_l^T += in_l^T dZ_l (accumulators of all layers stay in TMEM for the whole kernel) and
@@ -25,15 +25,17 @@ using namespace fieldcore;
 
 constexpr uint32_t kScatterThreads = 512;
 constexpr uint32_t kScatterGroups = kScatterThreads / kTile;
-constexpr uint32_t kBwsThreads = kScatterThreads + kTile;     // 640
-constexpr uint32_t kInStages = 2;
-constexpr uint32_t kEncStages = 2;
-constexpr uint32_t kBwsTmemCols = 256;
+constexpr uint32_t kBwsGroups = 2;                             // MLP groups; group g owns input stage g, d enc stage g, TMEM half g
+constexpr uint32_t kBwsThreads = kScatterThreads + kBwsGroups * kTile;     // 768
+constexpr uint32_t kInStages = kBwsGroups;
+constexpr uint32_t kEncStages = kBwsGroups;
+constexpr uint32_t kGroupCols = 256;
+constexpr uint32_t kBwsTmemCols = kBwsGroups * kGroupCols;
 constexpr uint32_t kBwsLayers = 3;
 
 // control block (byte offsets from ctrl_off)
 constexpr uint32_t kInFull = 0, kInEmpty = kInFull + 8 * kInStages, kEncFull = kInEmpty + 8 * kInStages,
-                   kEncEmpty = kEncFull + 8 * kEncStages, kDone = kEncEmpty + 8 * kEncStages, kSlot = kDone + 8;
+                   kEncEmpty = kEncFull + 8 * kEncStages, kDone = kEncEmpty + 8 * kEncStages, kSlot = kDone + 8 * kBwsGroups;
 constexpr uint32_t kBLevels = (kSlot + 4 + 15) & ~15u;
 constexpr uint32_t kBPlans = kBLevels + kMaxLevels * sizeof(LevelConst);
 constexpr uint32_t kBCtrlBytes = kBPlans + kInStages * kBwsLayers * 2 * sizeof(MmaPlan);
@@ -72,24 +74,24 @@ field_backward_ws_kernel(const BwsArgs a) {
     if (threadIdx.x == 32) {
         for (uint32_t s = 0; s < kInStages; s++) { tc::mbar_init(in_full + 8 * s, 1); tc::mbar_init(in_empty + 8 * s, kTile); }
         for (uint32_t s = 0; s < kEncStages; s++) { tc::mbar_init(enc_full + 8 * s, kTile); tc::mbar_init(enc_empty + 8 * s, kScatterThreads); }
-        tc::mbar_init(done, 1);
+        for (uint32_t gI = 0; gI < kBwsGroups; gI++) tc::mbar_init(done + 8 * gI, 1);
     }
     for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + a.w_off[l], a.w[l], a.dims[l + 1], a.dims[l]);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kInStages * L) {
         const uint32_t i = threadIdx.x - 64, st = i / L, l = i % L, K = a.dims[l], N = a.dims[l + 1];
         // dZ of layer l sits in the ping-pong buffer (L - 1 - l) & 1
-        const uint32_t dz_saddr = tc::smem_u32(smem + a.dz_off + ((L - 1 - l) & 1u) * a.dz_bytes);
+        const uint32_t dz_saddr = tc::smem_u32(smem + a.dz_off + (2 * st + ((L - 1 - l) & 1u)) * a.dz_bytes);
         const uint32_t in_saddr = tc::smem_u32(smem + a.in_off[l] + st * a.in_stage_bytes), w_saddr = tc::smem_u32(smem + a.w_off[l]);
         MmaPlan& dw = plans[(st * L + l) * 2];       // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]  (MN-major views of row tiles)
         dw.idesc = tc::instr_desc(kTile, N, true, true);
-        dw.n_steps = kTile / 16; dw.d_col = a.acc_col[l]; dw.pad = 0;
+        dw.n_steps = kTile / 16; dw.d_col = st * kGroupCols + a.acc_col[l]; dw.pad = 0;
         for (uint32_t ks = 0; ks < kTile / 16; ks++) {
             dw.step[ks].a = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
             dw.step[ks].b = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
         }
         MmaPlan& dh = plans[(st * L + l) * 2 + 1];   // dH [128 x K] = dZ_l [128 x N] * W_l [N x K]
         dh.idesc = tc::instr_desc(kTile, K, false, true);
-        dh.n_steps = N / 16; dh.d_col = 0; dh.pad = 0;
+        dh.n_steps = N / 16; dh.d_col = st * kGroupCols; dh.pad = 0;
         for (uint32_t ks = 0; ks < N / 16; ks++) {
             dh.step[ks].a = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
             dh.step[ks].b = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
@@ -133,9 +135,13 @@ field_backward_ws_kernel(const BwsArgs a) {
             }
         }
     } else {
-        // ================================ MLP group ================================
-        const uint32_t tg = threadIdx.x - kScatterThreads;               // row inside the tile == TMEM lane
-        const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16);
+        // ================================ MLP groups ================================
+        const uint32_t gI = (warp - kScatterThreads / 32) / 4;           // group: tiles gI, gI + 2, ...; stage gI everywhere
+        const uint32_t tg = threadIdx.x - kScatterThreads - gI * kTile;  // row inside the tile == TMEM lane
+        const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16) + gI * kGroupCols;
+        const uint32_t st = gI, e = gI;
+        const uint32_t done_g = done + 8 * gI;
+        uint8_t* dz_base = smem + a.dz_off + 2 * gI * a.dz_bytes;
         uint32_t in_bytes = 0;
         for (uint32_t l = 0; l < L; l++) in_bytes += kTile * a.dims[l] * 2;
         auto load_tile = [&](uint32_t tile, uint32_t st) {               // one thread: bulk async copies of the saved tiles
@@ -145,16 +151,13 @@ field_backward_ws_kernel(const BwsArgs a) {
                              kTile * a.dims[l] * 2, in_full + 8 * st);
         };
         if (tg == 0) {
-            for (uint32_t st = 0; st < kInStages; st++) {
-                const uint32_t tile = blockIdx.x + st * gridDim.x;
-                if (tile < n_tiles) load_tile(tile, st);
-            }
+            const uint32_t tile = blockIdx.x + gI * gridDim.x;
+            if (tile < n_tiles) load_tile(tile, st);
         }
         uint32_t ph = 0, iter = 0;
-        for (uint32_t it = 0;; it++, iter++) {
+        for (uint32_t it = gI;; it += kBwsGroups, iter++) {
             const uint32_t tile = blockIdx.x + it * gridDim.x;
             if (tile >= n_tiles) break;
-            const uint32_t st = it % kInStages, e = it % kEncStages;
             const uint32_t row = tile * kTile + tg;
             const bool live = row < M;
             // d out1 = [d sigma * d act / d out0, d feat(15)]
@@ -174,14 +177,14 @@ field_backward_ws_kernel(const BwsArgs a) {
                     z0.x = s0 | (u.x << 16); z0.y = (u.x >> 16) | (u.y << 16); z0.z = (u.y >> 16) | (u.z << 16); z0.w = (u.z >> 16) | (u.w << 16);
                     z1.x = (u.w >> 16) | (v.x << 16); z1.y = (v.x >> 16) | (v.y << 16); z1.z = (v.y >> 16) | (v.z << 16); z1.w = (v.z >> 16) | (v.w << 16);
                 }
-                uint8_t* dzt = smem + a.dz_off;
+                uint8_t* dzt = dz_base;
                 *reinterpret_cast<uint4*>(dzt + tg * 16) = z0;
                 *reinterpret_cast<uint4*>(dzt + kPanel + tg * 16) = z1;
             }
-            tc::mbar_wait(in_full + 8 * st, (it / kInStages) & 1u);
+            tc::mbar_wait(in_full + 8 * st, iter & 1u);
             tc::fence_async_smem();
             tc::fence_before_sync();
-            tc::named_bar_sync(1, kTile);
+            tc::named_bar_sync(1 + gI, kTile);
             uint32_t cur = 0;
             for (int l = (int)L - 1; l >= 0; l--) {
                 const uint32_t K = a.dims[l];
@@ -189,13 +192,13 @@ field_backward_ws_kernel(const BwsArgs a) {
                     tc::fence_after_sync();
                     issue_plan(tmem, plans[(st * L + l) * 2], iter > 0);
                     issue_plan(tmem, plans[(st * L + l) * 2 + 1], false);
-                    tc::mma_commit(done);
+                    tc::mma_commit(done_g);
                 }
-                tc::mbar_wait(done, ph);
+                tc::mbar_wait(done_g, ph);
                 ph ^= 1;
                 tc::fence_after_sync();
                 if (l > 0) {
-                    uint8_t* nxt = smem + a.dz_off + (cur ^ 1) * a.dz_bytes;
+                    uint8_t* nxt = dz_base + (cur ^ 1) * a.dz_bytes;
                     const uint8_t* in_tile = smem + a.in_off[l] + st * a.in_stage_bytes;
                     for (uint32_t c0 = 0; c0 < K; c0 += 16) {
                         float v[16];
@@ -216,12 +219,12 @@ field_backward_ws_kernel(const BwsArgs a) {
                     }
                     tc::fence_async_smem();
                     tc::fence_before_sync();
-                    tc::named_bar_sync(1, kTile);
+                    tc::named_bar_sync(1 + gI, kTile);
                 } else {
                     // every MMA that reads this stage's tiles has completed: hand the stage back and refill it
                     tc::mbar_arrive(in_empty + 8 * st);
                     // d enc -> fp16 tile for the scatter warps
-                    tc::mbar_wait(enc_empty + 8 * e, ((it / kEncStages) & 1u) ^ 1u);
+                    tc::mbar_wait(enc_empty + 8 * e, (iter & 1u) ^ 1u);
                     uint8_t* de = smem + a.enc_off + e * a.enc_stage_bytes;
                     for (uint32_t c0 = 0; c0 < F; c0 += 16) {
                         float v[16];
@@ -233,14 +236,14 @@ field_backward_ws_kernel(const BwsArgs a) {
                     }
                     tc::mbar_arrive(enc_full + 8 * e);
                     if (tg == 0) {
-                        const uint32_t nt = blockIdx.x + (it + kInStages) * gridDim.x;
+                        const uint32_t nt = blockIdx.x + (it + kBwsGroups) * gridDim.x;
                         if (nt < n_tiles) {
-                            tc::mbar_wait(in_empty + 8 * st, (it / kInStages) & 1u);
+                            tc::mbar_wait(in_empty + 8 * st, iter & 1u);
                             load_tile(nt, st);
                         }
                     }
                     tc::fence_before_sync();
-                    tc::named_bar_sync(1, kTile);      // TMEM work columns and dZ buffer 0 are rewritten by the next tile
+                    tc::named_bar_sync(1 + gI, kTile);      // TMEM work columns and dZ buffer 0 are rewritten by the next tile
                 }
                 cur ^= 1;
             }
@@ -302,7 +305,7 @@ extern "C" int ngp_field_backward_ws(const float* xyzs, const float* d_sigma, co
     }
     acc = max_k;
     for (uint32_t l = 0; l < kBwsLayers; l++) { a.acc_col[l] = acc; acc += dims[l + 1]; }
-    if (acc > kBwsTmemCols) return NGP_ERR_UNSUPPORTED;
+    if (acc > kGroupCols) return NGP_ERR_UNSUPPORTED;
     if (!aligned(grad_table, 16) || !aligned(d_in2, 16)) return NGP_ERR_ALIGN;
     off = (off + 127) & ~127u;
     uint32_t in_stage = 0;
@@ -312,7 +315,7 @@ extern "C" int ngp_field_backward_ws(const float* xyzs, const float* d_sigma, co
     a.in_stage_bytes = in_stage;
     off += kInStages * in_stage;
     a.dz_off = off; a.dz_bytes = kTile * std::max(max_n, max_k) * 2;
-    off += 2 * a.dz_bytes;
+    off += 2 * kBwsGroups * a.dz_bytes;
     a.enc_off = off; a.enc_stage_bytes = kTile * dims[0] * 2;
     off += kEncStages * a.enc_stage_bytes;
     a.ctrl_off = off;

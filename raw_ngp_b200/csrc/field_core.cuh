@@ -182,25 +182,35 @@ static __device__ __noinline__ uint32_t gather_level_generic(const __half* table
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
-// Two table rows that share a 16-byte block (4 rows of an fp16 F=2 table): one red.global.add.noftz.v4.f16x2 for both.
+// Two x-neighbour corners.  Rows that differ only in bit 0 share an aligned 8-byte slot of the fp16 F=2 table (dense
+// levels: consecutive rows with an even first row; hashed levels: the first hash prime is 1, so x even -> rows h and h^1):
+// one red.global.add.noftz.v2.f16x2 covers both.  Otherwise one packed reduction per corner.
 __device__ __forceinline__ void scatter_pair_h2(__half* glvl, uint32_t row0, uint32_t row1, uint32_t p0, uint32_t p1) {
-    if ((row0 >> 2) == (row1 >> 2)) {
-        const uint32_t a = row0 & 3u, b = row1 & 3u;
-        if (a == b) {   // both corners clamp to the same row (level border)
-            const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&p0), *reinterpret_cast<const __half2*>(&p1));
-            p0 = *reinterpret_cast<const uint32_t*>(&sum);
-            p1 = 0u;
-        }
-        uint32_t w[4];
-#pragma unroll
-        for (uint32_t s4 = 0; s4 < 4; s4++) w[s4] = (s4 == a ? p0 : 0u) | ((s4 == b && a != b) ? p1 : 0u);
-        red_add_v4_h2(glvl + (size_t)(row0 >> 2) * 8, w[0], w[1], w[2], w[3]);
+    if ((row0 ^ row1) == 1u) {
+        const bool swap = row0 & 1u;
+        red_add_v2_h2(glvl + (size_t)(row0 & ~1u) * 2, swap ? p1 : p0, swap ? p0 : p1);
     } else {
-        red_add_h2(glvl + (size_t)row0 * 2, p0);
-        red_add_h2(glvl + (size_t)row1 * 2, p1);
+        if (row0 == row1) {   // both corners clamp to the same row (level border)
+            const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&p0), *reinterpret_cast<const __half2*>(&p1));
+            red_add_h2(glvl + (size_t)row0 * 2, *reinterpret_cast<const uint32_t*>(&sum));
+        } else {
+            red_add_h2(glvl + (size_t)row0 * 2, p0);
+            red_add_h2(glvl + (size_t)row1 * 2, p1);
+        }
     }
 }
 
+// A whole level of the scatter through the generic index map (mode 2 levels): out of line, reductions issued per corner.
+static __device__ __noinline__ void scatter_corners_generic(__half* glvl, uint32_t gridtype, uint32_t hashmap_size, uint32_t res,
+                                                            uint32_t bx, uint32_t by, uint32_t bz, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                            uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
+    const uint32_t wg[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+    const uint32_t x1 = min(bx + 1, res - 1), y1 = min(by + 1, res - 1), z1 = min(bz + 1, res - 1);
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t q[3] = {(k & 1u) ? x1 : bx, (k & 2u) ? y1 : by, (k & 4u) ? z1 : bz};
+        red_add_h2(glvl + (size_t)entry_index<3>(gridtype, hashmap_size, res, q) * 2, wg[k]);
+    }
+}
 
 // One level of one sample of the table-gradient scatter.  `gh` is d enc (2 features) as it comes out of the grid_mlp
 // backward; it reaches the encoder as fp16 (autocast), optionally through the annealing window.  Must be called by all 32
@@ -240,21 +250,24 @@ __device__ __forceinline__ void scatter_level(const GridArgs& g, const LevelCons
             const bool take = lane + d <= end;
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++) {
-                const uint32_t o = __shfl_down_sync(0xffffffffu, wg[k], d);
-                if (take) {
-                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&wg[k]), *reinterpret_cast<const __half2*>(&o));
-                    wg[k] = *reinterpret_cast<const uint32_t*>(&sum);
-                }
+                uint32_t o = __shfl_down_sync(0xffffffffu, wg[k], d);
+                o = take ? o : 0u;          // (+0.0, +0.0): adding it leaves the value unchanged
+                const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&wg[k]), *reinterpret_cast<const __half2*>(&o));
+                wg[k] = *reinterpret_cast<const uint32_t*>(&sum);
             }
         }
     }
     if (valid && head) {
-        uint32_t rows[8];
-        if (lv.mode == 2) corner_rows_generic(g.gridtype, lv.hashmap_size, lv.res, base[0], base[1], base[2], rows);
-        else corner_rows(lv, base, rows);
         __half* glvl = grad_table + (size_t)lv.offset * 2;
+        if (lv.mode == 2) {     // warp-uniform, rare
+            scatter_corners_generic(glvl, g.gridtype, lv.hashmap_size, lv.res, base[0], base[1], base[2], wg[0], wg[1], wg[2], wg[3],
+                                    wg[4], wg[5], wg[6], wg[7]);
+        } else {
+            uint32_t rows[8];
+            corner_rows(lv, base, rows);
 #pragma unroll
-        for (uint32_t k = 0; k < 8; k += 2) scatter_pair_h2(glvl, rows[k], rows[k + 1], wg[k], wg[k + 1]);
+            for (uint32_t k = 0; k < 8; k += 2) scatter_pair_h2(glvl, rows[k], rows[k + 1], wg[k], wg[k + 1]);
+        }
     }
 }
 
