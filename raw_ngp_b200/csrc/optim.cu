@@ -10,6 +10,19 @@ namespace {
 
 template <typename G> __device__ __forceinline__ float load_g(const G* p, uint64_t i) { return to_f32(p[i]); }
 
+// 4 elements per thread and iteration: 16-byte accesses for the fp32 streams (master, m, v), 8-byte for fp16/bf16 ones.
+template <typename T> struct Vec4 { T v[4]; };
+template <typename T> __device__ __forceinline__ Vec4<T> load4(const T* p) {
+    Vec4<T> r;
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<uint4*>(r.v) = *reinterpret_cast<const uint4*>(p);
+    else *reinterpret_cast<uint2*>(r.v) = *reinterpret_cast<const uint2*>(p);
+    return r;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const Vec4<T>& r) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(r.v);
+    else *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(r.v);
+}
+
 template <typename G, typename P, bool HasLP>
 __global__ void __launch_bounds__(256)
 fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __restrict__ grad, float* __restrict__ m,
@@ -20,7 +33,35 @@ fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __res
     const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
     const float step_size = lr / bias1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t n4 = n / 4;      // the buffers are 16-byte aligned (checked by the host wrapper)
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+        const uint64_t i = q * 4;
+        if (!skip) {
+            const Vec4<G> g4 = load4(grad + i);
+            Vec4<float> p4 = load4(master + i), m4 = load4(m + i), v4 = load4(v + i);
+            Vec4<P> lp4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float g = to_f32(g4.v[k]) * inv_scale;
+                if (weight_decay != 0.f) g += weight_decay * p4.v[k];
+                m4.v[k] = beta1 * m4.v[k] + (1.f - beta1) * g;
+                v4.v[k] = beta2 * v4.v[k] + (1.f - beta2) * g * g;
+                const float denom = sqrtf(v4.v[k]) / bias2_sqrt + eps;
+                p4.v[k] -= step_size * (m4.v[k] / denom);
+                if (HasLP) lp4.v[k] = from_f32<P>(p4.v[k]);
+            }
+            store4(m + i, m4); store4(v + i, v4); store4(master + i, p4);
+            if (HasLP) store4(param_lp + i, lp4);
+        }
+        if (zero_grad) {
+            Vec4<G> z;
+#pragma unroll
+            for (int k = 0; k < 4; k++) z.v[k] = from_f32<G>(0.f);
+            store4(grad + i, z);
+        }
+    }
+    // tail (n % 4 elements)
+    for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         if (!skip) {
             float g = to_f32(grad[i]) * inv_scale;
             float p = master[i];
@@ -43,10 +84,15 @@ __global__ void __launch_bounds__(256)
 check_finite_kernel(const G* __restrict__ grad, uint64_t n, float* __restrict__ found_inf) {
     bool bad = false;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float g = to_f32(grad[i]);
-        bad |= !isfinite(g);
+    constexpr uint32_t PER = 16 / sizeof(G);        // elements per 16-byte load
+    const uint64_t nv = n / PER;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += stride) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(grad) + q);
+        const G* e = reinterpret_cast<const G*>(&u);
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) bad |= !isfinite(to_f32(e[k]));
     }
+    for (uint64_t i = nv * PER + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= !isfinite(to_f32(grad[i]));
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
 }
 
@@ -64,9 +110,11 @@ extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void*
     if (step == 0) return NGP_ERR_BAD_ARG;
     if (grad_dtype < NGP_F32 || grad_dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
     if (param_lp && (lp_dtype != NGP_F16 && lp_dtype != NGP_BF16)) return NGP_ERR_BAD_DTYPE;
+    if (!aligned(master, 16) || !aligned(grad, 16) || !aligned(exp_avg, 16) || !aligned(exp_avg_sq, 16) || (param_lp && !aligned(param_lp, 8)))
+        return NGP_ERR_ALIGN;
     const float bias1 = 1.f - powf(beta1, (float)step);
     const float bias2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(n, 256), (uint64_t)kNumSMs * 16);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(div_up<uint64_t>(n, 4), 256), (uint64_t)kNumSMs * 8);
     cudaStream_t st = (cudaStream_t)stream;
 #define NGP_ADAM(G, P, HAS)                                                                                      \
     fused_adam_kernel<G, P, HAS><<<blocks, 256, 0, st>>>(master, (P*)param_lp, (G*)grad, exp_avg, exp_avg_sq, n, lr, \
@@ -87,7 +135,8 @@ extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void*
 extern "C" int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev, ngp_stream_t stream) {
     if (n == 0) return NGP_OK;
     if (!grad || !found_inf_dev) return NGP_ERR_NULL;
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(n, 256), (uint64_t)kNumSMs * 16);
+    if (!aligned(grad, 16)) return NGP_ERR_ALIGN;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(n, 256 * 8), (uint64_t)kNumSMs * 8);
     cudaStream_t st = (cudaStream_t)stream;
     switch (grad_dtype) {
         case NGP_F32: check_finite_kernel<float><<<blocks, 256, 0, st>>>((const float*)grad, n, found_inf_dev); break;

@@ -406,9 +406,54 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
         float* tout = t_scratch + (size_t)n * max_steps;
         uint32_t step = 0;
         while (t < far && step < max_steps) {       // warp-uniform
-            // (1) lattice window starting at t: every lane runs the same chain, lane i%32 keeps u_i
+            // (1) lattice window starting at t
             uint32_t cnt = 0;
-            {
+            const float dt_c = clampf(0.f, p.dt_min, p.dt_max);      // the step when dt_gamma == 0 (raymarching.cu:412)
+            if (p.dt_gamma == 0.f && t >= dt_c && dt_c > 0.f) {
+                // Constant step (the reference default, --dt_gamma 0): u_{i+1} = fl(u_i + dt).  Inside one binade
+                // [2^e, 2^(e+1)) every u is a multiple of ulp = 2^(e-23), so fl(u + dt) = u + D * ulp with D = dt / ulp
+                // rounded to nearest -- the same D for the whole binade unless dt / ulp ends in exactly .5 (a tie, resolved
+                // by the parity of u; then the serial chain below is used).  Lanes fill 32 lattice points per step with
+                // integer arithmetic on the significand; the one add that crosses into the next binade is a real fp32 add.
+                const uint32_t dbits = __float_as_uint(dt_c), Md = (dbits & 0x7FFFFFu) | 0x800000u;
+                const int ed = (int)(dbits >> 23);            // biased exponent of dt (dt is a normal number)
+                float tt = t;
+                bool fallback = false;
+                while (cnt < kWin && tt < far) {
+                    const uint32_t tb = __float_as_uint(tt);
+                    const int sh = (int)(tb >> 23) - ed;       // ulp(tt) / ulp(dt) = 2^sh, sh >= 0 because tt >= dt
+                    uint32_t D;
+                    if (sh == 0) D = Md;
+                    else if (sh > 24) D = 0;
+                    else {
+                        const uint32_t rem = Md & ((1u << sh) - 1u), halfway = 1u << (sh - 1);
+                        if (rem == halfway) { fallback = true; break; }
+                        D = (Md >> sh) + (rem > halfway ? 1u : 0u);
+                    }
+                    if (D == 0) { fallback = true; break; }   // dt below half an ulp: t would stop advancing (degenerate)
+                    const uint32_t U0 = (tb & 0x7FFFFFu) | 0x800000u;
+                    uint32_t n_in = (0xFFFFFFu - U0) / D + 1u;           // lattice points of this binade, starting at tt
+                    n_in = min(n_in, kWin - cnt);
+                    uint32_t stored = 0;
+                    for (uint32_t k0 = 0; k0 < n_in; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        const float uk = __uint_as_float((tb & 0xFF800000u) | ((U0 + k * D) & 0x7FFFFFu));
+                        const bool ok = k < n_in && uk < far;
+                        if (ok) u[cnt + k] = uk;
+                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                        stored += __popc(m);
+                        if (m != 0xffffffffu) break;
+                    }
+                    cnt += stored;
+                    if (stored < n_in) break;                  // reached `far` (or the window is full: stored == n_in then)
+                    // last point of the binade + dt: the add that changes the exponent
+                    const float ulast = __uint_as_float((tb & 0xFF800000u) | ((U0 + (n_in - 1) * D) & 0x7FFFFFu));
+                    tt = ulast + dt_c;
+                }
+                if (fallback) cnt = 0;
+            }
+            if (cnt == 0) {
+                // general case: every lane runs the same serial chain, lane i%32 keeps u_i
                 float tt = t, mine = 0.f;
                 while (cnt < kWin && tt < far) {
                     if ((cnt & 31u) == lane) mine = tt;
@@ -429,25 +474,41 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
                 } else {
                     const float tt = voxel_exit(p, r, ti, q);
                     uint32_t lo = i + 1, hi = cnt;          // first j in (i, cnt) with u[j] >= tt, else cnt
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (u[mid] < tt) lo = mid + 1; else hi = mid;
+                    if (p.dt_gamma == 0.f) {
+                        // constant step: the target is near i + (tt - t_i) / dt; walk the few remaining entries
+                        const float est = (tt - ti) / clampf(0.f, p.dt_min, p.dt_max);
+                        uint32_t j = (est < (float)(cnt - i)) ? i + (uint32_t)fmaxf(est, 1.f) : cnt;
+                        j = min(max(j, lo), hi);
+                        while (j > lo && u[j - 1] >= tt) j--;
+                        while (j < hi && u[j] < tt) j++;
+                        lo = j;
+                    } else {
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (u[mid] < tt) lo = mid + 1; else hi = mid;
+                        }
                     }
                     code = lo;
                 }
                 nx[i] = (uint16_t)code;
             }
             __syncwarp();
-            // (3) pointer chase (all lanes redundantly: uniform, no divergence), kept t's go to the scratch list
+            // (3) pointer chase (uniform over the warp).  A run of consecutive kept lattice points is consumed in one
+            // step: its length comes from a ballot over the 32 entries around i and its t's are stored by parallel lanes.
             uint32_t i = 0;
             int exit_skip = -1;                     // lattice index of a skip whose target lies beyond the window
             while (i < cnt && step < max_steps) {
-                const uint32_t code = nx[i];
-                if (code & 0x8000u) {
-                    if (lane == 0) tout[step] = u[i];
-                    step++;
-                    i++;
+                const uint32_t c0 = i & ~31u;
+                const uint32_t code_l = (c0 + lane < cnt) ? (uint32_t)nx[c0 + lane] : 0u;
+                const uint32_t keep = __ballot_sync(0xffffffffu, (code_l & 0x8000u) != 0u) >> (i & 31u);
+                if (keep & 1u) {
+                    uint32_t run = (keep == 0xffffffffu) ? 32u : (uint32_t)__ffs(~keep) - 1u;   // bits past the chunk end are 0
+                    run = min(run, max_steps - step);
+                    if (lane < run) tout[step + lane] = u[i + lane];
+                    step += run;
+                    i += run;
                 } else {
+                    const uint32_t code = __shfl_sync(0xffffffffu, code_l, i & 31u);
                     if (code >= cnt) exit_skip = (int)i;
                     i = code;
                 }
