@@ -314,9 +314,11 @@ def run_ours(args):
         # algorithmic bytes per sample; the 512 B of corner payload / table-gradient reductions are
         # L2 traffic by design, everything else is compulsory HBM traffic
         per_sample = {
-            "ngp_field_forward_density": 12 + 12 + 512 + 64 + 256 + 4 + 64,
-            "ngp_field_backward_density": 12 + 4 + 4 + 32 + 64 + 256 + 512,
-            "ngp_mlp_forward_rgb": 64 + 256 + 12,
+            # xyz + dirs in; 16 levels x 8 corners x 4 B gathered; out: enc 64 + hidden 4 x 128 + in2 64 (saved, fp16) + sigma 4 + rgb 12
+            "ngp_field_forward_full": 12 + 12 + 512 + 64 + 4 * 128 + 64 + 4 + 12,
+            # xyz, d sigma, sigma, d in2 (32 B used), enc 64 + hidden 2 x 128 in; 16 x 8 x 4 B reduced into the table gradient
+            "ngp_field_backward_ws": 12 + 4 + 4 + 32 + 64 + 256 + 512,
+            # d rgb + rgb in, in2 64 + hidden 2 x 128 in, d in2 64 out
             "ngp_mlp_backward_rgb": 12 + 12 + 64 + 256 + 64,
             "ngp_march_rays_train_write": 4 + 32,
             "ngp_composite_train_mse": 2 * 24 + 16,

@@ -359,16 +359,20 @@ int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, co
                          uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
                          float* const* dweights, int tiled, ngp_stream_t stream);
 
-/* ngp_field_backward_density as a warp-specialised persistent kernel (csrc/field_bwd_ws.cu): one MLP group runs the
- * grid_mlp backward on the tensor cores (saved tiles fetched with bulk async copies, double buffered) and hands d enc to
- * 16 scatter warps through a shared-memory ring.  Inputs in the tile-panel layout of ngp_field_forward_full: d_in2
- * (width ld2), enc, acts[0..1]; three layers, dims = {2L, h, h, 16}.  grad_table / dweights are accumulated into. */
-int ngp_field_backward_ws(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
-                          uint32_t ld2, const void* enc, const int32_t* offsets, const float* feat_weights,
-                          float bound, float S, uint32_t H, uint32_t L, uint32_t gridtype, int align_corners,
-                          uint32_t interp, const void* const* weights, const void* const* acts,
-                          const uint32_t* dims, uint32_t M, const int32_t* m_dev, int density_act, float beta,
-                          void* grad_table, float* const* dweights, ngp_stream_t stream);
+/* The whole field backward in ONE warp-specialised persistent kernel (csrc/field_bwd_ws.cu): a view group (view_mlp
+ * backward from d_rgb), a grid group (grid_mlp backward from d_sigma and the view group's d feat, handed over in shared
+ * memory) and 16 scatter warps (hash-table gradient) run as a pipeline; saved tiles arrive by bulk async copies.
+ * Inputs are what ngp_field_forward_full saved (tile-panel layout): enc, grid_acts[0..1], in2, view_acts[0..1]; plus
+ * sigma [M], rgb [M,3] and the incoming d_sigma [M], d_rgb [M,3] (fp32).  grad_table [sO,2] fp16 and the fp32
+ * grid_dweights[l] / view_dweights[l] ([dims[l+1], dims[l]]) are ACCUMULATED into. */
+int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float* sigma, const float* d_rgb,
+                            const float* rgb, const void* enc, const void* const* grid_acts, const void* in2,
+                            const void* const* view_acts, const int32_t* offsets, const float* feat_weights,
+                            float bound, float S, uint32_t H, uint32_t L, uint32_t gridtype, int align_corners,
+                            uint32_t interp, const void* const* grid_weights, const uint32_t* grid_dims,
+                            const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
+                            const int32_t* m_dev, int density_act, float beta, int color_act, void* grad_table,
+                            float* const* grid_dweights, float* const* view_dweights, ngp_stream_t stream);
 
 /* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
  * shared-memory tiles while two groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.

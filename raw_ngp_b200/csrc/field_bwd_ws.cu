@@ -1,19 +1,22 @@
-// field_bwd_ws.cu -- grid_mlp backward + hash-table gradient scatter as ONE warp-specialised persistent kernel.
+// field_bwd_ws.cu -- the whole NeRF field backward as ONE warp-specialised persistent kernel:
 //
-//     [d sigma, d in2[:, :15]] --MLP warps--> grid_mlp backward (tcgen05: dW in TMEM, dH chain) --> d enc tile
-//                                                                  [ring in shared memory] --scatter warps--> table gradient
+//   d rgb --view group--> view_mlp backward --d in2[:, :15] ring--> grid group --> grid_mlp backward --d enc ring-->
+//                                                                   d sigma ---^                  scatter warps --> table gradient
 //
 // One CTA per SM, 24 warps:
-//   * warps 16-19 and 20-23 (two MLP groups, alternating tiles) own the tensor-core chain of a tile: the saved activations (enc, h1, h2 in the tile-panel
-//     layout written by field_ws.cu) arrive by BULK ASYNC COPIES (cp.async.bulk, one per tensor and tile, mbarrier
-//     complete_tx) into a double-buffered set of shared-memory tiles, so the next tile streams in while this one is being
-//     processed.  Per layer: dW_l^T += in_l^T dZ_l (accumulators of all layers stay in TMEM for the whole kernel) and
-//     dH = dZ_l W_l, ReLU-masked into the next dZ.  The last dH is d enc: it is rounded to fp16 and handed to the scatter
-//     warps through a 2-deep ring.
+//   * warps 16-19, the VIEW group: colour-activation backward, then the three view_mlp layers on the tensor cores
+//     (dW_l^T += in_l^T dZ_l with the accumulators of all layers resident in TMEM for the whole kernel; dH = dZ_l W_l,
+//     ReLU-masked into the next dZ).  The first 16 columns of its last dH (d feat; the SH inputs need no gradient) go to
+//     the grid group through a 2-deep shared-memory ring -- d in2 never touches HBM.
+//   * warps 20-23, the GRID group: the same chain for grid_mlp, one tile behind the view group; its last dH is d enc,
+//     handed to the scatter warps through a second ring.
+//   * both groups fetch their saved activations (tile-panel layout of field_ws.cu) with BULK ASYNC COPIES, one per tensor
+//     and tile, completing on an mbarrier; a tensor's slot is refilled for the next tile as soon as its layer is done, so
+//     the loads run two layers ahead without a second set of buffers.
 //   * warps 0-15 only scatter: thread (row, g) takes levels g, g+4, ... of its sample; runs of consecutive samples in the
-//     same cell are merged by a segmented shuffle reduction in packed fp16x2 and only run heads issue
-//     red.global.add.noftz.v4.f16x2 (x-neighbour corners share one 16-byte reduction).  The scatter is the throughput
-//     bound of the backward pass; the ring keeps these warps busy while the tensor-core chain of the next tile runs.
+//     same cell are merged by a segmented shuffle reduction in packed fp16x2 and only run heads issue reductions
+//     (red.global.add.noftz.v2.f16x2 for an aligned x-neighbour pair).  The scatter is the throughput bound of the backward
+//     pass; the rings keep these warps busy while the tensor-core chains of the next tiles run.
 #include "field_core.cuh"
 
 namespace ngp {
@@ -25,34 +28,36 @@ using namespace fieldcore;
 
 constexpr uint32_t kScatterThreads = 512;
 constexpr uint32_t kScatterGroups = kScatterThreads / kTile;
-constexpr uint32_t kBwsGroups = 2;                             // MLP groups; group g owns input stage g, d enc stage g, TMEM half g
-constexpr uint32_t kBwsThreads = kScatterThreads + kBwsGroups * kTile;     // 768
-constexpr uint32_t kInStages = kBwsGroups;
-constexpr uint32_t kEncStages = kBwsGroups;
-constexpr uint32_t kGroupCols = 256;
-constexpr uint32_t kBwsTmemCols = kBwsGroups * kGroupCols;
-constexpr uint32_t kBwsLayers = 3;
+constexpr uint32_t kChains = 2;                                 // 0 = view_mlp, 1 = grid_mlp
+constexpr uint32_t kBwsThreads = kScatterThreads + kChains * kTile;     // 768
+constexpr uint32_t kRing = 2;
+constexpr uint32_t kChainCols = 256;
+constexpr uint32_t kBwsTmemCols = kChains * kChainCols;
+constexpr uint32_t kL = 3;
 
 // control block (byte offsets from ctrl_off)
-constexpr uint32_t kInFull = 0, kInEmpty = kInFull + 8 * kInStages, kEncFull = kInEmpty + 8 * kInStages,
-                   kEncEmpty = kEncFull + 8 * kEncStages, kDone = kEncEmpty + 8 * kEncStages, kSlot = kDone + 8 * kBwsGroups;
-constexpr uint32_t kBLevels = (kSlot + 4 + 15) & ~15u;
-constexpr uint32_t kBPlans = kBLevels + kMaxLevels * sizeof(LevelConst);
-constexpr uint32_t kBCtrlBytes = kBPlans + kInStages * kBwsLayers * 2 * sizeof(MmaPlan);
+constexpr uint32_t kTFull = 0;                                   // [chain][layer]
+constexpr uint32_t kEncFull = kTFull + 8 * kChains * kL, kEncEmpty = kEncFull + 8 * kRing;
+constexpr uint32_t kDinFull = kEncEmpty + 8 * kRing, kDinEmpty = kDinFull + 8 * kRing;
+constexpr uint32_t kDone = kDinEmpty + 8 * kRing, kSlot = kDone + 8 * kChains;
+constexpr uint32_t kBLevels = (kSlot + 4 + 15) & ~15u;           // LevelConst[L], then the MMA plans
+
+struct Chain {
+    const __half* in[kL];          // tiled saved tensors: layer inputs (in2 | enc, h1, h2)
+    const __half* w[kL];
+    float* dw[kL];
+    uint32_t dims[kL + 1];
+    uint32_t w_off[kL], in_off[kL], dz_off, dz_bytes, acc_col[kL];
+};
 
 struct BwsArgs {
-    const float* xyzs; const float* d_sigma; const float* sigma;
-    const __half* d_in2; uint32_t ld2;          // tiled [tiles][ld2 / 8][128][8]
-    const __half* in[kBwsLayers];               // tiled enc, h1, h2
+    Chain c[kChains];
+    const float* xyzs; const float* d_sigma; const float* sigma; const float* d_rgb; const float* rgb;
     GridArgs g;
-    const __half* w[kBwsLayers];
-    float* dw[kBwsLayers];
-    uint32_t dims[kBwsLayers + 1];
     uint32_t M; const int* m_dev;
     __half* grad_table;
-    int density_act; float beta;
-    uint32_t w_off[kBwsLayers], in_off[kBwsLayers], in_stage_bytes, dz_off, dz_bytes, enc_off, enc_stage_bytes, ctrl_off;
-    uint32_t acc_col[kBwsLayers];
+    int density_act, color_act; float beta;
+    uint32_t enc_off, enc_stage_bytes, din_off, ctrl_off, plans_off;
 };
 
 __global__ void __launch_bounds__(kBwsThreads, 1)
@@ -62,36 +67,42 @@ field_backward_ws_kernel(const BwsArgs a) {
     if (a.m_dev) M = min(M, (uint32_t)__ldg(a.m_dev));
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint8_t* ctrl = smem + a.ctrl_off;
-    const uint32_t in_full = tc::smem_u32(ctrl + kInFull), in_empty = tc::smem_u32(ctrl + kInEmpty);
+    const uint32_t t_full = tc::smem_u32(ctrl + kTFull);
     const uint32_t enc_full = tc::smem_u32(ctrl + kEncFull), enc_empty = tc::smem_u32(ctrl + kEncEmpty);
+    const uint32_t din_full = tc::smem_u32(ctrl + kDinFull), din_empty = tc::smem_u32(ctrl + kDinEmpty);
     const uint32_t done = tc::smem_u32(ctrl + kDone);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kSlot);
     LevelConst* s_lv = reinterpret_cast<LevelConst*>(ctrl + kBLevels);
-    MmaPlan* plans = reinterpret_cast<MmaPlan*>(ctrl + kBPlans);      // [stage][layer][0 = dW, 1 = dH]
-    const uint32_t L = kBwsLayers;
+    MmaPlan* plans = reinterpret_cast<MmaPlan*>(ctrl + a.plans_off);  // [chain][layer][0 = dW, 1 = dH]
 
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kBwsTmemCols);
     if (threadIdx.x == 32) {
-        for (uint32_t s = 0; s < kInStages; s++) { tc::mbar_init(in_full + 8 * s, 1); tc::mbar_init(in_empty + 8 * s, kTile); }
-        for (uint32_t s = 0; s < kEncStages; s++) { tc::mbar_init(enc_full + 8 * s, kTile); tc::mbar_init(enc_empty + 8 * s, kScatterThreads); }
-        for (uint32_t gI = 0; gI < kBwsGroups; gI++) tc::mbar_init(done + 8 * gI, 1);
+        for (uint32_t i = 0; i < kChains * kL; i++) tc::mbar_init(t_full + 8 * i, 1);
+        for (uint32_t s = 0; s < kRing; s++) {
+            tc::mbar_init(enc_full + 8 * s, kTile); tc::mbar_init(enc_empty + 8 * s, kScatterThreads);
+            tc::mbar_init(din_full + 8 * s, kTile); tc::mbar_init(din_empty + 8 * s, kTile);
+        }
+        for (uint32_t ci = 0; ci < kChains; ci++) tc::mbar_init(done + 8 * ci, 1);
     }
-    for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + a.w_off[l], a.w[l], a.dims[l + 1], a.dims[l]);
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + kInStages * L) {
-        const uint32_t i = threadIdx.x - 64, st = i / L, l = i % L, K = a.dims[l], N = a.dims[l + 1];
-        // dZ of layer l sits in the ping-pong buffer (L - 1 - l) & 1
-        const uint32_t dz_saddr = tc::smem_u32(smem + a.dz_off + (2 * st + ((L - 1 - l) & 1u)) * a.dz_bytes);
-        const uint32_t in_saddr = tc::smem_u32(smem + a.in_off[l] + st * a.in_stage_bytes), w_saddr = tc::smem_u32(smem + a.w_off[l]);
-        MmaPlan& dw = plans[(st * L + l) * 2];       // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]  (MN-major views of row tiles)
+    for (uint32_t ci = 0; ci < kChains; ci++)
+        for (uint32_t l = 0; l < kL; l++) load_weight_tile(smem + a.c[ci].w_off[l], a.c[ci].w[l], a.c[ci].dims[l + 1], a.c[ci].dims[l]);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kChains * kL) {
+        const uint32_t i = threadIdx.x - 64, ci = i / kL, l = i % kL;
+        const Chain& c = a.c[ci];
+        const uint32_t K = c.dims[l], N = c.dims[l + 1];
+        // dZ of layer l sits in the chain's ping-pong buffer (kL - 1 - l) & 1
+        const uint32_t dz_saddr = tc::smem_u32(smem + c.dz_off + ((kL - 1 - l) & 1u) * c.dz_bytes);
+        const uint32_t in_saddr = tc::smem_u32(smem + c.in_off[l]), w_saddr = tc::smem_u32(smem + c.w_off[l]);
+        MmaPlan& dw = plans[i * 2];       // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]  (MN-major views of row tiles)
         dw.idesc = tc::instr_desc(kTile, N, true, true);
-        dw.n_steps = kTile / 16; dw.d_col = st * kGroupCols + a.acc_col[l]; dw.pad = 0;
+        dw.n_steps = kTile / 16; dw.d_col = ci * kChainCols + c.acc_col[l]; dw.pad = 0;
         for (uint32_t ks = 0; ks < kTile / 16; ks++) {
             dw.step[ks].a = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
             dw.step[ks].b = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
         }
-        MmaPlan& dh = plans[(st * L + l) * 2 + 1];   // dH [128 x K] = dZ_l [128 x N] * W_l [N x K]
+        MmaPlan& dh = plans[i * 2 + 1];   // dH [128 x K] = dZ_l [128 x N] * W_l [N x K]
         dh.idesc = tc::instr_desc(kTile, K, false, true);
-        dh.n_steps = N / 16; dh.d_col = st * kGroupCols; dh.pad = 0;
+        dh.n_steps = N / 16; dh.d_col = ci * kChainCols; dh.pad = 0;
         for (uint32_t ks = 0; ks < N / 16; ks++) {
             dh.step[ks].a = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
             dh.step[ks].b = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
@@ -105,7 +116,6 @@ field_backward_ws_kernel(const BwsArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     const GridArgs& g = a.g;
-    const uint32_t F = a.dims[0];
 
     if (warp < kScatterThreads / 32) {
         // ================================ scatter warps ================================
@@ -113,12 +123,12 @@ field_backward_ws_kernel(const BwsArgs a) {
         for (uint32_t it = 0;; it++) {
             const uint32_t tile = blockIdx.x + it * gridDim.x;
             if (tile >= n_tiles) break;
-            const uint32_t e = it % kEncStages;
+            const uint32_t e = it % kRing;
             const uint32_t row = tile * kTile + r;
             const bool live = row < M;
             float x[3] = {2.f, 2.f, 2.f};
             if (live) unit_cube(a.xyzs + (size_t)row * 3, g.bound, x);
-            tc::mbar_wait(enc_full + 8 * e, (it / kEncStages) & 1u);
+            tc::mbar_wait(enc_full + 8 * e, (it / kRing) & 1u);
             // this thread's d enc values (levels grp, grp + 4, ...) leave the ring at once, which frees the stage early
             const uint8_t* de = smem + a.enc_off + e * a.enc_stage_bytes;
             __half2 gh[kMaxLevels / kScatterGroups];
@@ -135,82 +145,111 @@ field_backward_ws_kernel(const BwsArgs a) {
             }
         }
     } else {
-        // ================================ MLP groups ================================
-        const uint32_t gI = (warp - kScatterThreads / 32) / 4;           // group: tiles gI, gI + 2, ...; stage gI everywhere
-        const uint32_t tg = threadIdx.x - kScatterThreads - gI * kTile;  // row inside the tile == TMEM lane
-        const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16) + gI * kGroupCols;
-        const uint32_t st = gI, e = gI;
-        const uint32_t done_g = done + 8 * gI;
-        uint8_t* dz_base = smem + a.dz_off + 2 * gI * a.dz_bytes;
-        uint32_t in_bytes = 0;
-        for (uint32_t l = 0; l < L; l++) in_bytes += kTile * a.dims[l] * 2;
-        auto load_tile = [&](uint32_t tile, uint32_t st) {               // one thread: bulk async copies of the saved tiles
-            tc::mbar_arrive_expect_tx(in_full + 8 * st, in_bytes);
-            for (uint32_t l = 0; l < L; l++)
-                tc::bulk_g2s(tc::smem_u32(smem + a.in_off[l] + st * a.in_stage_bytes), a.in[l] + (size_t)tile * (a.dims[l] * kTile),
-                             kTile * a.dims[l] * 2, in_full + 8 * st);
+        // ================================ MLP chains ================================
+        const uint32_t ci = (warp - kScatterThreads / 32) / 4;            // 0 = view group, 1 = grid group
+        const bool view = ci == 0;
+        const Chain& c = a.c[ci];
+        const uint32_t tg = threadIdx.x - kScatterThreads - ci * kTile;   // row inside the tile == TMEM lane
+        const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16) + ci * kChainCols;
+        const uint32_t done_c = done + 8 * ci, tf = t_full + 8 * ci * kL;
+        uint8_t* dz_base = smem + c.dz_off;
+        const MmaPlan* pl = plans + ci * kL * 2;
+        auto load_tensor = [&](uint32_t tile, uint32_t l) {               // one thread: bulk async copy of one saved tile
+            const uint32_t bytes = kTile * c.dims[l] * 2;
+            tc::mbar_arrive_expect_tx(tf + 8 * l, bytes);
+            tc::bulk_g2s(tc::smem_u32(smem + c.in_off[l]), c.in[l] + (size_t)tile * (c.dims[l] * kTile), bytes, tf + 8 * l);
         };
-        if (tg == 0) {
-            const uint32_t tile = blockIdx.x + gI * gridDim.x;
-            if (tile < n_tiles) load_tile(tile, st);
-        }
-        uint32_t ph = 0, iter = 0;
-        for (uint32_t it = gI;; it += kBwsGroups, iter++) {
+        if (tg == 0 && blockIdx.x < n_tiles)
+            for (uint32_t l = 0; l < kL; l++) load_tensor(blockIdx.x, l);
+        // per-sample head inputs, fetched one tile ahead: (d rgb, rgb) for the view group, (d sigma, sigma) for the grid group
+        float h0[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};
+        auto fetch_head = [&](uint32_t tile) {
+            const uint32_t row = tile * kTile + tg;
+            h0[0] = h0[1] = h0[2] = h1[0] = h1[1] = h1[2] = 0.f;
+            if (tile < n_tiles && row < M) {
+                if (view) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { h0[k] = __ldg(a.d_rgb + (size_t)row * 3 + k); h1[k] = __ldg(a.rgb + (size_t)row * 3 + k); }
+                } else {
+                    h0[0] = __ldg(a.d_sigma + row); h1[0] = __ldg(a.sigma + row);
+                }
+            }
+        };
+        fetch_head(blockIdx.x);
+        uint32_t ph = 0;
+        uint32_t it = 0;
+        for (;; it++) {
             const uint32_t tile = blockIdx.x + it * gridDim.x;
             if (tile >= n_tiles) break;
-            const uint32_t row = tile * kTile + tg;
-            const bool live = row < M;
-            // d out1 = [d sigma * d act / d out0, d feat(15)]
-            {
-                uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
+            const uint32_t e = it % kRing, rp = (it / kRing) & 1u;
+            const bool live = tile * kTile + tg < M;
+            // ---- dZ of the last layer (16 columns) ----
+            uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
+            if (view) {
                 if (live) {
-                    const float sg = __ldg(a.sigma + row);
+                    // d out = d rgb * d act / d out from the activated colour (exp: rgb; clamped exp: rgb below the clamp; sigmoid:
+                    // rgb (1 - rgb)); columns 3.. of the padded output carry no gradient
+                    float d[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (a.color_act == 2) d[k] = h0[k] * h1[k] * (1.0f - h1[k]);
+                        else if (a.color_act == 3) d[k] = (h1[k] < 5.0f) ? h0[k] * h1[k] : 0.f;
+                        else d[k] = h0[k] * h1[k];
+                    }
+                    z0.x = pack_h2(d[0], d[1]); z0.y = pack_h2(d[2], 0.f);
+                }
+            } else {
+                // [d sigma * d act / d out0, d feat(15)]: the feature gradients come from the view group through the ring
+                tc::mbar_wait(din_full + 8 * e, rp);
+                const uint8_t* di = smem + a.din_off + e * (2 * kPanel);
+                const uint4 u = *reinterpret_cast<const uint4*>(di + tg * 16);
+                const uint4 v = *reinterpret_cast<const uint4*>(di + kPanel + tg * 16);
+                tc::mbar_arrive(din_empty + 8 * e);
+                if (live) {
+                    const float sg = h1[0];
                     float dact;
                     if (a.density_act == 0) dact = sg;                        // trunc_exp backward: g * exp(x) (activation.py:18-21)
                     else dact = 1.0f - expf(-a.beta * sg);                    // softplus' = sigmoid(beta x) = 1 - exp(-beta y)
-                    const __half d0 = __float2half_rn(__ldg(a.d_sigma + row) * dact);
-                    const __half* d_tile = a.d_in2 + (size_t)tile * (a.ld2 * kTile);
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(d_tile + tg * 8));
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(d_tile + (kTile + tg) * 8));
+                    const uint32_t s0 = (uint32_t)__half_as_ushort(__float2half_rn(h0[0] * dact));
                     // shift the 15 feature gradients up by one half and put d out0 in front
-                    const uint32_t s0 = (uint32_t)__half_as_ushort(d0);
                     z0.x = s0 | (u.x << 16); z0.y = (u.x >> 16) | (u.y << 16); z0.z = (u.y >> 16) | (u.z << 16); z0.w = (u.z >> 16) | (u.w << 16);
                     z1.x = (u.w >> 16) | (v.x << 16); z1.y = (v.x >> 16) | (v.y << 16); z1.z = (v.y >> 16) | (v.z << 16); z1.w = (v.z >> 16) | (v.w << 16);
                 }
-                uint8_t* dzt = dz_base;
-                *reinterpret_cast<uint4*>(dzt + tg * 16) = z0;
-                *reinterpret_cast<uint4*>(dzt + kPanel + tg * 16) = z1;
             }
-            tc::mbar_wait(in_full + 8 * st, iter & 1u);
+            *reinterpret_cast<uint4*>(dz_base + tg * 16) = z0;
+            *reinterpret_cast<uint4*>(dz_base + kPanel + tg * 16) = z1;
+            fetch_head(blockIdx.x + (it + 1) * gridDim.x);      // next tile's head inputs: in flight during this tile's chain
             tc::fence_async_smem();
             tc::fence_before_sync();
-            tc::named_bar_sync(1 + gI, kTile);
+            tc::named_bar_sync(1 + ci, kTile);
+            const uint32_t next_tile = blockIdx.x + (it + 1) * gridDim.x;
             uint32_t cur = 0;
-            for (int l = (int)L - 1; l >= 0; l--) {
-                const uint32_t K = a.dims[l];
+            for (int l = (int)kL - 1; l >= 0; l--) {
+                const uint32_t K = c.dims[l];
+                tc::mbar_wait(tf + 8 * l, it & 1u);              // this layer's saved tile has landed
                 if (tg == 0) {
                     tc::fence_after_sync();
-                    issue_plan(tmem, plans[(st * L + l) * 2], iter > 0);
-                    issue_plan(tmem, plans[(st * L + l) * 2 + 1], false);
-                    tc::mma_commit(done_g);
+                    issue_plan(tmem, pl[2 * l], it > 0);
+                    issue_plan(tmem, pl[2 * l + 1], false);
+                    tc::mma_commit(done_c);
                 }
-                tc::mbar_wait(done_g, ph);
+                tc::mbar_wait(done_c, ph);
                 ph ^= 1;
                 tc::fence_after_sync();
                 if (l > 0) {
-                    uint8_t* nxt = dz_base + (cur ^ 1) * a.dz_bytes;
-                    const uint8_t* in_tile = smem + a.in_off[l] + st * a.in_stage_bytes;
+                    uint8_t* nxt = dz_base + (cur ^ 1) * c.dz_bytes;
+                    const uint8_t* in_tile = smem + c.in_off[l];
                     for (uint32_t c0 = 0; c0 < K; c0 += 16) {
                         float v[16];
                         tc::tmem_ld16(lane_addr + c0, v);
                         const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8) * kPanel + tg * 16);
                         const uint4 m1 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8 + 1) * kPanel + tg * 16);
-                        const __half* h0 = reinterpret_cast<const __half*>(&m0);
-                        const __half* h1 = reinterpret_cast<const __half*>(&m1);
+                        const __half* q0 = reinterpret_cast<const __half*>(&m0);
+                        const __half* q1 = reinterpret_cast<const __half*>(&m1);
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            if (!(__half2float(h0[i]) > 0.f)) v[i] = 0.f;
-                            if (!(__half2float(h1[i]) > 0.f)) v[8 + i] = 0.f;
+                            if (!(__half2float(q0[i]) > 0.f)) v[i] = 0.f;
+                            if (!(__half2float(q1[i]) > 0.f)) v[8 + i] = 0.f;
                         }
                         uint4 lo, hi;
                         pack16(v, lo, hi);
@@ -219,46 +258,53 @@ field_backward_ws_kernel(const BwsArgs a) {
                     }
                     tc::fence_async_smem();
                     tc::fence_before_sync();
-                    tc::named_bar_sync(1 + gI, kTile);
+                    tc::named_bar_sync(1 + ci, kTile);
+                    // every read of this layer's saved tile (MMA and ReLU mask) is done: refill its slot for the next tile
+                    if (tg == 0 && next_tile < n_tiles) load_tensor(next_tile, (uint32_t)l);
                 } else {
-                    // every MMA that reads this stage's tiles has completed: hand the stage back and refill it
-                    tc::mbar_arrive(in_empty + 8 * st);
-                    // d enc -> fp16 tile for the scatter warps
-                    tc::mbar_wait(enc_empty + 8 * e, (iter & 1u) ^ 1u);
-                    uint8_t* de = smem + a.enc_off + e * a.enc_stage_bytes;
-                    for (uint32_t c0 = 0; c0 < F; c0 += 16) {
+                    if (tg == 0 && next_tile < n_tiles) load_tensor(next_tile, 0u);
+                    if (view) {
+                        // d in2[:, :16] -> the grid group (column 15 is an SH input: ignored there)
+                        tc::mbar_wait(din_empty + 8 * e, rp ^ 1u);
                         float v[16];
-                        tc::tmem_ld16(lane_addr + c0, v);
+                        tc::tmem_ld16(lane_addr, v);
                         uint4 lo, hi;
                         pack16(v, lo, hi);
-                        *reinterpret_cast<uint4*>(de + (c0 / 8) * kPanel + tg * 16) = lo;
-                        *reinterpret_cast<uint4*>(de + (c0 / 8 + 1) * kPanel + tg * 16) = hi;
-                    }
-                    tc::mbar_arrive(enc_full + 8 * e);
-                    if (tg == 0) {
-                        const uint32_t nt = blockIdx.x + (it + kBwsGroups) * gridDim.x;
-                        if (nt < n_tiles) {
-                            tc::mbar_wait(in_empty + 8 * st, iter & 1u);
-                            load_tile(nt, st);
+                        uint8_t* di = smem + a.din_off + e * (2 * kPanel);
+                        *reinterpret_cast<uint4*>(di + tg * 16) = lo;
+                        *reinterpret_cast<uint4*>(di + kPanel + tg * 16) = hi;
+                        tc::mbar_arrive(din_full + 8 * e);
+                    } else {
+                        // d enc -> fp16 tile for the scatter warps
+                        tc::mbar_wait(enc_empty + 8 * e, rp ^ 1u);
+                        uint8_t* de = smem + a.enc_off + e * a.enc_stage_bytes;
+                        for (uint32_t c0 = 0; c0 < K; c0 += 16) {
+                            float v[16];
+                            tc::tmem_ld16(lane_addr + c0, v);
+                            uint4 lo, hi;
+                            pack16(v, lo, hi);
+                            *reinterpret_cast<uint4*>(de + (c0 / 8) * kPanel + tg * 16) = lo;
+                            *reinterpret_cast<uint4*>(de + (c0 / 8 + 1) * kPanel + tg * 16) = hi;
                         }
+                        tc::mbar_arrive(enc_full + 8 * e);
                     }
                     tc::fence_before_sync();
-                    tc::named_bar_sync(1 + gI, kTile);      // TMEM work columns and dZ buffer 0 are rewritten by the next tile
+                    tc::named_bar_sync(1 + ci, kTile);      // TMEM work columns and dZ buffer 0 are rewritten by the next tile
                 }
                 cur ^= 1;
             }
         }
-        // reduce this CTA's weight-gradient accumulators (TMEM lane i = input feature i) into global memory
-        if (iter > 0) {
+        // reduce this chain's weight-gradient accumulators (TMEM lane i = input feature i) into global memory
+        if (it > 0) {
             tc::fence_after_sync();
-            for (uint32_t l = 0; l < L; l++) {
-                const uint32_t K = a.dims[l], N = a.dims[l + 1];
+            for (uint32_t l = 0; l < kL; l++) {
+                const uint32_t K = c.dims[l], N = c.dims[l + 1];
                 for (uint32_t c0 = 0; c0 < N; c0 += 16) {
                     float v[16];
-                    tc::tmem_ld16(lane_addr + a.acc_col[l] + c0, v);   // warp-collective: every lane participates
+                    tc::tmem_ld16(lane_addr + c.acc_col[l] + c0, v);   // warp-collective: every lane participates
                     if (tg < K) {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) red_add_f32(a.dw[l] + (size_t)(c0 + i) * K + tg, v[i]);
+                        for (int i = 0; i < 16; i++) red_add_f32(c.dw[l] + (size_t)(c0 + i) * K + tg, v[i]);
                     }
                 }
             }
@@ -274,55 +320,72 @@ field_backward_ws_kernel(const BwsArgs a) {
 
 using namespace ngp;
 
-extern "C" int ngp_field_backward_ws(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
-                                     uint32_t ld2, const void* enc, const int32_t* offsets, const float* feat_weights,
-                                     float bound, float S, uint32_t H, uint32_t L, uint32_t gridtype, int align_corners,
-                                     uint32_t interp, const void* const* weights, const void* const* acts,
-                                     const uint32_t* dims, uint32_t M, const int32_t* m_dev, int density_act, float beta,
-                                     void* grad_table, float* const* dweights, ngp_stream_t stream) {
+extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float* sigma, const float* d_rgb,
+                                       const float* rgb, const void* enc, const void* const* grid_acts, const void* in2,
+                                       const void* const* view_acts, const int32_t* offsets, const float* feat_weights,
+                                       float bound, float S, uint32_t H, uint32_t L, uint32_t gridtype, int align_corners,
+                                       uint32_t interp, const void* const* grid_weights, const uint32_t* grid_dims,
+                                       const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
+                                       const int32_t* m_dev, int density_act, float beta, int color_act, void* grad_table,
+                                       float* const* grid_dweights, float* const* view_dweights, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
-    if (!xyzs || !d_sigma || !sigma || !d_in2 || !enc || !offsets || !weights || !acts || !dims || !grad_table || !dweights) return NGP_ERR_NULL;
-    if (L == 0 || L > kMaxLevels || L % 4 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
-    if (dims[0] != 2 * L || dims[3] != 16 || ld2 < 16 || ld2 % 8) return NGP_ERR_UNSUPPORTED;
+    if (!xyzs || !d_sigma || !sigma || !d_rgb || !rgb || !enc || !grid_acts || !in2 || !view_acts || !offsets || !grid_weights ||
+        !grid_dims || !view_weights || !view_dims || !grad_table || !grid_dweights || !view_dweights)
+        return NGP_ERR_NULL;
+    if (L == 0 || L > kMaxLevels || L % 4 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1 ||
+        color_act < 1 || color_act > 3)
+        return NGP_ERR_BAD_ARG;
+    if (grid_dims[0] != 2 * L || grid_dims[3] != 16 || view_dims[3] != 16 || view_dims[0] < 16) return NGP_ERR_UNSUPPORTED;
     BwsArgs a = {};
-    a.xyzs = xyzs; a.d_sigma = d_sigma; a.sigma = sigma; a.d_in2 = (const __half*)d_in2; a.ld2 = ld2;
+    a.xyzs = xyzs; a.d_sigma = d_sigma; a.sigma = sigma; a.d_rgb = d_rgb; a.rgb = rgb;
     a.g = {nullptr, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
-    uint32_t off = 0, max_n = 0, max_k = 0, acc = 0;
-    for (uint32_t l = 0; l <= kBwsLayers; l++) {
-        if (dims[l] == 0 || dims[l] % 16 || dims[l] > 128) return NGP_ERR_UNSUPPORTED;
-        a.dims[l] = dims[l];
+    uint32_t off = 0;
+    for (uint32_t ci = 0; ci < kChains; ci++) {
+        Chain& c = a.c[ci];
+        const uint32_t* dims = ci == 0 ? view_dims : grid_dims;
+        const void* const* w = ci == 0 ? view_weights : grid_weights;
+        float* const* dw = ci == 0 ? view_dweights : grid_dweights;
+        const void* const* acts = ci == 0 ? view_acts : grid_acts;
+        uint32_t max_k = 0, max_n = 0;
+        for (uint32_t l = 0; l <= kL; l++) {
+            if (dims[l] == 0 || dims[l] % 16 || dims[l] > 128) return NGP_ERR_UNSUPPORTED;
+            c.dims[l] = dims[l];
+        }
+        for (uint32_t l = 0; l < kL; l++) {
+            if (!w[l] || !dw[l] || (l > 0 && !acts[l - 1])) return NGP_ERR_NULL;
+            c.w[l] = (const __half*)w[l];
+            c.dw[l] = dw[l];
+            c.in[l] = (const __half*)(l == 0 ? (ci == 0 ? in2 : enc) : acts[l - 1]);
+            if (!aligned(c.w[l], 16) || !aligned(c.in[l], 16)) return NGP_ERR_ALIGN;
+            max_k = std::max(max_k, dims[l]);
+            max_n = std::max(max_n, dims[l + 1]);
+        }
+        uint32_t acc = max_k;
+        for (uint32_t l = 0; l < kL; l++) { c.acc_col[l] = acc; acc += dims[l + 1]; }
+        if (acc > kChainCols) return NGP_ERR_UNSUPPORTED;
+        c.dz_bytes = kTile * std::max(max_n, max_k) * 2;
     }
-    for (uint32_t l = 0; l < kBwsLayers; l++) {
-        if (!weights[l] || !dweights[l] || (l > 0 && !acts[l - 1])) return NGP_ERR_NULL;
-        a.w[l] = (const __half*)weights[l];
-        a.dw[l] = dweights[l];
-        a.in[l] = (const __half*)(l == 0 ? enc : acts[l - 1]);
-        if (!aligned(a.w[l], 16) || !aligned(a.in[l], 16)) return NGP_ERR_ALIGN;
-        a.w_off[l] = off;
-        off += dims[l] * dims[l + 1] * 2;
-        max_n = std::max(max_n, dims[l + 1]);
-        max_k = std::max(max_k, dims[l]);
-    }
-    acc = max_k;
-    for (uint32_t l = 0; l < kBwsLayers; l++) { a.acc_col[l] = acc; acc += dims[l + 1]; }
-    if (acc > kGroupCols) return NGP_ERR_UNSUPPORTED;
-    if (!aligned(grad_table, 16) || !aligned(d_in2, 16)) return NGP_ERR_ALIGN;
+    if (!aligned(grad_table, 16)) return NGP_ERR_ALIGN;
+    // shared memory: weights | saved tiles of both chains | dZ ping-pong of both chains | d enc ring | d in2 ring | control.
+    // The M = 128 MN-major A view of a saved tile spans 16 panels (32 KiB) from its start (rows past dims[l] only feed TMEM
+    // lanes that are never read): the buffers that follow the tiles are larger than that.
+    for (uint32_t ci = 0; ci < kChains; ci++)
+        for (uint32_t l = 0; l < kL; l++) { a.c[ci].w_off[l] = off; off += a.c[ci].dims[l] * a.c[ci].dims[l + 1] * 2; }
     off = (off + 127) & ~127u;
-    uint32_t in_stage = 0;
-    for (uint32_t l = 0; l < kBwsLayers; l++) { a.in_off[l] = off + in_stage; in_stage += kTile * dims[l] * 2; }
-    // the M = 128 MN-major A view of an input tile spans 16 panels (32 KiB) from the tile start: keep that inside the
-    // allocation (rows past dims[l] only feed TMEM lanes that are never read); the next stage / dZ buffers follow
-    a.in_stage_bytes = in_stage;
-    off += kInStages * in_stage;
-    a.dz_off = off; a.dz_bytes = kTile * std::max(max_n, max_k) * 2;
-    off += 2 * kBwsGroups * a.dz_bytes;
-    a.enc_off = off; a.enc_stage_bytes = kTile * dims[0] * 2;
-    off += kEncStages * a.enc_stage_bytes;
+    for (uint32_t ci = 0; ci < kChains; ci++)
+        for (uint32_t l = 0; l < kL; l++) { a.c[ci].in_off[l] = off; off += kTile * a.c[ci].dims[l] * 2; }
+    const uint32_t tiles_end = off;
+    for (uint32_t ci = 0; ci < kChains; ci++) { a.c[ci].dz_off = off; off += 2 * a.c[ci].dz_bytes; }
+    a.enc_off = off; a.enc_stage_bytes = kTile * grid_dims[0] * 2;
+    off += kRing * a.enc_stage_bytes;
+    a.din_off = off;
+    off += kRing * 2 * kPanel;
     a.ctrl_off = off;
-    const uint32_t last_in_end = a.in_off[kBwsLayers - 1] + (kInStages - 1) * in_stage + 18 * kPanel;
-    const uint32_t smem_bytes = std::max(off + kBCtrlBytes, last_in_end);
+    a.plans_off = (kBLevels + L * (uint32_t)sizeof(LevelConst) + 15) & ~15u;
+    const uint32_t smem_bytes = std::max(off + a.plans_off + kChains * kL * 2 * (uint32_t)sizeof(MmaPlan), tiles_end + 16 * kPanel);
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
-    a.M = M; a.m_dev = m_dev; a.grad_table = (__half*)grad_table; a.density_act = density_act; a.beta = beta;
+    a.M = M; a.m_dev = m_dev; a.grad_table = (__half*)grad_table;
+    a.density_act = density_act; a.color_act = color_act; a.beta = beta;
     static thread_local uint32_t configured = 0;
     if (smem_bytes > configured) {
         if (cudaFuncSetAttribute(field_backward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {

@@ -98,7 +98,6 @@ class _fused_field(Function):
         d_rgb = d_rgb.contiguous().float()
         dw1 = [torch.zeros(p1[l + 1], p1[l], dtype=torch.float32, device=dev) for l in range(n1)]
         dw2 = [torch.zeros(p2[l + 1], p2[l], dtype=torch.float32, device=dev) for l in range(n2)]
-        d_in2 = torch.empty(in2.shape[0], p2[0], dtype=torch.float16, device=dev)
         sink = enc.grad_sink
         if sink is not None:
             if sink.shape != table.shape or sink.dtype != table.dtype:
@@ -107,14 +106,12 @@ class _fused_field(Function):
         else:
             gtable = torch.zeros_like(table)
         S, H, L, gt, ac, ip = _grid_scalars(enc)
-        st = _lib.stream()
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
-        _lib.call("ngp_mlp_backward_rgb", _lib.ptr(d_rgb), _lib.ptr(rgb), int(color_act), _lib.ptr(in2), p2[0], _ptr_array(w2),
-                  _ptr_array(acts2), c2, n2, M, None, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), 1, st)
-        _lib.call("ngp_field_backward_ws", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_in2), p2[0],
-                  _lib.ptr(enc_buf), _lib.ptr(enc.offsets), _lib.ptr(fw) if has_fw else None, float(bound), S, H, L, gt, ac, ip,
-                  _ptr_array(w1), _ptr_array(acts1), c1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), st)
+        _lib.call("ngp_field_backward_full", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_rgb), _lib.ptr(rgb),
+                  _lib.ptr(enc_buf), _ptr_array(acts1), _lib.ptr(in2), _ptr_array(acts2), _lib.ptr(enc.offsets),
+                  _lib.ptr(fw) if has_fw else None, float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
+                  int(density_act), float(beta), int(color_act), _lib.ptr(gtable), _ptr_array(dw1), _ptr_array(dw2), _lib.stream())
         gw = [dw1[l][:d1[l + 1], :d1[l]].to(wdt[l]) for l in range(n1)]
         vw = [dw2[l][:d2[l + 1], :d2[l]].to(wdt[n1 + l]) for l in range(n2)]
         return (None, None, None, None if sink is not None else gtable, None, None, *gw, *vw)

@@ -133,9 +133,9 @@ class FusedTrainStep:
       * near_far_from_aabb (renderer.py:139-158, ~10 torch kernels)      -> inside the marching kernel
       * march pass 1, step_counter.item() HOST SYNC, allocation, pass 2   -> the sample count stays on the device
         (raymarching.py:301-311)                                             (m_dev), buffers have a fixed capacity
-      * dirs normalisation, encoder, MLPs, activations (~60 kernels)      -> ngp_field_forward_density + ngp_mlp_forward_rgb
+      * dirs normalisation, encoder, MLPs, activations (~60 kernels)      -> ngp_field_forward_full
       * composite fwd, bg blend, MSE, autograd of all that, composite bwd -> ngp_composite_train_mse
-      * MLP / encoder backward incl. zeros_like(embeddings)               -> ngp_mlp_backward_rgb + ngp_field_backward_density
+      * MLP / encoder backward incl. zeros_like(embeddings)               -> ngp_field_backward_full
       * GradScaler.unscale_/inf check/Adam/zero_grad                      -> ngp_check_finite + ngp_fused_adam
     Numerically it is the autograd path of TrainStep (same kernels for march / field / MLP / Adam, same loss); the
     equality is tested in tests/test_gpu_trainstep.py.  Eligibility = the fused-field conditions of NeRFNetwork plus an
@@ -216,7 +216,7 @@ class FusedTrainStep:
         self.enc_buf = torch.empty(cap_t, self.p1[0], **f16)
         self.acts1 = [torch.empty(cap_t, self.p1[l + 1], **f16) for l in range(2)]
         self.acts2 = [torch.empty(cap_t, self.p2[l + 1], **f16) for l in range(2)]
-        self.in2, self.d_in2 = torch.empty(cap_t, self.p2[0], **f16), torch.empty(cap_t, self.p2[0], **f16)
+        self.in2 = torch.empty(cap_t, self.p2[0], **f16)
         self.sigma, self.rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.d_sigma, self.d_rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.image, self.ray_loss, self.loss = torch.zeros(N, 3, **f32), torch.zeros(N, **f32), torch.zeros(1, **f32)
@@ -264,11 +264,10 @@ class FusedTrainStep:
         _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
                   float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
                   P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), st)
-        _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), self.p2[0], w2, a2, c2, 3, cap,
-                  self._m_dev, 1, P(self.d_in2), self.p2[0], self._ptrs(self._w_grad_views[3:]), 1, st)
-        _lib.call("ngp_field_backward_ws", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), self.p2[0],
-                  P(self.enc_buf), P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, cap,
-                  self._m_dev, self._density_act, float(opt.beta), P(self.table_grad), self._ptrs(self._w_grad_views[:3]), st)
+        _lib.call("ngp_field_backward_full", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_rgb), P(self.rgb), P(self.enc_buf),
+                  a1, P(self.in2), a2, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap,
+                  self._m_dev, self._density_act, float(opt.beta), self._color_act, P(self.table_grad),
+                  self._ptrs(self._w_grad_views[:3]), self._ptrs(self._w_grad_views[3:]), st)
 
     def _launch_check(self):
         st = _lib.stream()
