@@ -11,8 +11,9 @@
 //   * warps 20-23, the GRID group: the same chain for grid_mlp, one tile behind the view group; its last dH is d enc,
 //     handed to the scatter warps through a second ring.
 //   * both groups fetch their saved activations (tile-panel layout of field_ws.cu) with BULK ASYNC COPIES, one per tensor
-//     and tile, completing on an mbarrier; a tensor's slot is refilled for the next tile as soon as its layer is done, so
-//     the loads run two layers ahead without a second set of buffers.
+//     and tile, completing on an mbarrier; a tensor's slot is refilled for the next tile as soon as its layer's MMAs have
+//     retired, so the loads run two layers ahead without a second set of buffers.  Per layer dH is issued before dW: the
+//     epilogue only waits for dH, the dW accumulation overlaps it.
 //   * warps 0-15 only scatter: thread (row, g) takes levels g, g+4, ... of its sample; runs of consecutive samples in the
 //     same cell are merged by a segmented shuffle reduction in packed fp16x2 and only run heads issue reductions
 //     (red.global.add.noftz.v2.f16x2 for an aligned x-neighbour pair).  The scatter is the throughput bound of the backward
@@ -39,7 +40,7 @@ constexpr uint32_t kL = 3;
 constexpr uint32_t kTFull = 0;                                   // [chain][layer]
 constexpr uint32_t kEncFull = kTFull + 8 * kChains * kL, kEncEmpty = kEncFull + 8 * kRing;
 constexpr uint32_t kDinFull = kEncEmpty + 8 * kRing, kDinEmpty = kDinFull + 8 * kRing;
-constexpr uint32_t kDone = kDinEmpty + 8 * kRing, kSlot = kDone + 8 * kChains;
+constexpr uint32_t kDone = kDinEmpty + 8 * kRing, kTail = kDone + 8 * kChains, kSlot = kTail + 8 * kChains;
 constexpr uint32_t kBLevels = (kSlot + 4 + 15) & ~15u;           // LevelConst[L], then the MMA plans
 
 struct Chain {
@@ -70,7 +71,7 @@ field_backward_ws_kernel(const BwsArgs a) {
     const uint32_t t_full = tc::smem_u32(ctrl + kTFull);
     const uint32_t enc_full = tc::smem_u32(ctrl + kEncFull), enc_empty = tc::smem_u32(ctrl + kEncEmpty);
     const uint32_t din_full = tc::smem_u32(ctrl + kDinFull), din_empty = tc::smem_u32(ctrl + kDinEmpty);
-    const uint32_t done = tc::smem_u32(ctrl + kDone);
+    const uint32_t done = tc::smem_u32(ctrl + kDone), tail = tc::smem_u32(ctrl + kTail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kSlot);
     LevelConst* s_lv = reinterpret_cast<LevelConst*>(ctrl + kBLevels);
     MmaPlan* plans = reinterpret_cast<MmaPlan*>(ctrl + a.plans_off);  // [chain][layer][0 = dW, 1 = dH]
@@ -82,7 +83,7 @@ field_backward_ws_kernel(const BwsArgs a) {
             tc::mbar_init(enc_full + 8 * s, kTile); tc::mbar_init(enc_empty + 8 * s, kScatterThreads);
             tc::mbar_init(din_full + 8 * s, kTile); tc::mbar_init(din_empty + 8 * s, kTile);
         }
-        for (uint32_t ci = 0; ci < kChains; ci++) tc::mbar_init(done + 8 * ci, 1);
+        for (uint32_t ci = 0; ci < kChains; ci++) { tc::mbar_init(done + 8 * ci, 1); tc::mbar_init(tail + 8 * ci, 1); }
     }
     for (uint32_t ci = 0; ci < kChains; ci++)
         for (uint32_t l = 0; l < kL; l++) load_weight_tile(smem + a.c[ci].w_off[l], a.c[ci].w[l], a.c[ci].dims[l + 1], a.c[ci].dims[l]);
@@ -151,7 +152,7 @@ field_backward_ws_kernel(const BwsArgs a) {
         const Chain& c = a.c[ci];
         const uint32_t tg = threadIdx.x - kScatterThreads - ci * kTile;   // row inside the tile == TMEM lane
         const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16) + ci * kChainCols;
-        const uint32_t done_c = done + 8 * ci, tf = t_full + 8 * ci * kL;
+        const uint32_t done_c = done + 8 * ci, tail_c = tail + 8 * ci, tf = t_full + 8 * ci * kL;
         uint8_t* dz_base = smem + c.dz_off;
         const MmaPlan* pl = plans + ci * kL * 2;
         auto load_tensor = [&](uint32_t tile, uint32_t l) {               // one thread: bulk async copy of one saved tile
@@ -228,14 +229,19 @@ field_backward_ws_kernel(const BwsArgs a) {
                 const uint32_t K = c.dims[l];
                 tc::mbar_wait(tf + 8 * l, it & 1u);              // this layer's saved tile has landed
                 if (tg == 0) {
+                    // dH first: it is all the epilogue waits for.  The (longer) dW accumulation is issued behind it and runs on
+                    // the tensor core while the chain's warps do the epilogue; the NEXT commit covers it (MMAs retire in order).
                     tc::fence_after_sync();
-                    issue_plan(tmem, pl[2 * l], it > 0);
                     issue_plan(tmem, pl[2 * l + 1], false);
                     tc::mma_commit(done_c);
+                    issue_plan(tmem, pl[2 * l], it > 0);
+                    if (l == 0) tc::mma_commit(tail_c);          // the tile's last MMA group completes on its own barrier
                 }
                 tc::mbar_wait(done_c, ph);
                 ph ^= 1;
                 tc::fence_after_sync();
+                // dW of the previous layer (l + 1) has retired with this commit: its saved tile can be refilled for the next tile
+                if (tg == 0 && l + 1 < (int)kL && next_tile < n_tiles) load_tensor(next_tile, (uint32_t)(l + 1));
                 if (l > 0) {
                     uint8_t* nxt = dz_base + (cur ^ 1) * c.dz_bytes;
                     const uint8_t* in_tile = smem + c.in_off[l];
@@ -259,10 +265,7 @@ field_backward_ws_kernel(const BwsArgs a) {
                     tc::fence_async_smem();
                     tc::fence_before_sync();
                     tc::named_bar_sync(1 + ci, kTile);
-                    // every read of this layer's saved tile (MMA and ReLU mask) is done: refill its slot for the next tile
-                    if (tg == 0 && next_tile < n_tiles) load_tensor(next_tile, (uint32_t)l);
                 } else {
-                    if (tg == 0 && next_tile < n_tiles) load_tensor(next_tile, 0u);
                     if (view) {
                         // d in2[:, :16] -> the grid group (column 15 is an SH input: ignored there)
                         tc::mbar_wait(din_empty + 8 * e, rp ^ 1u);
@@ -288,6 +291,10 @@ field_backward_ws_kernel(const BwsArgs a) {
                         }
                         tc::mbar_arrive(enc_full + 8 * e);
                     }
+                    // dW of layer 0 still reads dZ buffer 0 and the layer-0 saved tile: wait for its commit before the next tile
+                    // rewrites them
+                    tc::mbar_wait(tail_c, it & 1u);
+                    if (tg == 0 && next_tile < n_tiles) load_tensor(next_tile, 0u);
                     tc::fence_before_sync();
                     tc::named_bar_sync(1 + ci, kTile);      // TMEM work columns and dZ buffer 0 are rewritten by the next tile
                 }
