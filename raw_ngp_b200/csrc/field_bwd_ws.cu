@@ -19,6 +19,7 @@
 //     (red.global.add.noftz.v2.f16x2 for an aligned x-neighbour pair).  The scatter is the throughput bound of the backward
 //     pass; the rings keep these warps busy while the tensor-core chains of the next tiles run.
 #include "field_core.cuh"
+#include "tile_sw.cuh"
 
 namespace ngp {
 namespace {
@@ -63,7 +64,7 @@ struct BwsArgs {
 
 __global__ void __launch_bounds__(kBwsThreads, 1)
 field_backward_ws_kernel(const BwsArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t M = a.M;
     if (a.m_dev) M = min(M, (uint32_t)__ldg(a.m_dev));
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -86,7 +87,7 @@ field_backward_ws_kernel(const BwsArgs a) {
         for (uint32_t ci = 0; ci < kChains; ci++) { tc::mbar_init(done + 8 * ci, 1); tc::mbar_init(tail + 8 * ci, 1); }
     }
     for (uint32_t ci = 0; ci < kChains; ci++)
-        for (uint32_t l = 0; l < kL; l++) load_weight_tile(smem + a.c[ci].w_off[l], a.c[ci].w[l], a.c[ci].dims[l + 1], a.c[ci].dims[l]);
+        for (uint32_t l = 0; l < kL; l++) tsw::load_weight_tile(smem + a.c[ci].w_off[l], a.c[ci].w[l], a.c[ci].dims[l + 1], a.c[ci].dims[l]);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kChains * kL) {
         const uint32_t i = threadIdx.x - 64, ci = i / kL, l = i % kL;
         const Chain& c = a.c[ci];
@@ -94,19 +95,21 @@ field_backward_ws_kernel(const BwsArgs a) {
         // dZ of layer l sits in the chain's ping-pong buffer (kL - 1 - l) & 1
         const uint32_t dz_saddr = tc::smem_u32(smem + c.dz_off + ((kL - 1 - l) & 1u) * c.dz_bytes);
         const uint32_t in_saddr = tc::smem_u32(smem + c.in_off[l]), w_saddr = tc::smem_u32(smem + c.w_off[l]);
-        MmaPlan& dw = plans[i * 2];       // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]  (MN-major views of row tiles)
+        // all operands are swizzled row-major tiles (tile_sw.cuh): saved input [128 x K], dZ [128 x N], weights [N x K]
+        MmaPlan& dw = plans[i * 2];       // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]: both MN-major views, k = sample rows
         dw.idesc = tc::instr_desc(kTile, N, true, true);
         dw.n_steps = kTile / 16; dw.d_col = ci * kChainCols + c.acc_col[l]; dw.pad = 0;
         for (uint32_t ks = 0; ks < kTile / 16; ks++) {
-            dw.step[ks].a = tc::smem_desc(in_saddr + ks * 256, 128, kPanel);
-            dw.step[ks].b = tc::smem_desc(dz_saddr + ks * 256, 128, kPanel);
+            // M = 128 > K: the MN blocks past the tile (stride = tile size) only feed TMEM lanes that are never read
+            dw.step[ks].a = tsw::desc_mnmajor(in_saddr, K, ks, kTile * K * 2);
+            dw.step[ks].b = tsw::desc_mnmajor(dz_saddr, N, ks, kTile * N * 2);
         }
-        MmaPlan& dh = plans[i * 2 + 1];   // dH [128 x K] = dZ_l [128 x N] * W_l [N x K]
+        MmaPlan& dh = plans[i * 2 + 1];   // dH [128 x K] = dZ_l [128 x N] (K-major) * W_l [N x K] (MN-major view: MN = K, k = N rows)
         dh.idesc = tc::instr_desc(kTile, K, false, true);
         dh.n_steps = N / 16; dh.d_col = ci * kChainCols; dh.pad = 0;
         for (uint32_t ks = 0; ks < N / 16; ks++) {
-            dh.step[ks].a = tc::smem_desc(dz_saddr + ks * 2 * kPanel, kPanel, 128);
-            dh.step[ks].b = tc::smem_desc(w_saddr + ks * 256, 128, N * 16);
+            dh.step[ks].a = tsw::desc_kmajor(dz_saddr, N, ks);
+            dh.step[ks].b = tsw::desc_mnmajor(w_saddr, K, ks, N * K * 2);
         }
     }
     load_level_consts(s_lv, a.g);
@@ -217,8 +220,8 @@ field_backward_ws_kernel(const BwsArgs a) {
                     z1.x = (u.w >> 16) | (v.x << 16); z1.y = (v.x >> 16) | (v.y << 16); z1.z = (v.y >> 16) | (v.z << 16); z1.w = (v.z >> 16) | (v.w << 16);
                 }
             }
-            *reinterpret_cast<uint4*>(dz_base + tg * 16) = z0;
-            *reinterpret_cast<uint4*>(dz_base + kPanel + tg * 16) = z1;
+            *reinterpret_cast<uint4*>(dz_base + tsw::chunk_off(16, tg, 0)) = z0;
+            *reinterpret_cast<uint4*>(dz_base + tsw::chunk_off(16, tg, 1)) = z1;
             fetch_head(blockIdx.x + (it + 1) * gridDim.x);      // next tile's head inputs: in flight during this tile's chain
             tc::fence_async_smem();
             tc::fence_before_sync();
@@ -248,8 +251,9 @@ field_backward_ws_kernel(const BwsArgs a) {
                     for (uint32_t c0 = 0; c0 < K; c0 += 16) {
                         float v[16];
                         tc::tmem_ld16(lane_addr + c0, v);
-                        const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8) * kPanel + tg * 16);
-                        const uint4 m1 = *reinterpret_cast<const uint4*>(in_tile + (c0 / 8 + 1) * kPanel + tg * 16);
+                        const uint32_t o0 = tsw::chunk_off(K, tg, c0 / 8), o1 = tsw::chunk_off(K, tg, c0 / 8 + 1);
+                        const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + o0);
+                        const uint4 m1 = *reinterpret_cast<const uint4*>(in_tile + o1);
                         const __half* q0 = reinterpret_cast<const __half*>(&m0);
                         const __half* q1 = reinterpret_cast<const __half*>(&m1);
 #pragma unroll
@@ -259,8 +263,8 @@ field_backward_ws_kernel(const BwsArgs a) {
                         }
                         uint4 lo, hi;
                         pack16(v, lo, hi);
-                        *reinterpret_cast<uint4*>(nxt + (c0 / 8) * kPanel + tg * 16) = lo;
-                        *reinterpret_cast<uint4*>(nxt + (c0 / 8 + 1) * kPanel + tg * 16) = hi;
+                        *reinterpret_cast<uint4*>(nxt + o0) = lo;        // dZ of layer l - 1 has the same width K
+                        *reinterpret_cast<uint4*>(nxt + o1) = hi;
                     }
                     tc::fence_async_smem();
                     tc::fence_before_sync();
@@ -355,7 +359,8 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
         const void* const* acts = ci == 0 ? view_acts : grid_acts;
         uint32_t max_k = 0, max_n = 0;
         for (uint32_t l = 0; l <= kL; l++) {
-            if (dims[l] == 0 || dims[l] % 16 || dims[l] > 128) return NGP_ERR_UNSUPPORTED;
+            // swizzled tiles of width 16 / 32 / 64 (tile_sw.cuh); wider layers use the two-kernel path of field.cu / mlp.cu
+            if (dims[l] != 16 && dims[l] != 32 && dims[l] != 64) return NGP_ERR_UNSUPPORTED;
             c.dims[l] = dims[l];
         }
         for (uint32_t l = 0; l < kL; l++) {
@@ -378,7 +383,7 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
     // lanes that are never read): the buffers that follow the tiles are larger than that.
     for (uint32_t ci = 0; ci < kChains; ci++)
         for (uint32_t l = 0; l < kL; l++) { a.c[ci].w_off[l] = off; off += a.c[ci].dims[l] * a.c[ci].dims[l + 1] * 2; }
-    off = (off + 127) & ~127u;
+    off = (off + 1023) & ~1023u;      // swizzle atoms are 1024-byte aligned
     for (uint32_t ci = 0; ci < kChains; ci++)
         for (uint32_t l = 0; l < kL; l++) { a.c[ci].in_off[l] = off; off += kTile * a.c[ci].dims[l] * 2; }
     const uint32_t tiles_end = off;

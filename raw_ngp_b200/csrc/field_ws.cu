@@ -12,12 +12,14 @@
 //     layers of grid_mlp and view_mlp as tcgen05.mma (M = 128, accumulators in the group's 128 TMEM columns), with the
 //     fp16 activations going TMEM -> registers -> shared memory between layers; tcgen05.commit on empty[s] hands the ring
 //     stage back to the gather warps as soon as the first layer has consumed it.
-// Saved activations (for the backward kernels) are written in the "tile-panel" layout, i.e. as the shared-memory image of
-// the tile: [tile][column / 8][row 0..127][8 halves], so that every warp store covers 512 contiguous bytes and the
-// backward kernels fetch a whole tile with one bulk copy.
+// All tiles are swizzled row-major (tile_sw.cuh: the UMMA SWIZZLE_32B/64B/128B canonical layouts), so the tensor core reads
+// its operands without bank conflicts.  Saved activations (for the backward kernel) are written to global memory as the
+// shared-memory image of the tile ("tile-panel" layout), so that the backward kernel fetches a whole tile with one bulk
+// async copy.
 //
 // The reference runs this as ~60 PyTorch kernels per step (encoder, 6 nn.Linear, activations, SHEncoder, cat, casts).
 #include "field_core.cuh"
+#include "tile_sw.cuh"
 
 namespace ngp {
 namespace {
@@ -60,7 +62,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_h2(a, 
 template <bool LDIR>
 __global__ void __launch_bounds__(kWsThreads, 1)
 field_forward_ws_kernel(const WsArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t M = a.M;
     if (a.m_dev) M = min(M, (uint32_t)__ldg(a.m_dev));   // sample count produced on the device (no host sync)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -79,7 +81,7 @@ field_forward_ws_kernel(const WsArgs a) {
         }
         for (uint32_t gI = 0; gI < kMlpGroups; gI++) tc::mbar_init(done_s + 8 * gI, 1);
     }
-    for (uint32_t l = 0; l < kWsLayers; l++) load_weight_tile(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
+    for (uint32_t l = 0; l < kWsLayers; l++) tsw::load_weight_tile(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kMlpGroups * kWsLayers) {
         const uint32_t i = threadIdx.x - 64, gI = i / kWsLayers, l = i % kWsLayers;
         const uint32_t K = a.K[l], N = a.N[l];
@@ -88,9 +90,9 @@ field_forward_ws_kernel(const WsArgs a) {
         MmaPlan& pl = plans[i];
         pl.idesc = tc::instr_desc(kTile, N, false, false);
         pl.n_steps = K / 16; pl.d_col = gI * kGroupTmemCols; pl.pad = 0;
-        for (uint32_t ks = 0; ks < K / 16; ks++) {
-            pl.step[ks].a = tc::smem_desc(a_saddr + ks * 2 * kPanel, kPanel, 128);
-            pl.step[ks].b = tc::smem_desc(w_saddr + ks * 2 * (N * 16), N * 16, 128);
+        for (uint32_t ks = 0; ks < K / 16; ks++) {     // both operands K-major swizzled tiles of width K
+            pl.step[ks].a = tsw::desc_kmajor(a_saddr, K, ks);
+            pl.step[ks].b = tsw::desc_kmajor(w_saddr, K, ks);
         }
     }
     load_level_consts(s_lv, a.g);
@@ -117,7 +119,6 @@ field_forward_ws_kernel(const WsArgs a) {
             const bool inside = x[0] >= 0 && x[0] <= 1 && x[1] >= 0 && x[1] <= 1 && x[2] >= 0 && x[2] <= 1;
             const float xc[3] = {fminf(fmaxf(x[0], 0.f), 1.f), fminf(fmaxf(x[1], 0.f), 1.f), fminf(fmaxf(x[2], 0.f), 1.f)};
             uint8_t* a0 = smem + a.a0_off + s * a.a0_stage_bytes;
-            __half* enc_tile = a.enc_out ? a.enc_out + (size_t)tile * (F * kTile) : nullptr;
             bool waited = false;
             for (uint32_t level = grp; level < g.L; level += 2 * kGatherGroups) {
                 const uint32_t la = level, lb = level + kGatherGroups;       // L % 8 == 0
@@ -138,14 +139,10 @@ field_forward_ws_kernel(const WsArgs a) {
                     tc::mbar_wait(empty_s + 8 * s, ((it / kStages) & 1u) ^ 1u);
                     waited = true;
                 }
-                // features 2l, 2l+1 of row r: panel l / 4, byte (l % 4) * 4 of the row's 16-byte chunk
-                const uint32_t oa = (la / 4) * kPanel + r * 16 + (la % 4) * 4, ob = (lb / 4) * kPanel + r * 16 + (lb % 4) * 4;
+                // features 2l, 2l+1 of row r: chunk l / 4 of the row, byte (l % 4) * 4 inside it
+                const uint32_t oa = tsw::chunk_off(F, r, la / 4) + (la % 4) * 4, ob = tsw::chunk_off(F, r, lb / 4) + (lb % 4) * 4;
                 *reinterpret_cast<__half2*>(a0 + oa) = f0;
                 *reinterpret_cast<__half2*>(a0 + ob) = f1;
-                if (enc_tile) {     // saved for the backward pass in the same (tile-panel) layout
-                    *reinterpret_cast<__half2*>(reinterpret_cast<uint8_t*>(enc_tile) + oa) = f0;
-                    *reinterpret_cast<__half2*>(reinterpret_cast<uint8_t*>(enc_tile) + ob) = f1;
-                }
             }
             tc::fence_async_smem();
             tc::mbar_arrive(full_s + 8 * s);
@@ -173,8 +170,18 @@ field_forward_ws_kernel(const WsArgs a) {
                     const uint64_t stage_add = (l == 0) ? (uint64_t)((s * a.a0_stage_bytes) >> 4) : 0ull;
                     for (uint32_t ks = 0; ks < pl[l].n_steps; ks++)
                         tc::mma_f16_ss(tmem + pl[l].d_col, pl[l].step[ks].a + stage_add, pl[l].step[ks].b, pl[l].idesc, ks > 0);
+                    // The A operand of this layer is also what the backward pass needs (enc, h1, h2 | in2, h1', h2'): its tile
+                    // image goes to global memory as ONE bulk async copy while the MMA runs.  The commit is issued after the
+                    // copy has finished reading shared memory, so "MMA done" also means "tile may be overwritten".
+                    __half* save = (l == 0) ? a.enc_out : (l == 3) ? a.in2_out : a.acts[l - 1];
+                    if (save) {
+                        const uint32_t bytes = kTile * a.K[l] * 2;
+                        const uint32_t src = tc::smem_u32((l == 0) ? smem + a.a0_off + s * a.a0_stage_bytes : h);
+                        tc::bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * bytes, src, bytes);
+                        tc::bulk_wait_read();
+                    }
                     tc::mma_commit(done);
-                    if (l == 0) tc::mma_commit(empty_s + 8 * s);      // ring stage free once layer 0 has read it
+                    if (l == 0) tc::mma_commit(empty_s + 8 * s);      // ring stage free once layer 0 (and the copy) has read it
                 }
                 tc::mbar_wait(done, ph);
                 ph ^= 1;
@@ -182,7 +189,6 @@ field_forward_ws_kernel(const WsArgs a) {
                 const uint32_t N = a.N[l];
                 if (l != 2 && l != 5) {
                     // hidden layer: ReLU, fp16, next layer's A operand (+ saved for the backward pass)
-                    __half* act_tile = a.acts[l] ? a.acts[l] + (size_t)tile * (N * kTile) : nullptr;
                     for (uint32_t c0 = 0; c0 < N; c0 += 16) {
                         float v[16];
                         tc::tmem_ld16(lane_addr + c0, v);
@@ -190,13 +196,9 @@ field_forward_ws_kernel(const WsArgs a) {
                         for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
                         uint4 lo, hi;
                         pack16(v, lo, hi);
-                        const uint32_t o0 = (c0 / 8) * kPanel + tg * 16;
+                        const uint32_t o0 = tsw::chunk_off(N, tg, c0 / 8), o1 = tsw::chunk_off(N, tg, c0 / 8 + 1);
                         *reinterpret_cast<uint4*>(h + o0) = lo;
-                        *reinterpret_cast<uint4*>(h + o0 + kPanel) = hi;
-                        if (act_tile) {
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act_tile) + o0) = lo;
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act_tile) + o0 + kPanel) = hi;
-                        }
+                        *reinterpret_cast<uint4*>(h + o1) = hi;
                     }
                 } else if (l == 2) {
                     // grid_mlp output: sigma (network.py:112-115: fp16 linear output, activation in fp32) and the view_mlp
@@ -244,12 +246,8 @@ field_forward_ws_kernel(const WsArgs a) {
                     } else {
                         ch[3] = make_uint4(pack2(sh[9], sh[10]), pack2(sh[11], sh[12]), pack2(sh[13], sh[14]), pack2(sh[15], 0.f));
                     }
-                    __half* in2_tile = a.in2_out ? a.in2_out + (size_t)tile * (a.K[3] * kTile) : nullptr;
 #pragma unroll
-                    for (uint32_t c = 0; c < (LDIR ? 6u : 4u); c++) {
-                        *reinterpret_cast<uint4*>(h + c * kPanel + tg * 16) = ch[c];
-                        if (in2_tile) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(in2_tile) + c * kPanel + tg * 16) = ch[c];
-                    }
+                    for (uint32_t c = 0; c < (LDIR ? 6u : 4u); c++) *reinterpret_cast<uint4*>(h + tsw::chunk_off(a.K[3], tg, c)) = ch[c];
                 } else {
                     // colour head (network.py:131-138): fp16 linear output, `color - 5` in fp16, exp in fp32
                     tc::tmem_ld16(lane_addr, out);
@@ -272,6 +270,7 @@ field_forward_ws_kernel(const WsArgs a) {
                 tc::named_bar_sync(1 + gI, kTile);
             }
         }
+        if (tg == 0) tc::bulk_wait_all();
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -307,7 +306,9 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
         const uint32_t* d = l < 3 ? grid_dims : view_dims;
         const void* const* w = l < 3 ? grid_weights : view_weights;
         const uint32_t j = l % 3;
-        if (d[j] == 0 || d[j] % 16 || d[j] > 128 || d[j + 1] == 0 || d[j + 1] % 16 || d[j + 1] > 128) return NGP_ERR_UNSUPPORTED;
+        // every layer input is a swizzled tile of width 16 / 32 / 64 (tile_sw.cuh); wider layers (rfield: 48, 80) use the
+        // two-kernel path of field.cu / mlp.cu
+        if ((d[j] != 16 && d[j] != 32 && d[j] != 64) || d[j + 1] == 0 || d[j + 1] % 16 || d[j + 1] > 128) return NGP_ERR_UNSUPPORTED;
         if (!w[j]) return NGP_ERR_NULL;
         if (!aligned(w[j], 16)) return NGP_ERR_ALIGN;
         a.w[l] = (const __half*)w[j];
@@ -324,7 +325,7 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
     a.sigma_out = sigma_out; a.rgb_out = rgb_out;
     a.M = M; a.m_dev = m_dev;
     a.density_act = density_act; a.color_act = color_act; a.beta = beta;
-    off = (off + 127) & ~127u;
+    off = (off + 1023) & ~1023u;      // swizzle atoms are 1024-byte aligned
     a.a0_off = off; a.a0_stage_bytes = kTile * 2 * L * 2;
     off += kStages * a.a0_stage_bytes;
     for (uint32_t gI = 0; gI < kMlpGroups; gI++) { a.h_off[gI] = off; off += kTile * hmax * 2; }

@@ -71,6 +71,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, ui
                  ::"r"(dst_saddr), "l"(src), "r"(bytes), "r"(mbar_saddr) : "memory");
 }
 
+// bulk async copy shared -> global (TMA engine, 1-D); completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_saddr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all of this thread's bulk stores have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all of this thread's bulk stores are complete
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Bounded wait: a mis-programmed pipeline traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t mbar_saddr, uint32_t parity) {
     uint32_t done = 0;

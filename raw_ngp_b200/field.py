@@ -42,6 +42,12 @@ def density_only(enc, grid_weights, xyzs, bound, density_act, beta, feat_weights
     return sigma
 
 
+def _ws_ok(p1, p2):
+    """The warp-specialised kernels keep every layer input as a swizzled tile of width 16 / 32 / 64 (csrc/tile_sw.cuh); wider
+    layers (rfield: 48-wide input, 80-wide hidden) take the two-kernel path."""
+    return all(d in (16, 32, 64) for d in list(p1[:3]) + list(p2[:3]))
+
+
 class _fused_field(Function):
     @staticmethod
     def forward(ctx, xyzs, dirs, ldirs, table, feat_weights, cfg, *weights):
@@ -58,22 +64,31 @@ class _fused_field(Function):
         w1 = [_pad_weight(w, p1[i + 1], p1[i]) for i, w in enumerate(gw)]
         w2 = [_pad_weight(w, p2[i + 1], p2[i]) for i, w in enumerate(vw)]
         keep = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward; this is the real signal)
+        ws = _ws_ok(p1, p2)
         f16 = dict(dtype=torch.float16, device=dev)
-        Mt = (M + 127) // 128 * 128          # saved activations use the tile-panel layout: whole 128-row tiles
+        Mt = (M + 127) // 128 * 128 if ws else M      # the WS kernels save whole 128-row tiles (tile-panel layout)
         enc_buf = torch.empty(Mt, p1[0], **f16) if keep else None
         acts1 = [torch.empty(Mt, p1[l + 1], **f16) if keep else None for l in range(len(w1) - 1)]
         acts2 = [torch.empty(Mt, p2[l + 1], **f16) if keep else None for l in range(len(w2) - 1)]
-        in2 = torch.empty(Mt, p2[0], **f16) if keep else None
+        in2 = torch.empty(Mt, p2[0], **f16) if (keep or not ws) else None
         sigma = torch.empty(M, dtype=torch.float32, device=dev)
         rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
         S, H, L, gt, ac, ip = _grid_scalars(enc)
         st = _lib.stream()
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
-        _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table), _lib.ptr(enc.offsets),
-                  _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
-                  int(density_act), float(beta), int(color_act), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None,
-                  _lib.ptr(in2), _ptr_array(acts2) if keep else None, _lib.ptr(sigma), _lib.ptr(rgb), st)
+        if ws:
+            _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table), _lib.ptr(enc.offsets),
+                      _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
+                      int(density_act), float(beta), int(color_act), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None,
+                      _lib.ptr(in2), _ptr_array(acts2) if keep else None, _lib.ptr(sigma), _lib.ptr(rgb), st)
+        else:
+            _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table),
+                      _lib.ptr(enc.offsets), _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, len(w1), M,
+                      None, int(density_act), float(beta), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None, _lib.ptr(sigma),
+                      _lib.ptr(in2), p2[0], st)
+            _lib.call("ngp_mlp_forward_rgb", _lib.ptr(in2), p2[0], _ptr_array(w2), c2, len(w2), M, None, NGP_ACT_RELU, int(color_act),
+                      _lib.ptr(rgb), _ptr_array(acts2) if keep else None, st)
         if keep:
             ctx.save_for_backward(xyzs, enc_buf, in2, sigma, rgb, table, feat_weights if feat_weights is not None else xyzs.new_empty(0),
                                   *acts1, *acts2, *w1, *w2)
@@ -106,12 +121,22 @@ class _fused_field(Function):
         else:
             gtable = torch.zeros_like(table)
         S, H, L, gt, ac, ip = _grid_scalars(enc)
+        st = _lib.stream()
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
-        _lib.call("ngp_field_backward_full", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_rgb), _lib.ptr(rgb),
-                  _lib.ptr(enc_buf), _ptr_array(acts1), _lib.ptr(in2), _ptr_array(acts2), _lib.ptr(enc.offsets),
-                  _lib.ptr(fw) if has_fw else None, float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
-                  int(density_act), float(beta), int(color_act), _lib.ptr(gtable), _ptr_array(dw1), _ptr_array(dw2), _lib.stream())
+        fwp = _lib.ptr(fw) if has_fw else None
+        if _ws_ok(p1, p2):
+            _lib.call("ngp_field_backward_full", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_rgb), _lib.ptr(rgb),
+                      _lib.ptr(enc_buf), _ptr_array(acts1), _lib.ptr(in2), _ptr_array(acts2), _lib.ptr(enc.offsets), fwp, float(bound),
+                      S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None, int(density_act), float(beta),
+                      int(color_act), _lib.ptr(gtable), _ptr_array(dw1), _ptr_array(dw2), st)
+        else:
+            d_in2 = torch.empty(M, p2[0], dtype=torch.float16, device=dev)
+            _lib.call("ngp_mlp_backward_rgb", _lib.ptr(d_rgb), _lib.ptr(rgb), int(color_act), _lib.ptr(in2), p2[0], _ptr_array(w2),
+                      _ptr_array(acts2), c2, n2, M, None, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), 0, st)
+            _lib.call("ngp_field_backward_density", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_in2), p2[0],
+                      _lib.ptr(enc_buf), None, _lib.ptr(enc.offsets), fwp, float(bound), S, H, L, gt, ac, ip, _ptr_array(w1),
+                      _ptr_array(acts1), c1, n1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), 0, st)
         gw = [dw1[l][:d1[l + 1], :d1[l]].to(wdt[l]) for l in range(n1)]
         vw = [dw2[l][:d2[l + 1], :d2[l]].to(wdt[n1 + l]) for l in range(n2)]
         return (None, None, None, None if sink is not None else gtable, None, None, *gw, *vw)

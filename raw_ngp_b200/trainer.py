@@ -177,6 +177,8 @@ class FusedTrainStep:
         self.d1 = [model.grid_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.grid_mlp.net]
         self.d2 = [model.view_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.view_mlp.net]
         self.p1, self.p2 = [_pad16(d) for d in self.d1], [_pad16(d) for d in self.d2]
+        if not _field._ws_ok(self.p1, self.p2):
+            raise RuntimeError("FusedTrainStep: layer widths outside {16, 32, 64} (rfield); use TrainStep")
         shapes = [(self.p1[i + 1], self.p1[i]) for i in range(3)] + [(self.p2[i + 1], self.p2[i]) for i in range(3)]
         n_w = sum(a * b for a, b in shapes)
         self.w_master = torch.zeros(n_w, device=dev, dtype=torch.float32)
