@@ -167,6 +167,34 @@ def encoder_micro(device, hbm_peak):
     return res
 
 
+def reference_cuda_step(device, model, o, d, tgt, steps=20, warm=3):
+    """The SAME training step through the reference's own, unmodified CUDA extensions (oracle/_ref, compiled for sm_100a) +
+    the PyTorch pieces the reference uses (nn.Linear under autocast, GradScaler, torch.optim.Adam) -- oracle/ref_gpu_step.py.
+    Context for the headline: how fast the reference itself is on this GPU.  None if oracle/_ref is not built."""
+    try:
+        from oracle import ref_cuda, ref_gpu_step
+        if not ref_cuda.available():
+            return {"unavailable": "oracle/_ref not built"}
+        enc = model.grid_encoder
+        torch.manual_seed(0)
+        ref = ref_gpu_step.RefNeRF(enc.offsets.cpu(), enc.per_level_scale, enc.base_resolution, 1.0).to(device)
+        rs = ref_gpu_step.RefTrainStep(ref, model.density_bitfield, model.aabb_train)
+        for _ in range(warm):
+            rs.step(o, d, tgt)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            rs.step(o, d, tgt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"ms_per_step": ms, "rays_per_s": RAYS_PER_GPU / (ms * 1e-3), "samples_per_step": rs.num_points,
+                "note": "reference extensions (unmodified source, sm_100a) + nn.Linear/autocast + GradScaler + torch Adam; fp32 table as in the fork"}
+    except Exception as e:  # the reference build is optional
+        return {"unavailable": str(e)[:160]}
+
+
 def cpu_baseline(steps=1, rays=CPU_SAMPLE_RAYS):
     """The CPU port on a bounded sample of the same workload (same scene, same ray distribution)."""
     from oracle import cpu_pipeline, raymarch_oracle
@@ -271,12 +299,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
-    for _ in range(W):
-        one_step(o, d, tgt)
+    # the clock sampler (nvidia-smi) is started before the warm-up so that its start-up cost is not inside the timed region
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        one_step(o, d, tgt)
+    barrier()
     l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -285,7 +314,6 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = _lib.launch_count - l0 + K * step.graph_kernels   # eager C-ABI calls + kernels replayed from the CUDA graph
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     M = step.last_num_points
     final_loss = float(loss.item())
@@ -301,6 +329,7 @@ def run_ours(args):
         loss_host.copy_(loss.reshape(1), non_blocking=False)
     f1.record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None      # sampled over warm-up + both timed regions
     ms_e2e = f0.elapsed_time(f1)
 
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
@@ -316,10 +345,8 @@ def run_ours(args):
         per_sample = {
             # xyz + dirs in; 16 levels x 8 corners x 4 B gathered; out: enc 64 + hidden 4 x 128 + in2 64 (saved, fp16) + sigma 4 + rgb 12
             "ngp_field_forward_full": 12 + 12 + 512 + 64 + 4 * 128 + 64 + 4 + 12,
-            # xyz, d sigma, sigma, d in2 (32 B used), enc 64 + hidden 2 x 128 in; 16 x 8 x 4 B reduced into the table gradient
-            "ngp_field_backward_ws": 12 + 4 + 4 + 32 + 64 + 256 + 512,
-            # d rgb + rgb in, in2 64 + hidden 2 x 128 in, d in2 64 out
-            "ngp_mlp_backward_rgb": 12 + 12 + 64 + 256 + 64,
+            # xyz, d sigma, sigma, d rgb, rgb in; saved enc 64 + in2 64 + hidden 4 x 128 in; 16 x 8 x 4 B reduced into the table gradient
+            "ngp_field_backward_full": 12 + 4 + 4 + 12 + 12 + 64 + 4 * 128 + 64 + 512,
             "ngp_march_rays_train_write": 4 + 32,
             "ngp_composite_train_mse": 2 * 24 + 16,
         }
@@ -338,6 +365,7 @@ def run_ours(args):
                 roofline["traffic"] = tj[dom].get("dram_bytes_per_launch")
                 roofline["traffic_note"] = tj[dom].get("note")
         micro = encoder_micro(device, hbm_peak)
+        ref_step = reference_cuda_step(device, model, o, d, tgt)
         cpu = cpu_baseline() if world == 1 else None
         total_rays = RAYS_PER_GPU * world
         line = {
@@ -354,6 +382,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(o_pin.numel() * 4 + d_pin.numel() * 4 + t_pin.numel() * 4), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "grid_encode": micro,
+            "reference_cuda_step": ref_step,
             "final_loss": final_loss,
         }
         if cpu is not None:
@@ -367,8 +396,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
