@@ -13,7 +13,7 @@ WANT = [
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
-    "launch__block_size", "smsp__inst_executed.sum",
+    "launch__block_size", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -29,7 +29,7 @@ def main():
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("unnamed>::", "").strip()
         per.setdefault(name, []).append(r)
     out = [f"# ncu --set full --clock-control none, round {tag}", "",
-           "Command: `python bench.py --steps 2 --warmup 3` (configs[1] training step, M ~ 721k samples/step, 4096 rays).",
+           "Command: `python tools/ncu_step.py 3` (eager launches of the bench step: configs[1], M ~ 721k samples/step, 4096 rays).",
            "One row per kernel = mean over the captured launches. Times are ncu's serialised cold-clock times: compare",
            "shares, not absolutes (bench.py times with CUDA events).", ""]
     out.append("| kernel | launches | " + " | ".join(f"{c} [{units[idx[c]]}]" for c in cols) + " |")
@@ -59,11 +59,28 @@ def main():
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
     out += ["", f"## Launch list ({launches.split('/')[-1]}): {sum(v[0] for v in agg.values())} launches, {tot / 1000:.2f} ms total", "",
-            "Whole `bench.py --steps 2 --warmup 3` process: 5 training steps + roofline/micro-benchmark launches (incl. the",
-            "reference extension's kernel_grid / kernel_grid_backward timed by the micro-benchmark).", "",
+            "First launches of a whole `bench.py --steps 2 --warmup 3` process (graph kernel nodes are listed individually): our",
+            "training steps + the per-kernel roofline pass + the micro-benchmark, followed by the reference-extension arm.", "",
             "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
         out.append(f"| {k} | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% |")
+    # the kernels of ONE training step (FusedTrainStep): average launch time and share of the step
+    step_names = ["march_train_count_coop_kernel", "march_train_write_coop_kernel", "field_forward_ws_kernel", "composite_train_mse_kernel",
+                  "field_backward_ws_kernel", "check_finite_kernel", "fused_adam_kernel"]
+    per_step = []
+    for sn in step_names:
+        hits = [(k, v) for k, v in agg.items() if sn in k]
+        if hits:
+            n = sum(v[0] for _, v in hits)
+            t = sum(v[1] for _, v in hits)
+            calls = 2 if sn in ("check_finite_kernel", "fused_adam_kernel") else 1     # table + MLP weights
+            per_step.append((sn, t / n * calls))
+    if per_step:
+        tot_step = sum(t for _, t in per_step)
+        out += ["", f"## One training step from the launch list: {tot_step:.1f} us of kernel time", "",
+                "| kernel | us per step | share |", "|---|---|---|"]
+        for sn, t in per_step:
+            out.append(f"| {sn} | {t:.1f} | {100 * t / tot_step:.1f}% |")
     open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(out) + "\n")
     print("\n".join(out[:14]))
 
