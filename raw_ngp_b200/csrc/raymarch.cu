@@ -498,20 +498,20 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
             uint32_t i = 0;
             int exit_skip = -1;                     // lattice index of a skip whose target lies beyond the window
             while (i < cnt && step < max_steps) {
+                const uint32_t code = nx[i];                   // same address in every lane: one broadcast read
+                if (!(code & 0x8000u)) {                        // empty voxel: follow the skip (the common case in free space)
+                    if (code >= cnt) exit_skip = (int)i;
+                    i = code;
+                    continue;
+                }
                 const uint32_t c0 = i & ~31u;
                 const uint32_t code_l = (c0 + lane < cnt) ? (uint32_t)nx[c0 + lane] : 0u;
                 const uint32_t keep = __ballot_sync(0xffffffffu, (code_l & 0x8000u) != 0u) >> (i & 31u);
-                if (keep & 1u) {
-                    uint32_t run = (keep == 0xffffffffu) ? 32u : (uint32_t)__ffs(~keep) - 1u;   // bits past the chunk end are 0
-                    run = min(run, max_steps - step);
-                    if (lane < run) tout[step + lane] = u[i + lane];
-                    step += run;
-                    i += run;
-                } else {
-                    const uint32_t code = __shfl_sync(0xffffffffu, code_l, i & 31u);
-                    if (code >= cnt) exit_skip = (int)i;
-                    i = code;
-                }
+                uint32_t run = (keep == 0xffffffffu) ? 32u : (uint32_t)__ffs(~keep) - 1u;   // bits past the chunk end are 0
+                run = min(run, max_steps - step);
+                if (lane < run) tout[step + lane] = u[i + lane];
+                step += run;
+                i += run;
             }
             if (step >= max_steps) break;
             if (cnt < kWin) break;                  // the window reached `far`: the ray is finished
@@ -543,26 +543,34 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x >= 32) return;
-    uint32_t carry = 0, fit = 0;
-    for (uint32_t base = 0; base < N; base += 32) {
-        const uint32_t i = base + lane;
-        const uint32_t c = (i < N) ? (uint32_t)__ldcg(rays + (size_t)i * 2 + 1) : 0u;
-        uint32_t incl = c;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, s);
-            if (lane >= (uint32_t)s) incl += v;
-        }
-        if (i < N) rays[(size_t)i * 2] = (int)(carry + incl - c);
-        if (i < N && carry + incl <= cap) fit = max(fit, carry + incl);
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+    // Block-wide exclusive scan of the N counts: thread t owns the contiguous chunk [t * per, (t + 1) * per) so that all loads
+    // of the block are in flight together (a single warp walking the array pays one L2 round trip per 32 rays).
+    __shared__ uint32_t s_part[kCoopWarps * 32];
+    const uint32_t T = kCoopWarps * 32, per = (N + T - 1) / T;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, N);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += (uint32_t)__ldcg(rays + (size_t)i * 2 + 1);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    uint32_t carry = 0;
+    for (uint32_t t = 0; t < threadIdx.x; t++) carry += s_part[t];        // T = 128 shared-memory reads
+    uint32_t fit = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t c = (uint32_t)__ldcg(rays + (size_t)i * 2 + 1);
+        rays[(size_t)i * 2] = (int)carry;
+        carry += c;
+        if (carry <= cap) fit = max(fit, carry);
     }
+    __shared__ uint32_t s_fit[kCoopWarps];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) fit = max(fit, __shfl_xor_sync(0xffffffffu, fit, s));
-    if (lane == 0) {
-        counter[0] = (int)carry; counter[1] = 0;
-        if (cap) counter[2] = (int)fit;
+    for (int sft = 16; sft > 0; sft >>= 1) fit = max(fit, __shfl_xor_sync(0xffffffffu, fit, sft));
+    if (lane == 0) s_fit[warp] = fit;
+    __syncthreads();
+    if (threadIdx.x == T - 1) {
+        uint32_t f = 0;
+        for (uint32_t w = 0; w < kCoopWarps; w++) f = max(f, s_fit[w]);
+        counter[0] = (int)carry; counter[1] = 0;       // the last thread's running sum is the total
+        if (cap) counter[2] = (int)f;
     }
 }
 
