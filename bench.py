@@ -287,6 +287,7 @@ def run_ours(args):
 
     def one_step(ro, rd, tg):
         if step.global_step % step.update_extra_interval == 0:
+            step.flush()                      # the occupancy update queries the density with the up-to-date weights
             model.update_extra_state()
             model.density_grid.copy_(scratch["grid"])
             model.density_bitfield.copy_(scratch["bits"])
@@ -306,14 +307,14 @@ def run_ours(args):
     for _ in range(W):
         one_step(o, d, tgt)
     barrier()
-    l0 = _lib.launch_count
+    l0, r0 = _lib.launch_count, step.kernels_replayed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
         loss = one_step(o, d, tgt)
     e1.record()
     barrier()
-    launches = _lib.launch_count - l0 + K * step.graph_kernels   # eager C-ABI calls + kernels replayed from the CUDA graph
+    launches = (_lib.launch_count - l0) + (step.kernels_replayed - r0)   # eager C-ABI calls + kernels replayed from the CUDA graphs
     ms = e0.elapsed_time(e1)
     M = step.last_num_points
     final_loss = float(loss.item())

@@ -402,8 +402,14 @@ int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ld
  * zero_grad != 0 the gradient buffer is cleared in the same pass.  step = 1-based step count. */
 int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype,
                    float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, uint32_t step, const float* inv_scale_dev,
+                   float eps, float weight_decay, uint32_t step, const int32_t* step_dev, const float* inv_scale_dev,
                    const float* found_inf_dev, int zero_grad, ngp_stream_t stream);
+
+/* step_dev (ngp_fused_adam): NULL, or a device int32 holding the optimizer step count; the bias corrections are then
+ * computed on the device from *step_dev (the host `step` is ignored), which lets the optimizer live inside a replayed
+ * CUDA graph.  ngp_adam_step_counter increments *step_dev unless *found_inf_dev != 0 (a skipped GradScaler step is not
+ * counted, as in torch). */
+int ngp_adam_step_counter(int32_t* step_dev, const float* found_inf_dev, ngp_stream_t stream);
 
 /* found_inf_dev[0] = 1.0f if any element of grad is inf/nan (accumulates; caller zero-fills). */
 int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev,

@@ -28,9 +28,14 @@ __global__ void __launch_bounds__(256)
 fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __restrict__ grad, float* __restrict__ m,
                   float* __restrict__ v, uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float bias1, float bias2_sqrt, const float* __restrict__ inv_scale_dev,
-                  const float* __restrict__ found_inf_dev, bool zero_grad) {
+                  const float* __restrict__ found_inf_dev, bool zero_grad, const int* __restrict__ step_dev) {
     const bool skip = found_inf_dev && (__ldg(found_inf_dev) != 0.f);
     const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
+    if (step_dev) {     // step count kept on the device (CUDA-graph replay): bias corrections computed here
+        const float t = (float)max(__ldg(step_dev), 1);
+        bias1 = 1.f - powf(beta1, t);
+        bias2_sqrt = sqrtf(1.f - powf(beta2, t));
+    }
     const float step_size = lr / bias1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n4 = n / 4;      // the buffers are 16-byte aligned (checked by the host wrapper)
@@ -96,6 +101,11 @@ check_finite_kernel(const G* __restrict__ grad, uint64_t n, float* __restrict__ 
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
 }
 
+// GradScaler semantics for a device-side step counter: the optimizer step is counted only when it is not skipped
+__global__ void adam_step_counter_kernel(int* __restrict__ step_dev, const float* __restrict__ found_inf_dev) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf_dev && *found_inf_dev != 0.f)) *step_dev += 1;
+}
+
 }  // namespace
 }  // namespace ngp
 
@@ -103,23 +113,23 @@ using namespace ngp;
 
 extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype, float* exp_avg,
                               float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2, float eps,
-                              float weight_decay, uint32_t step, const float* inv_scale_dev,
+                              float weight_decay, uint32_t step, const int32_t* step_dev, const float* inv_scale_dev,
                               const float* found_inf_dev, int zero_grad, ngp_stream_t stream) {
     if (n == 0) return NGP_OK;
     if (!master || !grad || !exp_avg || !exp_avg_sq) return NGP_ERR_NULL;
-    if (step == 0) return NGP_ERR_BAD_ARG;
+    if (step == 0 && !step_dev) return NGP_ERR_BAD_ARG;
     if (grad_dtype < NGP_F32 || grad_dtype > NGP_BF16) return NGP_ERR_BAD_DTYPE;
     if (param_lp && (lp_dtype != NGP_F16 && lp_dtype != NGP_BF16)) return NGP_ERR_BAD_DTYPE;
     if (!aligned(master, 16) || !aligned(grad, 16) || !aligned(exp_avg, 16) || !aligned(exp_avg_sq, 16) || (param_lp && !aligned(param_lp, 8)))
         return NGP_ERR_ALIGN;
-    const float bias1 = 1.f - powf(beta1, (float)step);
-    const float bias2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    const float bias1 = 1.f - powf(beta1, (float)std::max(step, 1u));
+    const float bias2_sqrt = sqrtf(1.f - powf(beta2, (float)std::max(step, 1u)));
     const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(div_up<uint64_t>(n, 4), 256), (uint64_t)kNumSMs * 8);
     cudaStream_t st = (cudaStream_t)stream;
 #define NGP_ADAM(G, P, HAS)                                                                                      \
     fused_adam_kernel<G, P, HAS><<<blocks, 256, 0, st>>>(master, (P*)param_lp, (G*)grad, exp_avg, exp_avg_sq, n, lr, \
                                                          beta1, beta2, eps, weight_decay, bias1, bias2_sqrt,      \
-                                                         inv_scale_dev, found_inf_dev, zero_grad != 0)
+                                                         inv_scale_dev, found_inf_dev, zero_grad != 0, step_dev)
 #define NGP_ADAM_G(G)                                                             \
     if (!param_lp) NGP_ADAM(G, __half, false);                                    \
     else if (lp_dtype == NGP_F16) NGP_ADAM(G, __half, true);                      \
@@ -129,6 +139,12 @@ extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void*
     else { NGP_ADAM_G(__nv_bfloat16); }
 #undef NGP_ADAM_G
 #undef NGP_ADAM
+    return finish_launch();
+}
+
+extern "C" int ngp_adam_step_counter(int32_t* step_dev, const float* found_inf_dev, ngp_stream_t stream) {
+    if (!step_dev) return NGP_ERR_NULL;
+    adam_step_counter_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev, found_inf_dev);
     return finish_launch();
 }
 

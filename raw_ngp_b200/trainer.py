@@ -18,10 +18,13 @@ from . import _lib, parallel
 class FusedAdam:
     """Adam over a list of (master fp32, low-precision copy or None, grad buffer) groups via ngp_fused_adam."""
 
-    def __init__(self, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0):
+    def __init__(self, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, device_step=None):
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.groups = []
         self.step_count = 0
+        # optional int32[1] CUDA tensor: the step count lives on the device (bias corrections computed in the kernel), so that
+        # the optimizer can be part of a replayed CUDA graph; incremented only for steps that are not skipped (GradScaler)
+        self.device_step = device_step
 
     def add_group(self, master, grad, param_lp=None):
         assert master.dtype == torch.float32 and master.is_contiguous() and grad.is_contiguous()
@@ -32,13 +35,15 @@ class FusedAdam:
         self.step_count += 1
         lr = self.lr if lr is None else lr
         st = _lib.stream()
+        if self.device_step is not None:
+            _lib.call("ngp_adam_step_counter", _lib.ptr(self.device_step), _lib.ptr(found_inf), st)
         for g in self.groups:
             lp = g["lp"]
             _lib.call("ngp_fused_adam", _lib.ptr(g["master"]), _lib.ptr(lp), _lib.dtype_id(lp.dtype) if lp is not None else 0,
                       _lib.ptr(g["grad"]), _lib.dtype_id(g["grad"].dtype), _lib.ptr(g["m"]), _lib.ptr(g["v"]),
                       g["master"].numel(), float(lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                      float(self.weight_decay), self.step_count, _lib.ptr(inv_scale), _lib.ptr(found_inf),
-                      int(zero_grad), st)
+                      float(self.weight_decay), self.step_count, _lib.ptr(self.device_step), _lib.ptr(inv_scale),
+                      _lib.ptr(found_inf), int(zero_grad), st)
 
 
 class TrainStep:
@@ -196,9 +201,11 @@ class FusedTrainStep:
             o += n * k
         self.w_lp.copy_(self.w_master)
 
-        self.opt = FusedAdam(lr=lr, betas=betas, eps=eps)
+        self.opt_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.opt = FusedAdam(lr=lr, betas=betas, eps=eps, device_step=self.opt_step_dev)
         self.opt.add_group(self.table_master, self.table_grad, enc.embeddings.data)
         self.opt.add_group(self.w_master, self.w_grad, self.w_lp)
+        self._pending = False          # gradients of the last step are waiting for their optimizer update
         self.inv_scale = torch.full((1,), parallel.unscale_factor(self.loss_scale, self.world), device=dev, dtype=torch.float32)
         self.found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
 
@@ -228,7 +235,7 @@ class FusedTrainStep:
         self._grid_scalars = _field._grid_scalars(enc)
         self.use_graph = use_graph
         self._graph = None
-        self.graph_kernels = 0
+        self.graph_kernels = self.pipe_kernels = self.kernels_replayed = 0
         self._m_dev = self.counter.data_ptr() + 8   # counter[2]: samples of the rays that fit in `cap`
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -238,8 +245,9 @@ class FusedTrainStep:
             arr[i] = t.data_ptr()
         return arr
 
-    def _launch_forward_backward(self):
-        """march -> field -> composite+loss -> backward, all on the current stream (graph-capturable)."""
+    def _launch_forward_backward(self, join=None):
+        """march -> field -> composite+loss -> backward, all on the current stream (graph-capturable).  `join`: a stream whose
+        work (the previous step's optimizer update) must finish before the field kernels read the weights."""
         m, opt, N, cap, ct = self.model, self.model.opt, self.N, self.cap, self._ct
         st = _lib.stream()
         P = _lib.ptr
@@ -254,6 +262,8 @@ class FusedTrainStep:
                   float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma), int(opt.max_steps), N, int(m.cascade),
                   int(m.grid_size), None, None, None, P(self.rays), cap, self._m_dev, P(self.t_scratch), P(self.xyzs),
                   P(self.dirs), P(self.ts), P(self.ldirs), st)
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
         S, H, L, gt, ac, ip = self._grid_scalars
         enc = m.grid_encoder
         c1 = (ct.c_uint32 * 4)(*self.p1)
@@ -277,9 +287,26 @@ class FusedTrainStep:
         _lib.call("ngp_check_finite", _lib.ptr(self.table_grad), _lib.NGP_F16, self.table_grad.numel(), _lib.ptr(self.found_inf), st)
         _lib.call("ngp_check_finite", _lib.ptr(self.w_grad), _lib.NGP_F32, self.w_grad.numel(), _lib.ptr(self.found_inf), st)
 
+    def _launch_optimizer(self):
+        """inf check (single GPU; with several ranks the check runs before the flag all-reduce) + fused Adam."""
+        if self.world == 1:
+            self._launch_check()
+        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+
+    def _launch_pipelined(self):
+        """[optimizer update of the PREVIOUS step]  ||  [march of this step]  ->  field forward -> composite -> backward.
+        The marcher depends on the rays and the occupancy bitfield only, and it is latency bound (one warp per ray) while
+        Adam streams 366 MB through HBM: on two streams they overlap almost completely."""
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._launch_optimizer()
+        self._launch_forward_backward(join=self._side)
+
     def _capture(self):
         # one eager pass first: sets the dynamic shared-memory attributes and warms the allocator outside the capture
         s = torch.cuda.Stream()
+        self._side = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self._launch_forward_backward()
@@ -288,19 +315,34 @@ class FusedTrainStep:
             self.w_grad.zero_()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self._graph_fb, self._graph_chk = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self._graph_fb, self._graph_pipe, self._graph_chk = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_fb):
             self._launch_forward_backward()
+        self.graph_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)      # + noises.uniform_
+        n_adam = self.opt.step_count
+        c0 = _lib.launch_count
+        with torch.cuda.graph(self._graph_pipe):
+            self._launch_pipelined()
+        self.pipe_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0) + (1 if self.world == 1 else 0)   # + found_inf.zero_
+        self.opt.step_count = n_adam        # capturing is not stepping
         with torch.cuda.graph(self._graph_chk):
             self._launch_check()
-        self.graph_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0) + 1   # + uniform_ + found_inf.zero_
         self.table_grad.zero_()
         self.w_grad.zero_()
+
+    def flush(self):
+        """Applies the optimizer update that is still pending (the update of step k normally runs at the start of step
+        k + 1, overlapped with its ray marching).  Call before using the model outside of step()."""
+        if not self._pending:
+            return
+        self._launch_optimizer()       # (with several ranks step() has already reduced the gradients and the inf flag)
+        self._pending = False
 
     def profile_kernels(self, iters=10):
         """Average device time (ms, CUDA events on the launching stream) of every kernel of the step, launched eagerly in
         step order on the current inputs (these are real optimisation steps: the model trains `iters` steps).  Returns {entry point: ms}."""
+        self.flush()
         names, events = [], []
         real_call = _lib.call
 
@@ -338,9 +380,11 @@ class FusedTrainStep:
         return int(self.counter[0].item())
 
     def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True):
-        """One optimisation step; returns the (unscaled) loss as a 1-element device tensor (overwritten by the next step)."""
+        """One optimisation step; returns the (unscaled) loss as a 1-element device tensor (overwritten by the next step).
+        The parameter update of this step is applied at the start of the next call (or by flush())."""
         model = self.model
         if update_grid and self.global_step % self.update_extra_interval == 0:
+            self.flush()                       # the density queries of the occupancy update see the updated weights
             model.update_extra_state()
         if rays_o is not None:
             self.set_rays(rays_o, rays_d, target_rgb, rays_ldir)
@@ -349,19 +393,23 @@ class FusedTrainStep:
         if self.use_graph:
             sig = (model.density_bitfield.data_ptr(), model.aabb_train.data_ptr(), model.grid_encoder.embeddings.data_ptr())
             if self._graph != sig:      # first step, or a captured buffer was re-allocated (update_aabb, load_state_dict)
+                self.flush()
                 self._capture()
                 self._graph = sig
-            self._graph_fb.replay()
+            if self._pending:
+                self._graph_pipe.replay()
+                self.opt.step_count += 1
+                self.kernels_replayed += self.pipe_kernels
+            else:
+                self._graph_fb.replay()
+                self.kernels_replayed += self.graph_kernels
         else:
+            self.flush()
             self._launch_forward_backward()
         if self.world > 1:
             parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
-        if self.use_graph:
-            self._graph_chk.replay()
-        else:
             self._launch_check()
-        if self.world > 1:
             dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
-        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+        self._pending = True
         self.global_step += 1
         return self.loss

@@ -24,10 +24,10 @@ def main():
         step.step(o, d, tgt, update_grid=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(10):
+    for _ in range(50):
         step.step(o, d, tgt, update_grid=False)
     torch.cuda.synchronize()
-    print(f"wall per step (no grid update): {(time.perf_counter() - t0) * 100:.3f} ms")
+    print(f"wall per step (no grid update): {(time.perf_counter() - t0) * 20:.3f} ms")
     t0 = time.perf_counter()
     model.update_extra_state()
     torch.cuda.synchronize()
