@@ -380,7 +380,8 @@ int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float
  * Outputs sigma_out [M], rgb_out [M,3] fp32.  Saved for the backward kernels (each may be NULL), all in the TILE-PANEL
  * layout [ceil(M/128)][width / 8][128][8] fp16 (the shared-memory image of a 128-row tile; buffers hold whole tiles):
  * enc_out (width 2L), grid_acts_out[0..1] (h), in2_out (32/48), view_acts_out[0..1] (h2).  Pass tiled = 1 to
- * ngp_mlp_backward_rgb / ngp_field_backward_density to consume them (x = in2, dx = d_in2 are tiled as well). */
+ * ngp_field_backward_full to consume them.  view_weights == NULL: density-only query (grid_mlp only; dirs, ldirs,
+ * view_dims, rgb_out and the view outputs are ignored) -- NeRFNetwork.density, the occupancy-grid update. */
 int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ldirs, const void* table,
                            const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
                            uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,

@@ -54,6 +54,7 @@ struct WsArgs {
     float* sigma_out; float* rgb_out;
     uint32_t M; const int* m_dev;
     int density_act, color_act; float beta;
+    uint32_t n_run;                    // layers to run: 6, or 3 for a density-only query (NeRFNetwork.density)
     uint32_t w_off[kWsLayers], a0_off, a0_stage_bytes, h_off[kMlpGroups], ctrl_off;
 };
 
@@ -81,8 +82,8 @@ field_forward_ws_kernel(const WsArgs a) {
         }
         for (uint32_t gI = 0; gI < kMlpGroups; gI++) tc::mbar_init(done_s + 8 * gI, 1);
     }
-    for (uint32_t l = 0; l < kWsLayers; l++) tsw::load_weight_tile(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + kMlpGroups * kWsLayers) {
+    for (uint32_t l = 0; l < a.n_run; l++) tsw::load_weight_tile(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kMlpGroups * kWsLayers && (threadIdx.x - 64) % kWsLayers < a.n_run) {
         const uint32_t i = threadIdx.x - 64, gI = i / kWsLayers, l = i % kWsLayers;
         const uint32_t K = a.K[l], N = a.N[l];
         // Y = A [128 x K] (K-major) * W_l^T; A = ring stage 0 for layer 0 (the issuer adds the stage offset), else the group's tile
@@ -164,7 +165,7 @@ field_forward_ws_kernel(const WsArgs a) {
             const bool live = row < M;
             tc::mbar_wait(full_s + 8 * s, (it / kStages) & 1u);
             float out[16];
-            for (uint32_t l = 0; l < kWsLayers; l++) {
+            for (uint32_t l = 0; l < a.n_run; l++) {
                 if (tg == 0) {
                     tc::fence_after_sync();
                     const uint64_t stage_add = (l == 0) ? (uint64_t)((s * a.a0_stage_bytes) >> 4) : 0ull;
@@ -210,6 +211,11 @@ field_forward_ws_kernel(const WsArgs a) {
                         if (a.density_act == 0) sg = expf(o0);
                         else { const float bx = a.beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / a.beta; }
                         a.sigma_out[row] = sg;
+                    }
+                    if (a.n_run == 3) {          // density only: no view branch
+                        tc::fence_before_sync();
+                        tc::named_bar_sync(1 + gI, kTile);
+                        continue;
                     }
                     float sh[LDIR ? 32 : 16];
                     {
@@ -291,18 +297,21 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
                                       void* const* grid_acts_out, void* in2_out, void* const* view_acts_out, float* sigma_out,
                                       float* rgb_out, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
-    if (!xyzs || !dirs || !table || !offsets || !grid_weights || !grid_dims || !view_weights || !view_dims || !sigma_out || !rgb_out)
-        return NGP_ERR_NULL;
+    const bool density_only = view_weights == nullptr;      /* NeRFNetwork.density: grid_mlp only, dirs / rgb_out unused */
+    if (!xyzs || !table || !offsets || !grid_weights || !grid_dims || !sigma_out) return NGP_ERR_NULL;
+    if (!density_only && (!dirs || !view_dims || !rgb_out)) return NGP_ERR_NULL;
     if (L == 0 || L > kMaxLevels || L % 8 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1 ||
         color_act < 1 || color_act > 3)
         return NGP_ERR_BAD_ARG;
     const uint32_t in2_w = ldirs ? 48u : 32u;
-    if (grid_dims[0] != 2 * L || grid_dims[3] != 16 || view_dims[0] != in2_w || view_dims[3] != 16) return NGP_ERR_UNSUPPORTED;
+    if (grid_dims[0] != 2 * L || grid_dims[3] != 16) return NGP_ERR_UNSUPPORTED;
+    if (!density_only && (view_dims[0] != in2_w || view_dims[3] != 16)) return NGP_ERR_UNSUPPORTED;
     WsArgs a = {};
+    a.n_run = density_only ? 3u : kWsLayers;
     a.xyzs = xyzs; a.dirs = dirs; a.ldirs = ldirs;
     a.g = {(const __half*)table, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
     uint32_t off = 0, hmax = in2_w;
-    for (uint32_t l = 0; l < kWsLayers; l++) {
+    for (uint32_t l = 0; l < a.n_run; l++) {
         const uint32_t* d = l < 3 ? grid_dims : view_dims;
         const void* const* w = l < 3 ? grid_weights : view_weights;
         const uint32_t j = l % 3;

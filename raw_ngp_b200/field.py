@@ -35,10 +35,15 @@ def density_only(enc, grid_weights, xyzs, bound, density_act, beta, feat_weights
     w16 = [_pad_weight(w, pdims[i + 1], pdims[i]) for i, w in enumerate(grid_weights)]
     sigma = torch.empty(M, dtype=torch.float32, device=xyzs.device)
     S, H, L, gt, ac, ip = _grid_scalars(enc)
-    _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
-              _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16),
-              (ctypes.c_uint32 * len(pdims))(*pdims), len(w16), M, None, int(density_act), float(beta), None, None, _lib.ptr(sigma),
-              None, 0, _lib.stream())
+    cd = (ctypes.c_uint32 * len(pdims))(*pdims)
+    if all(d in (16, 32, 64) for d in pdims[:3]) and L % 8 == 0:      # warp-specialised kernel, grid_mlp only
+        _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
+                  _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16), cd, None, None, M, None,
+                  int(density_act), float(beta), 1, None, None, None, None, _lib.ptr(sigma), None, _lib.stream())
+    else:
+        _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
+                  _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16), cd, len(w16), M, None,
+                  int(density_act), float(beta), None, None, _lib.ptr(sigma), None, 0, _lib.stream())
     return sigma
 
 
