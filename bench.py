@@ -333,6 +333,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None      # sampled over warm-up + both timed regions
     ms_e2e = f0.elapsed_time(f1)
 
+    step.flush()        # every rank applies its pending update here (collective with N > 1): nothing rank-0-only may flush later
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -248,7 +248,13 @@ class FusedTrainStep:
     def _launch_forward_backward(self, join=None):
         """march -> field -> composite+loss -> backward, all on the current stream (graph-capturable).  `join`: a stream whose
         work (the previous step's optimizer update) must finish before the field kernels read the weights."""
-        m, opt, N, cap, ct = self.model, self.model.opt, self.N, self.cap, self._ct
+        self._launch_march()
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
+        self._launch_field()
+
+    def _launch_march(self):
+        m, opt, N, cap = self.model, self.model.opt, self.N, self.cap
         st = _lib.stream()
         P = _lib.ptr
         if self.perturb:
@@ -262,8 +268,11 @@ class FusedTrainStep:
                   float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma), int(opt.max_steps), N, int(m.cascade),
                   int(m.grid_size), None, None, None, P(self.rays), cap, self._m_dev, P(self.t_scratch), P(self.xyzs),
                   P(self.dirs), P(self.ts), P(self.ldirs), st)
-        if join is not None:
-            torch.cuda.current_stream().wait_stream(join)
+
+    def _launch_field(self):
+        m, opt, N, cap, ct = self.model, self.model.opt, self.N, self.cap, self._ct
+        st = _lib.stream()
+        P = _lib.ptr
         S, H, L, gt, ac, ip = self._grid_scalars
         enc = m.grid_encoder
         c1 = (ct.c_uint32 * 4)(*self.p1)
@@ -328,15 +337,36 @@ class FusedTrainStep:
         self.opt.step_count = n_adam        # capturing is not stepping
         with torch.cuda.graph(self._graph_chk):
             self._launch_check()
+        if self.world > 1:      # data parallel: the collectives stay outside the graphs, between a march graph and a field graph
+            self._graph_march, self._graph_field = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            c0 = _lib.launch_count
+            with torch.cuda.graph(self._graph_march):
+                self._launch_march()
+            self.march_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)
+            c0 = _lib.launch_count
+            with torch.cuda.graph(self._graph_field):
+                self._launch_field()
+            self.field_kernels = _lib.launch_count - c0
         self.table_grad.zero_()
         self.w_grad.zero_()
+
+    def _reduce_and_update(self):
+        """Data parallel: all-reduce of the two gradient buffers, inf check, MAX of the flag, fused Adam -- on the current
+        (side) stream, so that it overlaps the ray marching of the next step on the main stream."""
+        parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
+        self._launch_check()
+        dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
+        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
 
     def flush(self):
         """Applies the optimizer update that is still pending (the update of step k normally runs at the start of step
         k + 1, overlapped with its ray marching).  Call before using the model outside of step()."""
         if not self._pending:
             return
-        self._launch_optimizer()       # (with several ranks step() has already reduced the gradients and the inf flag)
+        if self.world > 1:
+            self._reduce_and_update()
+        else:
+            self._launch_optimizer()
         self._pending = False
 
     def profile_kernels(self, iters=10):
@@ -396,7 +426,18 @@ class FusedTrainStep:
                 self.flush()
                 self._capture()
                 self._graph = sig
-            if self._pending:
+            if self.world > 1:
+                # [all-reduce + optimizer update of the previous step, side stream]  ||  [march graph]  ->  field graph
+                main = torch.cuda.current_stream()
+                if self._pending:
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        self._reduce_and_update()
+                self._graph_march.replay()
+                main.wait_stream(self._side)
+                self._graph_field.replay()
+                self.kernels_replayed += self.march_kernels + self.field_kernels
+            elif self._pending:
                 self._graph_pipe.replay()
                 self.opt.step_count += 1
                 self.kernels_replayed += self.pipe_kernels
@@ -406,10 +447,6 @@ class FusedTrainStep:
         else:
             self.flush()
             self._launch_forward_backward()
-        if self.world > 1:
-            parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
-            self._launch_check()
-            dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
         self._pending = True
         self.global_step += 1
         return self.loss
