@@ -254,15 +254,19 @@ field_backward_ws_kernel(const BwsArgs a) {
                         const uint32_t o0 = tsw::chunk_off(K, tg, c0 / 8), o1 = tsw::chunk_off(K, tg, c0 / 8 + 1);
                         const uint4 m0 = *reinterpret_cast<const uint4*>(in_tile + o0);
                         const uint4 m1 = *reinterpret_cast<const uint4*>(in_tile + o1);
-                        const __half* q0 = reinterpret_cast<const __half*>(&m0);
-                        const __half* q1 = reinterpret_cast<const __half*>(&m1);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            if (!(__half2float(q0[i]) > 0.f)) v[i] = 0.f;
-                            if (!(__half2float(q1[i]) > 0.f)) v[8 + i] = 0.f;
-                        }
                         uint4 lo, hi;
                         pack16(v, lo, hi);
+                        // ReLU mask on packed halves: the saved activation is a ReLU output (>= +0), so "was active" == "bits != 0";
+                        // __hgt2_mask gives 0xFFFF per active half and one AND zeroes the gradient of the inactive ones
+                        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+                        lo.x &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m0.x), zero2);
+                        lo.y &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m0.y), zero2);
+                        lo.z &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m0.z), zero2);
+                        lo.w &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m0.w), zero2);
+                        hi.x &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m1.x), zero2);
+                        hi.y &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m1.y), zero2);
+                        hi.z &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m1.z), zero2);
+                        hi.w &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m1.w), zero2);
                         *reinterpret_cast<uint4*>(nxt + o0) = lo;        // dZ of layer l - 1 has the same width K
                         *reinterpret_cast<uint4*>(nxt + o1) = hi;
                     }

@@ -193,10 +193,15 @@ field_forward_ws_kernel(const WsArgs a) {
                     for (uint32_t c0 = 0; c0 < N; c0 += 16) {
                         float v[16];
                         tc::tmem_ld16(lane_addr + c0, v);
-#pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
                         uint4 lo, hi;
                         pack16(v, lo, hi);
+                        {   // ReLU on the packed halves (8 HMNMX2 instead of 16 FMNMX; rounding is monotone, so the order is immaterial)
+                            const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+                            __half2* ql = reinterpret_cast<__half2*>(&lo);
+                            __half2* qh = reinterpret_cast<__half2*>(&hi);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { ql[i] = __hmax2(ql[i], zero2); qh[i] = __hmax2(qh[i], zero2); }
+                        }
                         const uint32_t o0 = tsw::chunk_off(N, tg, c0 / 8), o1 = tsw::chunk_off(N, tg, c0 / 8 + 1);
                         *reinterpret_cast<uint4*>(h + o0) = lo;
                         *reinterpret_cast<uint4*>(h + o1) = hi;
