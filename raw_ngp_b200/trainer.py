@@ -354,8 +354,9 @@ class FusedTrainStep:
         """Data parallel: all-reduce of the two gradient buffers, inf check, MAX of the flag, fused Adam -- on the current
         (side) stream, so that it overlaps the ray marching of the next step on the main stream."""
         parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
+        # The inf / nan check runs on the REDUCED buffers, which are bit-identical on every rank (a non-finite value of any
+        # rank survives the SUM), so all ranks take the same skip decision without a second collective for the flag.
         self._launch_check()
-        dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
         self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
 
     def flush(self):
