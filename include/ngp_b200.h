@@ -346,7 +346,7 @@ int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const fl
                                uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
                                const int32_t* m_dev, int density_act, float beta, void* grad_table,
-                               float* const* dweights, int tiled, ngp_stream_t stream);
+                               float* const* dweights, ngp_stream_t stream);
 
 /* ngp_mlp_forward whose last epilogue applies the colour activation to output columns 0..2 and writes rgb_out [M,3] fp32 */
 int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,
@@ -357,7 +357,7 @@ int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights,
 int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
                          const void* const* weights, const void* const* acts, const uint32_t* dims,
                          uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
-                         float* const* dweights, int tiled, ngp_stream_t stream);
+                         float* const* dweights, ngp_stream_t stream);
 
 /* The whole field backward in ONE warp-specialised persistent kernel (csrc/field_bwd_ws.cu): a view group (view_mlp
  * backward from d_rgb), a grid group (grid_mlp backward from d_sigma and the view group's d feat, handed over in shared
@@ -377,8 +377,10 @@ int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float
 /* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
  * shared-memory tiles while two groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.
  * grid_dims = {2L, h, h, 16}, view_dims = {32 (48 with ldirs), h2, h2, 16}, all multiples of 16 and <= 128.
- * Outputs sigma_out [M], rgb_out [M,3] fp32.  Saved for the backward kernels (each may be NULL), all in the TILE-PANEL
- * layout [ceil(M/128)][width / 8][128][8] fp16 (the shared-memory image of a 128-row tile; buffers hold whole tiles):
+ * Outputs sigma_out [M], rgb_out [M,3] fp32.  Saved for the backward kernel (each may be NULL), all in the TILE-PANEL
+ * layout: per 128-row tile the shared-memory image of the tile, i.e. [ceil(M/128)][128][width] fp16 row-major with the
+ * 16-byte chunks of a row XOR-swizzled like the UMMA SWIZZLE_32B/64B/128B layouts (csrc/tile_sw.cuh); buffers hold
+ * whole tiles; widths in {16, 32, 64} (else NGP_ERR_UNSUPPORTED: use the two-kernel path):
  * enc_out (width 2L), grid_acts_out[0..1] (h), in2_out (32/48), view_acts_out[0..1] (h2).  Pass tiled = 1 to
  * ngp_field_backward_full to consume them.  view_weights == NULL: density-only query (grid_mlp only; dirs, ldirs,
  * view_dims, rgb_out and the view outputs are ignored) -- NeRFNetwork.density, the occupancy-grid update. */

@@ -224,7 +224,7 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                               const __half* __restrict__ d_in2, uint32_t ld2, const __half* __restrict__ enc, GridArgs g,
                               MlpArgs p, uint32_t M, __half* __restrict__ grad_table, int density_act, float beta,
                               uint32_t dz_off, uint32_t dz_bytes, uint32_t w_base, uint32_t ctrl_off,
-                              const int* __restrict__ m_dev, bool tiled) {
+                              const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -290,11 +290,8 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
         for (uint32_t l = 0; l < L; l++) {
             const __half* src = (l == 0) ? enc : p.acts[l - 1];
             uint8_t* tile_s = smem + in_off[l];
-            // tiled: the saved tile is the shared-memory image itself ([column / 8][row][8 halves]): 512 contiguous bytes per warp
-            const __half* src_tile = src + (size_t)tile * (p.dims[l] * kTile);
             for (uint32_t c = grp; c < p.dims[l] / 8; c += kBwdGroups) {
-                if (live) tc::cp_async16(tc::smem_u32(tile_s + c * kPanel + t * 16),
-                                         tiled ? src_tile + (c * kTile + t) * 8 : src + (size_t)row * p.dims[l] + c * 8);
+                if (live) tc::cp_async16(tc::smem_u32(tile_s + c * kPanel + t * 16), src + (size_t)row * p.dims[l] + c * 8);
                 else *reinterpret_cast<uint4*>(tile_s + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
             }
         }
@@ -307,9 +304,8 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                 if (density_act == 0) dact = sg;                              // trunc_exp backward: g * exp(x) (activation.py:18-21)
                 else dact = 1.0f - expf(-beta * sg);                          // softplus' = sigmoid(beta x) = 1 - exp(-beta y)
                 dz[0] = __float2half_rn(__ldg(d_sigma + row) * dact);
-                const __half* d_tile = d_in2 + (size_t)tile * (ld2 * kTile);
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(tiled ? d_tile + t * 8 : d_in2 + (size_t)row * ld2));
-                const uint4 b = __ldg(reinterpret_cast<const uint4*>(tiled ? d_tile + (kTile + t) * 8 : d_in2 + (size_t)row * ld2 + 8));
+                const uint4* src = reinterpret_cast<const uint4*>(d_in2 + (size_t)row * ld2);
+                const uint4 a = __ldg(src), b = __ldg(src + 1);
                 const __half* ha = reinterpret_cast<const __half*>(&a);
                 const __half* hb = reinterpret_cast<const __half*>(&b);
 #pragma unroll
@@ -467,7 +463,7 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
                                           uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                           const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
                                           const int32_t* m_dev, int density_act, float beta, void* grad_table, float* const* dweights,
-                                          int tiled, ngp_stream_t stream) {
+                                          ngp_stream_t stream) {
     (void)table_unused;
     if (M == 0) return NGP_OK;
     if (!xyzs || !d_sigma || !sigma || !d_in2 || !enc || !offsets || !weights || !dims || !grad_table || !dweights) return NGP_ERR_NULL;
@@ -509,6 +505,6 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
     field_backward_density_kernel<<<grid, kBwdThreads, smem_bytes, (cudaStream_t)stream>>>(
         xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,
-        dz_off, dz_bytes, w_base, ctrl_off, m_dev, tiled != 0);
+        dz_off, dz_bytes, w_base, ctrl_off, m_dev);
     return finish_launch();
 }

@@ -48,7 +48,7 @@ struct WsArgs {
     GridArgs g;
     const __half* w[kWsLayers];        // grid_mlp 0..2, view_mlp 0..2; [N, K] row-major fp16
     uint32_t K[kWsLayers], N[kWsLayers];
-    __half* enc_out;                   // tiled [tiles][F/8][128][8] or nullptr
+    __half* enc_out;                   // tile-panel (swizzled tile images, tile_sw.cuh) or nullptr
     __half* acts[kWsLayers];           // tiled hidden activations of layers 0,1 (grid) and 3,4 (view) or nullptr
     __half* in2_out;                   // tiled view_mlp input or nullptr
     float* sigma_out; float* rgb_out;

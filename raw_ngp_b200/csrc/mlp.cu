@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTile)
 mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* __restrict__ x, uint32_t ldx, MlpArgs p,
                     uint32_t M, __half* __restrict__ dx, uint32_t lddx, const float* __restrict__ d_rgb,
                     const float* __restrict__ rgb, int head_act, uint32_t dz_off, uint32_t dz_bytes,
-                    uint32_t w_base, uint32_t ctrl_off, const int* __restrict__ m_dev, bool tiled) {
+                    uint32_t w_base, uint32_t ctrl_off, const int* __restrict__ m_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, warp = t >> 5;
     const uint32_t L = p.n_layers;
@@ -189,13 +189,8 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
             for (uint32_t c = 0; c < p.dims[L] / 8; c++)
                 *reinterpret_cast<uint4*>(dzt + c * kPanel + t * 16) = (c < 2) ? reinterpret_cast<const uint4*>(dz)[c] : make_uint4(0, 0, 0, 0);
         }
-        if (tiled) {   // x / saved activations in the tile-panel layout ([tile][column / 8][row][8 halves], ld == width)
-            load_panel_tile(smem + in_off[0], x + (size_t)tile * (p.dims[0] * kTile), p.dims[0], row, M);
-            for (uint32_t l = 1; l < L; l++) load_panel_tile(smem + in_off[l], p.acts[l - 1] + (size_t)tile * (p.dims[l] * kTile), p.dims[l], row, M);
-        } else {
-            load_row_tile(smem + in_off[0], x, ldx, p.dims[0], row, M);
-            for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
-        }
+        load_row_tile(smem + in_off[0], x, ldx, p.dims[0], row, M);
+        for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
         tc::cp_async_wait_all();
         tc::fence_async_smem();
         __syncthreads();
@@ -249,12 +244,6 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
                         pack16(v, lo, hi);
                         *reinterpret_cast<uint4*>(nxt + (c0 / 8) * kPanel + t * 16) = lo;
                         *reinterpret_cast<uint4*>(nxt + (c0 / 8 + 1) * kPanel + t * 16) = hi;
-                    } else if (tiled) {
-                        uint4 lo, hi;
-                        pack16(v, lo, hi);
-                        __half* dx_tile = dx + (size_t)tile * (lddx * kTile);
-                        *reinterpret_cast<uint4*>(dx_tile + ((c0 / 8) * kTile + t) * 8) = lo;
-                        *reinterpret_cast<uint4*>(dx_tile + ((c0 / 8 + 1) * kTile + t) * 8) = hi;
                     } else if (row < M) {
                         uint4 lo, hi;
                         pack16(v, lo, hi);
@@ -357,10 +346,9 @@ extern "C" int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* cons
 static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
                              const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
                              void* dx, uint32_t lddx, float* const* dweights, const float* d_rgb, const float* rgb,
-                             int head_act, const int32_t* m_dev, int tiled, ngp_stream_t stream) {
+                             int head_act, const int32_t* m_dev, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     if (!x || !weights || !dims || !dweights) return NGP_ERR_NULL;
-    if (tiled && (ldx != dims[0] || (dx && lddx != dims[0]))) return NGP_ERR_BAD_ARG;
     if (head_act == 0 && !dy) return NGP_ERR_NULL;
     if (head_act != 0 && (!d_rgb || !rgb)) return NGP_ERR_NULL;
     if (n_layers > 1 && !acts) return NGP_ERR_NULL;
@@ -405,20 +393,20 @@ static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint3
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
     mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
-                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off, m_dev, tiled != 0);
+                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off, m_dev);
     return finish_launch();
 }
 
 extern "C" int ngp_mlp_backward(const void* dy, uint32_t lddy, const void* x, uint32_t ldx, const void* const* weights,
                                 const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M, int act,
                                 void* dx, uint32_t lddx, float* const* dweights, ngp_stream_t stream) {
-    return mlp_backward_impl(dy, lddy, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, nullptr, nullptr, 0, nullptr, 0, stream);
+    return mlp_backward_impl(dy, lddy, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, nullptr, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, const void* x, uint32_t ldx,
                                     const void* const* weights, const void* const* acts, const uint32_t* dims,
                                     uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
-                                    float* const* dweights, int tiled, ngp_stream_t stream) {
+                                    float* const* dweights, ngp_stream_t stream) {
     if (color_act < 1 || color_act > 3) return NGP_ERR_BAD_ARG;
-    return mlp_backward_impl(nullptr, 16, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, d_rgb, rgb, color_act, m_dev, tiled, stream);
+    return mlp_backward_impl(nullptr, 16, x, ldx, weights, acts, dims, n_layers, M, act, dx, lddx, dweights, d_rgb, rgb, color_act, m_dev, stream);
 }

@@ -40,17 +40,6 @@ __device__ __forceinline__ void load_row_tile(uint8_t* tile, const __half* __res
     }
 }
 
-// this thread's row of a tile stored in the tile-panel layout in global memory ([column / 8][row][8 halves]) -> the same
-// place of the shared-memory tile; a warp moves 512 contiguous bytes per chunk
-__device__ __forceinline__ void load_panel_tile(uint8_t* tile, const __half* __restrict__ src_tile, uint32_t F, uint32_t row, uint32_t M) {
-    const uint32_t t = threadIdx.x;
-    if (row < M) {
-        for (uint32_t c = 0; c < F / 8; c++) tc::cp_async16(tc::smem_u32(tile + c * kPanel + t * 16), src_tile + (c * kTile + t) * 8);
-    } else {
-        for (uint32_t c = 0; c < F / 8; c++) *reinterpret_cast<uint4*>(tile + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
-    }
-}
-
 __device__ __forceinline__ void pack16(const float (&v)[16], uint4& lo, uint4& hi) {
     __half2 h[8];
 #pragma unroll
