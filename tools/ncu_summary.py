@@ -59,8 +59,7 @@ def main():
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
     out += ["", f"## Launch list ({launches.split('/')[-1]}): {sum(v[0] for v in agg.values())} launches, {tot / 1000:.2f} ms total", "",
-            "First launches of a whole `bench.py --steps 2 --warmup 3` process (graph kernel nodes are listed individually): our",
-            "training steps + the per-kernel roofline pass + the micro-benchmark, followed by the reference-extension arm.", "",
+            "Every launch of the same command (`python tools/ncu_step.py 4`: scene set-up + 4 eager training steps).", "",
             "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
         out.append(f"| {k} | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% |")
