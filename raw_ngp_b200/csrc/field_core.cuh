@@ -31,29 +31,31 @@ struct GridArgs {
 //   mode 2 (anything else: tiled grids that wrap, non power-of-two hash sizes): the generic entry_index()
 struct LevelConst { uint32_t res, hashmap_size, offset, cy, cz, mask, mode, pad; };
 
-__device__ __forceinline__ void load_level_consts(LevelConst* s_lv, const GridArgs& g) {
-    for (uint32_t l = threadIdx.x; l < g.L; l += blockDim.x) {
-        const uint32_t off = (uint32_t)__ldg(g.offsets + l);
-        const uint32_t hs = (uint32_t)__ldg(g.offsets + l + 1) - off;
-        const uint32_t res = level_resolution(l, g.S, g.H);
-        LevelConst lv;
-        lv.res = res; lv.offset = off; lv.hashmap_size = hs; lv.pad = 0;
-        uint32_t stride = 1, c[3] = {0, 0, 0};
-        bool all = true;
-        for (uint32_t d = 0; d < 3; d++) {
-            if (stride <= hs) { c[d] = stride; stride *= res; } else all = false;
-        }
-        const bool hashed = g.gridtype == 0 && stride > hs;
-        if (hashed) {
-            lv.cy = 2654435761u; lv.cz = 805459861u; lv.mask = hs - 1;
-            lv.mode = ((hs & (hs - 1)) == 0) ? 1u : 2u;
-        } else {
-            lv.cy = c[1]; lv.cz = c[2]; lv.mask = 0xFFFFFFFFu;
-            // all three strides accumulated and res^3 <= hs: the largest row is res^3 - 1 < hs, no wrap
-            lv.mode = (all && stride <= hs) ? 0u : 2u;
-        }
-        s_lv[l] = lv;
+__device__ __forceinline__ LevelConst make_level_const(uint32_t l, const GridArgs& g) {
+    const uint32_t off = (uint32_t)__ldg(g.offsets + l);
+    const uint32_t hs = (uint32_t)__ldg(g.offsets + l + 1) - off;
+    const uint32_t res = level_resolution(l, g.S, g.H);
+    LevelConst lv;
+    lv.res = res; lv.offset = off; lv.hashmap_size = hs; lv.pad = 0;
+    uint32_t stride = 1, c[3] = {0, 0, 0};
+    bool all = true;
+    for (uint32_t d = 0; d < 3; d++) {
+        if (stride <= hs) { c[d] = stride; stride *= res; } else all = false;
     }
+    const bool hashed = g.gridtype == 0 && stride > hs;
+    if (hashed) {
+        lv.cy = 2654435761u; lv.cz = 805459861u; lv.mask = hs - 1;
+        lv.mode = ((hs & (hs - 1)) == 0) ? 1u : 2u;
+    } else {
+        lv.cy = c[1]; lv.cz = c[2]; lv.mask = 0xFFFFFFFFu;
+        // all three strides accumulated and res^3 <= hs: the largest row is res^3 - 1 < hs, no wrap
+        lv.mode = (all && stride <= hs) ? 0u : 2u;
+    }
+    return lv;
+}
+
+__device__ __forceinline__ void load_level_consts(LevelConst* s_lv, const GridArgs& g) {
+    for (uint32_t l = threadIdx.x; l < g.L; l += blockDim.x) s_lv[l] = make_level_const(l, g);
 }
 
 // rows of the 8 corners of cell `base` (corner k: bit 0 = +x, bit 1 = +y, bit 2 = +z; +1 clamped to res-1); modes 0 and 1

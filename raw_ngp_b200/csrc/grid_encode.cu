@@ -14,6 +14,7 @@
 //     streamed out as dy_dx [B, L*D*C] in forward and back in (gridencoder/grid.py:54, gridencoder.cu:352-378).
 #include "common.cuh"
 #include "grid_core.cuh"
+#include "field_core.cuh"
 
 namespace ngp {
 namespace {
@@ -49,6 +50,30 @@ grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ tabl
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
+
+    // The model's configuration (fp16 table, D = 3, F = 2, reference rounding, no dy_dx): per-level index constants, a
+    // branch-free gather and native half2 accumulation (csrc/field_core.cuh) -- the code path of the fused field kernels.
+    if constexpr (std::is_same<T, __half>::value && D == 3 && C == 2 && RefRound) {
+        if (!dy_dx && level < max_level) {
+            const fieldcore::GridArgs g = {table, offsets, nullptr, S, 1.f, H, L, gridtype, interp, align_corners};
+            const fieldcore::LevelConst lv = fieldcore::make_level_const(level, g);
+            const float x[3] = {__ldg(inputs + (size_t)b * 3), __ldg(inputs + (size_t)b * 3 + 1), __ldg(inputs + (size_t)b * 3 + 2)};
+            const bool inside = x[0] >= 0 && x[0] <= 1 && x[1] >= 0 && x[1] <= 1 && x[2] >= 0 && x[2] <= 1;
+            const float xc[3] = {fminf(fmaxf(x[0], 0.f), 1.f), fminf(fmaxf(x[1], 0.f), 1.f), fminf(fmaxf(x[2], 0.f), 1.f)};
+            __half2 f;
+            if (lv.mode == 2) {
+                const uint32_t r = fieldcore::gather_level_generic(table, nullptr, gridtype, align_corners, interp, lv.res, lv.hashmap_size,
+                                                                   lv.offset, xc[0], xc[1], xc[2], level, inside);
+                f = *reinterpret_cast<const __half2*>(&r);
+            } else {
+                fieldcore::LevelGather q;
+                fieldcore::gather_issue(q, g, lv, xc);
+                f = fieldcore::gather_finish(q, g, level, inside);
+            }
+            *reinterpret_cast<__half2*>(outputs + (size_t)b * (L * C) + level * C) = f;
+            return;
+        }
+    }
 
     T* out = outputs + (size_t)b * (L * C) + level * C;
     T* dout = dy_dx ? dy_dx + ((size_t)b * L + level) * (D * C) : nullptr;
