@@ -223,12 +223,14 @@ int ngp_composite_rays_train_backward(const float* grad_weights, const float* gr
  *   image = composite + (1 - weights_sum) * bg_color ;  loss = mean_n mean_c (image - target)^2
  *   grad_sigmas / grad_rgbs = d (loss_scale * loss) / d sigmas, rgbs   (every row of a ray that fits is written)
  * target [N,3]; image_out [N,3] or NULL; ray_loss [N] scratch; loss_out [1] (unscaled loss, summed in a fixed
- * order by the last block); ticket: int32[1] zero-filled once.  m_dev as in the field kernels. */
+ * order by the last block); ticket: int32[1] zero-filled once.  m_dev as in the field kernels.
+ * loss_mode 0: the MSE above.  loss_mode 1: the raw/HDR loss of nerf/train_utils.py:529-536 -- c = min(1, image * exposure[n]),
+ * loss = mean_n mean_c ((c - target) / (1e-3 + stop_grad(c)))^2; exposure [N] or NULL (= 1). */
 int ngp_composite_train_mse(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
                             uint32_t M, const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color,
                             const float* target, float loss_scale, float* image_out, float* ray_loss,
                             float* loss_out, int32_t* ticket, float* grad_sigmas, float* grad_rgbs,
-                            ngp_stream_t stream);
+                            int loss_mode, const float* exposure, ngp_stream_t stream);
 
 /* Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329, which used
  * torch_scatter.segment_csr): dL/drays_o[n] = sum_seg dL/dxyz ; dL/drays_d[n] = sum_seg (dL/dxyz * t + dL/ddirs).

@@ -38,7 +38,7 @@ SIGNATURES = {
     "ngp_march_rays_train_count": [_p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p],
     "ngp_march_rays_train_count_aabb": [_p, _p, _p, _f32, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _u32, _p, _p, _p, _p, _p, _p],
     "ngp_march_rays_train_write": [_p, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _u32, _p, _p, _p, _p, _p, _p, _p],
-    "ngp_composite_train_mse": [_p, _p, _p, _p, _u32, _p, _u32, _f32, _f32, _p, _f32, _p, _p, _p, _p, _p, _p, _p],
+    "ngp_composite_train_mse": [_p, _p, _p, _p, _u32, _p, _u32, _f32, _f32, _p, _f32, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "ngp_composite_rays_train_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p, _p],
     "ngp_composite_rays_train_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_march_rays_train_backward": [_p, _p, _p, _p, _u32, _u32, _p, _p, _p],

@@ -750,7 +750,8 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
                            const int* __restrict__ rays, uint32_t M, const int* __restrict__ m_dev, uint32_t N, float T_thresh,
                            float bg, const float* __restrict__ target, float loss_scale, float* __restrict__ image_out,
                            float* __restrict__ ray_loss, float* __restrict__ loss_out, int* __restrict__ ticket,
-                           float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+                           float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, int loss_mode,
+                           const float* __restrict__ exposure) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
@@ -787,14 +788,27 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
             r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
         }
         const float ir = r + (1.0f - ws) * bg, ig = g + (1.0f - ws) * bg, ib = b + (1.0f - ws) * bg;
-        const float er = ir - __ldg(target + (size_t)n * 3), eg = ig - __ldg(target + (size_t)n * 3 + 1), eb = ib - __ldg(target + (size_t)n * 3 + 2);
+        // loss_mode 0: MSE (train_utils.py:540-541).  loss_mode 1: the clipped, tone-curve weighted MSE of the raw/HDR path
+        // (train_utils.py:529-536): c = min(1, pred * exposure), loss = mean (c - gt)^2 / (1e-3 + stop_grad(c))^2
+        const float tr = __ldg(target + (size_t)n * 3), tgn = __ldg(target + (size_t)n * 3 + 1), tb = __ldg(target + (size_t)n * 3 + 2);
+        float er, eg, eb, dr = 1.f, dg = 1.f, db = 1.f;     // residuals and d loss_c / d image_c = 2 * e_c * d_c / (3 N)
+        if (loss_mode == 1) {
+            const float ex = exposure ? __ldg(exposure + n) : 1.f;
+            const float pr_ = ir * ex, pg_ = ig * ex, pb_ = ib * ex;
+            const float cr_ = fminf(1.f, pr_), cg_ = fminf(1.f, pg_), cb_ = fminf(1.f, pb_);
+            const float sr = 1.f / (1e-3f + cr_), sg_ = 1.f / (1e-3f + cg_), sb = 1.f / (1e-3f + cb_);
+            er = (cr_ - tr) * sr; eg = (cg_ - tgn) * sg_; eb = (cb_ - tb) * sb;
+            dr = (pr_ < 1.f) ? ex * sr : 0.f; dg = (pg_ < 1.f) ? ex * sg_ : 0.f; db = (pb_ < 1.f) ? ex * sb : 0.f;
+        } else {
+            er = ir - tr; eg = ig - tgn; eb = ib - tb;
+        }
         if (lane == 0) {
             if (image_out) { image_out[(size_t)n * 3] = ir; image_out[(size_t)n * 3 + 1] = ig; image_out[(size_t)n * 3 + 2] = ib; }
             ray_loss[n] = (er * er + eg * eg + eb * eb) * (1.0f / 3.0f);
         }
         if (has) {
             const float gs = loss_scale * 2.0f / (3.0f * (float)N);
-            const float gi_r = gs * er, gi_g = gs * eg, gi_b = gs * eb;
+            const float gi_r = gs * er * dr, gi_g = gs * eg * dg, gi_b = gs * eb * db;
             const float g_ws = -bg * (gi_r + gi_g + gi_b);
             float T = 1.0f, r0 = 0, g0 = 0, b0 = 0, ws0 = 0;
             uint32_t base = 0;
@@ -1147,14 +1161,16 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights, cons
 extern "C" int ngp_composite_train_mse(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays, uint32_t M,
                                        const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color, const float* target,
                                        float loss_scale, float* image_out, float* ray_loss, float* loss_out, int32_t* ticket,
-                                       float* grad_sigmas, float* grad_rgbs, ngp_stream_t stream) {
+                                       float* grad_sigmas, float* grad_rgbs, int loss_mode, const float* exposure,
+                                       ngp_stream_t stream) {
     if (N == 0) return NGP_OK;
     if (!rays || !target || !ray_loss || !loss_out || !ticket) return NGP_ERR_NULL;
     if (M > 0 && (!sigmas || !rgbs || !ts || !grad_sigmas || !grad_rgbs)) return NGP_ERR_NULL;
     if (M > 0 && !aligned(ts, 8)) return NGP_ERR_ALIGN;
+    if (loss_mode < 0 || loss_mode > 1) return NGP_ERR_BAD_ARG;
     composite_train_mse_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, ts, rays, M, m_dev, N, T_thresh, bg_color, target, loss_scale, image_out, ray_loss, loss_out, ticket,
-        grad_sigmas, grad_rgbs);
+        grad_sigmas, grad_rgbs, loss_mode, exposure);
     return finish_launch();
 }
 

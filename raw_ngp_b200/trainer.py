@@ -147,7 +147,7 @@ class FusedTrainStep:
     MSE loss and a scalar background."""
 
     def __init__(self, model, n_rays, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, loss_scale=128.0, max_samples=None,
-                 process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True):
+                 process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True, loss="mse"):
         import ctypes
         from . import field as _field
         from .ffmlp import _pad16
@@ -164,6 +164,9 @@ class FusedTrainStep:
                 and opt.pose_opt in ("none", "barf") and model.grid_mlp.num_layers == 3 and model.view_mlp.num_layers == 3):
             raise RuntimeError("FusedTrainStep: configuration outside the fused field path; use TrainStep")
         self.rfield = bool(opt.rfield)
+        if loss not in ("mse", "hdr"):
+            raise ValueError("loss must be 'mse' or 'hdr' (nerf/train_utils.py:512-541)")
+        self.loss_mode = 0 if loss == "mse" else 1
         self.perturb = perturb
         self.bg_color = float(bg_color)
         self.loss_scale = float(loss_scale)
@@ -216,6 +219,7 @@ class FusedTrainStep:
         self.rays_o, self.rays_d, self.target = torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32)
         self.rays_ldir = torch.zeros(N, 3, **f32) if self.rfield else None
         self.noises = torch.zeros(N, **f32)
+        self.exposure = torch.ones(N, **f32)          # per-ray exposure of the HDR loss (train_utils.py:514)
         self.rays = torch.zeros(N, 2, device=dev, dtype=torch.int32)
         self.counter = torch.zeros(4, device=dev, dtype=torch.int32)
         self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -284,7 +288,7 @@ class FusedTrainStep:
                   float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), st)
         _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
                   float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
-                  P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), st)
+                  P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), self.loss_mode, P(self.exposure), st)
         _lib.call("ngp_field_backward_full", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_rgb), P(self.rgb), P(self.enc_buf),
                   a1, P(self.in2), a2, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap,
                   self._m_dev, self._density_act, float(opt.beta), self._color_act, P(self.table_grad),
@@ -399,9 +403,10 @@ class FusedTrainStep:
             out.setdefault(n, []).append(e0.elapsed_time(e1))
         return {n: sum(v) / iters for n, v in out.items()}
 
-    def set_rays(self, rays_o, rays_d, target_rgb, rays_ldir=None):
+    def set_rays(self, rays_o, rays_d, target_rgb, rays_ldir=None, exposure=None):
         """Copies the step's inputs into the static buffers (pinned host tensors are copied asynchronously)."""
-        for dst, src in ((self.rays_o, rays_o), (self.rays_d, rays_d), (self.target, target_rgb), (self.rays_ldir, rays_ldir)):
+        for dst, src in ((self.rays_o, rays_o), (self.rays_d, rays_d), (self.target, target_rgb), (self.rays_ldir, rays_ldir),
+                         (self.exposure, exposure)):
             if dst is None or src is None or (src.is_cuda and src.data_ptr() == dst.data_ptr()):
                 continue
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
@@ -410,7 +415,7 @@ class FusedTrainStep:
     def last_num_points(self):
         return int(self.counter[0].item())
 
-    def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True):
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True, exposure=None):
         """One optimisation step; returns the (unscaled) loss as a 1-element device tensor (overwritten by the next step).
         The parameter update of this step is applied at the start of the next call (or by flush())."""
         model = self.model
@@ -418,7 +423,7 @@ class FusedTrainStep:
             self.flush()                       # the density queries of the occupancy update see the updated weights
             model.update_extra_state()
         if rays_o is not None:
-            self.set_rays(rays_o, rays_d, target_rgb, rays_ldir)
+            self.set_rays(rays_o, rays_d, target_rgb, rays_ldir, exposure)
         if self.feat_weights is not None:
             self.feat_weights.copy_(model._feat_weights(self.dev))
         if self.use_graph:

@@ -107,3 +107,29 @@ def test_fused_step_capacity_overflow_drops_whole_rays():
     dropped = (ends > cap).cuda()
     assert torch.all(part.image[dropped] == 1.0)
     assert torch.isfinite(part.table_grad.float()).all()
+
+
+def test_fused_step_hdr_loss_matches_torch():
+    """loss_mode 1 = the clipped, tone-curve weighted MSE of the raw/HDR path (nerf/train_utils.py:529-536)."""
+    N = 1200
+    model, o, d, tgt = _scene(N, color_activation="exp")
+    ref_model = copy.deepcopy(model)
+    exposure = (torch.rand(N, generator=torch.Generator().manual_seed(3)) * 3 + 0.25).cuda()
+    ref = TrainStep(ref_model, loss_scale=128.0)
+    ref_model.train()
+    out = ref_model.render(o, d, bg_color=1.0, perturb=False)
+    pred = out["image"]
+    clip = torch.minimum(torch.tensor(1.0, device=pred.device), pred * exposure.unsqueeze(1))
+    scaling = 1.0 / (1e-3 + clip.detach())
+    loss_ref = ((clip - tgt) ** 2 * scaling ** 2).sum() / (3 * N)
+    (loss_ref * 128.0).backward()
+    g_table_ref = ref.table_grad.float().clone()
+
+    fs = FusedTrainStep(model, N, loss_scale=128.0, perturb=False, use_graph=False, loss="hdr")
+    fs.set_rays(o, d, tgt, exposure=exposure)
+    fs._launch_forward_backward()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(fs.loss[0], loss_ref.float(), rtol=5e-3, atol=1e-6)
+    scale = g_table_ref.abs().max().clamp(min=1e-8)
+    err = (fs.table_grad.float() - g_table_ref).abs() / scale
+    assert err.max().item() < 3e-2 and err.mean().item() < 1e-3, (err.max().item(), err.mean().item())
