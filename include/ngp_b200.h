@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NGP_B200_ABI_VERSION 2
+#define NGP_B200_ABI_VERSION 3
 
 typedef void* ngp_stream_t; /* cudaStream_t */
 
@@ -366,7 +366,12 @@ int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, co
  * memory) and 16 scatter warps (hash-table gradient) run as a pipeline; saved tiles arrive by bulk async copies.
  * Inputs are what ngp_field_forward_full saved (tile-panel layout): enc, grid_acts[0..1], in2, view_acts[0..1]; plus
  * sigma [M], rgb [M,3] and the incoming d_sigma [M], d_rgb [M,3] (fp32).  grad_table [sO,2] fp16 and the fp32
- * grid_dweights[l] / view_dweights[l] ([dims[l+1], dims[l]]) are ACCUMULATED into. */
+ * grid_dweights[l] / view_dweights[l] ([dims[l+1], dims[l]]) are ACCUMULATED into.
+ * Input gradients (BARF pose refinement: the positions and directions of the samples require grad, nerf/network.py with
+ * rays_o / rays_d from refined poses): d_xyzs [M,3] and d_dirs [M,3] fp32, both NULL or both set, are WRITTEN (rows
+ * < min(M, *m_dev)); they need the table [sO,2] fp16 (d feat / d x is recomputed from it: gridencoder.cu:216-245,
+ * 352-378 without the saved dy_dx) and the un-normalised march directions dirs [M,3] (SH Jacobian + the normalisations
+ * of renderer.py:544 and sphere_harmonics.py:81, shencoder.cu:358-382); view_dims[0] must be 32.  Otherwise pass NULLs. */
 int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float* sigma, const float* d_rgb,
                             const float* rgb, const void* enc, const void* const* grid_acts, const void* in2,
                             const void* const* view_acts, const int32_t* offsets, const float* feat_weights,
@@ -374,7 +379,8 @@ int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float
                             uint32_t interp, const void* const* grid_weights, const uint32_t* grid_dims,
                             const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
                             const int32_t* m_dev, int density_act, float beta, int color_act, void* grad_table,
-                            float* const* grid_dweights, float* const* view_dweights, ngp_stream_t stream);
+                            float* const* grid_dweights, float* const* view_dweights, const void* table,
+                            const float* dirs, float* d_xyzs, float* d_dirs, ngp_stream_t stream);
 
 /* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
  * shared-memory tiles while two groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.

@@ -39,7 +39,8 @@ constexpr uint32_t kTFull = 0;                                   // [chain][laye
 constexpr uint32_t kEncFull = kTFull + 8 * kChains * kL, kEncEmpty = kEncFull + 8 * kRing;
 constexpr uint32_t kDinFull = kEncEmpty + 8 * kRing, kDinEmpty = kDinFull + 8 * kRing;
 constexpr uint32_t kDzFull = kDinEmpty + 8 * kRing, kDzEmpty = kDzFull + 8 * kChains;      // dZ1 hand-over inside a chain
-constexpr uint32_t kDone = kDzEmpty + 8 * kChains, kTail = kDone + 8 * kRoles, kSlot = kTail + 8 * kRoles;
+constexpr uint32_t kDone = kDzEmpty + 8 * kChains, kTail = kDone + 8 * kRoles, kDxDone = kTail + 8 * kRoles, kSlot = kDxDone + 8;
+constexpr uint32_t kDxRing = 3;                                  // per-tile d xyz accumulators (input gradients)
 constexpr uint32_t kBLevels = (kSlot + 4 + 15) & ~15u;           // LevelConst[L], then the MMA plans
 
 struct Chain {
@@ -55,13 +56,22 @@ struct Chain {
 struct BwsArgs {
     Chain c[kChains];
     const float* xyzs; const float* d_sigma; const float* sigma; const float* d_rgb; const float* rgb;
+    const float* dirs; float* d_xyzs; float* d_dirs;       // input gradients (IG): march dirs in, d xyzs / d dirs [M,3] out
     GridArgs g;
     uint32_t M; const int* m_dev;
     __half* grad_table;
     int density_act, color_act; float beta;
-    uint32_t enc_off, enc_stage_bytes, din_off, ctrl_off, plans_off;
+    uint32_t enc_off, enc_stage_bytes, din_off, dx_off, ctrl_off, plans_off;
 };
 
+// IG: also produce the gradients with respect to the sample positions and view directions (BARF pose refinement):
+//   * the scatter warps gather the 8 corner rows of each level again and contract d feat / d x with d enc in registers;
+//     the four level groups of a sample meet in a ring of shared-memory accumulators (red.shared), which the G0 group
+//     writes out three tiles later -- by then every scatter thread has moved past that tile (it has acknowledged the
+//     d enc stage of the tile after it), so no extra barrier sits on the pipeline;
+//   * the V0 group turns d in2[:, 15:31] (the SH features) into d dirs through the SH Jacobian and the two
+//     normalisations of the forward (renderer.py:544, sphere_harmonics.py:81).
+template <bool IG>
 __global__ void __launch_bounds__(kBwsThreads, 1)
 field_backward_ws_kernel(const BwsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -73,7 +83,8 @@ field_backward_ws_kernel(const BwsArgs a) {
     const uint32_t enc_full = tc::smem_u32(ctrl + kEncFull), enc_empty = tc::smem_u32(ctrl + kEncEmpty);
     const uint32_t din_full = tc::smem_u32(ctrl + kDinFull), din_empty = tc::smem_u32(ctrl + kDinEmpty);
     const uint32_t dz_full = tc::smem_u32(ctrl + kDzFull), dz_empty = tc::smem_u32(ctrl + kDzEmpty);
-    const uint32_t done = tc::smem_u32(ctrl + kDone), tail = tc::smem_u32(ctrl + kTail);
+    const uint32_t done = tc::smem_u32(ctrl + kDone), tail = tc::smem_u32(ctrl + kTail), dx_done = tc::smem_u32(ctrl + kDxDone);
+    float* dx_ring = reinterpret_cast<float*>(smem + a.dx_off);          // [kDxRing][kTile][3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kSlot);
     LevelConst* s_lv = reinterpret_cast<LevelConst*>(ctrl + kBLevels);
     MmaPlan* plans = reinterpret_cast<MmaPlan*>(ctrl + a.plans_off);  // [chain][layer][0 = dW, 1 = dH]
@@ -87,7 +98,9 @@ field_backward_ws_kernel(const BwsArgs a) {
         }
         for (uint32_t ci = 0; ci < kChains; ci++) { tc::mbar_init(dz_full + 8 * ci, kTile); tc::mbar_init(dz_empty + 8 * ci, 1); }
         for (uint32_t r = 0; r < kRoles; r++) { tc::mbar_init(done + 8 * r, 1); tc::mbar_init(tail + 8 * r, 1); }
+        tc::mbar_init(dx_done, kScatterThreads);
     }
+    if (IG) for (uint32_t i = threadIdx.x; i < kDxRing * kTile * 3; i += blockDim.x) dx_ring[i] = 0.f;
     for (uint32_t ci = 0; ci < kChains; ci++)
         for (uint32_t l = 0; l < kL; l++) tsw::load_weight_tile(smem + a.c[ci].w_off[l], a.c[ci].w[l], a.c[ci].dims[l + 1], a.c[ci].dims[l]);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kChains * kL) {
@@ -143,12 +156,24 @@ field_backward_ws_kernel(const BwsArgs a) {
                 if (level < g.L) gh[j] = *reinterpret_cast<const __half2*>(de + (level / 4) * kPanel + r * 16 + (level % 4) * 4);
             }
             tc::mbar_arrive(enc_empty + 8 * e);
+            float dxa[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (uint32_t j = 0; j < kMaxLevels / kScatterGroups; j++) {
                 const uint32_t level = grp + j * kScatterGroups;
-                if (level < g.L) scatter_level(g, s_lv[level], level, x, live, gh[j], a.grad_table, lane);
+                if (level < g.L) {
+                    if (IG) input_grad_level(g, s_lv[level], level, x, live, gh[j], dxa);
+                    scatter_level(g, s_lv[level], level, x, live, gh[j], a.grad_table, lane);
+                }
+            }
+            if (IG) {
+                // the arrival on enc_empty of this thread's NEXT tile (a release) publishes these to the G0 group
+                float* acc = dx_ring + ((it % kDxRing) * kTile + r) * 3;
+                const float inv2b = __fdiv_rn(1.0f, 2.0f * g.bound);
+#pragma unroll
+                for (int d = 0; d < 3; d++) atomicAdd(acc + d, dxa[d] * inv2b);
             }
         }
+        if (IG) tc::mbar_arrive(dx_done);
     } else {
         // ================================ MLP groups ================================
         const uint32_t role = (warp - kScatterThreads / 32) / 4;          // 0 = V1, 1 = V0, 2 = G1, 3 = G0
@@ -319,9 +344,48 @@ field_backward_ws_kernel(const BwsArgs a) {
                     *reinterpret_cast<uint4*>(di + tg * 16) = lo;
                     *reinterpret_cast<uint4*>(di + kPanel + tg * 16) = hi;
                     tc::mbar_arrive(din_full + 8 * e);
+                    if (IG) {
+                        // d SH(dir) = d in2[:, 15:31] (fp16 like the autocast tensor) -> d dirs
+                        float g2[16], gs[16];
+                        tc::tmem_ld16(lane_addr + 16, g2);
+                        gs[0] = half_round(v[15]);
+#pragma unroll
+                        for (int k = 1; k < 16; k++) gs[k] = half_round(g2[k - 1]);
+                        const uint32_t row = tile * kTile + tg;
+                        if (row < M) {
+                            const float d0 = __ldg(a.dirs + (size_t)row * 3), d1 = __ldg(a.dirs + (size_t)row * 3 + 1), d2 = __ldg(a.dirs + (size_t)row * 3 + 2);
+                            const float inv0 = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);            // renderer.py:544
+                            const float u0 = d0 * inv0, u1 = d1 * inv0, u2 = d2 * inv0;
+                            const float inv1 = 1.0f / sqrtf(u0 * u0 + u1 * u1 + u2 * u2);            // sphere_harmonics.py:81
+                            const float x = u0 * inv1, y = u1 * inv1, z = u2 * inv1, zz = z * z;
+                            float gx = 0.f, gy = 0.f, gz = 0.f;
+                            constexpr int DEG = 4;
+#define SH_TERM(i, val, ddx, ddy, ddz) gx += gs[i] * (ddx); gy += gs[i] * (ddy); gz += gs[i] * (ddz);
+#include "sh_basis.inc"
+#undef SH_TERM
+                            // v = n / |n|  =>  d n = (d v - v (v . d v)) / |n|, twice
+                            float t = x * gx + y * gy + z * gz;
+                            gx = (gx - x * t) * inv1; gy = (gy - y * t) * inv1; gz = (gz - z * t) * inv1;
+                            t = u0 * gx + u1 * gy + u2 * gz;
+                            a.d_dirs[(size_t)row * 3] = (gx - u0 * t) * inv0;
+                            a.d_dirs[(size_t)row * 3 + 1] = (gy - u1 * t) * inv0;
+                            a.d_dirs[(size_t)row * 3 + 2] = (gz - u2 * t) * inv0;
+                        }
+                    }
                 } else {
                     // d enc -> fp16 tile for the scatter warps
                     tc::mbar_wait(enc_empty + 8 * e, rp ^ 1u);
+                    if (IG && it >= kDxRing) {
+                        // every scatter thread has acknowledged tile it - 2, hence finished tile it - 3: write its d xyz out and
+                        // clear the accumulators for tile `it` (same slot; published by the arrival on enc_full below)
+                        float* acc = dx_ring + ((it % kDxRing) * kTile + tg) * 3;
+                        const uint32_t row = (blockIdx.x + (it - kDxRing) * gridDim.x) * kTile + tg;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            if (row < M) a.d_xyzs[(size_t)row * 3 + d] = acc[d];
+                            acc[d] = 0.f;
+                        }
+                    }
                     uint8_t* de = smem + a.enc_off + e * a.enc_stage_bytes;
                     for (uint32_t c0 = 0; c0 < c.dims[0]; c0 += 16) {
                         float v[16];
@@ -341,6 +405,18 @@ field_backward_ws_kernel(const BwsArgs a) {
                 }
                 tc::fence_before_sync();
                 tc::named_bar_sync(1 + role, kTile);        // the TMEM work columns are rewritten by the next tile
+            }
+        }
+        if (IG && !upper && !view) {
+            // the last tiles' d xyz: wait until every scatter thread has left its loop
+            tc::mbar_wait(dx_done, 0);
+            for (uint32_t j = (it > kDxRing ? it - kDxRing : 0u); j < it; j++) {
+                const float* acc = dx_ring + ((j % kDxRing) * kTile + tg) * 3;
+                const uint32_t row = (blockIdx.x + j * gridDim.x) * kTile + tg;
+                if (row < M) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) a.d_xyzs[(size_t)row * 3 + d] = acc[d];
+                }
             }
         }
         // reduce this group's weight-gradient accumulators (TMEM lane i = input feature i) into global memory
@@ -376,8 +452,12 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
                                        uint32_t interp, const void* const* grid_weights, const uint32_t* grid_dims,
                                        const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
                                        const int32_t* m_dev, int density_act, float beta, int color_act, void* grad_table,
-                                       float* const* grid_dweights, float* const* view_dweights, ngp_stream_t stream) {
+                                       float* const* grid_dweights, float* const* view_dweights, const void* table,
+                                       const float* dirs, float* d_xyzs, float* d_dirs, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
+    const bool ig = d_xyzs != nullptr || d_dirs != nullptr;
+    if (ig && (!d_xyzs || !d_dirs || !table || !dirs)) return NGP_ERR_NULL;
+    if (ig && view_dims[0] != 32) return NGP_ERR_UNSUPPORTED;      // d dirs reads the 16 SH columns of a 32-wide view input
     if (!xyzs || !d_sigma || !sigma || !d_rgb || !rgb || !enc || !grid_acts || !in2 || !view_acts || !offsets || !grid_weights ||
         !grid_dims || !view_weights || !view_dims || !grad_table || !grid_dweights || !view_dweights)
         return NGP_ERR_NULL;
@@ -387,7 +467,8 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
     if (grid_dims[0] != 2 * L || grid_dims[3] != 16 || view_dims[3] != 16 || view_dims[0] < 16) return NGP_ERR_UNSUPPORTED;
     BwsArgs a = {};
     a.xyzs = xyzs; a.d_sigma = d_sigma; a.sigma = sigma; a.d_rgb = d_rgb; a.rgb = rgb;
-    a.g = {nullptr, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
+    a.g = {(const __half*)table, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
+    a.dirs = dirs; a.d_xyzs = d_xyzs; a.d_dirs = d_dirs;
     uint32_t off = 0;
     for (uint32_t ci = 0; ci < kChains; ci++) {
         Chain& c = a.c[ci];
@@ -448,6 +529,8 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
     off += kRing * a.enc_stage_bytes;
     a.din_off = off;
     off += kRing * 2 * kPanel;
+    a.dx_off = off;
+    if (ig) off += kDxRing * kTile * 3 * (uint32_t)sizeof(float);
     a.ctrl_off = off;
     a.plans_off = (kBLevels + L * (uint32_t)sizeof(LevelConst) + 15) & ~15u;
     const uint32_t smem_bytes = std::max(off + a.plans_off + kChains * kL * 2 * (uint32_t)sizeof(MmaPlan), tiles_end + 16 * kPanel);
@@ -455,15 +538,18 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
     a.M = M; a.m_dev = m_dev; a.grad_table = (__half*)grad_table;
     a.density_act = density_act; a.color_act = color_act; a.beta = beta;
-    static thread_local uint32_t configured = 0;
-    if (smem_bytes > configured) {
-        if (cudaFuncSetAttribute(field_backward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+    static thread_local uint32_t configured[2] = {0, 0};
+    if (smem_bytes > configured[ig]) {
+        const cudaError_t e = ig ? cudaFuncSetAttribute(field_backward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
+                                 : cudaFuncSetAttribute(field_backward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) {
             set_last_cuda_error(cudaGetLastError());
             return NGP_ERR_CUDA;
         }
-        configured = smem_bytes;
+        configured[ig] = smem_bytes;
     }
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs);
-    field_backward_ws_kernel<<<grid, kBwsThreads, smem_bytes, (cudaStream_t)stream>>>(a);
+    if (ig) field_backward_ws_kernel<true><<<grid, kBwsThreads, smem_bytes, (cudaStream_t)stream>>>(a);
+    else field_backward_ws_kernel<false><<<grid, kBwsThreads, smem_bytes, (cudaStream_t)stream>>>(a);
     return finish_launch();
 }

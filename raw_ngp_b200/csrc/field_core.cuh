@@ -214,6 +214,61 @@ static __device__ __noinline__ void scatter_corners_generic(__half* glvl, uint32
     }
 }
 
+// One level of one sample of the gradient with respect to the POSITION (BARF: rays_o / rays_d receive gradients):
+//   dx[d] += sum_c gh[c] * d feat_c / d x_d
+// The reference saves dy_dx [B, L*3*2] in its forward (192 B per sample in fp16) and contracts it with the incoming
+// gradient in kernel_input_backward (gridencoder.cu:216-245, 352-378); here the 8 corner rows -- L2 resident, the
+// scatter needs their indices anyway -- are gathered again and the contraction happens in registers, so nothing is saved.
+// x is the position in the unit cube; the caller multiplies by d unit / d xyz = 1 / (2 bound).
+__device__ __forceinline__ void input_grad_level(const GridArgs& g, const LevelConst& lv, uint32_t level, const float (&x)[3], bool live,
+                                                 __half2 gh, float (&dx)[3]) {
+    if (g.feat_weights) {
+        const float2 gf = __half22float2(gh);
+        gh = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
+    }
+    const float2 gf = __half22float2(gh);
+    const bool inside = live && !(x[0] < 0 || x[0] > 1 || x[1] < 0 || x[1] > 1 || x[2] < 0 || x[2] > 1);
+    uint32_t base[3];
+    float frac[3], dfrac[3];
+#pragma unroll
+    for (uint32_t d = 0; d < 3; d++) {
+        const float xc = fminf(fmaxf(x[d], 0.f), 1.f);      // dead / outside rows: loads stay in bounds, result discarded
+        float p;
+        if (g.align_corners) {
+            p = xc * (float)(lv.res - 1);
+            base[d] = min((uint32_t)floorf(p), lv.res - 2);
+        } else {
+            p = fminf(fmaxf(xc * (float)lv.res - 0.5f, 0.0f), (float)(lv.res - 1));
+            base[d] = (uint32_t)floorf(p);
+        }
+        p -= (float)base[d];
+        frac[d] = (g.interp == 1) ? smoothstep_f(p) : p;
+        dfrac[d] = (g.interp == 1) ? smoothstep_df(p) : 1.0f;
+    }
+    uint32_t rows[8];
+    if (lv.mode == 2) corner_rows_generic(g.gridtype, lv.hashmap_size, lv.res, base[0], base[1], base[2], rows);
+    else corner_rows(lv, base, rows);
+    const uint32_t* __restrict__ lvl = reinterpret_cast<const uint32_t*>(g.table) + lv.offset;
+    float dot[8];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t v = __ldg(lvl + rows[k]);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+        dot[k] = gf.x * f.x + gf.y * f.y;
+    }
+    const float x0 = 1 - frac[0], y0 = 1 - frac[1], z0 = 1 - frac[2];
+    const float sx = (y0 * z0) * (dot[1] - dot[0]) + (frac[1] * z0) * (dot[3] - dot[2]) + (y0 * frac[2]) * (dot[5] - dot[4]) +
+                     (frac[1] * frac[2]) * (dot[7] - dot[6]);
+    const float sy = (x0 * z0) * (dot[2] - dot[0]) + (frac[0] * z0) * (dot[3] - dot[1]) + (x0 * frac[2]) * (dot[6] - dot[4]) +
+                     (frac[0] * frac[2]) * (dot[7] - dot[5]);
+    const float sz = (x0 * y0) * (dot[4] - dot[0]) + (frac[0] * y0) * (dot[5] - dot[1]) + (x0 * frac[1]) * (dot[6] - dot[2]) +
+                     (frac[0] * frac[1]) * (dot[7] - dot[3]);
+    const float scale = inside ? (float)(g.align_corners ? lv.res - 1 : lv.res) : 0.f;
+    dx[0] += scale * sx * dfrac[0];
+    dx[1] += scale * sy * dfrac[1];
+    dx[2] += scale * sz * dfrac[2];
+}
+
 // One level of one sample of the table-gradient scatter.  `gh` is d enc (2 features) as it comes out of the grid_mlp
 // backward; it reaches the encoder as fp16 (autocast), optionally through the annealing window.  Must be called by all 32
 // lanes of a warp whose lanes hold consecutive samples (the warp aggregation below uses full-warp shuffles).

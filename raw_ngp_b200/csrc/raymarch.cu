@@ -876,11 +876,14 @@ march_train_bwd_kernel(const float* __restrict__ dL_dxyzs, const float* __restri
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (n >= N) return;
-    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2);
+    uint32_t count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
+    // a ray whose samples do not fit in the buffers was not rendered (composite_rays_train early-out, raymarching.cu:540-547;
+    // only possible with the fixed-capacity buffers of FusedTrainStep): no gradient
+    if ((uint64_t)offset + count > M) count = 0;
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
     for (uint32_t k = lane; k < count; k += 32) {
         const size_t i = (size_t)offset + k;
-        if (i >= M) break;
         const float gx = __ldg(dL_dxyzs + i * 3), gy = __ldg(dL_dxyzs + i * 3 + 1), gz = __ldg(dL_dxyzs + i * 3 + 2);
         const float t = __ldg(ts + i * 2);
         ox += gx; oy += gy; oz += gz;

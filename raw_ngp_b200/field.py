@@ -134,7 +134,7 @@ class _fused_field(Function):
             _lib.call("ngp_field_backward_full", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_rgb), _lib.ptr(rgb),
                       _lib.ptr(enc_buf), _ptr_array(acts1), _lib.ptr(in2), _ptr_array(acts2), _lib.ptr(enc.offsets), fwp, float(bound),
                       S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None, int(density_act), float(beta),
-                      int(color_act), _lib.ptr(gtable), _ptr_array(dw1), _ptr_array(dw2), st)
+                      int(color_act), _lib.ptr(gtable), _ptr_array(dw1), _ptr_array(dw2), None, None, None, None, st)
         else:
             d_in2 = torch.empty(M, p2[0], dtype=torch.float16, device=dev)
             _lib.call("ngp_mlp_backward_rgb", _lib.ptr(d_rgb), _lib.ptr(rgb), int(color_act), _lib.ptr(in2), p2[0], _ptr_array(w2),

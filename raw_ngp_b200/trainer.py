@@ -147,7 +147,8 @@ class FusedTrainStep:
     MSE loss and a scalar background."""
 
     def __init__(self, model, n_rays, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, loss_scale=128.0, max_samples=None,
-                 process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True, loss="mse"):
+                 process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True, loss="mse",
+                 ray_grads=False):
         import ctypes
         from . import field as _field
         from .ffmlp import _pad16
@@ -174,7 +175,7 @@ class FusedTrainStep:
         self.global_step = 0
         N = self.N
         self.cap = int(max_samples) if max_samples else N * int(opt.max_steps)
-        cap_t = (self.cap + 127) // 128 * 128      # saved activations are stored as whole 128-row tiles
+        cap_t = (self.cap + 127) // 128 * 128      # saved activations are stored as whole 128-row tiles (tile-panel layout)
 
         # ---- parameters: fp32 master + fp16 working copy + fp32/fp16 gradient buffers -------------------------------
         self.table_master = enc.embeddings.data.float().contiguous()
@@ -185,8 +186,14 @@ class FusedTrainStep:
         self.d1 = [model.grid_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.grid_mlp.net]
         self.d2 = [model.view_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.view_mlp.net]
         self.p1, self.p2 = [_pad16(d) for d in self.d1], [_pad16(d) for d in self.d2]
-        if not _field._ws_ok(self.p1, self.p2):
-            raise RuntimeError("FusedTrainStep: layer widths outside {16, 32, 64} (rfield); use TrainStep")
+        # widths in {16, 32, 64}: the warp-specialised one-kernel forward / backward; otherwise (rfield: 48-wide view input,
+        # 80-wide hidden layers) the density-field + view-MLP kernel pairs, with the same buffers and the same graph
+        self.ws = _field._ws_ok(self.p1, self.p2)
+        # ray_grads: also produce dL/d rays_o and dL/d rays_d (self.d_rays_o / self.d_rays_d, scaled by loss_scale like every
+        # gradient of the step) for pose refinement (BARF, --pose_opt barf: rays come from refined poses and require grad)
+        self.ray_grads = bool(ray_grads)
+        if self.ray_grads and not self.ws:
+            raise RuntimeError("FusedTrainStep: ray gradients need the warp-specialised kernels (layer widths in {16, 32, 64})")
         shapes = [(self.p1[i + 1], self.p1[i]) for i in range(3)] + [(self.p2[i + 1], self.p2[i]) for i in range(3)]
         n_w = sum(a * b for a, b in shapes)
         self.w_master = torch.zeros(n_w, device=dev, dtype=torch.float32)
@@ -230,8 +237,13 @@ class FusedTrainStep:
         self.acts1 = [torch.empty(cap_t, self.p1[l + 1], **f16) for l in range(2)]
         self.acts2 = [torch.empty(cap_t, self.p2[l + 1], **f16) for l in range(2)]
         self.in2 = torch.empty(cap_t, self.p2[0], **f16)
+        self.d_in2 = None if self.ws else torch.empty(cap, self.p2[0], **f16)
         self.sigma, self.rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.d_sigma, self.d_rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
+        self.d_xyzs = torch.empty(cap, 3, **f32) if self.ray_grads else None
+        self.d_dirs = torch.empty(cap, 3, **f32) if self.ray_grads else None
+        self.d_rays_o = torch.zeros(N, 3, **f32) if self.ray_grads else None
+        self.d_rays_d = torch.zeros(N, 3, **f32) if self.ray_grads else None
         self.image, self.ray_loss, self.loss = torch.zeros(N, 3, **f32), torch.zeros(N, **f32), torch.zeros(1, **f32)
         self.feat_weights = torch.ones(2 * enc.num_levels, **f32) if opt.pose_opt == "barf" else None
         self._density_act = model._density_act()
@@ -283,16 +295,38 @@ class FusedTrainStep:
         c2 = (ct.c_uint32 * 4)(*self.p2)
         w1, w2 = self._ptrs(self._w_lp_views[:3]), self._ptrs(self._w_lp_views[3:])
         a1, a2 = self._ptrs(self.acts1), self._ptrs(self.acts2)
-        _lib.call("ngp_field_forward_full", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
-                  P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap, self._m_dev, self._density_act,
-                  float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), st)
-        _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
-                  float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
-                  P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), self.loss_mode, P(self.exposure), st)
-        _lib.call("ngp_field_backward_full", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_rgb), P(self.rgb), P(self.enc_buf),
-                  a1, P(self.in2), a2, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap,
-                  self._m_dev, self._density_act, float(opt.beta), self._color_act, P(self.table_grad),
-                  self._ptrs(self._w_grad_views[:3]), self._ptrs(self._w_grad_views[3:]), st)
+        def composite():
+            _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
+                      float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
+                      P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), self.loss_mode, P(self.exposure), st)
+
+        dw1, dw2 = self._ptrs(self._w_grad_views[:3]), self._ptrs(self._w_grad_views[3:])
+        if self.ws:
+            _lib.call("ngp_field_forward_full", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
+                      P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap, self._m_dev, self._density_act,
+                      float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), st)
+            composite()
+            _lib.call("ngp_field_backward_full", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_rgb), P(self.rgb),
+                      P(self.enc_buf), a1, P(self.in2), a2, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip,
+                      w1, c1, w2, c2, cap, self._m_dev, self._density_act, float(opt.beta), self._color_act, P(self.table_grad),
+                      dw1, dw2, P(enc.embeddings) if self.ray_grads else None, P(self.dirs) if self.ray_grads else None,
+                      P(self.d_xyzs), P(self.d_dirs), st)
+            if self.ray_grads:
+                # dL/d rays_o = sum_seg dL/dxyz, dL/d rays_d = sum_seg (dL/dxyz * t + dL/ddirs)  (raymarching.py:319-329)
+                _lib.call("ngp_march_rays_train_backward", P(self.d_xyzs), P(self.d_dirs), P(self.ts), P(self.rays), N, cap,
+                          P(self.d_rays_o), P(self.d_rays_d), st)
+            return
+        ld2 = self.p2[0]
+        _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
+                  P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, 3, cap, self._m_dev, self._density_act,
+                  float(opt.beta), P(self.enc_buf), a1, P(self.sigma), P(self.in2), ld2, st)
+        _lib.call("ngp_mlp_forward_rgb", P(self.in2), ld2, w2, c2, 3, cap, self._m_dev, 1, self._color_act, P(self.rgb), a2, st)
+        composite()
+        _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), ld2, w2, a2, c2, 3, cap,
+                  self._m_dev, 1, P(self.d_in2), ld2, dw2, st)
+        _lib.call("ngp_field_backward_density", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), ld2, P(self.enc_buf),
+                  None, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap, self._m_dev,
+                  self._density_act, float(opt.beta), P(self.table_grad), dw1, st)
 
     def _launch_check(self):
         st = _lib.stream()

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in ngp_b200.h but not exported"
     assert declared == set(_lib.exported_symbols()), "ctypes signature table out of sync with the header"
     loaded = _lib.load()
-    assert loaded.ngp_abi_version() == 2
+    assert loaded.ngp_abi_version() == 3
     assert b"aligned" in loaded.ngp_status_string(-4)
 
 

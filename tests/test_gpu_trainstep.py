@@ -14,10 +14,12 @@ pytestmark = pytest.mark.gpu
 
 def _scene(N, **kw):
     torch.manual_seed(0)
-    opt = default_opt(bound=1, grid_size=64, max_steps=256, hashmap_size=15, hashgrid_resolution=256, **kw)
+    cfg = dict(bound=1, grid_size=64, max_steps=256, hashmap_size=15, hashgrid_resolution=256)
+    cfg.update(kw)
+    opt = default_opt(**cfg)
     model = NeRFNetwork(opt).cuda()
     model.grid_encoder.embeddings.data.uniform_(-0.5, 0.5)
-    grid = synthetic.ball_density_grid(H=64, cascade=1, bound=1.0, radius=0.5, sigma=50.0).cuda()
+    grid = synthetic.ball_density_grid(H=64, cascade=model.cascade, bound=float(model.bound), radius=0.5, sigma=50.0).cuda()
     model.density_grid.copy_(grid)
     model.density_bitfield = raymarching.packbits(model.density_grid, min(grid.clamp(min=0).mean().item(), 10.0), model.density_bitfield)
     o, d = synthetic.sphere_rays(N, seed=5)
@@ -62,6 +64,96 @@ def test_fused_step_gradients_match_autograd(kw):
         pad = fs._w_grad_views[i].clone()
         pad[:n, :k] = 0
         assert pad.abs().max().item() == 0.0      # padding rows / columns never receive gradient
+
+
+def test_fused_step_light_stage_config_matches_autograd():
+    """configs[2]: light-direction SH conditioning (view_mlp 47 -> 80 -> 80 -> 3), scene contraction (bound 2, 2 cascades through
+    the renderer, renderer.py:171-176), clamped_exp colour, HDR loss -- the widths outside the warp-specialised kernels take the
+    density-field + view-MLP kernel pairs inside the same sync-free step."""
+    N = 1100
+    model, o, d, tgt = _scene(N, bound=2, contract=True, rfield=True, color_activation="clamped_exp")
+    assert model.cascade == 2 and model.view_mlp.net[0].weight.shape == (80, 47)
+    ld = synthetic.unit_vectors(N, seed=3).cuda()
+    exposure = torch.tensor([1.0, 0.25, 1 / 16]).cuda()[torch.arange(N).cuda() % 3]
+    ref_model = copy.deepcopy(model)
+    ref = TrainStep(ref_model, loss_scale=128.0)
+    ref_model.train()
+    out = ref_model.render(o, d, rays_ldir=ld, bg_color=1.0, perturb=False)
+    pred = out["image"]
+    clip = torch.minimum(torch.tensor(1.0, device=pred.device), pred * exposure.unsqueeze(1))
+    loss_ref = ((clip - tgt) ** 2 * (1.0 / (1e-3 + clip.detach())) ** 2).sum() / (3 * N)
+    (loss_ref * 128.0).backward()
+    g_table_ref = ref.table_grad.float().clone()
+    g_mlp_ref = [p.grad.float().clone() for p in ref.mlp_params]
+
+    fs = FusedTrainStep(model, N, loss_scale=128.0, perturb=False, use_graph=False, loss="hdr")
+    assert not fs.ws
+    fs.set_rays(o, d, tgt, rays_ldir=ld, exposure=exposure)
+    fs._launch_forward_backward()
+    torch.cuda.synchronize()
+    assert fs.last_num_points == out["num_points"] and fs.last_num_points > 10 * N
+    torch.testing.assert_close(fs.image, pred.float(), rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(fs.loss[0], loss_ref.float(), rtol=5e-3, atol=1e-6)
+
+    def close(a, b, name):
+        scale = b.abs().max().clamp(min=1e-8)
+        err = (a - b).abs() / scale
+        assert err.max().item() < 3e-2 and err.mean().item() < 1e-3, (name, err.max().item(), err.mean().item())
+
+    close(fs.table_grad.float(), g_table_ref, "table")
+    layers = list(model.grid_mlp.net) + list(model.view_mlp.net)
+    for i, (lin, gref) in enumerate(zip(layers, g_mlp_ref)):
+        n, k = lin.weight.shape
+        close(fs._w_grad_views[i][:n, :k], gref, f"w{i}")
+
+    # and the graph-replayed step trains it
+    losses = [fs.step(o, d, tgt, rays_ldir=ld, update_grid=False, exposure=exposure).item() for _ in range(2)]
+    g = FusedTrainStep(copy.deepcopy(ref_model), N, perturb=False, use_graph=True, loss="hdr")
+    lg = [g.step(o, d, tgt, rays_ldir=ld, update_grid=False, exposure=exposure).item() for _ in range(15)]
+    assert lg[-1] < lg[0] and all(l == l for l in lg + losses)
+
+
+@pytest.mark.parametrize("kw", [dict(pose_opt="barf", start_annealing=0.0, end_annealing=0.5), dict(interpolation="smoothstep")],
+                         ids=["barf-window", "smoothstep"])
+def test_fused_step_ray_gradients_match_autograd(kw):
+    """BARF: rays_o / rays_d require grad.  The autograd path runs op by op (grid_encode with input gradients, SH backward,
+    march_rays_train.backward); the fused step produces the same dL/d rays in its backward kernel + one segment-sum kernel."""
+    N = 1300
+    kw = dict(kw)
+    smooth = kw.pop("interpolation", None) == "smoothstep"
+    model, o, d, tgt = _scene(N, **kw)
+    if smooth:
+        model.grid_encoder.interpolation, model.grid_encoder.interp_id = "smoothstep", 1
+    if kw.get("pose_opt") == "barf":
+        model.update_annealing(0.3)
+    d = d * (1.0 + 0.5 * torch.rand(N, 1, device=d.device))       # get_rays does not normalise (train_utils.py:157-160)
+    ref_model = copy.deepcopy(model)
+    ref = TrainStep(ref_model, loss_scale=128.0)
+    ref_model.train()
+    ro, rd = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    out = ref_model.render(ro, rd, bg_color=1.0, perturb=False)
+    loss_ref = torch.nn.functional.mse_loss(out["image"], tgt, reduction="none").mean(-1).mean()
+    (loss_ref * 128.0).backward()
+    g_table_ref = ref.table_grad.float().clone()
+
+    fs = FusedTrainStep(model, N, loss_scale=128.0, perturb=False, use_graph=False, ray_grads=True)
+    if kw.get("pose_opt") == "barf":
+        fs.feat_weights.copy_(model._feat_weights(o.device))
+    fs.set_rays(o, d, tgt)
+    fs._launch_forward_backward()
+    torch.cuda.synchronize()
+    assert fs.last_num_points == out["num_points"]
+    torch.testing.assert_close(fs.loss[0], loss_ref.float(), rtol=2e-3, atol=1e-6)
+
+    def close(a, b, name, mx=3e-2, mean=2e-3):
+        scale = b.abs().max().clamp(min=1e-8)
+        err = (a - b).abs() / scale
+        assert err.max().item() < mx and err.mean().item() < mean, (name, err.max().item(), err.mean().item())
+
+    close(fs.table_grad.float(), g_table_ref, "table")
+    assert ro.grad.abs().max().item() > 0 and rd.grad.abs().max().item() > 0
+    close(fs.d_rays_o, ro.grad.float(), "rays_o")
+    close(fs.d_rays_d, rd.grad.float(), "rays_d")
 
 
 def test_fused_step_graph_trains_and_matches_eager():
