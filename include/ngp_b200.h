@@ -402,6 +402,27 @@ int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ld
                            float* sigma_out, float* rgb_out, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Rays from refined camera poses (BARF pose refinement) -- SURVEY 8(f) row 2.
+ * Replaces CameraOptimizer.provide_refined_poses (barf/camera_optimizers.py:92-107: lie.se3_to_SE3 of
+ * barf/camera.py:93-153 composed with the dataset pose, camera.py:47-63) followed by get_rays
+ * (nerf/train_utils.py:96-172) and the autograd of both.
+ * ---------------------------------------------------------------------------------------- */
+
+/* se3 [n_cameras, 6] fp32 (rotation w, translation u; NULL = identity refinement); poses: camera-to-world matrices, row
+ * major, pose_stride floats apart (12 for [C,3,4], 16 for [C,4,4]; rows 0..2 are used); cam_idx [N] int32; dirs_cam [N,3]
+ * camera-space pixel directions ((i+0.5-cx)/fx, -(j+0.5-cy)/fy, -1), not normalised.
+ * rays_o[n] = R_p t_r + t_p, rays_d[n] = R_p R_r dirs_cam[n] with [R_r | t_r] = se3_to_SE3(se3[cam_idx[n]]). */
+int ngp_pose_rays_forward(const float* se3, const float* poses, uint32_t pose_stride, const int32_t* cam_idx,
+                          const float* dirs_cam, uint32_t N, uint32_t n_cameras, float* rays_o, float* rays_d,
+                          ngp_stream_t stream);
+
+/* d_se3 [n_cameras, 6] fp32 += sum over the rays of each camera of J^T [d_rays_o, d_rays_d] (ACCUMULATED with
+ * reductions; the Jacobian is evaluated in forward mode from se3, nothing is saved by the forward). */
+int ngp_pose_rays_backward(const float* d_rays_o, const float* d_rays_d, const float* se3, const float* poses,
+                           uint32_t pose_stride, const int32_t* cam_idx, const float* dirs_cam, uint32_t N,
+                           uint32_t n_cameras, float* d_se3, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (reference: torch.optim.Adam, main.py:245;
  * GradScaler unscale + inf check, nerf/train_utils.py:897-904) -- SURVEY 8(f) row 1.
  * ---------------------------------------------------------------------------------------- */
@@ -413,10 +434,13 @@ int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ld
  * zero_grad != 0 the gradient buffer is cleared in the same pass.  step = 1-based step count. */
 int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype,
                    float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, uint32_t step, const int32_t* step_dev, const float* inv_scale_dev,
-                   const float* found_inf_dev, int zero_grad, ngp_stream_t stream);
+                   float eps, float weight_decay, uint32_t step, const int32_t* step_dev, const float* lr_dev,
+                   const float* inv_scale_dev, const float* found_inf_dev, int zero_grad, ngp_stream_t stream);
 
-/* step_dev (ngp_fused_adam): NULL, or a device int32 holding the optimizer step count; the bias corrections are then
+/* lr_dev (ngp_fused_adam): NULL, or a device fp32 that overrides `lr` -- the learning-rate schedule (LambdaLR,
+ * main.py:258-261; ExponentialLR of the pose optimizer, barf/camera_optimizers.py:41-43) is then a 4-byte write between
+ * replays of the captured step.
+ * step_dev (ngp_fused_adam): NULL, or a device int32 holding the optimizer step count; the bias corrections are then
  * computed on the device from *step_dev (the host `step` is ignored), which lets the optimizer live inside a replayed
  * CUDA graph.  ngp_adam_step_counter increments *step_dev unless *found_inf_dev != 0 (a skipped GradScaler step is not
  * counted, as in torch). */

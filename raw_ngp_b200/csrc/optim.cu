@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(256)
 fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __restrict__ grad, float* __restrict__ m,
                   float* __restrict__ v, uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float bias1, float bias2_sqrt, const float* __restrict__ inv_scale_dev,
-                  const float* __restrict__ found_inf_dev, bool zero_grad, const int* __restrict__ step_dev) {
+                  const float* __restrict__ found_inf_dev, bool zero_grad, const int* __restrict__ step_dev,
+                  const float* __restrict__ lr_dev) {
+    if (lr_dev) lr = __ldg(lr_dev);     // learning-rate schedule without re-capturing the graph (LambdaLR, main.py:258-261)
     const bool skip = found_inf_dev && (__ldg(found_inf_dev) != 0.f);
     const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
     if (step_dev) {     // step count kept on the device (CUDA-graph replay): bias corrections computed here
@@ -113,8 +115,8 @@ using namespace ngp;
 
 extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype, float* exp_avg,
                               float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2, float eps,
-                              float weight_decay, uint32_t step, const int32_t* step_dev, const float* inv_scale_dev,
-                              const float* found_inf_dev, int zero_grad, ngp_stream_t stream) {
+                              float weight_decay, uint32_t step, const int32_t* step_dev, const float* lr_dev,
+                              const float* inv_scale_dev, const float* found_inf_dev, int zero_grad, ngp_stream_t stream) {
     if (n == 0) return NGP_OK;
     if (!master || !grad || !exp_avg || !exp_avg_sq) return NGP_ERR_NULL;
     if (step == 0 && !step_dev) return NGP_ERR_BAD_ARG;
@@ -129,7 +131,7 @@ extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void*
 #define NGP_ADAM(G, P, HAS)                                                                                      \
     fused_adam_kernel<G, P, HAS><<<blocks, 256, 0, st>>>(master, (P*)param_lp, (G*)grad, exp_avg, exp_avg_sq, n, lr, \
                                                          beta1, beta2, eps, weight_decay, bias1, bias2_sqrt,      \
-                                                         inv_scale_dev, found_inf_dev, zero_grad != 0, step_dev)
+                                                         inv_scale_dev, found_inf_dev, zero_grad != 0, step_dev, lr_dev)
 #define NGP_ADAM_G(G)                                                             \
     if (!param_lp) NGP_ADAM(G, __half, false);                                    \
     else if (lp_dtype == NGP_F16) NGP_ADAM(G, __half, true);                      \

@@ -20,16 +20,17 @@ class FusedAdam:
 
     def __init__(self, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, device_step=None):
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.lr_dev = None          # optional fp32[1] CUDA tensor overriding lr (a schedule under CUDA-graph replay)
         self.groups = []
         self.step_count = 0
         # optional int32[1] CUDA tensor: the step count lives on the device (bias corrections computed in the kernel), so that
         # the optimizer can be part of a replayed CUDA graph; incremented only for steps that are not skipped (GradScaler)
         self.device_step = device_step
 
-    def add_group(self, master, grad, param_lp=None):
+    def add_group(self, master, grad, param_lp=None, lr_dev=None):
         assert master.dtype == torch.float32 and master.is_contiguous() and grad.is_contiguous()
         self.groups.append(dict(master=master, lp=param_lp, grad=grad, m=torch.zeros_like(master),
-                                v=torch.zeros_like(master)))
+                                v=torch.zeros_like(master), lr_dev=lr_dev))
 
     def step(self, inv_scale, found_inf, zero_grad=True, lr=None):
         self.step_count += 1
@@ -42,7 +43,8 @@ class FusedAdam:
             _lib.call("ngp_fused_adam", _lib.ptr(g["master"]), _lib.ptr(lp), _lib.dtype_id(lp.dtype) if lp is not None else 0,
                       _lib.ptr(g["grad"]), _lib.dtype_id(g["grad"].dtype), _lib.ptr(g["m"]), _lib.ptr(g["v"]),
                       g["master"].numel(), float(lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                      float(self.weight_decay), self.step_count, _lib.ptr(self.device_step), _lib.ptr(inv_scale),
+                      float(self.weight_decay), self.step_count, _lib.ptr(self.device_step),
+                      _lib.ptr(g["lr_dev"] if g["lr_dev"] is not None else self.lr_dev), _lib.ptr(inv_scale),
                       _lib.ptr(found_inf), int(zero_grad), st)
 
 
@@ -148,7 +150,7 @@ class FusedTrainStep:
 
     def __init__(self, model, n_rays, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, loss_scale=128.0, max_samples=None,
                  process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True, loss="mse",
-                 ray_grads=False):
+                 ray_grads=False, pose_optimizer=None, poses=None, pose_lr=1e-3, pose_betas=(0.9, 0.999), pose_eps=1e-8):
         import ctypes
         from . import field as _field
         from .ffmlp import _pad16
@@ -191,7 +193,11 @@ class FusedTrainStep:
         self.ws = _field._ws_ok(self.p1, self.p2)
         # ray_grads: also produce dL/d rays_o and dL/d rays_d (self.d_rays_o / self.d_rays_d, scaled by loss_scale like every
         # gradient of the step) for pose refinement (BARF, --pose_opt barf: rays come from refined poses and require grad)
-        self.ray_grads = bool(ray_grads)
+        # pose_optimizer (raw_ngp_b200.pose.CameraOptimizer) + poses [C, 3|4, 4]: the rays of the step are generated on the
+        # device from (camera index, pixel direction) through the refined poses, and se3_refine is trained by its own Adam
+        # (torch defaults like barf/camera_optimizers.py:40) with its own inf check (GradScaler checks per optimizer)
+        self.pose = pose_optimizer
+        self.ray_grads = bool(ray_grads) or pose_optimizer is not None
         if self.ray_grads and not self.ws:
             raise RuntimeError("FusedTrainStep: ray gradients need the warp-specialised kernels (layer widths in {16, 32, 64})")
         shapes = [(self.p1[i + 1], self.p1[i]) for i in range(3)] + [(self.p2[i + 1], self.p2[i]) for i in range(3)]
@@ -213,9 +219,29 @@ class FusedTrainStep:
 
         self.opt_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.opt = FusedAdam(lr=lr, betas=betas, eps=eps, device_step=self.opt_step_dev)
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)      # see set_lr()
+        self.opt.lr_dev = self.lr_dev
         self.opt.add_group(self.table_master, self.table_grad, enc.embeddings.data)
         self.opt.add_group(self.w_master, self.w_grad, self.w_lp)
         self._pending = False          # gradients of the last step are waiting for their optimizer update
+        if self.pose is not None:
+            if poses is None:
+                raise ValueError("FusedTrainStep: pose_optimizer needs the dataset poses [C, 3|4, 4]")
+            self.poses = poses.to(dev).float().contiguous()
+            self.pose_stride = self.poses.shape[-2] * self.poses.shape[-1]
+            w = self.pose.se3_refine.weight
+            w.data = w.data.to(dev).float().contiguous()
+            self.se3 = w.data
+            if self.se3.shape[0] != self.poses.shape[0]:
+                raise ValueError("FusedTrainStep: one se3 row per dataset pose")
+            self.se3_grad = torch.zeros_like(self.se3)
+            self.cam_idx = torch.zeros(N, device=dev, dtype=torch.int32)
+            self.dirs_cam = torch.zeros(N, 3, device=dev, dtype=torch.float32)
+            self.pose_found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
+            self.pose_lr_dev = torch.full((1,), float(pose_lr), device=dev, dtype=torch.float32)
+            self.pose_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+            self.pose_opt = FusedAdam(lr=pose_lr, betas=pose_betas, eps=pose_eps, device_step=self.pose_step_dev)
+            self.pose_opt.add_group(self.se3, self.se3_grad, None, lr_dev=self.pose_lr_dev)
         self.inv_scale = torch.full((1,), parallel.unscale_factor(self.loss_scale, self.world), device=dev, dtype=torch.float32)
         self.found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
 
@@ -269,10 +295,21 @@ class FusedTrainStep:
             torch.cuda.current_stream().wait_stream(join)
         self._launch_field()
 
+    def _launch_pose_update(self):
+        """inf check + Adam of se3_refine for the PREVIOUS step's gradients: on the main stream, because the rays of this step
+        are generated from the updated poses (the table / MLP update runs beside the march on the side stream)."""
+        st = _lib.stream()
+        self.pose_found_inf.zero_()
+        _lib.call("ngp_check_finite", _lib.ptr(self.se3_grad), _lib.NGP_F32, self.se3_grad.numel(), _lib.ptr(self.pose_found_inf), st)
+        self.pose_opt.step(self.inv_scale, self.pose_found_inf, zero_grad=True)
+
     def _launch_march(self):
         m, opt, N, cap = self.model, self.model.opt, self.N, self.cap
         st = _lib.stream()
         P = _lib.ptr
+        if self.pose is not None:      # provide_refined_poses + get_rays (barf/camera_optimizers.py:92-107, train_utils.py:150-165)
+            _lib.call("ngp_pose_rays_forward", P(self.se3), P(self.poses), self.pose_stride, P(self.cam_idx), P(self.dirs_cam), N,
+                      self.se3.shape[0], P(self.rays_o), P(self.rays_d), st)
         if self.perturb:
             self.noises.uniform_()
         aabb = m.aabb_train
@@ -315,6 +352,9 @@ class FusedTrainStep:
                 # dL/d rays_o = sum_seg dL/dxyz, dL/d rays_d = sum_seg (dL/dxyz * t + dL/ddirs)  (raymarching.py:319-329)
                 _lib.call("ngp_march_rays_train_backward", P(self.d_xyzs), P(self.d_dirs), P(self.ts), P(self.rays), N, cap,
                           P(self.d_rays_o), P(self.d_rays_d), st)
+            if self.pose is not None:
+                _lib.call("ngp_pose_rays_backward", P(self.d_rays_o), P(self.d_rays_d), P(self.se3), P(self.poses), self.pose_stride,
+                          P(self.cam_idx), P(self.dirs_cam), N, self.se3.shape[0], P(self.se3_grad), st)
             return
         ld2 = self.p2[0]
         _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
@@ -348,6 +388,8 @@ class FusedTrainStep:
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
             self._launch_optimizer()
+        if self.pose is not None:
+            self._launch_pose_update()
         self._launch_forward_backward(join=self._side)
 
     def _capture(self):
@@ -360,6 +402,8 @@ class FusedTrainStep:
             self._launch_check()
             self.table_grad.zero_()
             self.w_grad.zero_()
+            if self.pose is not None:
+                self.se3_grad.zero_()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._graph_fb, self._graph_pipe, self._graph_chk = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -371,8 +415,11 @@ class FusedTrainStep:
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_pipe):
             self._launch_pipelined()
-        self.pipe_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0) + (1 if self.world == 1 else 0)   # + found_inf.zero_
+        self.pipe_kernels = (_lib.launch_count - c0 + (1 if self.perturb else 0) + (1 if self.world == 1 else 0)   # + found_inf.zero_
+                             + (1 if self.pose is not None else 0))
         self.opt.step_count = n_adam        # capturing is not stepping
+        if self.pose is not None:
+            self.pose_opt.step_count = n_adam
         with torch.cuda.graph(self._graph_chk):
             self._launch_check()
         if self.world > 1:      # data parallel: the collectives stay outside the graphs, between a march graph and a field graph
@@ -387,6 +434,16 @@ class FusedTrainStep:
             self.field_kernels = _lib.launch_count - c0
         self.table_grad.zero_()
         self.w_grad.zero_()
+        if self.pose is not None:
+            self.se3_grad.zero_()
+
+    def set_lr(self, lr=None, pose_lr=None):
+        """Learning-rate schedule (LambdaLR of main.py:258-261; ExponentialLR of the pose optimizer): the captured Adam kernels
+        read the rate from device memory, so a schedule is one 4-byte fill per step and no re-capture."""
+        if lr is not None:
+            self.lr_dev.fill_(float(lr))
+        if pose_lr is not None and self.pose is not None:
+            self.pose_lr_dev.fill_(float(pose_lr))
 
     def _reduce_and_update(self):
         """Data parallel: all-reduce of the two gradient buffers, inf check, MAX of the flag, fused Adam -- on the current
@@ -403,9 +460,13 @@ class FusedTrainStep:
         if not self._pending:
             return
         if self.world > 1:
+            if self.pose is not None:
+                parallel.all_reduce_gradients([self.se3_grad], None, self.pg)
             self._reduce_and_update()
         else:
             self._launch_optimizer()
+        if self.pose is not None:
+            self._launch_pose_update()
         self._pending = False
 
     def profile_kernels(self, iters=10):
@@ -429,6 +490,8 @@ class FusedTrainStep:
                 self._launch_forward_backward()
                 self._launch_check()
                 self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+                if self.pose is not None:
+                    self._launch_pose_update()
         finally:
             _lib.call = real_call
         torch.cuda.synchronize()
@@ -445,19 +508,31 @@ class FusedTrainStep:
                 continue
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
+    def set_camera_rays(self, cam_idx, dirs_cam, target_rgb, exposure=None):
+        """Pose mode: the step's rays as (camera index [N], camera-space pixel direction [N, 3]); rays_o / rays_d are produced
+        on the device from the refined poses inside the captured step."""
+        for dst, src in ((self.cam_idx, cam_idx), (self.dirs_cam, dirs_cam), (self.target, target_rgb), (self.exposure, exposure)):
+            if src is None or (src.is_cuda and src.data_ptr() == dst.data_ptr()):
+                continue
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
     @property
     def last_num_points(self):
         return int(self.counter[0].item())
 
-    def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True, exposure=None):
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True, exposure=None, cam_idx=None,
+             dirs_cam=None):
         """One optimisation step; returns the (unscaled) loss as a 1-element device tensor (overwritten by the next step).
-        The parameter update of this step is applied at the start of the next call (or by flush())."""
+        The parameter update of this step is applied at the start of the next call (or by flush()).
+        Pose mode (pose_optimizer given): pass cam_idx / dirs_cam instead of rays_o / rays_d."""
         model = self.model
         if update_grid and self.global_step % self.update_extra_interval == 0:
             self.flush()                       # the density queries of the occupancy update see the updated weights
             model.update_extra_state()
         if rays_o is not None:
             self.set_rays(rays_o, rays_d, target_rgb, rays_ldir, exposure)
+        if cam_idx is not None:
+            self.set_camera_rays(cam_idx, dirs_cam, target_rgb, exposure)
         if self.feat_weights is not None:
             self.feat_weights.copy_(model._feat_weights(self.dev))
         if self.use_graph:
@@ -470,9 +545,13 @@ class FusedTrainStep:
                 # [all-reduce + optimizer update of the previous step, side stream]  ||  [march graph]  ->  field graph
                 main = torch.cuda.current_stream()
                 if self._pending:
+                    if self.pose is not None:      # tiny, and the march below needs the updated poses: main stream, first
+                        parallel.all_reduce_gradients([self.se3_grad], None, self.pg)
                     self._side.wait_stream(main)
                     with torch.cuda.stream(self._side):
                         self._reduce_and_update()
+                    if self.pose is not None:
+                        self._launch_pose_update()
                 self._graph_march.replay()
                 main.wait_stream(self._side)
                 self._graph_field.replay()
@@ -480,6 +559,8 @@ class FusedTrainStep:
             elif self._pending:
                 self._graph_pipe.replay()
                 self.opt.step_count += 1
+                if self.pose is not None:
+                    self.pose_opt.step_count += 1
                 self.kernels_replayed += self.pipe_kernels
             else:
                 self._graph_fb.replay()

@@ -5,7 +5,7 @@ import copy
 import pytest
 import torch
 
-from raw_ngp_b200 import raymarching, synthetic
+from raw_ngp_b200 import pose, raymarching, synthetic
 from raw_ngp_b200.nerf import NeRFNetwork, default_opt
 from raw_ngp_b200.trainer import FusedTrainStep, TrainStep
 
@@ -154,6 +154,79 @@ def test_fused_step_ray_gradients_match_autograd(kw):
     assert ro.grad.abs().max().item() > 0 and rd.grad.abs().max().item() > 0
     close(fs.d_rays_o, ro.grad.float(), "rays_o")
     close(fs.d_rays_d, rd.grad.float(), "rays_d")
+
+
+def _camera_batch(N, C, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    poses = pose.look_at_poses(C, radius=2.0)
+    idx = torch.randint(0, C, (N,), generator=g)
+    # pixels of a 64 x 64 image, focal 80: the ball of radius 0.5 at distance 2 fills most of the frame
+    ij = torch.randint(0, 64, (N, 2), generator=g).float() + 0.5
+    dirs = pose.pixel_directions(ij[:, 0], ij[:, 1], (80.0, 80.0, 32.0, 32.0))
+    tgt = torch.rand(N, 3, generator=g)
+    return poses.cuda(), idx.cuda(), dirs.cuda(), tgt.cuda()
+
+
+def test_fused_step_pose_gradients_match_autograd():
+    """configs[4] ingredients: BARF window + rays generated from refined poses; d loss / d se3_refine of the captured step
+    (pose kernel -> march -> field -> composite -> backward -> segment sum -> pose backward) == autograd through the torch
+    formulation of barf/camera.py + get_rays and the op-by-op renderer."""
+    N, C = 1400, 10
+    model, _, _, _ = _scene(N, pose_opt="barf", start_annealing=0.0, end_annealing=0.5)
+    model.update_annealing(0.35)
+    poses, idx, dirs, tgt = _camera_batch(N, C)
+    cam = pose.CameraOptimizer(C, "cuda")
+    cam.se3_refine.weight.data.normal_(0, 0.02, generator=torch.Generator(device="cuda").manual_seed(1))
+
+    ref_model, ref_cam = copy.deepcopy(model), copy.deepcopy(cam)
+    ref = TrainStep(ref_model, loss_scale=128.0)
+    ref_model.train()
+    refined = ref_cam(poses[idx], idx)
+    rd = (dirs.unsqueeze(1) @ refined[:, :3, :3].transpose(-1, -2)).squeeze(1)
+    ro = refined[:, :3, 3]
+    out = ref_model.render(ro, rd, bg_color=1.0, perturb=False)
+    loss_ref = torch.nn.functional.mse_loss(out["image"], tgt, reduction="none").mean(-1).mean()
+    (loss_ref * 128.0).backward()
+    g_ref = ref_cam.se3_refine.weight.grad.float()
+    assert out["num_points"] > 10 * N and g_ref.abs().max().item() > 0
+
+    fs = FusedTrainStep(model, N, loss_scale=128.0, perturb=False, use_graph=False, pose_optimizer=cam, poses=poses)
+    fs.feat_weights.copy_(model._feat_weights("cuda"))
+    fs.set_camera_rays(idx, dirs, tgt)
+    fs._launch_forward_backward()
+    torch.cuda.synchronize()
+    assert fs.last_num_points == out["num_points"]
+    torch.testing.assert_close(fs.rays_o, ro.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(fs.rays_d, rd.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(fs.loss[0], loss_ref.float(), rtol=2e-3, atol=1e-6)
+    scale = g_ref.abs().max()
+    err = (fs.se3_grad - g_ref).abs() / scale
+    assert err.max().item() < 3e-2 and err.mean().item() < 5e-3, (err.max().item(), err.mean().item())
+
+
+def test_fused_step_pose_refinement_trains_under_graph():
+    """Graph-replayed steps with the pose optimizer: se3_refine moves, the loss stays finite and decreases, a learning rate of
+    zero (set_lr, read from device memory by the captured Adam) freezes the poses."""
+    N, C = 1024, 8
+    model, _, _, _ = _scene(N, pose_opt="barf", start_annealing=0.0, end_annealing=0.5)
+    model.update_annealing(1.0)
+    poses, idx, dirs, tgt = _camera_batch(N, C, seed=3)
+    cam = pose.CameraOptimizer(C, "cuda")
+    fs = FusedTrainStep(model, N, perturb=False, use_graph=True, pose_optimizer=cam, poses=poses, pose_lr=1e-3)
+    losses = [fs.step(cam_idx=idx, dirs_cam=dirs, target_rgb=tgt, update_grid=False).item() for _ in range(12)]
+    fs.flush()
+    torch.cuda.synchronize()
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    moved = cam.se3_refine.weight.data.abs().max().item()
+    assert 1e-4 < moved < 0.1                    # ~ lr * steps
+    assert cam.se3_refine.weight.data_ptr() == fs.se3.data_ptr()
+    fs.set_lr(pose_lr=0.0)
+    before = fs.se3.clone()
+    for _ in range(3):
+        fs.step(cam_idx=idx, dirs_cam=dirs, target_rgb=tgt, update_grid=False)
+    fs.flush()
+    torch.cuda.synchronize()
+    assert torch.equal(fs.se3, before)
 
 
 def test_fused_step_graph_trains_and_matches_eager():
