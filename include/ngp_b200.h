@@ -369,9 +369,10 @@ int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, co
  * grid_dweights[l] / view_dweights[l] ([dims[l+1], dims[l]]) are ACCUMULATED into.
  * Input gradients (BARF pose refinement: the positions and directions of the samples require grad, nerf/network.py with
  * rays_o / rays_d from refined poses): d_xyzs [M,3] and d_dirs [M,3] fp32, both NULL or both set, are WRITTEN (rows
- * < min(M, *m_dev)); they need the table [sO,2] fp16 (d feat / d x is recomputed from it: gridencoder.cu:216-245,
- * 352-378 without the saved dy_dx) and the un-normalised march directions dirs [M,3] (SH Jacobian + the normalisations
- * of renderer.py:544 and sphere_harmonics.py:81, shencoder.cu:358-382); view_dims[0] must be 32.  Otherwise pass NULLs. */
+ * < min(M, *m_dev)); they need dydx as written by ngp_field_forward_full (contracted with d enc like
+ * kernel_input_backward, gridencoder.cu:352-378) and the un-normalised march directions dirs [M,3] (SH Jacobian + the
+ * normalisations of renderer.py:544 and sphere_harmonics.py:81, shencoder.cu:358-382); view_dims[0] must be 32.
+ * Otherwise pass NULLs. */
 int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float* sigma, const float* d_rgb,
                             const float* rgb, const void* enc, const void* const* grid_acts, const void* in2,
                             const void* const* view_acts, const int32_t* offsets, const float* feat_weights,
@@ -379,7 +380,7 @@ int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float
                             uint32_t interp, const void* const* grid_weights, const uint32_t* grid_dims,
                             const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
                             const int32_t* m_dev, int density_act, float beta, int color_act, void* grad_table,
-                            float* const* grid_dweights, float* const* view_dweights, const void* table,
+                            float* const* grid_dweights, float* const* view_dweights, const void* dydx,
                             const float* dirs, float* d_xyzs, float* d_dirs, ngp_stream_t stream);
 
 /* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
@@ -391,7 +392,10 @@ int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float
  * whole tiles; widths in {16, 32, 64} (else NGP_ERR_UNSUPPORTED: use the two-kernel path):
  * enc_out (width 2L), grid_acts_out[0..1] (h), in2_out (32/48), view_acts_out[0..1] (h2).  Pass tiled = 1 to
  * ngp_field_backward_full to consume them.  view_weights == NULL: density-only query (grid_mlp only; dirs, ldirs,
- * view_dims, rgb_out and the view outputs are ignored) -- NeRFNetwork.density, the occupancy-grid update. */
+ * view_dims, rgb_out and the view outputs are ignored) -- NeRFNetwork.density, the occupancy-grid update.
+ * dydx_out (NULL, or ceil(M/128)*128 * 12L bytes, 16-byte aligned): d enc / d x in fp16 for the input gradients of the
+ * backward kernel -- the dy_dx of gridencoder.cu:216-245 (calc_grad_inputs), stored per 128-row tile as
+ * [4 level groups g][L/8 level pairs (g + 8p, g + 8p + 4)][2 levels x 3 dims][128 rows][2 channels]. */
 int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ldirs, const void* table,
                            const int32_t* offsets, const float* feat_weights, float bound, float S, uint32_t H,
                            uint32_t L, uint32_t gridtype, int align_corners, uint32_t interp,
@@ -399,7 +403,7 @@ int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ld
                            const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
                            const int32_t* m_dev, int density_act, float beta, int color_act, void* enc_out,
                            void* const* grid_acts_out, void* in2_out, void* const* view_acts_out,
-                           float* sigma_out, float* rgb_out, ngp_stream_t stream);
+                           float* sigma_out, float* rgb_out, void* dydx_out, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Rays from refined camera poses (BARF pose refinement) -- SURVEY 8(f) row 2.

@@ -57,6 +57,7 @@ struct BwsArgs {
     Chain c[kChains];
     const float* xyzs; const float* d_sigma; const float* sigma; const float* d_rgb; const float* rgb;
     const float* dirs; float* d_xyzs; float* d_dirs;       // input gradients (IG): march dirs in, d xyzs / d dirs [M,3] out
+    const __half* dydx;                                    // d enc / d x saved by the forward (layout: field_ws.cu)
     GridArgs g;
     uint32_t M; const int* m_dev;
     __half* grad_table;
@@ -65,7 +66,8 @@ struct BwsArgs {
 };
 
 // IG: also produce the gradients with respect to the sample positions and view directions (BARF pose refinement):
-//   * the scatter warps gather the 8 corner rows of each level again and contract d feat / d x with d enc in registers;
+//   * the scatter warps contract the dy_dx their thread's levels got from the forward (12 coalesced 4-byte loads per
+//     thread at L = 16) with d enc (kernel_input_backward, gridencoder.cu:352-378);
 //     the four level groups of a sample meet in a ring of shared-memory accumulators (red.shared), which the G0 group
 //     writes out three tiles later -- by then every scatter thread has moved past that tile (it has acknowledged the
 //     d enc stage of the tile after it), so no extra barrier sits on the pipeline;
@@ -161,7 +163,22 @@ field_backward_ws_kernel(const BwsArgs a) {
             for (uint32_t j = 0; j < kMaxLevels / kScatterGroups; j++) {
                 const uint32_t level = grp + j * kScatterGroups;
                 if (level < g.L) {
-                    if (IG) input_grad_level(g, s_lv[level], level, x, live, gh[j], dxa);
+                    if (IG && live) {
+                        // word (j % 2) * 3 + d of level pair j / 2, row-contiguous (layout: field_ws.cu)
+                        const uint32_t* dy = reinterpret_cast<const uint32_t*>(a.dydx) +
+                                             (((size_t)(tile * kScatterGroups + grp) * (g.L / 8) + j / 2) * 6 + (j % 2) * 3) * kTile + r;
+                        float2 gf = __half22float2(gh[j]);
+                        if (g.feat_weights) {      // the window multiplies the encoder output (network.py:99-109): chain rule
+                            const __half2 gw = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
+                            gf = __half22float2(gw);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const uint32_t u = __ldg(dy + d * kTile);
+                            const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&u));
+                            dxa[d] += gf.x * y.x + gf.y * y.y;
+                        }
+                    }
                     scatter_level(g, s_lv[level], level, x, live, gh[j], a.grad_table, lane);
                 }
             }
@@ -452,11 +469,12 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
                                        uint32_t interp, const void* const* grid_weights, const uint32_t* grid_dims,
                                        const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
                                        const int32_t* m_dev, int density_act, float beta, int color_act, void* grad_table,
-                                       float* const* grid_dweights, float* const* view_dweights, const void* table,
+                                       float* const* grid_dweights, float* const* view_dweights, const void* dydx,
                                        const float* dirs, float* d_xyzs, float* d_dirs, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     const bool ig = d_xyzs != nullptr || d_dirs != nullptr;
-    if (ig && (!d_xyzs || !d_dirs || !table || !dirs)) return NGP_ERR_NULL;
+    if (ig && (!d_xyzs || !d_dirs || !dydx || !dirs)) return NGP_ERR_NULL;
+    if (ig && !aligned(dydx, 16)) return NGP_ERR_ALIGN;
     if (ig && view_dims[0] != 32) return NGP_ERR_UNSUPPORTED;      // d dirs reads the 16 SH columns of a 32-wide view input
     if (!xyzs || !d_sigma || !sigma || !d_rgb || !rgb || !enc || !grid_acts || !in2 || !view_acts || !offsets || !grid_weights ||
         !grid_dims || !view_weights || !view_dims || !grad_table || !grid_dweights || !view_dweights)
@@ -467,8 +485,8 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
     if (grid_dims[0] != 2 * L || grid_dims[3] != 16 || view_dims[3] != 16 || view_dims[0] < 16) return NGP_ERR_UNSUPPORTED;
     BwsArgs a = {};
     a.xyzs = xyzs; a.d_sigma = d_sigma; a.sigma = sigma; a.d_rgb = d_rgb; a.rgb = rgb;
-    a.g = {(const __half*)table, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
-    a.dirs = dirs; a.d_xyzs = d_xyzs; a.d_dirs = d_dirs;
+    a.g = {nullptr, offsets, feat_weights, S, bound, H, L, gridtype, interp, align_corners != 0};
+    a.dirs = dirs; a.d_xyzs = d_xyzs; a.d_dirs = d_dirs; a.dydx = (const __half*)dydx;
     uint32_t off = 0;
     for (uint32_t ci = 0; ci < kChains; ci++) {
         Chain& c = a.c[ci];

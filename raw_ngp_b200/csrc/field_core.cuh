@@ -214,59 +214,64 @@ static __device__ __noinline__ void scatter_corners_generic(__half* glvl, uint32
     }
 }
 
-// One level of one sample of the gradient with respect to the POSITION (BARF: rays_o / rays_d receive gradients):
-//   dx[d] += sum_c gh[c] * d feat_c / d x_d
-// The reference saves dy_dx [B, L*3*2] in its forward (192 B per sample in fp16) and contracts it with the incoming
-// gradient in kernel_input_backward (gridencoder.cu:216-245, 352-378); here the 8 corner rows -- L2 resident, the
-// scatter needs their indices anyway -- are gathered again and the contraction happens in registers, so nothing is saved.
-// x is the position in the unit cube; the caller multiplies by d unit / d xyz = 1 / (2 bound).
-__device__ __forceinline__ void input_grad_level(const GridArgs& g, const LevelConst& lv, uint32_t level, const float (&x)[3], bool live,
-                                                 __half2 gh, float (&dx)[3]) {
-    if (g.feat_weights) {
-        const float2 gf = __half22float2(gh);
-        gh = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
-    }
-    const float2 gf = __half22float2(gh);
-    const bool inside = live && !(x[0] < 0 || x[0] > 1 || x[1] < 0 || x[1] > 1 || x[2] < 0 || x[2] > 1);
-    uint32_t base[3];
-    float frac[3], dfrac[3];
+// d (level features) / d x of one sample, for the gradient with respect to the POSITION (BARF: rays_o / rays_d receive
+// gradients).  Like the reference's forward with calc_grad_inputs (gridencoder.cu:216-245) the derivative is produced where
+// the 8 corner rows are already in registers -- the forward gather -- and saved in fp16 as dy_dx[level][dim][channel] (12 bytes
+// per level); kernel_input_backward's contraction with the incoming gradient (gridencoder.cu:352-378) happens in the scatter
+// warps of the backward kernel.
+// out[d] = packed (channel 0, channel 1) of dimension d.
+__device__ __forceinline__ void locate3_dfrac(const float (&x)[3], uint32_t res, bool align_corners, uint32_t interp, float (&dfrac)[3]) {
 #pragma unroll
     for (uint32_t d = 0; d < 3; d++) {
-        const float xc = fminf(fmaxf(x[d], 0.f), 1.f);      // dead / outside rows: loads stay in bounds, result discarded
         float p;
-        if (g.align_corners) {
-            p = xc * (float)(lv.res - 1);
-            base[d] = min((uint32_t)floorf(p), lv.res - 2);
+        if (align_corners) {
+            p = x[d] * (float)(res - 1);
+            p -= (float)min((uint32_t)floorf(p), res - 2);
         } else {
-            p = fminf(fmaxf(xc * (float)lv.res - 0.5f, 0.0f), (float)(lv.res - 1));
-            base[d] = (uint32_t)floorf(p);
+            p = fminf(fmaxf(x[d] * (float)res - 0.5f, 0.0f), (float)(res - 1));
+            p -= floorf(p);
         }
-        p -= (float)base[d];
-        frac[d] = (g.interp == 1) ? smoothstep_f(p) : p;
-        dfrac[d] = (g.interp == 1) ? smoothstep_df(p) : 1.0f;
+        dfrac[d] = (interp == 1) ? smoothstep_df(p) : 1.0f;
     }
-    uint32_t rows[8];
-    if (lv.mode == 2) corner_rows_generic(g.gridtype, lv.hashmap_size, lv.res, base[0], base[1], base[2], rows);
-    else corner_rows(lv, base, rows);
-    const uint32_t* __restrict__ lvl = reinterpret_cast<const uint32_t*>(g.table) + lv.offset;
-    float dot[8];
+}
+__device__ __forceinline__ void gather_finish_dydx(const LevelGather& q, const float (&dfrac)[3], float scale, bool inside,
+                                                   uint32_t (&out)[3]) {
+    // The derivative along one axis is the bilinear interpolation, over the two other axes, of the four corner differences
+    // along that axis.  Evaluated in packed fp16 (both channels per instruction: HADD2 / HFMA2) -- the gather warps are issue
+    // bound, and the reference accumulates these sums in fp16 as well (scalar_t results_grad, gridencoder.cu:222-243); the
+    // scale factor res * d smoothstep is applied in fp32 at the end.
+    const __half2* v = reinterpret_cast<const __half2*>(q.v);
+    const __half2 f[3] = {__float2half2_rn(q.frac[0]), __float2half2_rn(q.frac[1]), __float2half2_rn(q.frac[2])};
+    auto lerp = [](__half2 a, __half2 b, __half2 t) { return __hfma2(t, __hsub2(b, a), a); };
+    __half2 r[3];
+    // corner k: bit 0 = +x, bit 1 = +y, bit 2 = +z
+    r[0] = lerp(lerp(__hsub2(v[1], v[0]), __hsub2(v[3], v[2]), f[1]), lerp(__hsub2(v[5], v[4]), __hsub2(v[7], v[6]), f[1]), f[2]);
+    r[1] = lerp(lerp(__hsub2(v[2], v[0]), __hsub2(v[3], v[1]), f[0]), lerp(__hsub2(v[6], v[4]), __hsub2(v[7], v[5]), f[0]), f[2]);
+    r[2] = lerp(lerp(__hsub2(v[4], v[0]), __hsub2(v[5], v[1]), f[0]), lerp(__hsub2(v[6], v[2]), __hsub2(v[7], v[3]), f[0]), f[1]);
 #pragma unroll
-    for (uint32_t k = 0; k < 8; k++) {
-        const uint32_t v = __ldg(lvl + rows[k]);
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-        dot[k] = gf.x * f.x + gf.y * f.y;
+    for (uint32_t d = 0; d < 3; d++) {
+        const float2 c = __half22float2(r[d]);
+        const float k = scale * dfrac[d];
+        out[d] = inside ? pack_h2(k * c.x, k * c.y) : 0u;
     }
-    const float x0 = 1 - frac[0], y0 = 1 - frac[1], z0 = 1 - frac[2];
-    const float sx = (y0 * z0) * (dot[1] - dot[0]) + (frac[1] * z0) * (dot[3] - dot[2]) + (y0 * frac[2]) * (dot[5] - dot[4]) +
-                     (frac[1] * frac[2]) * (dot[7] - dot[6]);
-    const float sy = (x0 * z0) * (dot[2] - dot[0]) + (frac[0] * z0) * (dot[3] - dot[1]) + (x0 * frac[2]) * (dot[6] - dot[4]) +
-                     (frac[0] * frac[2]) * (dot[7] - dot[5]);
-    const float sz = (x0 * y0) * (dot[4] - dot[0]) + (frac[0] * y0) * (dot[5] - dot[1]) + (x0 * frac[1]) * (dot[6] - dot[2]) +
-                     (frac[0] * frac[1]) * (dot[7] - dot[3]);
-    const float scale = inside ? (float)(g.align_corners ? lv.res - 1 : lv.res) : 0.f;
-    dx[0] += scale * sx * dfrac[0];
-    dx[1] += scale * sy * dfrac[1];
-    dx[2] += scale * sz * dfrac[2];
+}
+
+// the same for a level on the generic index map (mode 2): out of line like gather_level_generic
+static __device__ __noinline__ void dydx_level_generic(const __half* table, uint32_t gridtype, bool align_corners, uint32_t interp, uint32_t res,
+                                                       uint32_t hashmap_size, uint32_t offset, float x0, float x1, float x2, bool inside,
+                                                       uint32_t* out) {
+    const float xc[3] = {x0, x1, x2};
+    uint32_t base[3], rows[8];
+    LevelGather q;
+    float dfrac[3];
+    locate3(xc, res, align_corners, interp, base, q.frac);
+    locate3_dfrac(xc, res, align_corners, interp, dfrac);
+    corner_rows_generic(gridtype, hashmap_size, res, base[0], base[1], base[2], rows);
+    const uint32_t* lvl = reinterpret_cast<const uint32_t*>(table) + offset;
+    for (uint32_t k = 0; k < 8; k++) q.v[k] = __ldg(lvl + rows[k]);
+    uint32_t o[3];
+    gather_finish_dydx(q, dfrac, (float)(align_corners ? res - 1 : res), inside, o);
+    out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
 }
 
 // One level of one sample of the table-gradient scatter.  `gh` is d enc (2 features) as it comes out of the grid_mlp

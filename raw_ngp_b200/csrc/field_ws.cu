@@ -51,6 +51,7 @@ struct WsArgs {
     __half* enc_out;                   // tile-panel (swizzled tile images, tile_sw.cuh) or nullptr
     __half* acts[kWsLayers];           // tiled hidden activations of layers 0,1 (grid) and 3,4 (view) or nullptr
     __half* in2_out;                   // tiled view_mlp input or nullptr
+    __half* dydx_out;                  // d enc / d x, [tile][gather group][level pair][2 levels x 3 dims][row][2 channels] fp16, or nullptr
     float* sigma_out; float* rgb_out;
     uint32_t M; const int* m_dev;
     int density_act, color_act; float beta;
@@ -60,7 +61,9 @@ struct WsArgs {
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_h2(a, b); }
 
-template <bool LDIR>
+// DYDX: the gather warps also produce d enc / d x (calc_grad_inputs of the reference, gridencoder.cu:216-245) for the input
+// gradients of the backward kernel, stored word-major / row-minor per gather group (coalesced 4-byte stores).
+template <bool LDIR, bool DYDX>
 __global__ void __launch_bounds__(kWsThreads, 1)
 field_forward_ws_kernel(const WsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -124,7 +127,14 @@ field_forward_ws_kernel(const WsArgs a) {
             for (uint32_t level = grp; level < g.L; level += 2 * kGatherGroups) {
                 const uint32_t la = level, lb = level + kGatherGroups;       // L % 8 == 0
                 __half2 f0, f1;
+                uint32_t dy[6];
                 if (s_lv[la].mode == 2 || s_lv[lb].mode == 2) {              // warp-uniform, rare
+                    if (DYDX) {
+                        dydx_level_generic(g.table, g.gridtype, g.align_corners, g.interp, s_lv[la].res, s_lv[la].hashmap_size, s_lv[la].offset,
+                                           xc[0], xc[1], xc[2], inside, dy);
+                        dydx_level_generic(g.table, g.gridtype, g.align_corners, g.interp, s_lv[lb].res, s_lv[lb].hashmap_size, s_lv[lb].offset,
+                                           xc[0], xc[1], xc[2], inside, dy + 3);
+                    }
                     const uint32_t ra = gather_level_generic(g.table, g.feat_weights, g.gridtype, g.align_corners, g.interp, s_lv[la].res,
                                                              s_lv[la].hashmap_size, s_lv[la].offset, xc[0], xc[1], xc[2], la, inside);
                     const uint32_t rb = gather_level_generic(g.table, g.feat_weights, g.gridtype, g.align_corners, g.interp, s_lv[lb].res,
@@ -135,6 +145,24 @@ field_forward_ws_kernel(const WsArgs a) {
                     gather_issue(q0, g, s_lv[la], xc);
                     gather_issue(q1, g, s_lv[lb], xc);
                     f0 = gather_finish(q0, g, la, inside); f1 = gather_finish(q1, g, lb, inside);
+                    if (DYDX) {
+                        float df[3];
+                        uint32_t o3[3];
+                        locate3_dfrac(xc, s_lv[la].res, g.align_corners, g.interp, df);
+                        gather_finish_dydx(q0, df, (float)(g.align_corners ? s_lv[la].res - 1 : s_lv[la].res), inside, o3);
+                        dy[0] = o3[0]; dy[1] = o3[1]; dy[2] = o3[2];
+                        locate3_dfrac(xc, s_lv[lb].res, g.align_corners, g.interp, df);
+                        gather_finish_dydx(q1, df, (float)(g.align_corners ? s_lv[lb].res - 1 : s_lv[lb].res), inside, o3);
+                        dy[3] = o3[0]; dy[4] = o3[1]; dy[5] = o3[2];
+                    }
+                }
+                if (DYDX) {
+                    // levels la, lb are this thread's pair number p: six 4-byte words, each stored row-contiguous
+                    // ([tile][group][pair][word][row]) so that a warp writes 128 contiguous bytes per word
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(a.dydx_out) +
+                                    ((size_t)(tile * kGatherGroups + grp) * (g.L / 8) + (level - grp) / 8) * (6 * kTile) + r;
+#pragma unroll
+                    for (uint32_t k = 0; k < 6; k++) dst[k * kTile] = dy[k];
                 }
                 if (!waited) {      // the ring stage is needed only now: the first gathers of the tile overlap the wait
                     tc::mbar_wait(empty_s + 8 * s, ((it / kStages) & 1u) ^ 1u);
@@ -300,7 +328,7 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
                                       const void* const* view_weights, const uint32_t* view_dims, uint32_t M,
                                       const int32_t* m_dev, int density_act, float beta, int color_act, void* enc_out,
                                       void* const* grid_acts_out, void* in2_out, void* const* view_acts_out, float* sigma_out,
-                                      float* rgb_out, ngp_stream_t stream) {
+                                      float* rgb_out, void* dydx_out, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     const bool density_only = view_weights == nullptr;      /* NeRFNetwork.density: grid_mlp only, dirs / rgb_out unused */
     if (!xyzs || !table || !offsets || !grid_weights || !grid_dims || !sigma_out) return NGP_ERR_NULL;
@@ -335,7 +363,8 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
         if (a.acts[l] && !aligned(a.acts[l], 16)) return NGP_ERR_ALIGN;
     }
     if (!aligned(table, 4) || (enc_out && !aligned(enc_out, 16)) || (in2_out && !aligned(in2_out, 16))) return NGP_ERR_ALIGN;
-    a.enc_out = (__half*)enc_out; a.in2_out = (__half*)in2_out;
+    if (dydx_out && !aligned(dydx_out, 16)) return NGP_ERR_ALIGN;
+    a.enc_out = (__half*)enc_out; a.in2_out = (__half*)in2_out; a.dydx_out = (__half*)dydx_out;
     a.sigma_out = sigma_out; a.rgb_out = rgb_out;
     a.M = M; a.m_dev = m_dev;
     a.density_act = density_act; a.color_act = color_act; a.beta = beta;
@@ -348,20 +377,21 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs);
-#define NGP_LAUNCH_WS(LD)                                                                                                   \
+#define NGP_LAUNCH_WS(LD, DY)                                                                                               \
     {                                                                                                                       \
         static thread_local uint32_t configured = 0;                                                                        \
         if (smem_bytes > configured) {                                                                                      \
-            if (cudaFuncSetAttribute(field_forward_ws_kernel<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+            if (cudaFuncSetAttribute(field_forward_ws_kernel<LD, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                      (int)smem_bytes) != cudaSuccess) {                                                     \
                 set_last_cuda_error(cudaGetLastError());                                                                    \
                 return NGP_ERR_CUDA;                                                                                        \
             }                                                                                                               \
             configured = smem_bytes;                                                                                        \
         }                                                                                                                   \
-        field_forward_ws_kernel<LD><<<grid, kWsThreads, smem_bytes, st>>>(a);                                               \
+        field_forward_ws_kernel<LD, DY><<<grid, kWsThreads, smem_bytes, st>>>(a);                                           \
     }
-    if (ldirs) NGP_LAUNCH_WS(true) else NGP_LAUNCH_WS(false)
+    if (dydx_out) { if (ldirs) NGP_LAUNCH_WS(true, true) else NGP_LAUNCH_WS(false, true) }
+    else { if (ldirs) NGP_LAUNCH_WS(true, false) else NGP_LAUNCH_WS(false, false) }
 #undef NGP_LAUNCH_WS
     return finish_launch();
 }

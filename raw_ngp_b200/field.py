@@ -39,7 +39,7 @@ def density_only(enc, grid_weights, xyzs, bound, density_act, beta, feat_weights
     if all(d in (16, 32, 64) for d in pdims[:3]) and L % 8 == 0:      # warp-specialised kernel, grid_mlp only
         _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
                   _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16), cd, None, None, M, None,
-                  int(density_act), float(beta), 1, None, None, None, None, _lib.ptr(sigma), None, _lib.stream())
+                  int(density_act), float(beta), 1, None, None, None, None, _lib.ptr(sigma), None, None, _lib.stream())
     else:
         _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), None, None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
                   _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w16), cd, len(w16), M, None,
@@ -86,7 +86,7 @@ class _fused_field(Function):
             _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table), _lib.ptr(enc.offsets),
                       _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
                       int(density_act), float(beta), int(color_act), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None,
-                      _lib.ptr(in2), _ptr_array(acts2) if keep else None, _lib.ptr(sigma), _lib.ptr(rgb), st)
+                      _lib.ptr(in2), _ptr_array(acts2) if keep else None, _lib.ptr(sigma), _lib.ptr(rgb), None, st)
         else:
             _lib.call("ngp_field_forward_density", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table),
                       _lib.ptr(enc.offsets), _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, len(w1), M,

@@ -266,6 +266,7 @@ class FusedTrainStep:
         self.d_in2 = None if self.ws else torch.empty(cap, self.p2[0], **f16)
         self.sigma, self.rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.d_sigma, self.d_rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
+        self.dydx = torch.empty(cap_t, 6 * enc.num_levels, **f16) if self.ray_grads else None   # d enc / d x, saved by the forward
         self.d_xyzs = torch.empty(cap, 3, **f32) if self.ray_grads else None
         self.d_dirs = torch.empty(cap, 3, **f32) if self.ray_grads else None
         self.d_rays_o = torch.zeros(N, 3, **f32) if self.ray_grads else None
@@ -341,12 +342,13 @@ class FusedTrainStep:
         if self.ws:
             _lib.call("ngp_field_forward_full", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
                       P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap, self._m_dev, self._density_act,
-                      float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), st)
+                      float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb),
+                      P(self.dydx), st)
             composite()
             _lib.call("ngp_field_backward_full", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_rgb), P(self.rgb),
                       P(self.enc_buf), a1, P(self.in2), a2, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip,
                       w1, c1, w2, c2, cap, self._m_dev, self._density_act, float(opt.beta), self._color_act, P(self.table_grad),
-                      dw1, dw2, P(enc.embeddings) if self.ray_grads else None, P(self.dirs) if self.ray_grads else None,
+                      dw1, dw2, P(self.dydx), P(self.dirs) if self.ray_grads else None,
                       P(self.d_xyzs), P(self.d_dirs), st)
             if self.ray_grads:
                 # dL/d rays_o = sum_seg dL/dxyz, dL/d rays_d = sum_seg (dL/dxyz * t + dL/ddirs)  (raymarching.py:319-329)
