@@ -259,9 +259,10 @@ int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_
 
 /* Device-side stream compaction of rays_alive (replaces `rays_alive[rays_alive >= 0]`,
  * nerf/renderer.py:612): writes the surviving ids, in order, to alive_out and their number to
- * n_out[0].  n_out int32[1]. */
+ * n_out[0].  n_out int32[1].  workspace: NULL (one block does it all) or int32[ceil(n_alive / 4096)] scratch for the
+ * two-pass multi-block version (a 1080p frame starts with 2 M ids). */
 int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* alive_out,
-                           int32_t* n_out, ngp_stream_t stream);
+                           int32_t* n_out, int32_t* workspace, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Occupancy-grid update  (reference: nerf/renderer.py:811-897, Python loop over torch ops)

@@ -44,7 +44,7 @@ SIGNATURES = {
     "ngp_march_rays_train_backward": [_p, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "ngp_march_rays": [_u32, _u32, _p, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _p],
     "ngp_composite_rays": [_u32, _u32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "ngp_compact_rays_alive": [_p, _u32, _p, _p, _p],
+    "ngp_compact_rays_alive": [_p, _u32, _p, _p, _p, _p],
     "ngp_occ_sample_positions": [_p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_occ_scatter_sigmas": [_p, _p, _u32, _p, _p],
     "ngp_occ_ema_update": [_p, _p, _u32, _f32, _p, _p, _p],
@@ -120,6 +120,7 @@ def require_cuda(*tensors):
             raise RuntimeError("raw_ngp_b200: operator called with a CPU tensor; these operators are CUDA-only (sm_100a)")
 
 
+weights_epoch = 0  # bumped whenever a native optimizer may have written parameters behind torch's version counters
 launch_count = 0  # kernels launched through the C ABI by this process (every entry point is one launch)
 
 

@@ -1014,6 +1014,84 @@ compact_alive_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* 
     if (tid == 0) n_out[0] = (int)s_carry;
 }
 
+// The same over many blocks (a 1080p frame starts with 2 M ids): every block owns 4096 consecutive ids, 16 per thread.
+// Pass 1 counts the survivors per block; pass 2 sums the counts of the blocks before it (<= 512 values), scans its own
+// threads and writes -- order preserved, two launches, no spinning.
+constexpr uint32_t kCompactThreads = 256, kCompactPer = 16, kCompactTile = kCompactThreads * kCompactPer;
+
+__device__ __forceinline__ uint32_t compact_load(const int* __restrict__ rays_alive, uint32_t n_alive, uint32_t first, int (&v)[kCompactPer]) {
+    uint32_t cnt = 0;
+    if (first + kCompactPer <= n_alive) {
+#pragma unroll
+        for (uint32_t q = 0; q < kCompactPer / 4; q++) {
+            const int4 u = __ldg(reinterpret_cast<const int4*>(rays_alive + first) + q);
+            v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < kCompactPer; k++) v[k] = (first + k < n_alive) ? __ldg(rays_alive + first + k) : -1;
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < kCompactPer; k++) cnt += v[k] >= 0;
+    return cnt;
+}
+
+// exclusive prefix of `cnt` over the block's threads; total in *block_total
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t cnt, uint32_t* s_warp, uint32_t* block_total) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= (uint32_t)s) incl += u;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kCompactThreads / 32; w++) {
+        const uint32_t c = s_warp[w];
+        if (w < wid) before += c;
+        total += c;
+    }
+    *block_total = total;
+    return before + incl - cnt;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_count_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* __restrict__ block_counts) {
+    __shared__ uint32_t s_warp[kCompactThreads / 32];
+    int v[kCompactPer];
+    const uint32_t cnt = compact_load(rays_alive, n_alive, blockIdx.x * kCompactTile + threadIdx.x * kCompactPer, v);
+    uint32_t total;
+    block_exclusive_scan(cnt, s_warp, &total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (int)total;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_write_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, const int* __restrict__ block_counts, int* __restrict__ out,
+                     int* __restrict__ n_out) {
+    __shared__ uint32_t s_warp[kCompactThreads / 32];
+    __shared__ uint32_t s_red[kCompactThreads / 32];
+    // survivors in the blocks before this one
+    uint32_t part = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kCompactThreads) part += (uint32_t)__ldg(block_counts + b);
+    part = __reduce_add_sync(0xffffffffu, part);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    int v[kCompactPer];
+    const uint32_t cnt = compact_load(rays_alive, n_alive, blockIdx.x * kCompactTile + threadIdx.x * kCompactPer, v);
+    uint32_t total;
+    uint32_t pos = block_exclusive_scan(cnt, s_warp, &total);      // (its __syncthreads also publishes s_red)
+    uint32_t base = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kCompactThreads / 32; w++) base += s_red[w];
+    pos += base;
+#pragma unroll
+    for (uint32_t k = 0; k < kCompactPer; k++)
+        if (v[k] >= 0) out[pos++] = v[k];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) n_out[0] = (int)(base + total);
+}
+
 }  // namespace
 }  // namespace ngp
 
@@ -1215,9 +1293,15 @@ extern "C" int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thr
 }
 
 extern "C" int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* alive_out, int32_t* n_out,
-                                      ngp_stream_t stream) {
+                                      int32_t* workspace, ngp_stream_t stream) {
     if (!n_out) return NGP_ERR_NULL;
     if (n_alive > 0 && (!rays_alive || !alive_out)) return NGP_ERR_NULL;
-    compact_alive_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, alive_out, n_out);
+    if (!workspace || n_alive <= kCompactTile || !aligned(rays_alive, 16)) {
+        compact_alive_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, alive_out, n_out);
+        return finish_launch();
+    }
+    const uint32_t blocks = div_up(n_alive, kCompactTile);
+    compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace);
+    compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, alive_out, n_out);
     return finish_launch();
 }

@@ -16,8 +16,20 @@ COLOR_ACT = {"exp": 1, "sigmoid": 2, "clamped_exp": 3}
 
 
 def _pad_weight(w, n, k):
+    """fp16 copy of w [N, K] zero-padded to [n, k].  The copy is cached ON the weight tensor object and reused until the
+    tensor is written again (its version counter changes): inference evaluates the field ~40 times per frame with fixed
+    weights.  The native optimizers write parameters through raw pointers, also from replayed CUDA graphs, where torch's
+    version counter does not move: _lib.weights_epoch stands in for it."""
+    ver = (w._version, _lib.weights_epoch, w.data_ptr(), tuple(w.shape), n, k, w.device)
+    hit = getattr(w, "_ngp_padded", None)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
     wp = torch.zeros(n, k, dtype=torch.float16, device=w.device)
-    wp[:w.shape[0], :w.shape[1]] = w
+    wp[:w.shape[0], :w.shape[1]] = w.detach()
+    try:
+        w._ngp_padded = (ver, wp)
+    except (AttributeError, RuntimeError):
+        pass
     return wp
 
 

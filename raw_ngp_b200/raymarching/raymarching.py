@@ -331,5 +331,6 @@ def compact_rays_alive(rays_alive, n_alive=None):
     n = rays_alive.shape[0] if n_alive is None else int(n_alive)
     out = torch.empty_like(rays_alive)
     n_out = torch.zeros(1, dtype=torch.int32, device=rays_alive.device)
-    _lib.call("ngp_compact_rays_alive", _lib.ptr(rays_alive), n, _lib.ptr(out), _lib.ptr(n_out), _lib.stream())
+    ws = torch.empty((n + 4095) // 4096, dtype=torch.int32, device=rays_alive.device) if n > 4096 else None
+    _lib.call("ngp_compact_rays_alive", _lib.ptr(rays_alive), n, _lib.ptr(out), _lib.ptr(n_out), _lib.ptr(ws), _lib.stream())
     return out, n_out

@@ -34,6 +34,7 @@ class FusedAdam:
 
     def step(self, inv_scale, found_inf, zero_grad=True, lr=None):
         self.step_count += 1
+        _lib.weights_epoch += 1
         lr = self.lr if lr is None else lr
         st = _lib.stream()
         if self.device_step is not None:
@@ -559,6 +560,7 @@ class FusedTrainStep:
                 self._graph_field.replay()
                 self.kernels_replayed += self.march_kernels + self.field_kernels
             elif self._pending:
+                _lib.weights_epoch += 1          # the replayed graph contains the optimizer update
                 self._graph_pipe.replay()
                 self.opt.step_count += 1
                 if self.pose is not None:

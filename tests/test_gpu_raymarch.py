@@ -244,3 +244,17 @@ def test_march_count_at_scale_and_properties(ref_march):
     seg = torch.repeat_interleave(torch.arange(rays.shape[0], device="cuda"), rays[:, 1].long())
     same = seg[1:] == seg[:-1]
     assert (ts[1:, 0][same] > ts[:-1, 0][same]).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 70001, 2073600])
+def test_compact_rays_alive_sizes(n):
+    """single-block and two-pass multi-block compaction against the boolean mask of renderer.py:612, ragged sizes"""
+    g = torch.Generator().manual_seed(n)
+    alive = torch.arange(n, dtype=torch.int32)
+    dead = torch.rand(n, generator=g) < (0.85 if n > 4096 else 0.4)
+    alive[dead] = -1
+    alive = alive.cuda()
+    out, cnt = raymarching.compact_rays_alive(alive)
+    expect = alive[alive >= 0]
+    assert cnt.item() == expect.shape[0]
+    assert torch.equal(out[:cnt.item()], expect)

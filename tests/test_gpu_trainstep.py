@@ -298,3 +298,27 @@ def test_fused_step_hdr_loss_matches_torch():
     scale = g_table_ref.abs().max().clamp(min=1e-8)
     err = (fs.table_grad.float() - g_table_ref).abs() / scale
     assert err.max().item() < 3e-2 and err.mean().item() < 1e-3, (err.max().item(), err.mean().item())
+
+
+def test_padded_weight_cache_sees_native_updates():
+    """field._pad_weight caches the padded fp16 weights per tensor version; the native optimizers write parameters through raw
+    pointers (also from replayed graphs), so the cache key carries _lib.weights_epoch."""
+    N = 1024
+    model, o, d, tgt = _scene(N)
+    fs = FusedTrainStep(model, N, perturb=False, use_graph=True)
+
+    def render():
+        model.eval()
+        with torch.no_grad():
+            return model.render(o, d, bg_color=1.0, perturb=False)["image"].clone()
+
+    img0 = render()                       # fills the cache
+    for _ in range(4):
+        fs.step(o, d, tgt, update_grid=False)
+    fs.flush()
+    img1 = render()
+    for lin in list(model.grid_mlp.net) + list(model.view_mlp.net):
+        lin.weight._ngp_padded = None         # drop the cached copies
+    img2 = render()
+    assert torch.equal(img1, img2)
+    assert not torch.equal(img0, img1)

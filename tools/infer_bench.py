@@ -26,7 +26,7 @@ def main():
     dirs = torch.stack([(i - W / 2) / f, -(j - H / 2) / f, -torch.ones_like(i, dtype=torch.float32)], -1).reshape(-1, 3)
     rays_o = torch.tensor([0.0, 0.0, 2.0], device=dev).expand_as(dirs).contiguous()        # camera on r = 2 looking at the origin
     lo, hi = parallel.shard_range(dirs.shape[0], rank, world)
-    chunk = 1 << 19
+    chunk = 1 << int(os.environ.get('INFER_CHUNK_LOG2', '21'))
     def frame():
         outs = []
         with torch.no_grad():
