@@ -902,46 +902,92 @@ march_train_bwd_kernel(const float* __restrict__ dL_dxyzs, const float* __restri
 // inference march / composite
 // ---------------------------------------------------------------------------------------------------
 
-// raymarching.cu:730-846
+// raymarching.cu:730-846.  One thread per alive ray marches up to n_step samples; the samples of a warp's 32 rays form one
+// contiguous block of each output ([n_alive, n_step, 3|3|2]), so they are staged in shared memory and written with
+// coalesced stores -- per-thread stores at a stride of n_step samples cost one L2 transaction per 4-byte word, which is
+// what bounded this kernel (8x the sector writes).
 __global__ void __launch_bounds__(128)
 march_infer_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
                    const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, bool contract, float dt_gamma,
                    uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ nears,
                    const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ ts,
-                   const float* __restrict__ noises) {
+                   const float* __restrict__ noises, bool staged) {
+    extern __shared__ float s_stage[];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_alive) return;
-    const int index = __ldg(rays_alive + n);
-    const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
-    const Ray r = load_ray(rays_o, rays_d, (size_t)index, true);
-    const float far = __ldg(fars + index);
+    const uint32_t n0 = n - lane;                           // first ray of the warp
+    if (n0 >= n_alive) return;                              // whole warp
+    const bool active = n < n_alive;
+    // staged: odd per-lane strides in shared memory (no bank conflicts); otherwise (n_step too large for shared memory) every
+    // thread writes its own rows of the outputs directly
+    const uint32_t sx_stride = staged ? 3 * n_step + 1 : 3 * n_step, st_stride = staged ? 2 * n_step + 1 : 2 * n_step;
+    float* sx = staged ? s_stage + wid * 32 * (sx_stride + st_stride) : xyzs + (size_t)n0 * sx_stride;
+    float* st = staged ? sx + 32 * sx_stride : ts + (size_t)n0 * st_stride;
     (void)nears;
-    float t = __ldg(rays_t + index);
-    t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
-
-    float* px = xyzs + (size_t)n * n_step * 3;
-    float* pd = dirs + (size_t)n * n_step * 3;
-    float* pt = ts + (size_t)n * n_step * 2;
     uint32_t step = 0;
-    while (t < far && step < n_step) {
-        Probe q;
-        if (probe(p, r, t, q)) {
-            px[0] = q.cx; px[1] = q.cy; px[2] = q.cz;
-            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-            t += q.dt;
-            *reinterpret_cast<float2*>(pt) = make_float2(t, q.dt);
-            px += 3; pd += 3; pt += 2;
-            step++;
-        } else {
-            t = skip_voxel(p, r, t, q);
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (active) {
+        const int index = __ldg(rays_alive + n);
+        const MarchParams p = make_params(grid, bound, contract, dt_gamma, max_steps, C, H);
+        const Ray r = load_ray(rays_o, rays_d, (size_t)index, true);
+        dx = r.dx; dy = r.dy; dz = r.dz;
+        const float far = __ldg(fars + index);
+        float t = __ldg(rays_t + index);
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
+        float* px = sx + lane * sx_stride;
+        float* pt = st + lane * st_stride;
+        while (t < far && step < n_step) {
+            Probe q;
+            if (probe(p, r, t, q)) {
+                px[0] = q.cx; px[1] = q.cy; px[2] = q.cz;
+                t += q.dt;
+                pt[0] = t; pt[1] = q.dt;
+                px += 3; pt += 2;
+                step++;
+            } else {
+                t = skip_voxel(p, r, t, q);
+            }
+        }
+        // unwritten tail: ts[0] == 0 is the "ray finished" sentinel read by composite_rays (raymarching.cu:893-894)
+        for (uint32_t k = step; k < n_step; k++) {
+            px[0] = px[1] = px[2] = 0.f;
+            pt[0] = pt[1] = 0.f;
+            px += 3; pt += 2;
         }
     }
-    // unwritten tail: ts[0] == 0 is the "ray finished" sentinel read by composite_rays (raymarching.cu:893-894)
-    for (; step < n_step; step++) {
-        px[0] = px[1] = px[2] = 0.f;
-        pd[0] = pd[1] = pd[2] = 0.f;
-        *reinterpret_cast<float2*>(pt) = make_float2(0.f, 0.f);
-        px += 3; pd += 3; pt += 2;
+    if (!staged) {
+        if (active) {
+            float* pd = dirs + (size_t)n * 3 * n_step;
+            for (uint32_t k = 0; k < n_step; k++) {
+                pd[3 * k] = k < step ? dx : 0.f; pd[3 * k + 1] = k < step ? dy : 0.f; pd[3 * k + 2] = k < step ? dz : 0.f;
+            }
+        }
+        return;
+    }
+    __syncwarp();
+    const uint32_t rays_here = min(32u, n_alive - n0);
+    {   // xyzs and dirs: 3 * n_step words per ray
+        const uint32_t per = 3 * n_step, total = rays_here * per;
+        float* gx = xyzs + (size_t)n0 * per;
+        float* gd = dirs + (size_t)n0 * per;
+        for (uint32_t i = lane; i < ((total + 31u) & ~31u); i += 32) {
+            const uint32_t ray = min(i / per, 31u), rem = i - (i / per) * per;
+            const uint32_t k = rem / 3, c = rem - k * 3;
+            const uint32_t cnt = __shfl_sync(0xffffffffu, step, ray);
+            const float d0 = __shfl_sync(0xffffffffu, dx, ray), d1 = __shfl_sync(0xffffffffu, dy, ray), d2 = __shfl_sync(0xffffffffu, dz, ray);
+            if (i < total) {
+                gx[i] = sx[ray * sx_stride + rem];
+                gd[i] = (k < cnt) ? (c == 0 ? d0 : (c == 1 ? d1 : d2)) : 0.f;
+            }
+        }
+    }
+    {   // ts: 2 * n_step words per ray
+        const uint32_t per = 2 * n_step, total = rays_here * per;
+        float* gt = ts + (size_t)n0 * per;
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t ray = i / per, rem = i - ray * per;
+            gt[i] = st[ray * st_stride + rem];
+        }
     }
 }
 
@@ -1275,9 +1321,12 @@ extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* 
     if (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !ts || !noises) return NGP_ERR_NULL;
     if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
-    march_infer_kernel<<<div_up(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(
+    uint32_t stage_bytes = 4u * 32u * (5u * n_step + 2u) * (uint32_t)sizeof(float);      // 4 warps per block
+    const bool staged = stage_bytes <= 48u * 1024u;                                    // n_step <= 19 (the renderer uses <= 8)
+    if (!staged) stage_bytes = 0;
+    march_infer_kernel<<<div_up(n_alive, 128u), 128, stage_bytes, (cudaStream_t)stream>>>(
         n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, contract != 0, dt_gamma, max_steps, C, H, grid, nears, fars,
-        xyzs, dirs, ts, noises);
+        xyzs, dirs, ts, noises, staged);
     return finish_launch();
 }
 

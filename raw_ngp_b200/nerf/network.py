@@ -88,6 +88,38 @@ class NeRFNetwork(NeRFRenderer):
                 and torch.is_autocast_enabled("cuda") and self.grid_mlp.num_layers == 3 and self.view_mlp.num_layers == 3
                 and not any(t is not None and t.requires_grad for t in tensors))
 
+    def _fast_infer_args(self, rays_ldir, shading):
+        """Inference loop of the renderer: the whole field as one launch per iteration, no tensors allocated (renderer.py)."""
+        import ctypes
+        from .. import _lib
+        from ..ffmlp import _pad16, _ptr_array
+        enc = self.grid_encoder
+        if not (self.FUSED and self.opt.fp16 and not self.opt.rfield and rays_ldir is None and enc.embeddings.is_cuda
+                and enc.embeddings.dtype == torch.float16 and enc.level_dim == 2 and enc.input_dim == 3 and enc.num_levels % 8 == 0
+                and self.opt.internal_activation == "relu" and self.opt.density_activation in ("clamped_exp", "softplus")
+                and self.opt.color_activation in _field.COLOR_ACT and self.opt.pose_opt in ("none", "barf")
+                and self.grid_mlp.num_layers == 3 and self.view_mlp.num_layers == 3):
+            return None
+        gw, vw = [l.weight for l in self.grid_mlp.net], [l.weight for l in self.view_mlp.net]
+        p1 = [_pad16(d) for d in [gw[0].shape[1]] + [w.shape[0] for w in gw]]
+        p2 = [_pad16(d) for d in [vw[0].shape[1]] + [w.shape[0] for w in vw]]
+        if not _field._ws_ok(p1, p2):
+            return None
+        w1 = [_field._pad_weight(w, p1[i + 1], p1[i]) for i, w in enumerate(gw)]
+        w2 = [_field._pad_weight(w, p2[i + 1], p2[i]) for i, w in enumerate(vw)]
+        a1, a2 = _ptr_array(w1), _ptr_array(w2)
+        c1, c2 = (ctypes.c_uint32 * 4)(*p1), (ctypes.c_uint32 * 4)(*p2)
+        S, H, L, gt, ac, ip = _field._grid_scalars(enc)
+        fw = self._feat_weights(enc.embeddings.device)
+        dens, col, beta, bound = self._density_act(), _field.COLOR_ACT[self.opt.color_activation], float(self.opt.beta), float(self.bound)
+        keep = (w1, w2, fw)      # the launch arguments below hold raw pointers into these
+
+        def field(xyzs, dirs, M, sigmas, rgbs, st, _keep=keep):
+            _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
+                      _lib.ptr(fw), bound, S, H, L, gt, ac, ip, a1, c1, a2, c2, M, None, dens, beta, col, None, None, None, None,
+                      _lib.ptr(sigmas), _lib.ptr(rgbs), None, st)
+        return field
+
     def _feat_weights(self, device):
         if self.opt.pose_opt != "barf":
             return None

@@ -137,8 +137,12 @@ class NeRFRenderer(nn.Module):
             weights_sum = torch.zeros(N, dtype=dtype, device=device)
             depth = torch.zeros(N, dtype=dtype, device=device)
             image = torch.zeros(N, 3, dtype=dtype, device=device)
-            self._march_composite_loop(N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, weights_sum,
-                                       depth, image, normals=False)
+            fast = self._fast_infer_args(rays_ldir, shading) if self.FAST_INFER else None
+            if fast is not None:
+                self._march_composite_loop_fast(N, rays_o, rays_d, nears, fars, perturb, weights_sum, depth, image, fast)
+            else:
+                self._march_composite_loop(N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, weights_sum,
+                                           depth, image, normals=False)
             if getattr(self.opt, "compute_normals", False):
                 ws_n = torch.zeros(N, dtype=dtype, device=device)
                 depth_n = torch.zeros(N, dtype=dtype, device=device)
@@ -151,6 +155,47 @@ class NeRFRenderer(nn.Module):
         results["depth"] = depth
         results["image"] = image
         return results
+
+    FAST_INFER = True
+
+    def _fast_infer_args(self, rays_ldir, shading):
+        """Subclasses whose field is one fused kernel return its launch arguments (see NeRFNetwork); None = generic loop."""
+        return None
+
+    def _march_composite_loop_fast(self, N, rays_o, rays_d, nears, fars, perturb, weights_sum, depth, image, field):
+        """The alive-ray loop of renderer.py:588-616 with four C-ABI launches per iteration (march, fused field, composite,
+        compaction) on buffers allocated once per frame: n_alive * n_step never exceeds N, the marcher writes every row of
+        its outputs (finished rays as zeros), and the field kernel normalises the directions itself -- so the per-iteration
+        zero fills, the torch normalisation and the autograd / autocast plumbing of the generic loop disappear.  The host
+        still reads the surviving count once per iteration (it sizes the next launches, as in the reference)."""
+        from .. import _lib
+        P, st = _lib.ptr, _lib.stream()
+        dev = rays_o.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        xyzs, dirs, ts = torch.empty(N, 3, **f32), torch.empty(N, 3, **f32), torch.empty(N, 2, **f32)
+        sigmas, rgbs = torch.empty(N, **f32), torch.empty(N, 3, **f32)
+        alive = torch.arange(N, dtype=torch.int32, device=dev)
+        alive_next = torch.empty_like(alive)
+        rays_t = nears.clone().view(-1).contiguous()
+        nears, fars = nears.view(-1).contiguous(), fars.view(-1).contiguous()
+        zeros = torch.zeros(N, **f32)
+        noises = torch.rand(N, **f32) if perturb else zeros
+        n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty((N + 4095) // 4096, dtype=torch.int32, device=dev)
+        n_alive, step = N, 0
+        while step < self.opt.max_steps and n_alive > 0:
+            n_step = max(min(N // n_alive, 8), 1)
+            _lib.call("ngp_march_rays", n_alive, n_step, P(alive), P(rays_t), P(rays_o), P(rays_d), float(self.real_bound),
+                      int(bool(self.opt.contract)), float(self.opt.dt_gamma), int(self.opt.max_steps), int(self.cascade),
+                      int(self.grid_size), P(self.density_bitfield), P(nears), P(fars), P(xyzs), P(dirs), P(ts),
+                      P(noises if step == 0 else zeros), st)
+            field(xyzs, dirs, n_alive * n_step, sigmas, rgbs, st)
+            _lib.call("ngp_composite_rays", n_alive, n_step, float(self.opt.T_thresh), P(alive), P(rays_t), P(sigmas), P(rgbs),
+                      P(ts), P(weights_sum), P(depth), P(image), st)
+            _lib.call("ngp_compact_rays_alive", P(alive), n_alive, P(alive_next), P(n_out), P(ws), st)
+            alive, alive_next = alive_next, alive
+            n_alive = int(n_out.item())
+            step += n_step
 
     def _march_composite_loop(self, N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, weights_sum,
                               depth, image, normals):

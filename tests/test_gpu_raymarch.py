@@ -258,3 +258,23 @@ def test_compact_rays_alive_sizes(n):
     expect = alive[alive >= 0]
     assert cnt.item() == expect.shape[0]
     assert torch.equal(out[:cnt.item()], expect)
+
+
+@pytest.mark.parametrize("n_step", [1, 3, 8, 19, 32])
+def test_march_rays_step_counts_match_reference(n_step, ref_march):
+    """one inference march call: staged (shared memory, coalesced stores; n_step <= 19) and direct output paths, ragged
+    last warp, against the reference kernel"""
+    from oracle import ref_cuda
+    grid, thresh = _scene(cascade=2, bound=2.0)
+    bitfield = raymarching.packbits(grid, thresh)
+    N = 5003
+    o, d, aabb, nears, fars = _rays(N, bound=2.0)
+    nears = nears.view(-1).contiguous(); fars = fars.view(-1).contiguous()
+    alive = torch.arange(N, dtype=torch.int32, device="cuda")[torch.randperm(N, device="cuda")][:4001].contiguous()
+    n_alive = alive.shape[0]
+    t = nears.clone()
+    noises = torch.zeros(n_alive, device="cuda")
+    x1, d1, t1 = raymarching.march_rays(n_alive, n_step, alive, t, o, d, 2.0, False, bitfield, 2, 128, nears, fars, False, 0.0, 1024)
+    x2, d2, t2 = ref_cuda.march_rays(n_alive, n_step, alive, t, o, d, 2.0, False, bitfield, 2, 128, nears, fars, noises, 0.0, 1024)
+    assert torch.equal(x1, x2) and torch.equal(d1, d2) and torch.equal(t1, t2)
+    assert (t1[:, 0] > 0).float().mean().item() > 0.2

@@ -28,3 +28,15 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         model.render(rays_o, dirs, bg_color=1.0, perturb=False)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=14, max_name_column_width=60))
+
+# per-call device time of the marcher (first call = all rays of the frame, most of them crossing empty space)
+evs = []
+def timed(n_alive, n_step, *a, **k):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); r = orig(n_alive, n_step, *a, **k); e1.record()
+    evs.append((n_alive, n_step, e0, e1)); return r
+R.raymarching.march_rays = timed
+with torch.no_grad():
+    model.render(rays_o, dirs, bg_color=1.0, perturb=False)
+torch.cuda.synchronize()
+print('march per call (n_alive, n_step, us):', [(a, b, round(e0.elapsed_time(e1) * 1e3)) for a, b, e0, e1 in evs][:12], '...')
