@@ -451,6 +451,28 @@ int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int 
  * counted, as in torch). */
 int ngp_adam_step_counter(int32_t* step_dev, const float* found_inf_dev, ngp_stream_t stream);
 
+/* Data parallel over NVLink peer memory: reduce-scatter + Adam + all-gather in one kernel.  peer_grads[r] /
+ * peer_params_lp[r] (host arrays of `world` device pointers, r = rank) are the SAME buffer on every rank -- gradient
+ * (grad_dtype fp16 / fp32) and low-precision parameters (lp_dtype) -- mapped into this process (symmetric memory / CUDA
+ * IPC).  This rank owns elements [lo, hi) (multiples of 8 for fp16 gradients, 4 for fp32): it sums that range of all
+ * ranks' gradients in fp32, updates its fp32 master / exp_avg / exp_avg_sq SHARDS (hi - lo elements each) exactly like
+ * ngp_fused_adam (step count and optional learning rate on the device, *inv_scale_dev, skip on *found_inf_dev) and writes
+ * the updated parameters to peer_params_lp[0 .. n_store) (n_store = world: every rank's copy; n_store = 1 with
+ * peer_params_lp[0] = the local copy and lo..hi = everything: replicated update of a small tensor).  Gradients are not
+ * cleared (peers may still be reading them): the caller clears after its barrier.  The caller orders the ranks with
+ * barriers on the stream before (all gradients and flags complete) and after (all parameter stores landed). */
+int ngp_dp_fused_adam(const void* const* peer_grads, int grad_dtype, void* const* peer_params_lp, int lp_dtype,
+                      uint32_t world, uint32_t n_store, float* master_shard, float* exp_avg_shard,
+                      float* exp_avg_sq_shard, uint64_t lo, uint64_t hi, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, const int32_t* step_dev, const float* lr_dev, const float* inv_scale_dev,
+                      const float* found_inf_dev, ngp_stream_t stream);
+
+/* GradScaler flag across ranks without a collective: every rank stores its flag into slot `rank` of every rank's float[world]
+ * array (peer_flags[r]); after the barrier ngp_dp_merge_flags takes the maximum of the local array. */
+int ngp_dp_publish_flag(const float* found_inf_local, void* const* peer_flags, uint32_t world, uint32_t rank,
+                        ngp_stream_t stream);
+int ngp_dp_merge_flags(const float* flags, uint32_t world, float* found_inf, ngp_stream_t stream);
+
 /* found_inf_dev[0] = 1.0f if any element of grad is inf/nan (accumulates; caller zero-fills). */
 int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev,
                      ngp_stream_t stream);

@@ -103,6 +103,91 @@ check_finite_kernel(const G* __restrict__ grad, uint64_t n, float* __restrict__ 
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
 }
 
+
+// ---- data parallel: reduce-scatter + Adam + all-gather in ONE kernel over NVLink peer memory ------------------------
+// Every rank owns one contiguous shard [lo, hi) of the parameters (fp32 master, exp_avg, exp_avg_sq exist for the shard
+// only).  For its shard it LOADS the gradients of all ranks straight from their buffers (peer-mapped symmetric memory,
+// 16-byte loads over NVLink / NVSwitch), sums them in fp32 in rank order (the same order on every rank's shard, and only
+// the owner computes: the result is written, not recomputed, so all ranks end up bit-identical), applies unscale + Adam,
+// and STORES the updated low-precision parameters into the parameter buffer of every rank.  Compared with
+// all-reduce -> replicated Adam this moves the same bytes over the links once, runs Adam on 1/world of the parameters
+// and needs no staging buffer; the transfers overlap the arithmetic element by element.
+// Cross-rank ordering (all gradients complete before the loads, all stores landed before the next forward) is provided
+// by the caller's barriers on the same stream.
+constexpr uint32_t kMaxPeers = 8;
+struct PeerPtrs { const void* grad[kMaxPeers]; void* lp[kMaxPeers]; };
+
+template <typename G, typename P>
+__global__ void __launch_bounds__(256)
+dp_fused_adam_kernel(const PeerPtrs peers, uint32_t world, uint32_t n_store, float* __restrict__ master, float* __restrict__ m,
+                     float* __restrict__ v, uint64_t lo, uint64_t hi, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     const float* __restrict__ inv_scale_dev, const float* __restrict__ found_inf_dev, const int* __restrict__ step_dev,
+                     const float* __restrict__ lr_dev) {
+    if (found_inf_dev && __ldg(found_inf_dev) != 0.f) return;      // GradScaler: the whole step is skipped, on every rank alike
+    if (lr_dev) lr = __ldg(lr_dev);
+    const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
+    const float t = (float)max(__ldg(step_dev), 1);
+    const float step_size = lr / (1.f - powf(beta1, t)), bias2_sqrt = sqrtf(1.f - powf(beta2, t));
+    constexpr uint32_t PER = 16 / sizeof(G);           // elements per 16-byte gradient load
+    const uint64_t n_vec = (hi - lo) / PER;            // the shard is a multiple of PER (host-checked)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_vec; q += stride) {
+        const uint64_t i = lo + q * PER, s = q * PER;  // global element index, index inside the shard
+        float g[PER];
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) g[k] = 0.f;
+        uint4 u[kMaxPeers];
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; r++)       // all peer loads in flight before the first add
+            if (r < world) u[r] = *reinterpret_cast<const uint4*>(reinterpret_cast<const G*>(peers.grad[r]) + i);
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; r++) {
+            if (r < world) {
+                const G* e = reinterpret_cast<const G*>(&u[r]);
+#pragma unroll
+                for (uint32_t k = 0; k < PER; k++) g[k] += to_f32(e[k]);
+            }
+        }
+        P out[PER];
+#pragma unroll
+        for (uint32_t k0 = 0; k0 < PER; k0 += 4) {
+            Vec4<float> p4 = load4(master + s + k0), m4 = load4(m + s + k0), v4 = load4(v + s + k0);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                float gg = g[k0 + k] * inv_scale;
+                if (weight_decay != 0.f) gg += weight_decay * p4.v[k];
+                m4.v[k] = beta1 * m4.v[k] + (1.f - beta1) * gg;
+                v4.v[k] = beta2 * v4.v[k] + (1.f - beta2) * gg * gg;
+                p4.v[k] -= step_size * (m4.v[k] / (sqrtf(v4.v[k]) / bias2_sqrt + eps));
+                out[k0 + k] = from_f32<P>(p4.v[k]);
+            }
+            store4(m + s + k0, m4); store4(v + s + k0, v4); store4(master + s + k0, p4);
+        }
+        // PER low-precision parameters = PER * sizeof(P) bytes to every rank's copy (own copy included)
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; r++) {
+            if (r < n_store) {
+                P* dst = reinterpret_cast<P*>(peers.lp[r]) + i;
+                if constexpr (PER * sizeof(P) == 16) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+                else if constexpr (PER * sizeof(P) == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(out);
+                else { for (uint32_t k = 0; k < PER; k++) dst[k] = out[k]; }
+            }
+        }
+    }
+}
+
+// found_inf of this rank -> slot `rank` of every rank's flag array (peer stores); merged after the barrier
+__global__ void dp_publish_flag_kernel(const float* __restrict__ found_inf_local, PeerPtrs flags, uint32_t world, uint32_t rank) {
+    if (threadIdx.x < world) reinterpret_cast<float*>(flags.lp[threadIdx.x])[rank] = *found_inf_local;
+}
+__global__ void dp_merge_flags_kernel(const float* __restrict__ flags, uint32_t world, float* __restrict__ found_inf) {
+    if (threadIdx.x == 0) {
+        float f = 0.f;
+        for (uint32_t r = 0; r < world; r++) f = fmaxf(f, flags[r] != 0.f ? 1.f : 0.f);
+        *found_inf = f;
+    }
+}
+
 // GradScaler semantics for a device-side step counter: the optimizer step is counted only when it is not skipped
 __global__ void adam_step_counter_kernel(int* __restrict__ step_dev, const float* __restrict__ found_inf_dev) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf_dev && *found_inf_dev != 0.f)) *step_dev += 1;
@@ -141,6 +226,60 @@ extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void*
     else { NGP_ADAM_G(__nv_bfloat16); }
 #undef NGP_ADAM_G
 #undef NGP_ADAM
+    return finish_launch();
+}
+
+
+extern "C" int ngp_dp_fused_adam(const void* const* peer_grads, int grad_dtype, void* const* peer_params_lp, int lp_dtype,
+                                 uint32_t world, uint32_t n_store, float* master_shard, float* exp_avg_shard,
+                                 float* exp_avg_sq_shard, uint64_t lo, uint64_t hi, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, const int32_t* step_dev, const float* lr_dev, const float* inv_scale_dev,
+                                 const float* found_inf_dev, ngp_stream_t stream) {
+    if (hi <= lo) return NGP_OK;
+    if (!peer_grads || !peer_params_lp || !master_shard || !exp_avg_shard || !exp_avg_sq_shard || !step_dev) return NGP_ERR_NULL;
+    if (world == 0 || world > kMaxPeers || n_store > world) return NGP_ERR_BAD_ARG;
+    if (grad_dtype != NGP_F32 && grad_dtype != NGP_F16) return NGP_ERR_BAD_DTYPE;
+    if (lp_dtype != NGP_F32 && lp_dtype != NGP_F16) return NGP_ERR_BAD_DTYPE;
+    const uint32_t per = grad_dtype == NGP_F16 ? 8u : 4u;
+    if (lo % per || (hi - lo) % per) return NGP_ERR_ALIGN;
+    PeerPtrs pp = {};
+    for (uint32_t r = 0; r < world; r++) {
+        if (!peer_grads[r] || !aligned(peer_grads[r], 16)) return NGP_ERR_ALIGN;
+        pp.grad[r] = peer_grads[r];
+        if (r < n_store) {
+            if (!peer_params_lp[r] || !aligned(peer_params_lp[r], 16)) return NGP_ERR_ALIGN;
+            pp.lp[r] = peer_params_lp[r];
+        }
+    }
+    if (!aligned(master_shard, 16) || !aligned(exp_avg_shard, 16) || !aligned(exp_avg_sq_shard, 16)) return NGP_ERR_ALIGN;
+    const uint64_t n_vec = (hi - lo) / per;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(n_vec, 256), (uint64_t)kNumSMs * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+#define NGP_DP(G, P) dp_fused_adam_kernel<G, P><<<blocks, 256, 0, st>>>(pp, world, n_store, master_shard, exp_avg_shard, exp_avg_sq_shard, \
+                                                                        lo, hi, lr, beta1, beta2, eps, weight_decay, inv_scale_dev,     \
+                                                                        found_inf_dev, step_dev, lr_dev)
+    if (grad_dtype == NGP_F16 && lp_dtype == NGP_F16) NGP_DP(__half, __half);
+    else if (grad_dtype == NGP_F32 && lp_dtype == NGP_F16) NGP_DP(float, __half);
+    else if (grad_dtype == NGP_F32 && lp_dtype == NGP_F32) NGP_DP(float, float);
+    else return NGP_ERR_UNSUPPORTED;
+#undef NGP_DP
+    return finish_launch();
+}
+
+extern "C" int ngp_dp_publish_flag(const float* found_inf_local, void* const* peer_flags, uint32_t world, uint32_t rank,
+                                   ngp_stream_t stream) {
+    if (!found_inf_local || !peer_flags) return NGP_ERR_NULL;
+    if (world == 0 || world > kMaxPeers || rank >= world) return NGP_ERR_BAD_ARG;
+    PeerPtrs pp = {};
+    for (uint32_t r = 0; r < world; r++) { if (!peer_flags[r]) return NGP_ERR_NULL; pp.lp[r] = peer_flags[r]; }
+    dp_publish_flag_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(found_inf_local, pp, world, rank);
+    return finish_launch();
+}
+
+extern "C" int ngp_dp_merge_flags(const float* flags, uint32_t world, float* found_inf, ngp_stream_t stream) {
+    if (!flags || !found_inf) return NGP_ERR_NULL;
+    if (world == 0 || world > kMaxPeers) return NGP_ERR_BAD_ARG;
+    dp_merge_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, found_inf);
     return finish_launch();
 }
 

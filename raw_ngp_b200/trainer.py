@@ -9,10 +9,40 @@ What is native here:
   * GradScaler semantics (scale, unscale, skip on inf/nan, growth/backoff) with the check on the device;
   * Adam (eps=1e-15 like main.py:245) fused with the unscale, the low-precision copy and the gradient clear.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import _lib, parallel
+
+
+class _PeerMemory:
+    """Symmetric (peer-mapped) device buffers of the ranks of one node: torch.distributed._symmetric_memory allocates and
+    exchanges the handles; the kernels get plain arrays of device pointers, one per rank."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._sm, self.group, self.device = symm_mem, (group if group is not None else dist.group.WORLD), device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ptrs, self._handles = {}, {}
+
+    def empty(self, n, dtype):
+        return self._sm.empty(int(n), dtype=dtype, device=self.device)
+
+    def empty_like(self, t, dtype):
+        return self._sm.empty(*t.shape, dtype=dtype, device=self.device)
+
+    def rendezvous(self, **tensors):
+        import ctypes
+        for name, t in tensors.items():
+            h = self._sm.rendezvous(t, group=self.group)
+            self._handles[name] = h
+            self.ptrs[name] = (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+        self._barrier_handle = self._handles[next(iter(tensors))]
+
+    def barrier(self, channel):
+        self._barrier_handle.barrier(channel=channel)      # a kernel on the current stream
 
 
 class FusedAdam:
@@ -182,13 +212,36 @@ class FusedTrainStep:
 
         # ---- parameters: fp32 master + fp16 working copy + fp32/fp16 gradient buffers -------------------------------
         self.table_master = enc.embeddings.data.float().contiguous()
-        enc.embeddings.data = self.table_master.half()
-        self.table_grad = torch.zeros_like(enc.embeddings.data)
-        enc.grad_sink = self.table_grad
-        layers = [l for l in model.grid_mlp.net] + [l for l in model.view_mlp.net]
+        # Data parallel over NVLink peer memory (csrc/optim.cu: dp_fused_adam_kernel): the gradient buffers and the fp16 table
+        # live in symmetric memory, every rank owns a shard of the optimizer state.  Needs CUDA + NCCL ranks on one node;
+        # NGP_DP_PEER=0 (or a failing rendezvous) selects the NCCL all-reduce + replicated Adam path.
+        self.peer = None
         self.d1 = [model.grid_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.grid_mlp.net]
         self.d2 = [model.view_mlp.net[0].weight.shape[1]] + [l.weight.shape[0] for l in model.view_mlp.net]
         self.p1, self.p2 = [_pad16(d) for d in self.d1], [_pad16(d) for d in self.d2]
+        shapes = [(self.p1[i + 1], self.p1[i]) for i in range(3)] + [(self.p2[i + 1], self.p2[i]) for i in range(3)]
+        n_w = sum(a * b for a, b in shapes)
+        if self.world > 1 and dev.type == "cuda" and self.world <= 8 and os.environ.get("NGP_DP_PEER", "1") != "0" \
+                and dist.get_backend(process_group) == "nccl":
+            try:
+                pm = _PeerMemory(process_group, dev)
+                table_lp = pm.empty_like(self.table_master, torch.float16).copy_(self.table_master)
+                table_grad = pm.empty_like(self.table_master, torch.float16).zero_()
+                w_grad = pm.empty(n_w, torch.float32).zero_()
+                flags = pm.empty(8, torch.float32).zero_()
+                pm.rendezvous(grad=table_grad, table=table_lp, w_grad=w_grad, flags=flags)
+                self.peer = pm
+            except Exception as e:       # no symmetric memory on this system (all ranks fail alike): NCCL path
+                import warnings
+                warnings.warn(f"FusedTrainStep: peer-memory data parallel path unavailable ({e!r}); using NCCL all-reduce")
+        if self.peer is not None:
+            enc.embeddings.data, self.table_grad, self.w_grad, self.flags = table_lp, table_grad, w_grad, flags
+        else:
+            enc.embeddings.data = self.table_master.half()
+            self.table_grad = torch.zeros_like(enc.embeddings.data)
+            self.w_grad = torch.zeros(n_w, device=dev, dtype=torch.float32)
+        enc.grad_sink = self.table_grad
+        layers = [l for l in model.grid_mlp.net] + [l for l in model.view_mlp.net]
         # widths in {16, 32, 64}: the warp-specialised one-kernel forward / backward; otherwise (rfield: 48-wide view input,
         # 80-wide hidden layers) the density-field + view-MLP kernel pairs, with the same buffers and the same graph
         self.ws = _field._ws_ok(self.p1, self.p2)
@@ -201,10 +254,7 @@ class FusedTrainStep:
         self.ray_grads = bool(ray_grads) or pose_optimizer is not None
         if self.ray_grads and not self.ws:
             raise RuntimeError("FusedTrainStep: ray gradients need the warp-specialised kernels (layer widths in {16, 32, 64})")
-        shapes = [(self.p1[i + 1], self.p1[i]) for i in range(3)] + [(self.p2[i + 1], self.p2[i]) for i in range(3)]
-        n_w = sum(a * b for a, b in shapes)
         self.w_master = torch.zeros(n_w, device=dev, dtype=torch.float32)
-        self.w_grad = torch.zeros(n_w, device=dev, dtype=torch.float32)
         self.w_lp = torch.zeros(n_w, device=dev, dtype=torch.float16)
         self._w_master_views, self._w_lp_views, self._w_grad_views = [], [], []
         o = 0
@@ -217,13 +267,26 @@ class FusedTrainStep:
             self._w_grad_views.append(self.w_grad[o:o + n * k].view(n, k))
             o += n * k
         self.w_lp.copy_(self.w_master)
+        self._w_lp_local = (ctypes.c_void_p * 1)(self.w_lp.data_ptr())
 
         self.opt_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.opt = FusedAdam(lr=lr, betas=betas, eps=eps, device_step=self.opt_step_dev)
         self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)      # see set_lr()
         self.opt.lr_dev = self.lr_dev
-        self.opt.add_group(self.table_master, self.table_grad, enc.embeddings.data)
-        self.opt.add_group(self.w_master, self.w_grad, self.w_lp)
+        if self.peer is None:
+            self.opt.add_group(self.table_master, self.table_grad, enc.embeddings.data)
+            self.opt.add_group(self.w_master, self.w_grad, self.w_lp)
+        else:
+            # shard [lo, hi) of the flattened table: fp32 master + Adam moments exist for the shard only
+            n = self.table_master.numel()
+            per = (n + 8 * self.world - 1) // (8 * self.world) * 8
+            rank = dist.get_rank(process_group)
+            self.shard = (min(rank * per, n), min((rank + 1) * per, n))
+            lo, hi = self.shard
+            self.table_master_shard = self.table_master.view(-1)[lo:hi].clone()
+            self.table_master = None                         # see gather_table_master()
+            self.shard_m, self.shard_v = torch.zeros_like(self.table_master_shard), torch.zeros_like(self.table_master_shard)
+            self.w_m, self.w_v = torch.zeros_like(self.w_master), torch.zeros_like(self.w_master)
         self._pending = False          # gradients of the last step are waiting for their optimizer update
         if self.pose is not None:
             if poses is None:
@@ -451,11 +514,51 @@ class FusedTrainStep:
     def _reduce_and_update(self):
         """Data parallel: all-reduce of the two gradient buffers, inf check, MAX of the flag, fused Adam -- on the current
         (side) stream, so that it overlaps the ray marching of the next step on the main stream."""
+        if self.peer is not None:
+            return self._peer_update()
         parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
         # The inf / nan check runs on the REDUCED buffers, which are bit-identical on every rank (a non-finite value of any
         # rank survives the SUM), so all ranks take the same skip decision without a second collective for the flag.
         self._launch_check()
         self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+
+    def _peer_update(self):
+        """reduce-scatter + Adam + all-gather of the table as ONE kernel over peer memory (and a replicated variant of the same
+        kernel for the 57 KB of MLP weights); the GradScaler flag travels through peer stores; two symmetric-memory barriers
+        order the ranks.  No NCCL call, no staging buffer, Adam on 1 / world of the table."""
+        st, P, pm = _lib.stream(), _lib.ptr, self.peer
+        world, rank = self.world, pm.rank
+        _lib.weights_epoch += 1
+        self.opt.step_count += 1
+        b1, b2 = self.opt.betas
+        self._launch_check()                                       # local gradients -> self.found_inf
+        _lib.call("ngp_dp_publish_flag", P(self.found_inf), pm.ptrs["flags"], world, rank, st)
+        pm.barrier(0)                                              # every rank's gradients and flags are complete
+        _lib.call("ngp_dp_merge_flags", P(self.flags), world, P(self.found_inf), st)
+        _lib.call("ngp_adam_step_counter", P(self.opt_step_dev), P(self.found_inf), st)
+        lo, hi = self.shard
+        _lib.call("ngp_dp_fused_adam", pm.ptrs["grad"], _lib.NGP_F16, pm.ptrs["table"], _lib.NGP_F16, world, world,
+                  P(self.table_master_shard), P(self.shard_m), P(self.shard_v), lo, hi, float(self.opt.lr), float(b1), float(b2),
+                  float(self.opt.eps), float(self.opt.weight_decay), P(self.opt_step_dev), P(self.lr_dev), P(self.inv_scale),
+                  P(self.found_inf), st)
+        _lib.call("ngp_dp_fused_adam", pm.ptrs["w_grad"], _lib.NGP_F32, self._w_lp_local, _lib.NGP_F16, world, 1, P(self.w_master),
+                  P(self.w_m), P(self.w_v), 0, self.w_master.numel(), float(self.opt.lr), float(b1), float(b2), float(self.opt.eps),
+                  float(self.opt.weight_decay), P(self.opt_step_dev), P(self.lr_dev), P(self.inv_scale), P(self.found_inf), st)
+        pm.barrier(1)                                              # all parameter stores have landed, all gradient loads are done
+        self.table_grad.zero_()
+        self.w_grad.zero_()
+
+    def gather_table_master(self):
+        """fp32 master copy of the whole table (checkpoints).  In peer mode every rank holds only its shard: all-gather them."""
+        if self.peer is None:
+            return self.table_master
+        n = self.table_grad.numel()
+        per = (n + 8 * self.world - 1) // (8 * self.world) * 8
+        mine = torch.zeros(per, device=self.dev, dtype=torch.float32)
+        mine[:self.table_master_shard.numel()] = self.table_master_shard
+        full = torch.empty(per * self.world, device=self.dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, mine, group=self.pg)
+        return full[:n].view_as(self.table_grad)
 
     def flush(self):
         """Applies the optimizer update that is still pending (the update of step k normally runs at the start of step
