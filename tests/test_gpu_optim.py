@@ -54,3 +54,86 @@ def test_inf_skips_the_step(pos):
     assert torch.equal(master, before)                                # parameters, m, v untouched
     assert opt.groups[0]["m"].abs().max().item() == 0.0
     assert grad.float().abs().max().item() == 0.0                     # but the gradient buffer is cleared for the next step
+
+
+def _ptrs(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_dp_fused_adam_matches_allreduce_then_adam(world):
+    """csrc/optim.cu dp_fused_adam_kernel (reduce-scatter + Adam + all-gather over peer pointers), with the `world` ranks
+    emulated by `world` sets of buffers on one GPU: every rank's launch updates its shard from ALL gradient buffers and
+    stores into ALL parameter copies.  Expected: all copies bit-identical and equal to fused_adam on the fp32 sum."""
+    torch.manual_seed(world)
+    dev, n = "cuda", 8 * 12345
+    per = (n + 8 * world - 1) // (8 * world) * 8
+    master0 = torch.randn(n, device=dev)
+    grads = [(torch.randn(n, device=dev) * 0.1 * 128).half() for _ in range(world)]
+    tables = [master0.half().clone() for _ in range(world)]
+    step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    inv_scale = torch.full((1,), 1.0 / (128.0 * world), device=dev)
+    found_inf = torch.zeros(1, device=dev)
+    shards = []
+    for r in range(world):
+        lo, hi = min(r * per, n), min((r + 1) * per, n)
+        shards.append(dict(lo=lo, hi=hi, master=master0[lo:hi].clone(), m=torch.zeros(hi - lo, device=dev), v=torch.zeros(hi - lo, device=dev)))
+    # reference: sum in fp32 in rank order, then the single-GPU fused Adam
+    ref_master = master0.clone()
+    ref_lp = master0.half()
+    ref_opt = FusedAdam(lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    ref_grad = torch.zeros(n, device=dev)
+    ref_opt.add_group(ref_master, ref_grad, ref_lp)
+    st = _lib.stream()
+    for it in range(3):
+        for g in grads:
+            g.copy_((torch.randn(n, device=dev) * 0.1 * 128).half())
+        ref_grad.zero_()
+        for g in grads:
+            ref_grad += g.float()
+        ref_opt.step(inv_scale, found_inf, zero_grad=False)
+        _lib.call("ngp_adam_step_counter", _lib.ptr(step_dev), _lib.ptr(found_inf), st)
+        for r, sh in enumerate(shards):
+            _lib.call("ngp_dp_fused_adam", _ptrs(grads), _lib.NGP_F16, _ptrs(tables), _lib.NGP_F16, world, world, _lib.ptr(sh["master"]),
+                      _lib.ptr(sh["m"]), _lib.ptr(sh["v"]), sh["lo"], sh["hi"], 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None,
+                      _lib.ptr(inv_scale), _lib.ptr(found_inf), st)
+        torch.cuda.synchronize()
+        for t in tables[1:]:
+            assert torch.equal(t, tables[0])
+        full = torch.cat([sh["master"] for sh in shards])
+        torch.testing.assert_close(full, ref_master, rtol=1e-6, atol=1e-7)
+        assert (tables[0].float() - ref_lp.float()).abs().max().item() <= 2e-3      # same values up to one fp16 rounding
+    # inf on any rank: nothing moves
+    found_inf.fill_(1.0)
+    before = [t.clone() for t in tables]
+    sh = shards[0]
+    _lib.call("ngp_dp_fused_adam", _ptrs(grads), _lib.NGP_F16, _ptrs(tables), _lib.NGP_F16, world, world, _lib.ptr(sh["master"]),
+              _lib.ptr(sh["m"]), _lib.ptr(sh["v"]), sh["lo"], sh["hi"], 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None,
+              _lib.ptr(inv_scale), _lib.ptr(found_inf), st)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(before, tables))
+
+
+def test_dp_flags_and_argument_checks():
+    dev, world = "cuda", 4
+    flags = [torch.zeros(8, device=dev) for _ in range(world)]
+    st = _lib.stream()
+    for r in range(world):
+        local = torch.full((1,), 1.0 if r == 2 else 0.0, device=dev)
+        _lib.call("ngp_dp_publish_flag", _lib.ptr(local), _ptrs(flags), world, r, st)
+    merged = torch.zeros(1, device=dev)
+    for r in range(world):
+        assert flags[r][:world].tolist() == [0.0, 0.0, 1.0, 0.0]
+        _lib.call("ngp_dp_merge_flags", _lib.ptr(flags[r]), world, _lib.ptr(merged), st)
+        assert merged.item() == 1.0
+    # shard bounds must be multiples of the 16-byte vector, at most 8 peers
+    g, t = [torch.zeros(64, device=dev).half()], [torch.zeros(64, device=dev).half()]
+    m = torch.zeros(64, device=dev)
+    step_dev = torch.ones(1, dtype=torch.int32, device=dev)
+    with pytest.raises(RuntimeError):
+        _lib.call("ngp_dp_fused_adam", _ptrs(g), _lib.NGP_F16, _ptrs(t), _lib.NGP_F16, 1, 1, _lib.ptr(m), _lib.ptr(m.clone()), _lib.ptr(m.clone()),
+                  3, 35, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, st)
+    with pytest.raises(RuntimeError):
+        _lib.call("ngp_dp_fused_adam", _ptrs(g * 9), _lib.NGP_F16, _ptrs(t * 9), _lib.NGP_F16, 9, 9, _lib.ptr(m), _lib.ptr(m.clone()),
+                  _lib.ptr(m.clone()), 0, 64, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, st)

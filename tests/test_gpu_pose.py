@@ -47,3 +47,21 @@ def test_pose_rays_kernels_match_torch(zero_init):
     ((o * go).sum() + (d * gd).sum()).backward()
     scale = a.grad.abs().max()
     assert ((b.grad - a.grad).abs().max() / scale).item() < 1e-4
+
+
+def test_pose_rays_edge_cases():
+    """no rays; rays whose gradient is exactly zero contribute nothing; identity refinement passes the dataset pose through"""
+    C = 5
+    poses = pose.look_at_poses(C).cuda()
+    se3 = torch.zeros(C, 6, device="cuda", requires_grad=True)
+    o, d = pose.pose_rays(se3, poses, torch.zeros(0, dtype=torch.int32, device="cuda"), torch.zeros(0, 3, device="cuda"))
+    assert o.shape == (0, 3) and d.shape == (0, 3)
+    idx = torch.tensor([0, 4, 4, 2], dtype=torch.int32, device="cuda")
+    dirs = torch.tensor([[0.0, 0.0, -1.0], [0.1, 0.2, -1.0], [0.0, 0.0, -1.0], [-0.3, 0.0, -1.0]], device="cuda")
+    o, d = pose.pose_rays(se3, poses, idx, dirs)
+    torch.testing.assert_close(o, poses[idx.long(), :3, 3], rtol=0, atol=1e-6)
+    torch.testing.assert_close(d, (poses[idx.long(), :3, :3] @ dirs.unsqueeze(-1)).squeeze(-1), rtol=1e-6, atol=1e-6)
+    (o * 0).sum().backward()
+    assert se3.grad.abs().max().item() == 0.0
+    cam1 = se3.grad[1].clone()
+    assert cam1.abs().max().item() == 0.0          # a camera without rays never receives gradient
