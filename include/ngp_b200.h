@@ -362,8 +362,8 @@ int ngp_mlp_backward_rgb(const float* d_rgb, const float* rgb, int color_act, co
                          uint32_t n_layers, uint32_t M, const int32_t* m_dev, int act, void* dx, uint32_t lddx,
                          float* const* dweights, ngp_stream_t stream);
 
-/* The whole field backward in ONE warp-specialised persistent kernel (csrc/field_bwd_ws.cu): a view group (view_mlp
- * backward from d_rgb), a grid group (grid_mlp backward from d_sigma and the view group's d feat, handed over in shared
+/* The whole field backward in ONE warp-specialised persistent kernel (csrc/field_bwd_ws.cu): two view groups (view_mlp
+ * backward from d_rgb), two grid groups (grid_mlp backward from d_sigma and the view groups' d feat, handed over in shared
  * memory) and 16 scatter warps (hash-table gradient) run as a pipeline; saved tiles arrive by bulk async copies.
  * Inputs are what ngp_field_forward_full saved (tile-panel layout): enc, grid_acts[0..1], in2, view_acts[0..1]; plus
  * sigma [M], rgb [M,3] and the incoming d_sigma [M], d_rgb [M,3] (fp32).  grad_table [sO,2] fp16 and the fp32
@@ -385,14 +385,14 @@ int ngp_field_backward_full(const float* xyzs, const float* d_sigma, const float
                             const float* dirs, float* d_xyzs, float* d_dirs, ngp_stream_t stream);
 
 /* The whole field forward in ONE warp-specialised persistent kernel (csrc/field_ws.cu): gather warps encode into a ring of
- * shared-memory tiles while two groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.
+ * shared-memory tiles while three groups of MLP warps run grid_mlp -> sigma / SH -> view_mlp -> colour on the tensor cores.
  * grid_dims = {2L, h, h, 16}, view_dims = {32 (48 with ldirs), h2, h2, 16}, all multiples of 16 and <= 128.
  * Outputs sigma_out [M], rgb_out [M,3] fp32.  Saved for the backward kernel (each may be NULL), all in the TILE-PANEL
  * layout: per 128-row tile the shared-memory image of the tile, i.e. [ceil(M/128)][128][width] fp16 row-major with the
  * 16-byte chunks of a row XOR-swizzled like the UMMA SWIZZLE_32B/64B/128B layouts (csrc/tile_sw.cuh); buffers hold
  * whole tiles; widths in {16, 32, 64} (else NGP_ERR_UNSUPPORTED: use the two-kernel path):
- * enc_out (width 2L), grid_acts_out[0..1] (h), in2_out (32/48), view_acts_out[0..1] (h2).  Pass tiled = 1 to
- * ngp_field_backward_full to consume them.  view_weights == NULL: density-only query (grid_mlp only; dirs, ldirs,
+ * enc_out (width 2L), grid_acts_out[0..1] (h), in2_out (32/48), view_acts_out[0..1] (h2); ngp_field_backward_full
+ * consumes exactly these.  view_weights == NULL: density-only query (grid_mlp only; dirs, ldirs,
  * view_dims, rgb_out and the view outputs are ignored) -- NeRFNetwork.density, the occupancy-grid update.
  * dydx_out (NULL, or ceil(M/128)*128 * 12L bytes, 16-byte aligned): d enc / d x in fp16 for the input gradients of the
  * backward kernel -- the dy_dx of gridencoder.cu:216-245 (calc_grad_inputs), stored per 128-row tile as

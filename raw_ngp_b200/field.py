@@ -1,7 +1,9 @@
-"""Fused NeRF field: NeRFNetwork.forward / .density (nerf/network.py:74-156) in three kernels per training step
-(csrc/field_ws.cu forward, csrc/mlp.cu + csrc/field.cu backward) instead of ~60 PyTorch ops.  Used by raw_ngp_b200.nerf.NeRFNetwork when the configuration
-is eligible (fp16 table with F=2, ReLU MLPs, autocast, no gradient w.r.t. positions/directions); otherwise the network
-composes the individual operators exactly like the reference does."""
+"""Fused NeRF field: NeRFNetwork.forward / .density (nerf/network.py:74-156) as one forward and one backward kernel
+(csrc/field_ws.cu, csrc/field_bwd_ws.cu; layer widths outside {16, 32, 64}, i.e. the light-stage view_mlp, use the kernel
+pairs of csrc/field.cu + csrc/mlp.cu) instead of ~60 PyTorch ops.  Used by raw_ngp_b200.nerf.NeRFNetwork when the
+configuration is eligible (fp16 table with F=2, ReLU MLPs, autocast, no gradient w.r.t. positions/directions); otherwise
+the network composes the individual operators exactly like the reference does.  (Gradients w.r.t. positions / directions
+inside the fused path exist in FusedTrainStep, raw_ngp_b200/trainer.py.)"""
 import ctypes
 
 import numpy as np
