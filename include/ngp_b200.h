@@ -473,6 +473,13 @@ int ngp_dp_publish_flag(const float* found_inf_local, void* const* peer_flags, u
                         ngp_stream_t stream);
 int ngp_dp_merge_flags(const float* flags, uint32_t world, float* found_inf, ngp_stream_t stream);
 
+/* The GradScaler bookkeeping of a step in one launch: found_inf_dev[0] = 1.0f if any element of any of the n_buffers (<= 4)
+ * gradient buffers is inf / nan, else 0.0f (OVERWRITTEN, no zero-fill needed); *step_dev (optional) is incremented when
+ * the step is not skipped (like ngp_adam_step_counter).  scratch: device uint32[2], zero before the first call; the
+ * kernel leaves it zero. */
+int ngp_check_finite_multi(const void* const* grads, const int* dtypes, const uint64_t* counts, uint32_t n_buffers,
+                           float* found_inf_dev, int32_t* step_dev, uint32_t* scratch, ngp_stream_t stream);
+
 /* found_inf_dev[0] = 1.0f if any element of grad is inf/nan (accumulates; caller zero-fills). */
 int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev,
                      ngp_stream_t stream);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "ngp_dp_publish_flag": [_p, _p, _u32, _u32, _p],
     "ngp_dp_merge_flags": [_p, _u32, _p, _p],
     "ngp_check_finite": [_p, _i, c_uint64, _p, _p],
+    "ngp_check_finite_multi": [_p, _p, _p, _u32, _p, _p, _p, _p],
 }
 _SPECIAL = {
     "ngp_abi_version": ([], c_int),

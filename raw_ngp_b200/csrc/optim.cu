@@ -188,6 +188,61 @@ __global__ void dp_merge_flags_kernel(const float* __restrict__ flags, uint32_t 
     }
 }
 
+
+// inf / nan check of up to four gradient buffers + GradScaler bookkeeping in ONE launch (the captured training step ran
+// fill(found_inf) + check(table) + check(mlp) + step counter as four tiny kernels on the critical side stream).
+// Blocks are split between the buffers in proportion to their size; every block publishes "bad" into scratch[1]; the last
+// block to arrive (ticket scratch[0]) writes found_inf = 0 / 1 (overwrites: no zero-fill needed), counts the optimizer
+// step when it is not skipped, and resets the scratch words for the next launch.
+struct CheckBuffers { const void* p[4]; uint64_t n[4]; int dtype[4]; uint32_t first_block[5]; uint32_t count; };
+
+template <typename G>
+__device__ __forceinline__ bool block_has_nonfinite(const G* __restrict__ grad, uint64_t n, uint32_t block, uint32_t n_blocks) {
+    bool bad = false;
+    constexpr uint32_t PER = 16 / sizeof(G);
+    const uint64_t nv = n / PER, stride = (uint64_t)n_blocks * blockDim.x;
+    uint64_t q = (uint64_t)block * blockDim.x + threadIdx.x;
+    // two 16-byte loads in flight per thread
+    for (; q + stride < nv; q += 2 * stride) {
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(grad) + q), u1 = __ldg(reinterpret_cast<const uint4*>(grad) + q + stride);
+        const G* e0 = reinterpret_cast<const G*>(&u0);
+        const G* e1 = reinterpret_cast<const G*>(&u1);
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) bad |= !isfinite(to_f32(e0[k])) || !isfinite(to_f32(e1[k]));
+    }
+    for (; q < nv; q += stride) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(grad) + q);
+        const G* e = reinterpret_cast<const G*>(&u);
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) bad |= !isfinite(to_f32(e[k]));
+    }
+    for (uint64_t i = nv * PER + (uint64_t)block * blockDim.x + threadIdx.x; i < n; i += stride) bad |= !isfinite(to_f32(grad[i]));
+    return bad;
+}
+
+__global__ void __launch_bounds__(256)
+check_finite_multi_kernel(const CheckBuffers b, float* __restrict__ found_inf, int* __restrict__ step_dev, uint32_t* __restrict__ scratch) {
+    uint32_t which = 0;
+    while (which + 1 < b.count && blockIdx.x >= b.first_block[which + 1]) which++;
+    const uint32_t block = blockIdx.x - b.first_block[which], n_blocks = b.first_block[which + 1] - b.first_block[which];
+    bool bad;
+    if (b.dtype[which] == NGP_F32) bad = block_has_nonfinite(reinterpret_cast<const float*>(b.p[which]), b.n[which], block, n_blocks);
+    else if (b.dtype[which] == NGP_F16) bad = block_has_nonfinite(reinterpret_cast<const __half*>(b.p[which]), b.n[which], block, n_blocks);
+    else bad = block_has_nonfinite(reinterpret_cast<const __nv_bfloat16*>(b.p[which]), b.n[which], block, n_blocks);
+    const bool any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (any_bad) atomicOr(scratch + 1, 1u);
+        __threadfence();
+        if (atomicAdd(scratch, 1u) == gridDim.x - 1) {          // last block: all flags are in
+            __threadfence();
+            const bool inf = *reinterpret_cast<volatile uint32_t*>(scratch + 1) != 0u;
+            *found_inf = inf ? 1.0f : 0.0f;
+            if (!inf && step_dev) *step_dev += 1;                 // a skipped GradScaler step is not counted
+            scratch[0] = 0u; scratch[1] = 0u;
+        }
+    }
+}
+
 // GradScaler semantics for a device-side step counter: the optimizer step is counted only when it is not skipped
 __global__ void adam_step_counter_kernel(int* __restrict__ step_dev, const float* __restrict__ found_inf_dev) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf_dev && *found_inf_dev != 0.f)) *step_dev += 1;
@@ -286,6 +341,27 @@ extern "C" int ngp_dp_merge_flags(const float* flags, uint32_t world, float* fou
 extern "C" int ngp_adam_step_counter(int32_t* step_dev, const float* found_inf_dev, ngp_stream_t stream) {
     if (!step_dev) return NGP_ERR_NULL;
     adam_step_counter_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev, found_inf_dev);
+    return finish_launch();
+}
+
+
+extern "C" int ngp_check_finite_multi(const void* const* grads, const int* dtypes, const uint64_t* counts, uint32_t n_buffers,
+                                      float* found_inf_dev, int32_t* step_dev, uint32_t* scratch, ngp_stream_t stream) {
+    if (!grads || !dtypes || !counts || !found_inf_dev || !scratch) return NGP_ERR_NULL;
+    if (n_buffers == 0 || n_buffers > 4) return NGP_ERR_BAD_ARG;
+    CheckBuffers b = {};
+    b.count = n_buffers;
+    uint32_t blocks = 0;
+    for (uint32_t i = 0; i < n_buffers; i++) {
+        if (counts[i] && !grads[i]) return NGP_ERR_NULL;
+        if (dtypes[i] < NGP_F32 || dtypes[i] > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+        if (!aligned(grads[i], 16)) return NGP_ERR_ALIGN;
+        b.p[i] = grads[i]; b.n[i] = counts[i]; b.dtype[i] = dtypes[i];
+        b.first_block[i] = blocks;
+        blocks += (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(counts[i], 256 * 16), (uint64_t)kNumSMs * 8));
+    }
+    b.first_block[n_buffers] = blocks;
+    check_finite_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, found_inf_dev, step_dev, scratch);
     return finish_launch();
 }
 

@@ -62,12 +62,13 @@ class FusedAdam:
         self.groups.append(dict(master=master, lp=param_lp, grad=grad, m=torch.zeros_like(master),
                                 v=torch.zeros_like(master), lr_dev=lr_dev))
 
-    def step(self, inv_scale, found_inf, zero_grad=True, lr=None):
+    def step(self, inv_scale, found_inf, zero_grad=True, lr=None, count_step=True):
+        """count_step=False: the caller has already counted the step on the device (ngp_check_finite_multi does)."""
         self.step_count += 1
         _lib.weights_epoch += 1
         lr = self.lr if lr is None else lr
         st = _lib.stream()
-        if self.device_step is not None:
+        if self.device_step is not None and count_step:
             _lib.call("ngp_adam_step_counter", _lib.ptr(self.device_step), _lib.ptr(found_inf), st)
         for g in self.groups:
             lp = g["lp"]
@@ -434,17 +435,23 @@ class FusedTrainStep:
                   None, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap, self._m_dev,
                   self._density_act, float(opt.beta), P(self.table_grad), dw1, st)
 
-    def _launch_check(self):
-        st = _lib.stream()
-        self.found_inf.zero_()
-        _lib.call("ngp_check_finite", _lib.ptr(self.table_grad), _lib.NGP_F16, self.table_grad.numel(), _lib.ptr(self.found_inf), st)
-        _lib.call("ngp_check_finite", _lib.ptr(self.w_grad), _lib.NGP_F32, self.w_grad.numel(), _lib.ptr(self.found_inf), st)
+    def _launch_check(self, count_step=False):
+        """inf / nan check of both gradient buffers -> self.found_inf (overwritten) in one launch; count_step: the same kernel
+        advances the device-side Adam step counter unless the step will be skipped."""
+        ct = self._ct
+        if not hasattr(self, "_chk_args"):
+            self._chk_scratch = torch.zeros(2, device=self.dev, dtype=torch.int32)
+            self._chk_args = ((ct.c_void_p * 2)(self.table_grad.data_ptr(), self.w_grad.data_ptr()), (ct.c_int * 2)(_lib.NGP_F16, _lib.NGP_F32),
+                              (ct.c_uint64 * 2)(self.table_grad.numel(), self.w_grad.numel()))
+        g, d, n = self._chk_args
+        _lib.call("ngp_check_finite_multi", g, d, n, 2, _lib.ptr(self.found_inf), _lib.ptr(self.opt_step_dev) if count_step else None,
+                  _lib.ptr(self._chk_scratch), _lib.stream())
 
     def _launch_optimizer(self):
-        """inf check (single GPU; with several ranks the check runs before the flag all-reduce) + fused Adam."""
+        """inf check + step count (one kernel) + fused Adam of the table and of the MLP weights."""
         if self.world == 1:
-            self._launch_check()
-        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+            self._launch_check(count_step=True)
+        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=self.world != 1)
 
     def _launch_pipelined(self):
         """[optimizer update of the PREVIOUS step]  ||  [march of this step]  ->  field forward -> composite -> backward.
@@ -481,8 +488,8 @@ class FusedTrainStep:
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_pipe):
             self._launch_pipelined()
-        self.pipe_kernels = (_lib.launch_count - c0 + (1 if self.perturb else 0) + (1 if self.world == 1 else 0)   # + found_inf.zero_
-                             + (1 if self.pose is not None else 0))
+        self.pipe_kernels = (_lib.launch_count - c0 + (1 if self.perturb else 0)       # + noises.uniform_
+                             + (1 if self.pose is not None else 0))                 # + pose_found_inf.zero_
         self.opt.step_count = n_adam        # capturing is not stepping
         if self.pose is not None:
             self.pose_opt.step_count = n_adam
@@ -519,8 +526,8 @@ class FusedTrainStep:
         parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
         # The inf / nan check runs on the REDUCED buffers, which are bit-identical on every rank (a non-finite value of any
         # rank survives the SUM), so all ranks take the same skip decision without a second collective for the flag.
-        self._launch_check()
-        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+        self._launch_check(count_step=True)
+        self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=False)
 
     def _peer_update(self):
         """reduce-scatter + Adam + all-gather of the table as ONE kernel over peer memory (and a replicated variant of the same
@@ -594,8 +601,8 @@ class FusedTrainStep:
             _lib.call = timed_call
             for _ in range(iters):
                 self._launch_forward_backward()
-                self._launch_check()
-                self.opt.step(self.inv_scale, self.found_inf, zero_grad=True)
+                self._launch_check(count_step=True)
+                self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=False)
                 if self.pose is not None:
                     self._launch_pose_update()
         finally:

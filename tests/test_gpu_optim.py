@@ -137,3 +137,28 @@ def test_dp_flags_and_argument_checks():
     with pytest.raises(RuntimeError):
         _lib.call("ngp_dp_fused_adam", _ptrs(g * 9), _lib.NGP_F16, _ptrs(t * 9), _lib.NGP_F16, 9, 9, _lib.ptr(m), _lib.ptr(m.clone()),
                   _lib.ptr(m.clone()), 0, 64, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, st)
+
+
+@pytest.mark.parametrize("bad", [None, ("table", 0), ("table", 12196239), ("mlp", 13000), ("mlp", 3)])
+def test_check_finite_multi(bad):
+    """one launch: inf/nan over two buffers of different dtype -> found_inf overwritten (no zero-fill), step counted unless
+    skipped, scratch self-resetting (called repeatedly)."""
+    import ctypes
+    dev = "cuda"
+    table = (torch.randn(12196240, device=dev) * 0.1).half()
+    mlp = torch.randn(13440, device=dev)
+    found = torch.full((1,), 7.0, device=dev)              # garbage: must be overwritten
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(2, dtype=torch.int32, device=dev)
+    args = ((ctypes.c_void_p * 2)(table.data_ptr(), mlp.data_ptr()), (ctypes.c_int * 2)(_lib.NGP_F16, _lib.NGP_F32),
+            (ctypes.c_uint64 * 2)(table.numel(), mlp.numel()))
+    for rep in range(3):
+        if bad is not None and rep == 1:
+            (table if bad[0] == "table" else mlp)[bad[1]] = float("nan") if rep % 2 else float("inf")
+        if rep == 2 and bad is not None:
+            (table if bad[0] == "table" else mlp)[bad[1]] = 0.0
+        _lib.call("ngp_check_finite_multi", *args, 2, _lib.ptr(found), _lib.ptr(step), _lib.ptr(scratch), _lib.stream())
+        expect_inf = bad is not None and rep == 1
+        assert found.item() == (1.0 if expect_inf else 0.0)
+        assert scratch.tolist() == [0, 0]
+    assert step.item() == (2 if bad is not None else 3)
