@@ -321,15 +321,26 @@ def run_ours(args):
 
     # ---------------- end to end: pinned host inputs, loss read back ----------------
     o_pin, d_pin, t_pin = o_cpu.pin_memory(), d_cpu.pin_memory(), tgt_cpu.pin_memory()
-    loss_host = torch.empty(1, pin_memory=True)
+    # Every step's loss is read back into pinned host memory; the host consumes it one step late (double buffer + event), the
+    # way a training loop logs it, so that the read-back of step k does not stall the launch of step k + 1.
+    loss_host = [torch.empty(1, pin_memory=True), torch.empty(1, pin_memory=True)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    host_losses = []
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(K):
+    for k in range(K):
         loss = one_step(o_pin, d_pin, t_pin)            # pinned host -> static device buffers (async H2D) inside step()
-        loss_host.copy_(loss.reshape(1), non_blocking=False)
+        loss_host[k & 1].copy_(loss.reshape(1), non_blocking=True)
+        loss_ready[k & 1].record()
+        if k > 0:
+            loss_ready[(k - 1) & 1].synchronize()
+            host_losses.append(float(loss_host[(k - 1) & 1][0]))
+    loss_ready[(K - 1) & 1].synchronize()
+    host_losses.append(float(loss_host[(K - 1) & 1][0]))
     f1.record()
     barrier()
+    assert len(host_losses) == K and all(v == v for v in host_losses)
     clocks = sampler.stop() if rank == 0 else None      # sampled over warm-up + both timed regions
     ms_e2e = f0.elapsed_time(f1)
 
