@@ -407,6 +407,21 @@ int ngp_field_forward_full(const float* xyzs, const float* dirs, const float* ld
                            float* sigma_out, float* rgb_out, void* dydx_out, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Frequency encoder (encoding.get_encoder('frequency'))
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces freq_encode_forward          freqencoder/src/freqencoder.h, freqencoder.cu:31-58,97-111
+ * inputs [B, D] fp32 -> outputs [B, C] fp32, C = D + 2 D degree: the inputs, then per octave f < degree
+ * __sinf(x 2^f) for all dims followed by __sinf(x 2^f + pi/2) for all dims. */
+int ngp_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t degree, uint32_t C, float* outputs,
+                            ngp_stream_t stream);
+
+/* replaces freq_encode_backward         freqencoder.cu:60-94,114-130
+ * grad, outputs [B, C] (the forward's outputs carry the derivatives) -> grad_inputs [B, D] (written). */
+int ngp_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t degree, uint32_t C,
+                             float* grad_inputs, ngp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Rays from refined camera poses (BARF pose refinement) -- SURVEY 8(f) row 2.
  * Replaces CameraOptimizer.provide_refined_poses (barf/camera_optimizers.py:92-107: lie.se3_to_SE3 of
  * barf/camera.py:93-153 composed with the dataset pose, camera.py:47-63) followed by get_rays

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE ONLY -- builds the *unmodified* reference CUDA extensions
 # (sources stay where they lie under /root/reference) for sm_100a into oracle/_ref/.
-# The resulting pybind modules (_gridencoder, _raymarching_mob, _shencoder) are the
+# The resulting pybind modules (_gridencoder, _raymarching_mob, _shencoder, _freqencoder) are the
 # GPU-side parity oracle used by tests/ -m gpu and by bench.py's reference_cuda leg.
 # Nothing under raw_ngp_b200/ may import them.
 #
@@ -46,5 +46,6 @@ build_one() { # dir  cu-basename  module-name
 build_one raymarching raymarching _raymarching_mob &
 build_one shencoder   shencoder   _shencoder &
 build_one gridencoder gridencoder _gridencoder &
+build_one freqencoder freqencoder _freqencoder &
 wait
 ls -la "$OUT"

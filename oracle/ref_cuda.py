@@ -111,6 +111,25 @@ def sh_backward(grad, inputs, degree, dy_dx):
     return grad_inputs
 
 
+# ---- freqencoder/freq.py:17-53 -----------------------------------------------------------------------------------
+def freq_forward(inputs, degree):
+    be = module("_freqencoder")
+    inputs = inputs.contiguous()
+    B, D = inputs.shape
+    C = D + D * 2 * degree
+    outputs = torch.empty(B, C, dtype=inputs.dtype, device=inputs.device)
+    be.freq_encode_forward(inputs, B, D, degree, C, outputs)
+    return outputs
+
+
+def freq_backward(grad, outputs, D, degree):
+    be = module("_freqencoder")
+    B, C = outputs.shape
+    grad_inputs = torch.zeros(B, D, dtype=outputs.dtype, device=outputs.device)
+    be.freq_encode_backward(grad.contiguous(), outputs, B, D, degree, C, grad_inputs)
+    return grad_inputs
+
+
 # ---- raymarching/raymarching.py ---------------------------------------------------------------------------------
 def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):  # :35-57
     be = module("_raymarching_mob")

@@ -1,7 +1,8 @@
 """get_encoder -- string -> encoder module dispatcher (encoding.py:47-78).
 
-Only the encoders of the hot path exist here: 'hashgrid', 'tiledgrid', 'sh' and 'None'.  'frequency' is outside
-the scope of this build and raises."""
+'hashgrid', 'tiledgrid', 'sh', 'frequency' and 'None'; the pure-torch 'frequency_torch' variant of the reference needs no
+native code and is not provided."""
+from .freqencoder import FreqEncoder
 from .gridencoder import GridEncoder
 from .shencoder import SHEncoder
 
@@ -10,7 +11,9 @@ def get_encoder(encoding, input_dim=3, multires=6, degree=4, num_levels=16, leve
                 log2_hashmap_size=19, desired_resolution=2048, align_corners=False, interpolation="linear", **kwargs):
     if encoding == "None":
         return (lambda x, **kw: x), input_dim
-    if encoding == "sh":
+    if encoding == "frequency":
+        encoder = FreqEncoder(input_dim=input_dim, degree=multires)
+    elif encoding == "sh":
         encoder = SHEncoder(input_dim=input_dim, degree=degree)
     elif encoding in ("hashgrid", "tiledgrid"):
         encoder = GridEncoder(input_dim=input_dim, num_levels=num_levels, level_dim=level_dim,
@@ -20,5 +23,5 @@ def get_encoder(encoding, input_dim=3, multires=6, degree=4, num_levels=16, leve
                               interpolation=interpolation)
     else:
         raise NotImplementedError(
-            f"Unknown / out-of-scope encoding '{encoding}', choose from [None, sh, hashgrid, tiledgrid]")
+            f"Unknown / out-of-scope encoding '{encoding}', choose from [None, frequency, sh, hashgrid, tiledgrid]")
     return encoder, encoder.output_dim

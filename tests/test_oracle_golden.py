@@ -146,3 +146,15 @@ def test_raymarch_oracle_matches_reference_kernels(path):
     np.testing.assert_allclose(iws, z["inf_weights_sum"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(idp, z["inf_depth"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(iim, z["inf_image"], rtol=1e-5, atol=1e-6)
+
+
+def test_freq_oracle_matches_reference_kernel_outputs():
+    """tests/golden/freq.npz: outputs / input gradients of the reference's freqencoder kernels (tools/make_golden.py on a B200)."""
+    from oracle import freq_oracle
+    path = os.path.join(GOLD, "freq.npz")
+    z = np.load(path)
+    deg, D = int(z["degree"]), int(z["inputs"].shape[1])
+    out = freq_oracle.forward(z["inputs"], deg)
+    np.testing.assert_allclose(out, z["outputs"], rtol=0, atol=float(z["atol"]))          # __sinf vs np.sin
+    assert np.array_equal(out[:, :D], z["outputs"][:, :D])                                   # the pass-through columns are exact
+    np.testing.assert_allclose(freq_oracle.backward(z["grad"], z["outputs"], D, deg), z["grad_inputs"], rtol=1e-6, atol=1e-6)

@@ -132,7 +132,26 @@ def util_case(out_dir):
                         flat=npy(flat))
 
 
+def freq_case(out_dir):
+    """freqencoder kernels (unmodified reference source): outputs + input gradients on 96 points, degree 6"""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(96, 3, generator=g) * 2 - 1
+    x[:3] = torch.tensor([[0.0, 1.0, -1.0], [0.5, -0.5, 0.25], [1e-3, -1e-3, 0.999]])
+    deg = 6
+    xc = x.cuda()
+    out = ref_cuda.freq_forward(xc, deg)
+    grad = torch.randn(96, out.shape[1], generator=g)
+    gx = ref_cuda.freq_backward(grad.cuda(), out, 3, deg)
+    # __sinf against the correctly rounded sine: the absolute error grows with |argument| (here <= 2^5 + pi/2)
+    np.savez_compressed(os.path.join(out_dir, "freq.npz"), degree=deg, inputs=x.numpy(), outputs=npy(out), grad=grad.numpy(),
+                        grad_inputs=npy(gx), atol=2e-5)
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[2] == "freq":      # only the frequency-encoder fixture
+        os.makedirs(sys.argv[1], exist_ok=True)
+        freq_case(sys.argv[1])
+        return
     out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     assert torch.cuda.is_available(), "make_golden.py runs the reference CUDA kernels and needs a GPU"
@@ -142,6 +161,7 @@ def main():
     grid_case("fp32_smooth_align_tiled", out_dir, L=8, log2T=15, desired=256, gridtype=1, align_corners=True, interp=1)
     grid_case("fp32_d2_c4", out_dir, D=2, C=4, L=8, log2T=14, desired=512)
     sh_case(out_dir)
+    freq_case(out_dir)
     march_case("ball_h32", out_dir)
     march_case("cone_h32", out_dir, dt_gamma=1 / 64)
     march_case("contract_c2", out_dir, N=32, cascade=2, bound=2.0, contract=True, ldir=True, max_steps=256)
