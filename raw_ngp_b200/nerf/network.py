@@ -54,9 +54,12 @@ class NeRFNetwork(NeRFRenderer):
     def __init__(self, opt):
         super().__init__(opt)
         self.annealing = 0.0
-        if opt.pose_opt != "none" and getattr(opt, "pose_optimizer_factory", None) is not None:
-            # barf/camera_optimizers.CameraOptimizer is not part of the hot path; plug one in through the factory
-            self.pose_optimizer = opt.pose_optimizer_factory(opt)
+        if opt.pose_opt != "none":      # network.py:42-44
+            if getattr(opt, "pose_optimizer_factory", None) is not None:
+                self.pose_optimizer = opt.pose_optimizer_factory(opt)
+            elif getattr(opt, "num_cameras", 0) > 0:
+                from ..pose import CameraOptimizer
+                self.pose_optimizer = CameraOptimizer(num_cameras=opt.num_cameras, device=opt.device, opt=opt)
 
         self.level_dim = 2
         self.grid_encoder, self.grid_in_dim = get_encoder(
