@@ -158,3 +158,20 @@ def test_freq_oracle_matches_reference_kernel_outputs():
     np.testing.assert_allclose(out, z["outputs"], rtol=0, atol=float(z["atol"]))          # __sinf vs np.sin
     assert np.array_equal(out[:, :D], z["outputs"][:, :D])                                   # the pass-through columns are exact
     np.testing.assert_allclose(freq_oracle.backward(z["grad"], z["outputs"], D, deg), z["grad_inputs"], rtol=1e-6, atol=1e-6)
+
+
+def test_torch_near_far_matches_reference_renderer():
+    """tests/golden/near_far_py.npz: nerf/renderer.py:139-158 run from the reference (tools/make_golden_state_dict.py), values
+    and gradients; both restatements in this repo (the renderer's and the synthetic helper) must reproduce it exactly."""
+    import torch
+    from raw_ngp_b200 import synthetic
+    from raw_ngp_b200.nerf.renderer import near_far_from_aabb
+    z = np.load(os.path.join(GOLD, "near_far_py.npz"))
+    for fn in (near_far_from_aabb, synthetic.near_far_torch):
+        o = torch.from_numpy(z["rays_o"]).requires_grad_(True)
+        d = torch.from_numpy(z["rays_d"]).requires_grad_(True)
+        near, far = fn(o, d, torch.from_numpy(z["aabb"]), float(z["min_near"]))
+        assert np.array_equal(near.detach().numpy(), z["nears"]) and np.array_equal(far.detach().numpy(), z["fars"])
+        ((near * torch.from_numpy(z["g_near"])).sum() + (far * torch.from_numpy(z["g_far"])).sum()).backward()
+        np.testing.assert_allclose(o.grad.numpy(), z["d_rays_o"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(d.grad.numpy(), z["d_rays_d"], rtol=1e-6, atol=1e-7)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Generates tests/golden/state_dict.json: names, shapes and dtypes of the state_dict of the REFERENCE's NeRFNetwork
+"""Generates tests/golden/near_far_py.npz (the renderer's torch near_far_from_aabb, values and gradients) and
+tests/golden/state_dict.json: names, shapes and dtypes of the state_dict of the REFERENCE's NeRFNetwork
 (nerf/network.py) for three option sets, by importing the reference's Python modules from /root/reference in the build
 container (CPU; the compiled extensions of oracle/_ref are put on the path under the names the reference imports, absent
 third-party packages are stubbed -- none is touched by the constructors).  tests/test_abi_and_host.py checks that
@@ -65,6 +66,42 @@ def main(out_dir):
         opt = SimpleNamespace(**dict(base, **kw))
         model = NeRFNetwork(opt)
         out[tag] = dict(opt=kw, entries={k: [list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()})
+    # the differentiable slab test the renderer actually uses (nerf/renderer.py:139-158), outputs and gradients
+    import numpy as np
+    from nerf.renderer import near_far_from_aabb
+    g = torch.Generator().manual_seed(21)
+    o = torch.randn(257, 3, generator=g) * 1.5
+    d = torch.randn(257, 3, generator=g)
+    d[:8] = torch.tensor([0.0, 0.0, 1.0])                   # axis-parallel rays (division by d + 1e-15)
+    o[8:16] = 0.0                                            # origins inside the box
+    o, d = o.requires_grad_(True), d.requires_grad_(True)
+    aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0])
+    near, far = near_far_from_aabb(o, d, aabb, 0.05)
+    gn, gf = torch.randn(near.shape, generator=g), torch.randn(far.shape, generator=g)
+    ((near * gn).sum() + (far * gf).sum()).backward()
+    np.savez_compressed(os.path.join(out_dir, "near_far_py.npz"), rays_o=o.detach().numpy(), rays_d=d.detach().numpy(), aabb=aabb.numpy(),
+                        min_near=0.05, nears=near.detach().numpy(), fars=far.detach().numpy(), g_near=gn.numpy(), g_far=gf.numpy(),
+                        d_rays_o=o.grad.numpy(), d_rays_d=d.grad.numpy())
+    # BARF / BAA-NGP annealing windows (network.py:77-109): run the reference's common_forward with a fixed ramp as the
+    # encoder output and an identity grid_mlp, so that its outputs expose the per-feature weighting / blending
+    class _Identity(torch.nn.Module):
+        dim_out = 16
+        def forward(self, x, **kw):
+            return x
+    class _Ones(torch.nn.Module):
+        def forward(self, x, bound=1):
+            return (torch.arange(1, 33, dtype=torch.float32) / 8).repeat(x.shape[0], 1)
+    windows = {}
+    for mode in ("barf", "baangp"):
+        opt = SimpleNamespace(**dict(base, bound=1, pose_opt=mode, num_cameras=3, start_annealing=0.1, end_annealing=0.6))
+        model = NeRFNetwork(opt)
+        model.grid_encoder = _Ones()
+        model.grid_mlp = _Identity()
+        for a in (0.0, 0.1, 0.17, 0.3, 0.45, 0.6, 0.9):
+            model.annealing = a
+            sigma, feat = model.common_forward(torch.zeros(2, 3))
+            windows[f"{mode}_{a}"] = torch.cat([torch.log(sigma[:1]), feat[0]]).numpy()      # = weighted features 0..31
+    np.savez_compressed(os.path.join(out_dir, "annealing_py.npz"), **windows)
     with open(os.path.join(out_dir, "state_dict.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print({k: len(v["entries"]) for k, v in out.items()})
