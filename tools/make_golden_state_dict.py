@@ -65,7 +65,10 @@ def main(out_dir):
                     ("barf", dict(bound=1, pose_opt="barf", num_cameras=7))):
         opt = SimpleNamespace(**dict(base, **kw))
         model = NeRFNetwork(opt)
-        out[tag] = dict(opt=kw, entries={k: [list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()})
+        enc = model.grid_encoder
+        out[tag] = dict(opt=kw, entries={k: [list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()},
+                        grid=dict(offsets=[int(v) for v in enc.offsets.tolist()], per_level_scale=float(enc.per_level_scale),
+                                  base_resolution=int(enc.base_resolution), n_params=int(enc.n_params), output_dim=int(enc.output_dim)))
     # the differentiable slab test the renderer actually uses (nerf/renderer.py:139-158), outputs and gradients
     import numpy as np
     from nerf.renderer import near_far_from_aabb
