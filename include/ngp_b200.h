@@ -499,6 +499,15 @@ int ngp_check_finite_multi(const void* const* grads, const int* dtypes, const ui
 int ngp_check_finite(const void* grad, int grad_dtype, uint64_t n, float* found_inf_dev,
                      ngp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics (tools/l2_ceiling.py): the random-row gather rate out of an L2-resident table and the random packed-fp16
+ * reduction rate into one -- the ceilings of the forward's corner gathers and of the backward's scatter.  mode 0: 4-byte
+ * gathers, 1: red.add.f16x2, 2: red.add.v2.f16x2 (aligned row pairs).  n_rows: power of two; every thread of
+ * blocks x 512 does `rounds` x 8 row operations.  Adds +0.0: the table is unchanged.  Used by no operator.
+ * ---------------------------------------------------------------------------------------- */
+int ngp_diag_l2_rate(void* table, uint32_t n_rows, uint32_t blocks, uint32_t rounds, int mode, void* sink,
+                     ngp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

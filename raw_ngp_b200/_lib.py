@@ -57,6 +57,7 @@ SIGNATURES = {
     "ngp_mlp_forward_rgb": [_p, _u32, _p, _p, _u32, _u32, _p, _i, _i, _p, _p, _p],
     "ngp_mlp_backward_rgb": [_p, _p, _i, _p, _u32, _p, _p, _p, _u32, _u32, _p, _i, _p, _u32, _p, _p],
     "ngp_fused_adam": [_p, _p, _i, _p, _i, _p, _p, c_uint64, _f32, _f32, _f32, _f32, _f32, _u32, _p, _p, _p, _p, _i, _p],
+    "ngp_diag_l2_rate": [_p, _u32, _u32, _u32, _i, _p, _p],
     "ngp_freq_encode_forward": [_p, _u32, _u32, _u32, _u32, _p, _p],
     "ngp_freq_encode_backward": [_p, _p, _u32, _u32, _u32, _u32, _p, _p],
     "ngp_pose_rays_forward": [_p, _p, _u32, _p, _p, _u32, _u32, _p, _p, _p],
