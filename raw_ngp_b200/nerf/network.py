@@ -123,6 +123,22 @@ class NeRFNetwork(NeRFRenderer):
                       _lib.ptr(sigmas), _lib.ptr(rgbs), None, st)
         return field
 
+    def _feat_weights_host(self):
+        """The BARF window of _feat_weights as a numpy array (fp32 arithmetic like the torch expression): lets the captured
+        training step refresh it with one small host-to-device copy instead of ten elementwise kernels."""
+        if self.opt.pose_opt != "barf":
+            return None
+        L = self.grid_mlp.dim_out
+        start, end = np.float32(self.opt.start_annealing), np.float32(self.opt.end_annealing)
+        if end == 0:
+            end = np.float32(1e-12)
+        k = np.arange(L, dtype=np.float32)
+        alpha = np.float32((np.float32(self.annealing) - start) / (end - start) * np.float32(L))
+        w = (np.float32(1) - np.cos(np.clip(alpha - k, 0, 1).astype(np.float32) * np.float32(np.pi), dtype=np.float32)) / np.float32(2)
+        w = np.repeat(w.astype(np.float32), self.level_dim)
+        w[0:2] = 1
+        return w
+
     def _feat_weights(self, device):
         if self.opt.pose_opt != "barf":
             return None

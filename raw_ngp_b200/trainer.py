@@ -338,6 +338,8 @@ class FusedTrainStep:
         self.d_rays_d = torch.zeros(N, 3, **f32) if self.ray_grads else None
         self.image, self.ray_loss, self.loss = torch.zeros(N, 3, **f32), torch.zeros(N, **f32), torch.zeros(1, **f32)
         self.feat_weights = torch.ones(2 * enc.num_levels, **f32) if opt.pose_opt == "barf" else None
+        self._feat_host = torch.ones(2 * enc.num_levels, dtype=torch.float32).pin_memory() if self.feat_weights is not None else None
+        self._feat_annealing = None
         self._density_act = model._density_act()
         self._color_act = _field.COLOR_ACT[opt.color_activation]
         self._grid_scalars = _field._grid_scalars(enc)
@@ -646,8 +648,11 @@ class FusedTrainStep:
             self.set_rays(rays_o, rays_d, target_rgb, rays_ldir, exposure)
         if cam_idx is not None:
             self.set_camera_rays(cam_idx, dirs_cam, target_rgb, exposure)
-        if self.feat_weights is not None:
-            self.feat_weights.copy_(model._feat_weights(self.dev))
+        if self.feat_weights is not None and self._feat_annealing != model.annealing:
+            # BARF window: computed on the host, one 128-byte copy (the torch expression is ~10 elementwise kernels)
+            self._feat_host.copy_(torch.from_numpy(model._feat_weights_host()))
+            self.feat_weights.copy_(self._feat_host, non_blocking=True)
+            self._feat_annealing = model.annealing
         if self.use_graph:
             sig = (model.density_bitfield.data_ptr(), model.aabb_train.data_ptr(), model.grid_encoder.embeddings.data_ptr())
             if self._graph != sig:      # first step, or a captured buffer was re-allocated (update_aabb, load_state_dict)

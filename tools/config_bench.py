@@ -115,7 +115,13 @@ def config5(args, device, barrier, report, world, rank):
     fs = FusedTrainStep(model, N_RAYS, loss_scale=128.0, pose_optimizer=cam, poses=poses, pose_lr=1e-3, process_group=pg,
                         max_samples=args.max_samples)
     fs.set_camera_rays(idx, dirs, tgt)
-    ms = timed(lambda: fs.step(update_grid=False), args.steps, args.warmup, barrier)
+    progress = [0.25]
+
+    def one():
+        progress[0] += 1e-5                      # the annealing window moves every step, as in training
+        model.update_annealing(progress[0])
+        return fs.step(update_grid=False)
+    ms = timed(one, args.steps, args.warmup, barrier)
     t = torch.tensor([ms], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
