@@ -488,6 +488,13 @@ int ngp_dp_publish_flag(const float* found_inf_local, void* const* peer_flags, u
                         ngp_stream_t stream);
 int ngp_dp_merge_flags(const float* flags, uint32_t world, float* found_inf, ngp_stream_t stream);
 
+/* GradScaler + Adam step of a small fp32 tensor (n <= 2^20; the se3 pose corrections) in ONE single-block launch: inf / nan
+ * check of grad, *step_dev += 1 unless skipped, unscale by *inv_scale_dev, Adam (torch semantics as ngp_fused_adam, learning
+ * rate from *lr_dev if given), gradient cleared; found_inf_out (optional) receives 0 / 1. */
+int ngp_small_adam(float* master, float* grad, float* exp_avg, float* exp_avg_sq, uint32_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int32_t* step_dev, const float* lr_dev,
+                   const float* inv_scale_dev, float* found_inf_out, ngp_stream_t stream);
+
 /* The GradScaler bookkeeping of a step in one launch: found_inf_dev[0] = 1.0f if any element of any of the n_buffers (<= 4)
  * gradient buffers is inf / nan, else 0.0f (OVERWRITTEN, no zero-fill needed); *step_dev (optional) is incremented when
  * the step is not skipped (like ngp_adam_step_counter).  scratch: device uint32[2], zero before the first call; the

@@ -243,6 +243,41 @@ check_finite_multi_kernel(const CheckBuffers b, float* __restrict__ found_inf, i
     }
 }
 
+// A whole GradScaler + Adam step of a SMALL tensor (the se3 pose corrections: 600 values) in one single-block launch:
+// inf / nan check, step count, unscale + Adam, gradient clear.  The pose update sits on the main stream in front of the ray
+// generation of the next step, so its four tiny launches (fill, check, count, Adam) were on the critical path.
+__global__ void __launch_bounds__(256)
+small_adam_kernel(float* __restrict__ master, float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, uint32_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int* __restrict__ step_dev, const float* __restrict__ lr_dev,
+                  const float* __restrict__ inv_scale_dev, float* __restrict__ found_inf_out) {
+    bool bad = false;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) bad |= !isfinite(grad[i]);
+    const bool skip = __syncthreads_or(bad);
+    __shared__ int s_step;
+    if (threadIdx.x == 0) {
+        if (!skip) *step_dev += 1;
+        s_step = *step_dev;
+        if (found_inf_out) *found_inf_out = skip ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    if (lr_dev) lr = __ldg(lr_dev);
+    const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
+    const float t = (float)max(s_step, 1);
+    const float step_size = lr / (1.f - powf(beta1, t)), bias2_sqrt = sqrtf(1.f - powf(beta2, t));
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!skip) {
+            float g = grad[i] * inv_scale;
+            float p = master[i];
+            if (weight_decay != 0.f) g += weight_decay * p;
+            const float mi = beta1 * m[i] + (1.f - beta1) * g;
+            const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+            m[i] = mi; v[i] = vi;
+            master[i] = p - step_size * (mi / (sqrtf(vi) / bias2_sqrt + eps));
+        }
+        grad[i] = 0.f;
+    }
+}
+
 // GradScaler semantics for a device-side step counter: the optimizer step is counted only when it is not skipped
 __global__ void adam_step_counter_kernel(int* __restrict__ step_dev, const float* __restrict__ found_inf_dev) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf_dev && *found_inf_dev != 0.f)) *step_dev += 1;
@@ -335,6 +370,17 @@ extern "C" int ngp_dp_merge_flags(const float* flags, uint32_t world, float* fou
     if (!flags || !found_inf) return NGP_ERR_NULL;
     if (world == 0 || world > kMaxPeers) return NGP_ERR_BAD_ARG;
     dp_merge_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, found_inf);
+    return finish_launch();
+}
+
+extern "C" int ngp_small_adam(float* master, float* grad, float* exp_avg, float* exp_avg_sq, uint32_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int32_t* step_dev, const float* lr_dev,
+                              const float* inv_scale_dev, float* found_inf_out, ngp_stream_t stream) {
+    if (n == 0) return NGP_OK;
+    if (!master || !grad || !exp_avg || !exp_avg_sq || !step_dev) return NGP_ERR_NULL;
+    if (n > (1u << 20)) return NGP_ERR_BAD_ARG;      // one block: meant for small tensors
+    small_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(master, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                          step_dev, lr_dev, inv_scale_dev, found_inf_out);
     return finish_launch();
 }
 

@@ -366,10 +366,14 @@ class FusedTrainStep:
     def _launch_pose_update(self):
         """inf check + Adam of se3_refine for the PREVIOUS step's gradients: on the main stream, because the rays of this step
         are generated from the updated poses (the table / MLP update runs beside the march on the side stream)."""
-        st = _lib.stream()
-        self.pose_found_inf.zero_()
-        _lib.call("ngp_check_finite", _lib.ptr(self.se3_grad), _lib.NGP_F32, self.se3_grad.numel(), _lib.ptr(self.pose_found_inf), st)
-        self.pose_opt.step(self.inv_scale, self.pose_found_inf, zero_grad=True)
+        g = self.pose_opt.groups[0]
+        b1, b2 = self.pose_opt.betas
+        self.pose_opt.step_count += 1
+        _lib.weights_epoch += 1
+        _lib.call("ngp_small_adam", _lib.ptr(self.se3), _lib.ptr(self.se3_grad), _lib.ptr(g["m"]), _lib.ptr(g["v"]), self.se3.numel(),
+                  float(self.pose_opt.lr), float(b1), float(b2), float(self.pose_opt.eps), float(self.pose_opt.weight_decay),
+                  _lib.ptr(self.pose_step_dev), _lib.ptr(self.pose_lr_dev), _lib.ptr(self.inv_scale), _lib.ptr(self.pose_found_inf),
+                  _lib.stream())
 
     def _launch_march(self):
         m, opt, N, cap = self.model, self.model.opt, self.N, self.cap
@@ -490,8 +494,7 @@ class FusedTrainStep:
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_pipe):
             self._launch_pipelined()
-        self.pipe_kernels = (_lib.launch_count - c0 + (1 if self.perturb else 0)       # + noises.uniform_
-                             + (1 if self.pose is not None else 0))                 # + pose_found_inf.zero_
+        self.pipe_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)        # + noises.uniform_
         self.opt.step_count = n_adam        # capturing is not stepping
         if self.pose is not None:
             self.pose_opt.step_count = n_adam

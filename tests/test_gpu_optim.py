@@ -162,3 +162,35 @@ def test_check_finite_multi(bad):
         assert found.item() == (1.0 if expect_inf else 0.0)
         assert scratch.tolist() == [0, 0]
     assert step.item() == (2 if bad is not None else 3)
+
+
+def test_small_adam_matches_torch_and_skips_on_inf():
+    """ngp_small_adam (one single-block launch: inf check + step count + unscale + Adam + clear) against torch.optim.Adam"""
+    torch.manual_seed(3)
+    dev, n = "cuda", 600
+    master = torch.randn(n, device=dev) * 0.01
+    ref = torch.nn.Parameter(master.clone())
+    opt_ref = torch.optim.Adam([ref], lr=1e-3)                      # torch defaults, like barf/camera_optimizers.py:40
+    grad, m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    lr_dev = torch.full((1,), 1e-3, device=dev)
+    inv_scale = torch.full((1,), 1 / 128.0, device=dev)
+    found = torch.full((1,), 5.0, device=dev)
+
+    def launch():
+        _lib.call("ngp_small_adam", _lib.ptr(master), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), n, 123.0, 0.9, 0.999, 1e-8, 0.0,
+                  _lib.ptr(step), _lib.ptr(lr_dev), _lib.ptr(inv_scale), _lib.ptr(found), _lib.stream())
+
+    for it in range(4):
+        g = torch.randn(n, device=dev)
+        grad.copy_(g * 128.0)
+        ref.grad = g.clone()
+        launch()
+        opt_ref.step()
+        assert found.item() == 0.0 and step.item() == it + 1 and grad.abs().max().item() == 0.0
+        torch.testing.assert_close(master, ref.data, rtol=1e-5, atol=1e-7)
+    before = master.clone()
+    grad.fill_(1.0)
+    grad[577] = float("nan")
+    launch()
+    assert found.item() == 1.0 and step.item() == 4 and torch.equal(master, before) and grad.abs().max().item() == 0.0
