@@ -316,12 +316,15 @@ class NeRFRenderer(nn.Module):
                 quarter = H3 // 4
                 coords = torch.randint(0, H, (quarter, 3), device=dev)
                 uniform_idx = raymarching.morton3D(coords)
-                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                if occ_indices.shape[0] > 0:
-                    rand_mask = torch.randint(0, occ_indices.shape[0], [quarter], dtype=torch.long, device=dev)
-                    cells = torch.cat([uniform_idx, occ_indices[rand_mask].int()], dim=0).contiguous()
-                else:
-                    cells = uniform_idx
+                # H^3/4 random OCCUPIED cells (renderer.py:862-866 does nonzero() + randint, a host sync); here the occupied
+                # ids are compacted on the device and drawn with floor(u * count), the count never leaves the GPU.  With no
+                # occupied cell the reference samples the uniform cells only; the second half then repeats them.
+                ids = torch.arange(H3, dtype=torch.int32, device=dev)
+                occ_list, occ_count = raymarching.compact_rays_alive(torch.where(self.density_grid[cas] > 0, ids, -1))
+                pick = (torch.rand(quarter, device=dev) * occ_count.float()).long()
+                pick = torch.minimum(pick, (occ_count.long() - 1).clamp(min=0))
+                occ_cells = torch.where(occ_count > 0, occ_list[pick], uniform_idx)
+                cells = torch.cat([uniform_idx, occ_cells], dim=0).contiguous()
                 n = cells.shape[0]
                 noise = torch.rand(n, 3, device=dev)
             xyzs = torch.empty(n, 3, device=dev)

@@ -75,7 +75,12 @@ def test_update_extra_state_partial_invariants():
         model.density_grid.uniform_(0, 5)
         model.density_grid[0, ::7] = -1
     before = model.density_grid.clone()
-    model.update_extra_state(decay=0.9)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")                  # the update must not synchronise with the host
+    try:
+        model.update_extra_state(decay=0.9)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
     after = model.density_grid
     assert (after[before < 0] == -1).all()
     changed = after != before
@@ -87,6 +92,19 @@ def test_update_extra_state_partial_invariants():
     th = min(model.mean_density, model.density_thresh)
     exp = synthetic.packbits_torch(after.cpu(), th)
     assert (bits.cpu() != exp).sum().item() <= 2
+
+
+def test_update_extra_state_partial_with_empty_grid():
+    """no occupied cell: the reference samples only the uniform cells (renderer.py:862-869); here the second half repeats them"""
+    model = _model(bound=1, grid_size=32, hashmap_size=14, hashgrid_resolution=128)
+    model.iter_density = 16
+    with torch.no_grad():
+        model.density_grid.zero_()
+    model.update_extra_state(decay=0.9)
+    after = model.density_grid
+    assert torch.isfinite(after).all() and (after >= 0).all()
+    frac = (after > 0).float().mean().item()
+    assert 0.1 < frac < 0.3                                    # ~ H^3/4 distinct uniform cells were refreshed
 
 
 def test_mark_untrained_grid_matches_reference_loop(ref_march):
