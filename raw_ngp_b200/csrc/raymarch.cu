@@ -60,6 +60,10 @@ struct MarchParams {
     float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf;
     uint32_t H;
     bool contract;
+    // one cascade and no contraction (bound <= 1): the cascade level is always 0 and mip_bound a constant, so probe() skips
+    // the two frexpf, the scalbnf, the division and the contraction test -- about half of its instructions, same results
+    bool simple;
+    float mip_bound0, mip_rbound0;
 };
 
 __device__ __forceinline__ MarchParams make_params(const uint8_t* grid, float bound, bool contract, float dt_gamma,
@@ -76,6 +80,9 @@ __device__ __forceinline__ MarchParams make_params(const uint8_t* grid, float bo
     p.Hf = (float)H;
     p.Cf = (float)C;
     p.H = H;
+    p.simple = (C == 1) && !contract;
+    p.mip_bound0 = fminf(1.0f, bound);            // fminf(scalbnf(1.0f, 0), bound)
+    p.mip_rbound0 = 1 / p.mip_bound0;
     return p;
 }
 
@@ -95,16 +102,21 @@ __device__ __forceinline__ bool probe(const MarchParams& p, const Ray& r, float 
     const float z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
     q.dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
 
-    const int level = max(cascade_from_pos(x, y, z, p.Cf), cascade_from_dt(q.dt, p.Hf, p.Cf));
-    q.mip_bound = fminf(scalbnf(1.0f, level), p.bound);
-    const float mip_rbound = 1 / q.mip_bound;
-
+    int level = 0;
+    float mip_rbound = p.mip_rbound0;
+    bool outer = false;
+    q.mip_bound = p.mip_bound0;
     q.cx = x; q.cy = y; q.cz = z;
-    const float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-    const bool outer = p.contract && mag > 1;
-    if (outer) {  // L-inf contraction, all axes scaled (raymarching.cu:423-429)
-        const float s = (2 - 1 / mag) / mag;
-        q.cx *= s; q.cy *= s; q.cz *= s;
+    if (!p.simple) {        // uniform over the launch
+        level = max(cascade_from_pos(x, y, z, p.Cf), cascade_from_dt(q.dt, p.Hf, p.Cf));
+        q.mip_bound = fminf(scalbnf(1.0f, level), p.bound);
+        mip_rbound = 1 / q.mip_bound;
+        const float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+        outer = p.contract && mag > 1;
+        if (outer) {  // L-inf contraction, all axes scaled (raymarching.cu:423-429)
+            const float s = (2 - 1 / mag) / mag;
+            q.cx *= s; q.cy *= s; q.cz *= s;
+        }
     }
     // 0.5*(c/mip_bound + 1)*H, clamped to [0, H-1], truncated
     q.nx = (int)clampf((0.5f * (q.cx * mip_rbound + 1)) * p.Hf, 0.0f, (float)(p.H - 1));
