@@ -11,7 +11,6 @@ kernel (csrc/pose.cu), differentiable with respect to se3 through a second kerne
 Precision note: the reference evaluates provide_refined_poses under autocast, so its `@` products (wx @ wx, V @ u, the
 compose) are rounded to fp16 before `Pose.__call__` casts back to fp32 (camera.py:33-34); here everything stays fp32.
 """
-import numpy as np
 import torch
 from torch import nn
 from torch.autograd import Function

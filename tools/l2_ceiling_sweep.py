@@ -1,6 +1,6 @@
 """Developer tool: the gather / reduction ceilings of tools/l2_ceiling.py as a function of how many SMs (512-thread blocks) take
 part -- shows which side bounds them (per-SM L1 sector rate for gathers, the chip-wide L2 rate for reductions)."""
-import os, sys, torch
+import sys, torch
 sys.path.insert(0, '/root/repo')
 from raw_ngp_b200 import _lib
 dev = torch.device("cuda:0")

@@ -4,7 +4,7 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from raw_ngp_b200 import raymarching, _lib
+from raw_ngp_b200 import _lib
 dev = torch.device("cuda:0")
 model, _, _, _ = bench.build_scene(dev, 0)
 W, H, f = 1920, 1080, 1200.0

@@ -21,7 +21,6 @@ def main():
     mode = sys.argv[2] if len(sys.argv) > 2 else "step"
     dev = torch.device("cuda:0")
     if mode == "pose":
-        import argparse
         import config_bench
         from raw_ngp_b200 import pose
         model = config_bench.build_model(dev, bound=1, pose_opt="barf", start_annealing=0.0, end_annealing=0.5)

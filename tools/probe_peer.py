@@ -1,5 +1,5 @@
 """Probe: which way of getting peer-accessible buffers across ranks works on this box (symmetric memory, CUDA IPC)."""
-import os, sys, traceback
+import os, traceback
 import torch
 import torch.distributed as dist
 
