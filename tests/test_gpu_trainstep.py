@@ -322,3 +322,32 @@ def test_padded_weight_cache_sees_native_updates():
     img2 = render()
     assert torch.equal(img1, img2)
     assert not torch.equal(img0, img1)
+
+
+def test_composite_hdr_loss_kernel_matches_reference_lines():
+    """The fused composite + loss kernel in HDR mode against tests/golden/hdr_loss.npz (the reference's train_utils.py:512-541
+    executed on seeded inputs): every ray has one opaque sample, so the composited colour IS that sample's colour and the
+    kernel's loss / d loss / d rgb must be the fixture's."""
+    import os
+    import numpy as np
+    from raw_ngp_b200 import _lib
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hdr_loss.npz"))
+    dev = "cuda"
+    pred = torch.from_numpy(z["pred_rgb"]).to(dev).contiguous()
+    gt = torch.from_numpy(z["gt_rgb"]).to(dev).contiguous()
+    exposure = torch.from_numpy(z["exposure"]).to(dev).contiguous()
+    N = pred.shape[0]
+    sigma = torch.full((N,), 1e6, device=dev)                     # alpha = 1 - exp(-sigma dt) == 1: the sample is opaque
+    ts = torch.stack([torch.full((N,), 1.0, device=dev), torch.full((N,), 0.01, device=dev)], dim=-1).contiguous()
+    rays = torch.stack([torch.arange(N, device=dev), torch.ones(N, device=dev)], dim=-1).int().contiguous()
+    image, ray_loss, loss = torch.zeros(N, 3, device=dev), torch.zeros(N, device=dev), torch.zeros(1, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_sigma, d_rgb = torch.zeros(N, device=dev), torch.zeros(N, 3, device=dev)
+    scale = 128.0
+    P = _lib.ptr
+    _lib.call("ngp_composite_train_mse", P(sigma), P(pred), P(ts), P(rays), N, None, N, 1e-4, 1.0, P(gt), scale, P(image), P(ray_loss),
+              P(loss), P(ticket), P(d_sigma), P(d_rgb), 1, P(exposure), _lib.stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(image, pred, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(loss.item(), float(z["loss"]), rtol=1e-5)
+    torch.testing.assert_close(d_rgb / scale, torch.from_numpy(z["d_pred"]).to(dev), rtol=1e-4, atol=1e-6)

@@ -175,3 +175,22 @@ def test_torch_near_far_matches_reference_renderer():
         ((near * torch.from_numpy(z["g_near"])).sum() + (far * torch.from_numpy(z["g_far"])).sum()).backward()
         np.testing.assert_allclose(o.grad.numpy(), z["d_rays_o"], rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(d.grad.numpy(), z["d_rays_d"], rtol=1e-6, atol=1e-7)
+
+
+def _hdr_loss_torch(pred, gt, exposure):
+    """the restatement of nerf/train_utils.py:529-536 used by the GPU tests (loss_weight 'none', lossmult 1)"""
+    import torch
+    clip = torch.minimum(torch.tensor(1.0), pred * exposure.unsqueeze(1))
+    scaling = 1.0 / (1e-3 + clip.detach())
+    return ((clip - gt) ** 2 * scaling ** 2).sum() / (3 * pred.shape[0])
+
+
+def test_hdr_loss_restatement_matches_reference_lines():
+    """tests/golden/hdr_loss.npz was produced by executing the reference's own lines (tools/make_golden_hdr.py)"""
+    import torch
+    z = np.load(os.path.join(GOLD, "hdr_loss.npz"))
+    pred = torch.from_numpy(z["pred_rgb"]).requires_grad_(True)
+    loss = _hdr_loss_torch(pred, torch.from_numpy(z["gt_rgb"]), torch.from_numpy(z["exposure"]))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(z["loss"]), rtol=1e-6)
+    np.testing.assert_allclose(pred.grad.numpy(), z["d_pred"], rtol=1e-5, atol=1e-7)
