@@ -114,96 +114,84 @@ def grid_encode_with_jacobian(inputs, embeddings, offsets, per_level_scale, base
 
 
 def level_table_offsets(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size):
-    """Per-level entry offsets, float64 on the host exactly as the reference (grid.py:124-134)."""
-    max_params = 2 ** log2_hashmap_size
-    offsets, offset = [], 0
-    for i in range(num_levels):
-        resolution = int(np.ceil(base_resolution * per_level_scale ** i))
-        params_in_level = min(max_params, resolution ** input_dim)
-        params_in_level = int(np.ceil(params_in_level / 8) * 8)
-        offsets.append(offset)
-        offset += params_in_level
-    offsets.append(offset)
-    return offsets
+    """Row offset of every level inside the embedding table, plus the total as last entry.
+
+    Level i has resolution ceil(base * scale^i) (float64 on the host, as the reference computes it, grid.py:124-134) and
+    min(2^log2_hashmap_size, resolution^D) rows, rounded up to a multiple of 8 so that every level starts 32-byte aligned."""
+    cap = 2 ** log2_hashmap_size
+    rows = []
+    for level in range(num_levels):
+        res = int(np.ceil(base_resolution * per_level_scale ** level))
+        rows.append(int(np.ceil(min(cap, res ** input_dim) / 8) * 8))
+    return [int(v) for v in np.concatenate([[0], np.cumsum(rows, dtype=np.int64)])]
 
 
 class GridEncoder(nn.Module):
+    """Multiresolution hash / tiled grid with trainable fp32 / fp16 / bf16 embeddings (GridEncoder of the reference)."""
+
     def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16,
                  log2_hashmap_size=19, desired_resolution=None, gridtype="hash", align_corners=False,
                  interpolation="linear"):
         super().__init__()
-        if desired_resolution is not None:
+        if desired_resolution is not None:      # geometric progression from base_resolution up to desired_resolution
             per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
-
-        self.input_dim = input_dim
-        self.num_levels = num_levels
-        self.level_dim = level_dim
-        self.per_level_scale = per_level_scale
-        self.log2_hashmap_size = log2_hashmap_size
-        self.base_resolution = base_resolution
+        self.input_dim, self.num_levels, self.level_dim = input_dim, num_levels, level_dim
+        self.per_level_scale, self.base_resolution = per_level_scale, base_resolution
+        self.log2_hashmap_size, self.max_params = log2_hashmap_size, 2 ** log2_hashmap_size
         self.output_dim = num_levels * level_dim
-        self.gridtype = gridtype
-        self.gridtype_id = _gridtype_to_id[gridtype]
-        self.interpolation = interpolation
-        self.interp_id = _interp_to_id[interpolation]
+        self.gridtype, self.gridtype_id = gridtype, _gridtype_to_id[gridtype]
+        self.interpolation, self.interp_id = interpolation, _interp_to_id[interpolation]
         self.align_corners = align_corners
-        self.max_params = 2 ** log2_hashmap_size
 
-        offsets = level_table_offsets(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size)
-        self.register_buffer("offsets", torch.from_numpy(np.array(offsets, dtype=np.int32)))
+        table = level_table_offsets(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size)
+        self.register_buffer("offsets", torch.tensor(table, dtype=torch.int32))
         self.n_params = self.offsets[-1] * level_dim
-        self.embeddings = nn.Parameter(torch.empty(offsets[-1], level_dim))
+        self.embeddings = nn.Parameter(torch.empty(table[-1], level_dim))
         self.grad_sink = None   # set by raw_ngp_b200.trainer: table gradients accumulate here, embeddings.grad stays None
         self.reset_parameters()
 
     def reset_parameters(self):
-        std = 1e-4
-        self.embeddings.data.uniform_(-std, std)
+        self.embeddings.data.uniform_(-1e-4, 1e-4)
 
     def __repr__(self):
+        finest = int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))
         return (f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "
-                f"resolution={self.base_resolution} -> "
-                f"{int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))} "
-                f"per_level_scale={self.per_level_scale:.4f} params={tuple(self.embeddings.shape)} "
-                f"gridtype={self.gridtype} align_corners={self.align_corners} interpolation={self.interpolation}")
+                f"resolution={self.base_resolution} -> {finest} per_level_scale={self.per_level_scale:.4f} "
+                f"params={tuple(self.embeddings.shape)} gridtype={self.gridtype} align_corners={self.align_corners} "
+                f"interpolation={self.interpolation}")
 
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(self, inputs, bound=1, max_level=None):
-        # inputs [..., input_dim] in [-bound, bound]  ->  [..., num_levels * level_dim]
-        inputs = (inputs + bound) / (2 * bound)
-        prefix_shape = list(inputs.shape[:-1])
-        inputs = inputs.view(-1, self.input_dim)
-        outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
-                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id, max_level,
-                              self.grad_sink)
-        return outputs.view(prefix_shape + [self.output_dim])
+        # [..., input_dim] in [-bound, bound] -> unit cube -> [..., num_levels * level_dim]
+        lead = inputs.shape[:-1]
+        unit = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
+        feats = grid_encode(unit, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution, unit.requires_grad,
+                            self.gridtype_id, self.align_corners, self.interp_id, max_level, self.grad_sink)
+        return feats.view(*lead, self.output_dim)
+
+    def _table_grad(self):
+        if self.embeddings.grad is None:
+            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
+        return self.embeddings.grad
 
     @torch.amp.autocast("cuda", enabled=False)
     def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
-        D = self.input_dim
-        C = self.embeddings.shape[1]
-        L = self.offsets.shape[0] - 1
-        S = float(np.log2(self.per_level_scale))
-        H = self.base_resolution
+        """Adds weight * d TV / d table to embeddings.grad, TV sampled at `inputs` (or at B uniform points)."""
+        table = self.embeddings
         if inputs is None:
-            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
+            points = torch.rand(B, self.input_dim, device=table.device)
         else:
-            inputs = (inputs + bound) / (2 * bound)
-            inputs = inputs.view(-1, self.input_dim)
-            B = inputs.shape[0]
-        if self.embeddings.grad is None:
-            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
-        inputs = inputs.to(self.embeddings.dtype).contiguous()
-        _lib.call("ngp_grid_grad_total_variation", _lib.ptr(inputs), _lib.ptr(self.embeddings),
-                  _lib.ptr(self.embeddings.grad), _lib.ptr(self.offsets), float(weight), B, D, C, L, S, H,
-                  self.gridtype_id, int(self.align_corners), _lib.dtype_id(self.embeddings.dtype), _lib.stream())
+            points = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
+        grad = self._table_grad()
+        points = points.to(table.dtype).contiguous()
+        _lib.call("ngp_grid_grad_total_variation", _lib.ptr(points), _lib.ptr(table), _lib.ptr(grad), _lib.ptr(self.offsets),
+                  float(weight), points.shape[0], self.input_dim, table.shape[1], self.offsets.shape[0] - 1,
+                  float(np.log2(self.per_level_scale)), self.base_resolution, self.gridtype_id, int(self.align_corners),
+                  _lib.dtype_id(table.dtype), _lib.stream())
 
     @torch.amp.autocast("cuda", enabled=False)
     def grad_weight_decay(self, weight=0.1):
-        B = self.embeddings.shape[0]
-        C = self.embeddings.shape[1]
-        L = self.offsets.shape[0] - 1
-        if self.embeddings.grad is None:
-            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
-        _lib.call("ngp_grid_grad_weight_decay", _lib.ptr(self.embeddings), _lib.ptr(self.embeddings.grad),
-                  _lib.ptr(self.offsets), float(weight), B, C, L, _lib.dtype_id(self.embeddings.dtype), _lib.stream())
+        """Adds the L2 penalty's gradient, normalised per level, to embeddings.grad."""
+        table, grad = self.embeddings, self._table_grad()
+        _lib.call("ngp_grid_grad_weight_decay", _lib.ptr(table), _lib.ptr(grad), _lib.ptr(self.offsets), float(weight),
+                  table.shape[0], table.shape[1], self.offsets.shape[0] - 1, _lib.dtype_id(table.dtype), _lib.stream())

@@ -62,22 +62,24 @@ def sh_encode_with_jacobian(inputs, degree):
 
 
 class SHEncoder(nn.Module):
+    """Real spherical harmonics of a direction, degree 1..8 -> degree^2 coefficients (SHEncoder of the reference)."""
+
     def __init__(self, input_dim=3, degree=4):
         super().__init__()
-        self.input_dim = input_dim
-        self.degree = degree
-        self.output_dim = degree ** 2
-        assert self.input_dim == 3, "SH encoder only support input dim == 3"
-        assert self.degree > 0 and self.degree <= 8, "SH encoder only supports degree in [1, 8]"
+        if input_dim != 3:
+            raise AssertionError("SH encoder only support input dim == 3")
+        if not 0 < degree <= 8:
+            raise AssertionError("SH encoder only supports degree in [1, 8]")
+        self.input_dim, self.degree, self.output_dim = input_dim, degree, degree * degree
 
     def __repr__(self):
         return f"SHEncoder: input_dim={self.input_dim} degree={self.degree}"
 
     def forward(self, inputs, size=1):
-        # inputs [..., 3] in [-size, size]  ->  [..., degree^2]
-        inputs = inputs / size
-        inputs = inputs / torch.norm(inputs, dim=-1, keepdim=True)
-        prefix_shape = list(inputs.shape[:-1])
-        inputs = inputs.reshape(-1, self.input_dim)
-        outputs = sh_encode(inputs, self.degree, inputs.requires_grad)
-        return outputs.reshape(prefix_shape + [self.output_dim])
+        # [..., 3] in [-size, size]: scaled to the unit cube, renormalised to the unit sphere (sphere_harmonics.py:76-81),
+        # encoded; gradients with respect to the directions only when they are asked for
+        lead = inputs.shape[:-1]
+        unit = inputs / size
+        unit = unit / torch.norm(unit, dim=-1, keepdim=True)
+        flat = unit.reshape(-1, self.input_dim)
+        return sh_encode(flat, self.degree, flat.requires_grad).reshape(*lead, self.output_dim)
