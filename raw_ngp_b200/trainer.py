@@ -589,8 +589,11 @@ class FusedTrainStep:
 
     def profile_kernels(self, iters=10):
         """Average device time (ms, CUDA events on the launching stream) of every kernel of the step, launched eagerly in
-        step order on the current inputs (these are real optimisation steps: the model trains `iters` steps).  Returns {entry point: ms}."""
+        step order on the current inputs (these are real optimisation steps: the model trains `iters` steps).  Returns {entry point: ms}.
+        With the peer-memory data-parallel update (a collective) only the rank-local kernels are timed: gradients are discarded
+        and no optimizer step is taken or counted, so a single rank may call this."""
         self.flush()
+        local_only = self.peer is not None
         names, events = [], []
         real_call = _lib.call
 
@@ -606,7 +609,13 @@ class FusedTrainStep:
             _lib.call = timed_call
             for _ in range(iters):
                 self._launch_forward_backward()
-                self._launch_check(count_step=True)
+                self._launch_check(count_step=not local_only)
+                if local_only:
+                    self.table_grad.zero_()
+                    self.w_grad.zero_()
+                    if self.pose is not None:
+                        self.se3_grad.zero_()
+                    continue
                 self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=False)
                 if self.pose is not None:
                     self._launch_pose_update()
