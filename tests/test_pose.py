@@ -47,3 +47,20 @@ def test_look_at_poses_are_rigid_and_face_the_origin():
     fwd = -R[:, :, 2]                                    # the camera looks down -z
     c = P[:, :3, 3]
     torch.testing.assert_close(fwd, -c / c.norm(dim=-1, keepdim=True), rtol=0, atol=1e-5)
+
+
+def test_numpy_oracle_matches_reference_fixture():
+    """oracle/pose_oracle.py (independent numpy / float64 restatement) against the reference's outputs AND its autograd
+    gradients (by central differences)"""
+    from oracle import pose_oracle
+    z = np.load(GOLD)
+    np.testing.assert_allclose(pose_oracle.se3_to_SE3(z["se3"]), z["SE3"], rtol=0, atol=2e-6)
+    H, W = int(z["H"]), int(z["W"])
+    fx, fy, cx, cy = z["intrinsics"].tolist()
+    i, j = z["i"].astype(np.float64) + 0.5, z["j"].astype(np.float64) + 0.5
+    dirs = np.stack([(i - cx) / fx, -(j - cy) / fy, -np.ones_like(i)], axis=-1)
+    o, d = pose_oracle.refined_rays(z["se3"], z["poses"], z["idx"], dirs)
+    np.testing.assert_allclose(o, z["rays_o"], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(d, z["rays_d"], rtol=0, atol=3e-6)
+    g = pose_oracle.d_se3_numeric(z["se3"], z["poses"], z["idx"], dirs, z["g_rays_o"].astype(np.float64), z["g_rays_d"].astype(np.float64))
+    np.testing.assert_allclose(g, z["d_se3"], rtol=2e-4, atol=2e-4)
