@@ -288,6 +288,15 @@ int ngp_occ_scatter_sigmas(const int32_t* indices, const float* sigmas, uint32_t
 int ngp_occ_ema_update(float* density_grid, const float* tmp_grid, uint32_t n_cells, float decay,
                        double* accum, float* mean_out, ngp_stream_t stream);
 
+/* NeRFRenderer.mark_untrained_grid (nerf/renderer.py:716-809) as one launch: cell (cascade, Morton index) of density_grid
+ * [cascade, H^3] is set to -1 unless its centre lies inside aabb [6] grown by half a cell AND inside the frustum of at least
+ * one of the B cameras.  poses: camera-to-world, row-major [B, 3|4, 4] with `pose_stride` floats per camera; half_fov
+ * [n_intr, 2] = (cx / fx, cy / fy) with n_intr = 1 (shared intrinsics) or B; cam_near [B] or NULL (then min_near for all);
+ * grid_bound = NeRFRenderer.bound (cascade c spans min(2^c, grid_bound)). */
+int ngp_mark_untrained_grid(float* density_grid, const float* poses, uint32_t pose_stride, uint32_t B,
+                            const float* half_fov, uint32_t n_intr, const float* cam_near, float min_near,
+                            const float* aabb, uint32_t H, uint32_t cascade, float grid_bound, ngp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused MLP (reference: nerf/network.py:12-35, nn.Linear stack -> cuBLAS)
  * ---------------------------------------------------------------------------------------- */

@@ -43,6 +43,26 @@ build_one() { # dir  cu-basename  module-name
   echo "[build_ref] built $so"
 }
 
+# The reference's own Python modules of the hot path, staged UNMODIFIED (byte copies + sha256 manifest) next to the compiled
+# extensions so that tests on the GPU box (where /root/reference does not exist) can run the reference's nerf/network.py and
+# nerf/renderer.py::run_cuda (a) over the reference kernels and (b) over raw_ngp_b200/dropin -- oracle/ref_stack.py.
+# oracle/_ref/ is git-ignored: no reference source enters the history.
+stage_py() {
+  local PYOUT="$OUT/py"
+  rm -rf "$PYOUT"; mkdir -p "$PYOUT"
+  : > "$OUT/py_manifest.sha256"
+  for f in nerf/network.py nerf/renderer.py encoding.py activation.py \
+           gridencoder/__init__.py gridencoder/grid.py raymarching/__init__.py raymarching/raymarching.py \
+           shencoder/__init__.py shencoder/sphere_harmonics.py freqencoder/__init__.py freqencoder/freq.py \
+           barf/camera.py barf/camera_optimizers.py; do
+    mkdir -p "$PYOUT/$(dirname "$f")"
+    cp "$REF/$f" "$PYOUT/$f"
+    (cd "$REF" && sha256sum "$f") >> "$OUT/py_manifest.sha256"
+  done
+  echo "[build_ref] staged $(wc -l < "$OUT/py_manifest.sha256") reference python modules under $PYOUT"
+}
+stage_py
+
 build_one raymarching raymarching _raymarching_mob &
 build_one shencoder   shencoder   _shencoder &
 build_one gridencoder gridencoder _gridencoder &

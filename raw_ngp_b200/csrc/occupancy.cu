@@ -98,6 +98,79 @@ occ_ema_kernel(float* __restrict__ density_grid, const float* __restrict__ tmp_g
     }
 }
 
+
+// renderer.py:716-809: a cell is "trainable" iff it lies inside the training AABB (grown by half a cell) and inside the view
+// frustum of at least one training camera.  The reference evaluates this with a Python loop over 64^3 chunks x cascades x camera
+// batches of torch ops (meshgrid, morton3D, batched matmul, boolean masks, index_put); here one thread owns one cell of one
+// cascade, the camera poses are staged through shared memory in chunks, and the loop over cameras stops at the first that
+// sees the cell.  Arithmetic follows the torch expression chain (scalars rounded to fp32 where torch rounds them; the 3-term
+// dot products of the batched matmul as one multiplication + two FMAs).
+constexpr uint32_t kCamChunk = 128;
+struct CamRec { float r[9]; float t[3]; float cxfx, cyfy, near_z; };
+
+__global__ void __launch_bounds__(256)
+mark_untrained_kernel(float* __restrict__ density_grid, const float* __restrict__ poses, uint32_t pose_stride, uint32_t B,
+                      const float* __restrict__ half_fov, uint32_t n_intr, const float* __restrict__ cam_near, float min_near,
+                      const float* __restrict__ aabb, uint32_t H, uint32_t cascade, float grid_bound) {
+    __shared__ CamRec s_cam[kCamChunk];
+    const uint32_t H3 = H * H * H;
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;       // Morton index inside the cascade
+    const uint32_t cas = blockIdx.y;
+    const bool live = cell < H3;
+    // python-double arithmetic of the reference (renderer.py:757-760), cast to fp32 where torch casts the scalar
+    const double bound_d = fmin((double)(1u << cas), (double)grid_bound);
+    const double hgs_d = bound_d / (double)H;
+    const float span = (float)(bound_d - hgs_d), hgs = (float)hgs_d, hgs2 = (float)(hgs_d * 2.0);
+    float w[3] = {0.f, 0.f, 0.f};
+    bool in_aabb = false;
+    if (live) {
+        const uint32_t c[3] = {compact3(cell), compact3(cell >> 1), compact3(cell >> 2)};
+        const float inv_hm1 = __fdiv_rn(1.0f, (float)(H - 1));
+        in_aabb = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            w[a] = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.0f, (float)c[a]), inv_hm1), -1.0f), span);
+            in_aabb = in_aabb && (w[a] >= __fsub_rn(__ldg(aabb + a), hgs)) && (w[a] <= __fadd_rn(__ldg(aabb + 3 + a), hgs));
+        }
+    }
+    bool seen = false;
+    for (uint32_t head = 0; head < B; head += kCamChunk) {
+        const uint32_t n = min(kCamChunk, B - head);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const float* p = poses + (size_t)(head + i) * pose_stride;          // row-major [3|4, 4] camera-to-world
+            CamRec cr;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) cr.r[r * 3 + k] = __ldg(p + r * 4 + k);
+                cr.t[r] = __ldg(p + r * 4 + 3);
+            }
+            const float* q = half_fov + (size_t)(n_intr > 1 ? head + i : 0) * 2;     // (cx / fx, cy / fy)
+            cr.cxfx = __ldg(q);
+            cr.cyfy = __ldg(q + 1);
+            cr.near_z = cam_near ? __ldg(cam_near + head + i) : min_near;
+            s_cam[i] = cr;
+        }
+        __syncthreads();
+        if (live && in_aabb && !seen) {
+            for (uint32_t i = 0; i < n; i++) {
+                const CamRec& cr = s_cam[i];
+                const float d0 = __fsub_rn(w[0], cr.t[0]), d1 = __fsub_rn(w[1], cr.t[1]), d2 = __fsub_rn(w[2], cr.t[2]);
+                // cam = d @ R  (world -> camera: R is camera-to-world, so its transpose applies; renderer.py:771-773)
+                const float x = __fmaf_rn(d2, cr.r[6], __fmaf_rn(d1, cr.r[3], __fmul_rn(d0, cr.r[0])));
+                const float y = __fmaf_rn(d2, cr.r[7], __fmaf_rn(d1, cr.r[4], __fmul_rn(d0, cr.r[1])));
+                const float z = -__fmaf_rn(d2, cr.r[8], __fmaf_rn(d1, cr.r[5], __fmul_rn(d0, cr.r[2])));
+                if (z > cr.near_z && fabsf(x) < __fadd_rn(__fmul_rn(cr.cxfx, z), hgs2) && fabsf(y) < __fadd_rn(__fmul_rn(cr.cyfy, z), hgs2)) {
+                    seen = true;
+                    break;
+                }
+            }
+        }
+    }
+    if (live && !(in_aabb && seen)) density_grid[(size_t)cas * H3 + cell] = -1.0f;
+}
+
 }  // namespace
 }  // namespace ngp
 
@@ -132,5 +205,17 @@ extern "C" int ngp_occ_ema_update(float* density_grid, const float* tmp_grid, ui
     const uint32_t blocks = min(div_up(n_cells, 256u), (uint32_t)(kNumSMs * 8));
     occ_ema_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(density_grid, tmp_grid, n_cells, decay, accum, mean_out,
                                                              reinterpret_cast<unsigned int*>(accum + 1));
+    return finish_launch();
+}
+
+extern "C" int ngp_mark_untrained_grid(float* density_grid, const float* poses, uint32_t pose_stride, uint32_t B,
+                                       const float* half_fov, uint32_t n_intr, const float* cam_near, float min_near,
+                                       const float* aabb, uint32_t H, uint32_t cascade, float grid_bound, ngp_stream_t stream) {
+    if (!density_grid || !poses || !half_fov || !aabb) return NGP_ERR_NULL;
+    if (H < 2 || H > 1024 || cascade == 0 || cascade > 16 || pose_stride < 12 || (n_intr != 1 && n_intr != B)) return NGP_ERR_BAD_ARG;
+    const uint32_t H3 = H * H * H;
+    mark_untrained_kernel<<<dim3(div_up(H3, 256u), cascade), 256, 0, (cudaStream_t)stream>>>(density_grid, poses, pose_stride, B, half_fov,
+                                                                                            n_intr, cam_near, min_near, aabb, H, cascade,
+                                                                                            grid_bound);
     return finish_launch();
 }

@@ -236,58 +236,30 @@ class NeRFRenderer(nn.Module):
     @torch.no_grad()
     def mark_untrained_grid(self, dataset, S=64):
         """Cells seen by no training camera, or outside the training AABB, get density -1 and never become occupied
-        (renderer.py:716-809).  `dataset` provides poses [B,4,4] (camera-to-world), intrinsics (fx, fy, cx, cy) and
-        optionally cam_near_far [B,2]."""
-        poses = dataset.poses
-        intrinsics = dataset.intrinsics
-        cam_near_far = dataset.cam_near_far if hasattr(dataset, "cam_near_far") else None
-        if isinstance(poses, np.ndarray):
-            poses = torch.from_numpy(poses)
+        (renderer.py:716-809).  `dataset` provides poses [B, 3|4, 4] (camera-to-world), intrinsics (fx, fy, cx, cy) -- one
+        4-vector or [B, 4] -- and optionally cam_near_far [B, 2].  One kernel: a thread per (cascade, cell), cameras staged
+        through shared memory, early exit at the first camera that sees the cell (csrc/occupancy.cu); `S`, the chunk size of
+        the reference's Python loops, has no meaning here and is accepted for signature compatibility."""
+        dev = self.density_grid.device
+        poses = torch.as_tensor(dataset.poses).to(dev).float().contiguous()
         B = poses.shape[0]
-        dev = self.aabb_train.device
-        if isinstance(intrinsics, np.ndarray):
-            fx, fy, cx, cy = [torch.as_tensor(float(v)) for v in intrinsics]
+        intr = dataset.intrinsics
+        if torch.is_tensor(intr):
+            # renderer.py:731,776-777: fp32 tensor division, per camera when intrinsics is [B, 4]
+            intr = intr.to(dev).float().reshape(-1, 4)
+            half_fov = torch.stack([intr[:, 2] / intr[:, 0], intr[:, 3] / intr[:, 1]], dim=-1)
         else:
-            fx, fy, cx, cy = torch.chunk(intrinsics, 4, dim=-1)
-        fx, fy, cx, cy = fx.to(dev).float(), fy.to(dev).float(), cx.to(dev).float(), cy.to(dev).float()
-        per_cam = fx.numel() > 1
-        poses = poses.to(dev).float()
-        mask_cam = torch.zeros_like(self.density_grid)
-        mask_aabb = torch.zeros_like(self.density_grid)
-        H = self.grid_size
-        ar = torch.arange(H, dtype=torch.int32, device=dev)
-        for xs in ar.split(S):
-            for ys in ar.split(S):
-                for zs in ar.split(S):
-                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
-                    coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    world_xyzs = (2 * coords.float() / (H - 1) - 1).unsqueeze(0)
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        hgs = bound / H
-                        cas_world_xyzs = world_xyzs * (bound - hgs)
-                        mask_min = (cas_world_xyzs >= (self.aabb_train[:3] - hgs)).sum(-1) == 3
-                        mask_max = (cas_world_xyzs <= (self.aabb_train[3:] + hgs)).sum(-1) == 3
-                        mask_aabb[cas, indices] += (mask_min & mask_max).reshape(-1)
-                        head = 0
-                        while head < B:
-                            tail = min(head + S, B)
-                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
-                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]   # world -> camera
-                            cam_xyzs[:, :, 2] *= -1                          # camera looks down -z
-                            cx_div_fx = (cx[head:tail] / fx[head:tail]) if per_cam else cx / fx
-                            cy_div_fy = (cy[head:tail] / fy[head:tail]) if per_cam else cy / fy
-                            if cam_near_far is None:
-                                min_near = torch.as_tensor(float(self.opt.min_near), device=dev)
-                            else:
-                                min_near = torch.as_tensor(cam_near_far[head:tail, 0]).to(dev).float().unsqueeze(1)
-                            mask_z = cam_xyzs[:, :, 2] > min_near
-                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < (cx_div_fx * cam_xyzs[:, :, 2] + hgs * 2)
-                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < (cy_div_fy * cam_xyzs[:, :, 2] + hgs * 2)
-                            mask_cam[cas, indices] += (mask_z & mask_x & mask_y).sum(0).bool().reshape(-1)
-                            head += S
-        self.density_grid[(mask_cam == 0) | (mask_aabb == 0)] = -1
+            # renderer.py:729,779-780,784-785: numpy scalars divide in float64, the quotient is cast when it meets the fp32 tensor
+            fx, fy, cx, cy = [float(v) for v in np.asarray(intr).reshape(-1)[:4]]
+            half_fov = torch.tensor([[cx / fx, cy / fy]], dtype=torch.float64).float().to(dev)
+        half_fov = half_fov.contiguous()
+        if half_fov.shape[0] not in (1, B):
+            raise ValueError("mark_untrained_grid: intrinsics must be one (fx, fy, cx, cy) or one per pose")
+        cnf = getattr(dataset, "cam_near_far", None)
+        cam_near = None if cnf is None else torch.as_tensor(cnf).to(dev).float()[:, 0].contiguous()
+        _lib.call("ngp_mark_untrained_grid", _lib.ptr(self.density_grid), _lib.ptr(poses), poses.shape[-2] * poses.shape[-1], B,
+                  _lib.ptr(half_fov), half_fov.shape[0], _lib.ptr(cam_near), float(self.opt.min_near), _lib.ptr(self.aabb_train),
+                  int(self.grid_size), int(self.cascade), float(self.bound), _lib.stream())
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
