@@ -61,6 +61,8 @@ const char* ngp_last_cuda_error(void);
 /* flags for ngp_grid_encode_forward / backward */
 #define NGP_GRID_REF_ROUNDING 1u /* fp16 tables: accumulate in half exactly like the reference
                                     (gridencoder.cu:168,191); without it: fp32 accumulate, one rounding */
+#define NGP_GRID_POINT_LEVEL_KERNELS 2u /* diagnostics: force the one-thread-per-(point, level) kernels (the reference's
+                                           launch shape) instead of the tile kernels; results are identical */
 
 /* replaces grid_encode_forward            gridencoder/src/gridencoder.h:12, gridencoder.cu:467-490
  * inputs      [B, D]       fp32 in [0,1]
@@ -201,6 +203,22 @@ int ngp_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, co
                                     uint32_t cap, float* nears_out, float* fars_out, int32_t* rays,
                                     int32_t* counter, float* t_scratch, ngp_stream_t stream);
 
+/* ngp_march_rays_train_count_aabb + the per-ray camera clip of run_cuda (nears = max(nears, cam_near_far[:, 0]), fars =
+ * min(fars, cam_near_far[:, 1]); nerf/renderer.py:529-533; cam_near_far [N,2] or NULL) + a device-side live ray count for the
+ * adaptive ray count of Trainer.train_step (nerf/train_utils.py:563-564; n_rays_dev int32[1] or NULL): rays at or beyond
+ * *n_rays_dev get no samples. */
+int ngp_march_rays_train_count_ex(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
+                                  const float* cam_near_far, const int32_t* n_rays_dev, const uint8_t* grid, float bound,
+                                  int contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                  const float* noises, uint32_t cap, float* nears_out, float* fars_out, int32_t* rays,
+                                  int32_t* counter, float* t_scratch, ngp_stream_t stream);
+
+/* Adaptive ray count on the device (nerf/train_utils.py:563-564, main.py:59-61): after a step that produced *m_dev samples from
+ * *n_rays_dev rays, *n_rays_dev = clamp(round(target_points / m * n), 1, n_max) -- the reference computes the same on the
+ * host after reading the sample count back. */
+int ngp_adaptive_num_rays(int32_t* n_rays_dev, const int32_t* m_dev, uint32_t target_points, uint32_t n_max,
+                          ngp_stream_t stream);
+
 /* replaces composite_rays_train_forward   raymarching/src/raymarching.h:15, raymarching.cu:519-608
  * weights [M] must be zero-filled by the caller (raymarching/raymarching.py:356). */
 int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ts,
@@ -218,6 +236,22 @@ int ngp_composite_rays_train_backward(const float* grad_weights, const float* gr
                                       float T_thresh, float* grad_sigmas, float* grad_rgbs,
                                       ngp_stream_t stream);
 
+/* Optional inputs / outputs of ngp_composite_train_loss: the parts of Trainer.train_step (nerf/train_utils.py:481-568) around
+ * the MSE / HDR loss that the reference evaluates with torch ops.  Every pointer may be NULL (feature off). */
+typedef struct ngp_loss_opts {
+    const float* bg_rays;        /* [N,3] per-ray background (background == 'random', train_utils.py:495-496); NULL: scalar bg_color */
+    const float* target_alpha;   /* [N]   alpha of RGBA targets: gt = rgb * a + bg * (1 - a)   (train_utils.py:503-506) */
+    const float* lossmult;       /* [N,3] Bayer mask of mosaiced raw data (train_utils.py:516-518) */
+    const float* loss_weight;    /* [N,3] gaussian / planck / hanning weighting of the ground truth (train_utils.py:520-527) */
+    const float* inv_norm_dev;   /* [1]   1 / sum(lossmult) on the device (train_utils.py:536); NULL: 1 / (3 * live rays) */
+    const int32_t* n_rays_dev;   /* [1]   live rays of the batch, <= N (adaptive ray count, train_utils.py:563-564); NULL: N */
+    float lambda_entropy;        /*       weight of the opacity entropy regulariser (train_utils.py:553-556); needs entropy_ray */
+    float* entropy_ray;          /* [N]   scratch: per-ray entropy */
+    float* weights_sum_out;      /* [N]   composited opacity (renderer results['weights_sum']) */
+    float* depth_out;            /* [N]   composited depth (results['depth']) */
+    float* parts_out;            /* [2]   data term and entropy term of loss_out */
+} ngp_loss_opts;
+
 /* composite_rays_train forward + background blend + MSE loss + composite_rays_train backward for one training step
  * (raymarching.cu:519-723, nerf/renderer.py:553,672, nerf/train_utils.py:540-541) in one launch, one warp per ray:
  *   image = composite + (1 - weights_sum) * bg_color ;  loss = mean_n mean_c (image - target)^2
@@ -231,6 +265,13 @@ int ngp_composite_train_mse(const float* sigmas, const float* rgbs, const float*
                             const float* target, float loss_scale, float* image_out, float* ray_loss,
                             float* loss_out, int32_t* ticket, float* grad_sigmas, float* grad_rgbs,
                             int loss_mode, const float* exposure, ngp_stream_t stream);
+
+/* ngp_composite_train_mse with the optional terms of ngp_loss_opts (opts may be NULL). */
+int ngp_composite_train_loss(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
+                             uint32_t M, const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color,
+                             const float* target, float loss_scale, float* image_out, float* ray_loss,
+                             float* loss_out, int32_t* ticket, float* grad_sigmas, float* grad_rgbs, int loss_mode,
+                             const float* exposure, const ngp_loss_opts* opts, ngp_stream_t stream);
 
 /* Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329, which used
  * torch_scatter.segment_csr): dL/drays_o[n] = sum_seg dL/dxyz ; dL/drays_d[n] = sum_seg (dL/dxyz * t + dL/ddirs).

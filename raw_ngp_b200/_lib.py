@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libngp_b200.so")
 
 NGP_F32, NGP_F16, NGP_BF16 = 0, 1, 2
 NGP_GRID_REF_ROUNDING = 1
+NGP_GRID_POINT_LEVEL_KERNELS = 2
 
 _DTYPE_ID = {torch.float32: NGP_F32, torch.float16: NGP_F16, torch.bfloat16: NGP_BF16}
 
@@ -39,6 +40,9 @@ SIGNATURES = {
     "ngp_march_rays_train_count_aabb": [_p, _p, _p, _f32, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _u32, _p, _p, _p, _p, _p, _p],
     "ngp_march_rays_train_write": [_p, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _u32, _p, _p, _p, _p, _p, _p, _p],
     "ngp_composite_train_mse": [_p, _p, _p, _p, _u32, _p, _u32, _f32, _f32, _p, _f32, _p, _p, _p, _p, _p, _p, _i, _p, _p],
+    "ngp_composite_train_loss": [_p, _p, _p, _p, _u32, _p, _u32, _f32, _f32, _p, _f32, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p],
+    "ngp_march_rays_train_count_ex": [_p, _p, _p, _f32, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _u32, _p, _p, _p, _p, _p, _p],
+    "ngp_adaptive_num_rays": [_p, _p, _u32, _u32, _p],
     "ngp_composite_rays_train_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p, _p],
     "ngp_composite_rays_train_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_march_rays_train_backward": [_p, _p, _p, _p, _u32, _u32, _p, _p, _p],
@@ -76,6 +80,14 @@ _SPECIAL = {
     "ngp_status_string": ([c_int], c_char_p),
     "ngp_last_cuda_error": ([], c_char_p),
 }
+
+
+
+class LossOpts(ctypes.Structure):
+    """ngp_loss_opts of include/ngp_b200.h (optional terms of ngp_composite_train_loss)."""
+    _fields_ = [("bg_rays", _p), ("target_alpha", _p), ("lossmult", _p), ("loss_weight", _p), ("inv_norm_dev", _p), ("n_rays_dev", _p),
+                ("lambda_entropy", _f32), ("entropy_ray", _p), ("weights_sum_out", _p), ("depth_out", _p), ("parts_out", _p)]
+
 
 _lib = None
 

@@ -154,6 +154,150 @@ grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ tabl
     }
 }
 
+
+// ---- forward, tile kernel (the model's shape: D = 3, C = 2, L % 8 == 0, no dy_dx) ---------------------------------
+// The reference launches one thread per (point, level) with blockIdx.y = level: every level re-reads the input, writes 4
+// (8) bytes per thread at a 64 (128) byte stride, and a thread has 8 loads in flight (gridencoder.cu:82-249, :467-490).
+// Here a persistent CTA takes tiles of 128 points; thread (row, g) encodes levels g, g + 4, g + 8, ... of its point -- coarse
+// dense levels (L1 hits) and fine hashed levels (L2 round trips) mixed in every thread, two levels = 16 table rows in flight
+// per thread, branch-free with per-level index constants (field_core.cuh) -- and leaves the features in a shared-memory
+// image of the tile's [128, L * C] output block, which then goes out as whole contiguous rows (4-byte words of consecutive
+// threads are consecutive in global memory: every store instruction of a warp writes one full 128-byte line).  The input is
+// read once per point (4 threads share the 12 bytes through L1).
+constexpr uint32_t kTilePts = 128, kTileGroups = 4, kTileThreads = kTilePts * kTileGroups;
+
+template <typename T> struct Row2;                       // one table row (C = 2) as a register value
+template <> struct Row2<__half> {
+    using raw = uint32_t;
+    static constexpr uint32_t kWords = 1;
+    static __device__ __forceinline__ float2 f2(raw v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+};
+template <> struct Row2<__nv_bfloat16> {
+    using raw = uint32_t;
+    static constexpr uint32_t kWords = 1;
+    static __device__ __forceinline__ float2 f2(raw v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+};
+template <> struct Row2<float> {
+    using raw = float2;
+    static constexpr uint32_t kWords = 2;
+    static __device__ __forceinline__ float2 f2(raw v) { return v; }
+};
+
+// interpolates the 8 gathered rows of one level and writes the level's two features into the tile image
+template <typename T, bool RefRound>
+__device__ __forceinline__ void tile_finish(const typename Row2<T>::raw (&v)[8], const float (&frac)[3], bool inside, uint32_t* dst) {
+    float w[8];
+    fieldcore::corner_weights(frac, w);
+    if constexpr (std::is_same<T, __half>::value && RefRound) {
+        // at::Half accumulation of the reference: product rounded to fp16, fp16 + fp16 rounded once (field_core.cuh)
+        __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) {
+            const float2 f = Row2<T>::f2(v[k]);
+            acc = __hadd2(acc, __floats2half2_rn(w[k] * f.x, w[k] * f.y));
+        }
+        dst[0] = inside ? *reinterpret_cast<const uint32_t*>(&acc) : 0u;
+    } else {
+        float a0 = 0.f, a1 = 0.f;                       // fp32 accumulation in corner order (FFMA chain like the reference's)
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) {
+            const float2 f = Row2<T>::f2(v[k]);
+            a0 = fmaf(w[k], f.x, a0);
+            a1 = fmaf(w[k], f.y, a1);
+        }
+        if (!inside) { a0 = 0.f; a1 = 0.f; }
+        if constexpr (std::is_same<T, float>::value) { dst[0] = __float_as_uint(a0); dst[1] = __float_as_uint(a1); }
+        else if constexpr (std::is_same<T, __half>::value) dst[0] = pack_h2(a0, a1);
+        else dst[0] = pack_bf2(a0, a1);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void tile_issue(typename Row2<T>::raw (&v)[8], float (&frac)[3], const T* __restrict__ table,
+                                           const fieldcore::LevelConst& lv, bool align_corners, uint32_t interp, const float (&xc)[3]) {
+    using raw = typename Row2<T>::raw;
+    uint32_t base[3], rows[8];
+    fieldcore::locate3(xc, lv.res, align_corners, interp, base, frac);
+    fieldcore::corner_rows(lv, base, rows);
+    const raw* __restrict__ lvl = reinterpret_cast<const raw*>(table) + lv.offset;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) v[k] = __ldg(lvl + rows[k]);
+}
+
+// a whole level through the generic index map (mode 2: tiled grids that wrap, hash sizes that are not powers of two): out of
+// line, so that the common path keeps its corner rows in registers
+template <typename T, bool RefRound>
+static __device__ __noinline__ void tile_level_generic(const T* table, uint32_t gridtype, bool align_corners, uint32_t interp, uint32_t res,
+                                                       uint32_t hashmap_size, uint32_t offset, float x0, float x1, float x2, bool inside,
+                                                       uint32_t* dst) {
+    using raw = typename Row2<T>::raw;
+    const float xc[3] = {x0, x1, x2};
+    uint32_t base[3], rows[8];
+    float frac[3];
+    raw v[8];
+    fieldcore::locate3(xc, res, align_corners, interp, base, frac);
+    fieldcore::corner_rows_generic(gridtype, hashmap_size, res, base[0], base[1], base[2], rows);
+    const raw* lvl = reinterpret_cast<const raw*>(table) + offset;
+    for (uint32_t k = 0; k < 8; k++) v[k] = __ldg(lvl + rows[k]);
+    tile_finish<T, RefRound>(v, frac, inside, dst);
+}
+
+template <typename T, bool RefRound>
+__global__ void __launch_bounds__(kTileThreads, 2)
+grid_forward_tile_kernel(const float* __restrict__ inputs, const T* __restrict__ table, const int* __restrict__ offsets,
+                         T* __restrict__ outputs, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                         uint32_t gridtype, bool align_corners, uint32_t interp) {
+    using raw = typename Row2<T>::raw;
+    constexpr uint32_t W = Row2<T>::kWords;
+    extern __shared__ uint32_t s_tile[];                 // [128][L * W + 1] words: odd row stride, conflict-free both ways
+    __shared__ fieldcore::LevelConst s_lv[fieldcore::kMaxLevels];
+    {
+        const fieldcore::GridArgs g = {nullptr, offsets, nullptr, S, 1.f, H, L, gridtype, interp, align_corners};
+        fieldcore::load_level_consts(s_lv, g);
+    }
+    __syncthreads();
+    const uint32_t r = threadIdx.x & (kTilePts - 1), grp = threadIdx.x / kTilePts;
+    const uint32_t stride = L * W + 1, row_words = L * W;
+    const uint32_t n_tiles = div_up(B, kTilePts);
+    uint32_t* out_words = reinterpret_cast<uint32_t*>(outputs);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTilePts + r;
+        float x[3] = {2.f, 2.f, 2.f};
+        if (row < B) { x[0] = __ldg(inputs + (size_t)row * 3); x[1] = __ldg(inputs + (size_t)row * 3 + 1); x[2] = __ldg(inputs + (size_t)row * 3 + 2); }
+        const bool inside = x[0] >= 0 && x[0] <= 1 && x[1] >= 0 && x[1] <= 1 && x[2] >= 0 && x[2] <= 1;
+        const float xc[3] = {fminf(fmaxf(x[0], 0.f), 1.f), fminf(fmaxf(x[1], 0.f), 1.f), fminf(fmaxf(x[2], 0.f), 1.f)};
+        uint32_t* my = s_tile + r * stride;
+        for (uint32_t level = grp; level < L; level += 2 * kTileGroups) {
+            const uint32_t la = level, lb = level + kTileGroups;          // L % 8 == 0
+            // levels at or above max_level are zero-filled (grid.py:41,52); clamping the level keeps the code branch-free
+            const fieldcore::LevelConst& lva = s_lv[min(la, max_level - 1)];
+            const fieldcore::LevelConst& lvb = s_lv[min(lb, max_level - 1)];
+            if (lva.mode == 2 || lvb.mode == 2) {                        // warp-uniform, rare
+                tile_level_generic<T, RefRound>(table, gridtype, align_corners, interp, lva.res, lva.hashmap_size, lva.offset, xc[0], xc[1],
+                                                xc[2], inside && la < max_level, my + la * W);
+                tile_level_generic<T, RefRound>(table, gridtype, align_corners, interp, lvb.res, lvb.hashmap_size, lvb.offset, xc[0], xc[1],
+                                                xc[2], inside && lb < max_level, my + lb * W);
+                continue;
+            }
+            raw va[8], vb[8];
+            float fa[3], fb[3];
+            tile_issue<T>(va, fa, table, lva, align_corners, interp, xc);
+            tile_issue<T>(vb, fb, table, lvb, align_corners, interp, xc);
+            tile_finish<T, RefRound>(va, fa, inside && la < max_level, my + la * W);
+            tile_finish<T, RefRound>(vb, fb, inside && lb < max_level, my + lb * W);
+        }
+        __syncthreads();
+        // the tile's output block is contiguous in global memory: word i of the block = row i / row_words, word i % row_words
+        const uint32_t live_words = min(kTilePts, B - tile * kTilePts) * row_words;
+        uint32_t* dst = out_words + (size_t)tile * kTilePts * row_words;
+        for (uint32_t i = threadIdx.x; i < live_words; i += kTileThreads) {
+            const uint32_t rr = i / row_words;
+            dst[i] = s_tile[i + rr];
+        }
+        __syncthreads();
+    }
+}
+
 // Backward: scatter w * grad into the table gradient and, if asked, recompute d out / d x from the table and reduce
 // over the level's channels into grad_inputs.
 //
@@ -372,7 +516,16 @@ __global__ void level_resolution_kernel(uint32_t L, float S, uint32_t H, uint32_
 template <typename T, uint32_t D>
 int launch_forward(const float* inputs, const T* table, const int* offsets, T* outputs, T* dy_dx, uint32_t B,
                    uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H, uint32_t gridtype,
-                   bool align_corners, uint32_t interp, bool ref_round, cudaStream_t st) {
+                   bool align_corners, uint32_t interp, bool ref_round, bool point_level, cudaStream_t st) {
+    if constexpr (D == 3) {
+        if (!point_level && C == 2 && !dy_dx && L % 8 == 0 && L <= fieldcore::kMaxLevels && max_level > 0) {
+            const uint32_t smem = kTilePts * (L * Row2<T>::kWords + 1) * 4;
+            const uint32_t blocks = std::min<uint32_t>(div_up(B, kTilePts), 2 * kNumSMs);
+            if (ref_round) grid_forward_tile_kernel<T, true><<<blocks, kTileThreads, smem, st>>>(inputs, table, offsets, outputs, B, L, max_level, S, H, gridtype, align_corners, interp);
+            else grid_forward_tile_kernel<T, false><<<blocks, kTileThreads, smem, st>>>(inputs, table, offsets, outputs, B, L, max_level, S, H, gridtype, align_corners, interp);
+            return finish_launch();
+        }
+    }
     const dim3 grid(div_up(B, kFwdThreads), L, 1);
 #define NGP_FWD(CC)                                                                                              \
     if (ref_round)                                                                                               \
@@ -483,8 +636,8 @@ extern "C" int ngp_grid_encode_forward(const float* inputs, const void* embeddin
     cudaStream_t st = (cudaStream_t)stream;
     int rc = NGP_ERR_UNSUPPORTED;
     NGP_DISPATCH_DTYPE(dtype, {
-        if (D == 3) rc = launch_forward<T, 3>(inputs, (const T*)embeddings, offsets, (T*)outputs, (T*)dy_dx, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, ref_round, st);
-        else if (D == 2) rc = launch_forward<T, 2>(inputs, (const T*)embeddings, offsets, (T*)outputs, (T*)dy_dx, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, ref_round, st);
+        if (D == 3) rc = launch_forward<T, 3>(inputs, (const T*)embeddings, offsets, (T*)outputs, (T*)dy_dx, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, ref_round, (flags & NGP_GRID_POINT_LEVEL_KERNELS) != 0, st);
+        else if (D == 2) rc = launch_forward<T, 2>(inputs, (const T*)embeddings, offsets, (T*)outputs, (T*)dy_dx, B, C, L, max_level, S, H, gridtype, align_corners != 0, interp, ref_round, (flags & NGP_GRID_POINT_LEVEL_KERNELS) != 0, st);
     });
     return rc;
 }

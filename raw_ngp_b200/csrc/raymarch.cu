@@ -396,7 +396,8 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
                               const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
                               int* __restrict__ rays, int* __restrict__ counter, float* __restrict__ t_scratch,
                               const float* __restrict__ aabb, float min_near, float* __restrict__ nears_out,
-                              float* __restrict__ fars_out, uint32_t cap) {
+                              float* __restrict__ fars_out, uint32_t cap, const float* __restrict__ cam_near_far,
+                              const int* __restrict__ n_rays_dev) {
     __shared__ float s_u[kCoopWarps][kWin];
     __shared__ uint16_t s_next[kCoopWarps][kWin];   // bit 15: keep, low bits: next lattice index (kWin = leaves the window)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -407,11 +408,18 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
         float far, t;
         if (NF) {
             near_far_torch(r, aabb, min_near, t, far);
+            if (cam_near_far) {      // renderer.py:529-533: nears = max(nears, cam_near), fars = min(fars, cam_far)
+                t = fmaxf(t, __ldg(cam_near_far + (size_t)n * 2));
+                far = fminf(far, __ldg(cam_near_far + (size_t)n * 2 + 1));
+            }
             if (lane == 0 && nears_out) { nears_out[n] = t; fars_out[n] = far; }
         } else {
             far = __ldg(fars + n);
             t = __ldg(nears + n);
         }
+        // adaptive ray count (train_utils.py:563-564): only the first *n_rays_dev rays of the batch are live, the others get
+        // no samples (and no loss, see composite_train_mse_kernel)
+        if (n_rays_dev && n >= (uint32_t)__ldg(n_rays_dev)) far = -1.0f;
         t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * __ldg(noises + n);
         float* u = s_u[warp];
         uint16_t* nx = s_next[warp];
@@ -763,11 +771,21 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
                            float bg, const float* __restrict__ target, float loss_scale, float* __restrict__ image_out,
                            float* __restrict__ ray_loss, float* __restrict__ loss_out, int* __restrict__ ticket,
                            float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, int loss_mode,
-                           const float* __restrict__ exposure) {
+                           const float* __restrict__ exposure, const ngp_loss_opts x) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
-    if (n < N) {
+    // live rays of the batch (adaptive ray count): rays at or beyond it carry no samples, no loss and no gradient
+    const uint32_t n_live = x.n_rays_dev ? min(N, (uint32_t)max(__ldg(x.n_rays_dev), 1)) : N;
+    if (n < N && n >= n_live) {
+        if (lane == 0) {
+            ray_loss[n] = 0.f;
+            if (x.entropy_ray) x.entropy_ray[n] = 0.f;
+            if (image_out) { image_out[(size_t)n * 3] = 0.f; image_out[(size_t)n * 3 + 1] = 0.f; image_out[(size_t)n * 3 + 2] = 0.f; }
+            if (x.weights_sum_out) x.weights_sum_out[n] = 0.f;
+            if (x.depth_out) x.depth_out[n] = 0.f;
+        }
+    } else if (n < N) {
         const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
         const bool has = count != 0 && offset + count <= M;
         float r = 0, g = 0, b = 0, ws = 0, d = 0;
@@ -799,11 +817,24 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
             }
             r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
         }
-        const float ir = r + (1.0f - ws) * bg, ig = g + (1.0f - ws) * bg, ib = b + (1.0f - ws) * bg;
+        // background: one scalar, or per ray (train_utils.py:495-496, background == 'random')
+        float bgr = bg, bgg = bg, bgb = bg;
+        if (x.bg_rays) { bgr = __ldg(x.bg_rays + (size_t)n * 3); bgg = __ldg(x.bg_rays + (size_t)n * 3 + 1); bgb = __ldg(x.bg_rays + (size_t)n * 3 + 2); }
+        const float ir = r + (1.0f - ws) * bgr, ig = g + (1.0f - ws) * bgg, ib = b + (1.0f - ws) * bgb;
         // loss_mode 0: MSE (train_utils.py:540-541).  loss_mode 1: the clipped, tone-curve weighted MSE of the raw/HDR path
         // (train_utils.py:529-536): c = min(1, pred * exposure), loss = mean (c - gt)^2 / (1e-3 + stop_grad(c))^2
-        const float tr = __ldg(target + (size_t)n * 3), tgn = __ldg(target + (size_t)n * 3 + 1), tb = __ldg(target + (size_t)n * 3 + 2);
-        float er, eg, eb, dr = 1.f, dg = 1.f, db = 1.f;     // residuals and d loss_c / d image_c = 2 * e_c * d_c / (3 N)
+        float tr = __ldg(target + (size_t)n * 3), tgn = __ldg(target + (size_t)n * 3 + 1), tb = __ldg(target + (size_t)n * 3 + 2);
+        if (x.target_alpha) {      // RGBA images: gt = rgb * a + bg * (1 - a)   (train_utils.py:504-505)
+            const float a = __ldg(x.target_alpha + n);
+            tr = tr * a + bgr * (1.f - a); tgn = tgn * a + bgg * (1.f - a); tb = tb * a + bgb * (1.f - a);
+        }
+        // per-channel weights of the loss: lossmult (Bayer mask of mosaiced raw data) and loss_weight (train_utils.py:515-536);
+        // the normaliser is sum(lossmult) (there: lossmult_tensor.sum()), handed in as its reciprocal, else 3 * live rays
+        float wr = 1.f, wgn = 1.f, wb = 1.f;
+        if (x.lossmult) { wr = __ldg(x.lossmult + (size_t)n * 3); wgn = __ldg(x.lossmult + (size_t)n * 3 + 1); wb = __ldg(x.lossmult + (size_t)n * 3 + 2); }
+        if (x.loss_weight) { wr *= __ldg(x.loss_weight + (size_t)n * 3); wgn *= __ldg(x.loss_weight + (size_t)n * 3 + 1); wb *= __ldg(x.loss_weight + (size_t)n * 3 + 2); }
+        const float inv_norm = x.inv_norm_dev ? __ldg(x.inv_norm_dev) : 1.0f / (3.0f * (float)n_live);
+        float er, eg, eb, dr = 1.f, dg = 1.f, db = 1.f;     // residuals and d loss_c / d image_c = 2 * w_c * e_c * d_c * inv_norm
         if (loss_mode == 1) {
             const float ex = exposure ? __ldg(exposure + n) : 1.f;
             const float pr_ = ir * ex, pg_ = ig * ex, pb_ = ib * ex;
@@ -814,14 +845,24 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
         } else {
             er = ir - tr; eg = ig - tgn; eb = ib - tb;
         }
+        // entropy regulariser on the opacity (train_utils.py:553-556): lambda * mean_n H2(clamp(ws, 1e-5, 1 - 1e-5))
+        float ent = 0.f, g_ent = 0.f;
+        if (x.lambda_entropy > 0.f) {
+            const float wc = fminf(fmaxf(ws, 1e-5f), 1.0f - 1e-5f);
+            ent = -wc * log2f(wc) - (1.f - wc) * log2f(1.f - wc);
+            if (ws > 1e-5f && ws < 1.0f - 1e-5f) g_ent = x.lambda_entropy * (log2f(1.f - wc) - log2f(wc)) / (float)n_live;
+        }
         if (lane == 0) {
             if (image_out) { image_out[(size_t)n * 3] = ir; image_out[(size_t)n * 3 + 1] = ig; image_out[(size_t)n * 3 + 2] = ib; }
-            ray_loss[n] = (er * er + eg * eg + eb * eb) * (1.0f / 3.0f);
+            ray_loss[n] = (wr * er * er + wgn * eg * eg + wb * eb * eb) * inv_norm;
+            if (x.entropy_ray) x.entropy_ray[n] = ent;
+            if (x.weights_sum_out) x.weights_sum_out[n] = ws;
+            if (x.depth_out) x.depth_out[n] = d;
         }
         if (has) {
-            const float gs = loss_scale * 2.0f / (3.0f * (float)N);
-            const float gi_r = gs * er * dr, gi_g = gs * eg * dg, gi_b = gs * eb * db;
-            const float g_ws = -bg * (gi_r + gi_g + gi_b);
+            const float gs = loss_scale * 2.0f * inv_norm;
+            const float gi_r = gs * wr * er * dr, gi_g = gs * wgn * eg * dg, gi_b = gs * wb * eb * db;
+            const float g_ws = -(bgr * gi_r + bgg * gi_g + bgb * gi_b) + loss_scale * g_ent;
             float T = 1.0f, r0 = 0, g0 = 0, b0 = 0, ws0 = 0;
             uint32_t base = 0;
             for (; base < count; base += 32) {
@@ -875,10 +916,17 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
     __syncthreads();
     if (!s_last || threadIdx.x >= 32) return;
     __threadfence();
-    float acc = 0.f;
+    float acc = 0.f, acc_e = 0.f;
     for (uint32_t i = lane; i < N; i += 32) acc += __ldcg(ray_loss + i);
+    if (x.entropy_ray) for (uint32_t i = lane; i < N; i += 32) acc_e += __ldcg(x.entropy_ray + i);
     acc = warp_sum(acc);
-    if (lane == 0) { loss_out[0] = acc / (float)N; *ticket = 0; }
+    acc_e = warp_sum(acc_e);
+    if (lane == 0) {
+        const float e = x.lambda_entropy * acc_e / (float)n_live;
+        loss_out[0] = acc + e;                 // ray_loss already carries the normaliser
+        if (x.parts_out) { x.parts_out[0] = acc; x.parts_out[1] = e; }
+        *ticket = 0;
+    }
 }
 
 // Segmented sums of _march_rays_train.backward (raymarching/raymarching.py:319-329); one warp per ray.
@@ -1212,7 +1260,7 @@ extern "C" int ngp_march_rays_train_count(const float* rays_o, const float* rays
     if (t_scratch)
         march_train_count_coop_kernel<false><<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
             rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, t_scratch,
-            nullptr, 0.f, nullptr, nullptr, 0u);
+            nullptr, 0.f, nullptr, nullptr, 0u, nullptr, nullptr);
     else
         march_train_count_kernel<<<div_up(N, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
             rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter);
@@ -1231,7 +1279,24 @@ extern "C" int ngp_march_rays_train_count_aabb(const float* rays_o, const float*
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024 || cap == 0) return NGP_ERR_BAD_ARG;
     march_train_count_coop_kernel<true><<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nullptr, nullptr, noises, rays, counter,
-        t_scratch, aabb, min_near, nears_out, fars_out, cap);
+        t_scratch, aabb, min_near, nears_out, fars_out, cap, nullptr, nullptr);
+    return finish_launch();
+}
+
+extern "C" int ngp_march_rays_train_count_ex(const float* rays_o, const float* rays_d, const float* aabb, float min_near,
+                                             const float* cam_near_far, const int32_t* n_rays_dev, const uint8_t* grid, float bound,
+                                             int contract, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                             const float* noises, uint32_t cap, float* nears_out, float* fars_out, int32_t* rays,
+                                             int32_t* counter, float* t_scratch, ngp_stream_t stream) {
+    if (!counter) return NGP_ERR_NULL;
+    if (N == 0) return NGP_OK;
+    if (!rays_o || !rays_d || !aabb || !grid || !noises || !rays || !t_scratch) return NGP_ERR_NULL;
+    if ((nears_out != nullptr) != (fars_out != nullptr)) return NGP_ERR_NULL;
+    if (max_steps == 0 || H == 0 || C == 0 || H > 1024 || cap == 0) return NGP_ERR_BAD_ARG;
+    if (cam_near_far && !aligned(cam_near_far, 4)) return NGP_ERR_ALIGN;
+    march_train_count_coop_kernel<true><<<div_up(N, kCoopWarps), kCoopWarps * 32, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, grid, bound, contract != 0, dt_gamma, max_steps, N, C, H, nullptr, nullptr, noises, rays, counter,
+        t_scratch, aabb, min_near, nears_out, fars_out, cap, cam_near_far, n_rays_dev);
     return finish_launch();
 }
 
@@ -1307,9 +1372,29 @@ extern "C" int ngp_composite_train_mse(const float* sigmas, const float* rgbs, c
     if (M > 0 && (!sigmas || !rgbs || !ts || !grad_sigmas || !grad_rgbs)) return NGP_ERR_NULL;
     if (M > 0 && !aligned(ts, 8)) return NGP_ERR_ALIGN;
     if (loss_mode < 0 || loss_mode > 1) return NGP_ERR_BAD_ARG;
+    ngp_loss_opts none = {};
     composite_train_mse_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, ts, rays, M, m_dev, N, T_thresh, bg_color, target, loss_scale, image_out, ray_loss, loss_out, ticket,
-        grad_sigmas, grad_rgbs, loss_mode, exposure);
+        grad_sigmas, grad_rgbs, loss_mode, exposure, none);
+    return finish_launch();
+}
+
+extern "C" int ngp_composite_train_loss(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays, uint32_t M,
+                                        const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color, const float* target,
+                                        float loss_scale, float* image_out, float* ray_loss, float* loss_out, int32_t* ticket,
+                                        float* grad_sigmas, float* grad_rgbs, int loss_mode, const float* exposure,
+                                        const ngp_loss_opts* opts, ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    if (!rays || !target || !ray_loss || !loss_out || !ticket) return NGP_ERR_NULL;
+    if (M > 0 && (!sigmas || !rgbs || !ts || !grad_sigmas || !grad_rgbs)) return NGP_ERR_NULL;
+    if (M > 0 && !aligned(ts, 8)) return NGP_ERR_ALIGN;
+    if (loss_mode < 0 || loss_mode > 1) return NGP_ERR_BAD_ARG;
+    ngp_loss_opts x = {};
+    if (opts) x = *opts;
+    if (x.lambda_entropy < 0.f || (x.lambda_entropy > 0.f && !x.entropy_ray)) return NGP_ERR_BAD_ARG;
+    composite_train_mse_kernel<<<div_up(N * 32u, kCompThreads), kCompThreads, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, ts, rays, M, m_dev, N, T_thresh, bg_color, target, loss_scale, image_out, ray_loss, loss_out, ticket,
+        grad_sigmas, grad_rgbs, loss_mode, exposure, x);
     return finish_launch();
 }
 
@@ -1365,4 +1450,25 @@ extern "C" int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_aliv
     compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace);
     compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, alive_out, n_out);
     return finish_launch();
+}
+
+namespace ngp {
+namespace {
+__global__ void adaptive_num_rays_kernel(int* __restrict__ n_rays, const int* __restrict__ m_dev, uint32_t target_points, uint32_t n_max) {
+    const int m = *m_dev, n = *n_rays;
+    if (m <= 0) return;                                // no sample at all: keep the count (the reference would divide by zero)
+    // int(round((num_points / outputs['num_points']) * num_rays)) in double like python, banker's rounding like round()
+    const double v = ((double)target_points / (double)m) * (double)n;
+    const long long r = llrint(v);
+    *n_rays = (int)max(1ll, min((long long)n_max, r));
+}
+}  // namespace
+}  // namespace ngp
+
+extern "C" int ngp_adaptive_num_rays(int32_t* n_rays_dev, const int32_t* m_dev, uint32_t target_points, uint32_t n_max,
+                                     ngp_stream_t stream) {
+    if (!n_rays_dev || !m_dev) return NGP_ERR_NULL;
+    if (n_max == 0 || target_points == 0) return NGP_ERR_BAD_ARG;
+    ngp::adaptive_num_rays_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_rays_dev, m_dev, target_points, n_max);
+    return ngp::finish_launch();
 }

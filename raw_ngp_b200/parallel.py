@@ -30,3 +30,15 @@ def shard_range(n, rank, world):
     base, rem = divmod(int(n), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def interleaved_tiles(n, rank, world, tile=4096):
+    """Ray ids of `rank` when the n rays of a frame are dealt out in tiles of `tile` consecutive rays, round robin: every rank
+    gets the same mix of image regions (rays that hit the scene and rays that miss it), unlike contiguous N / world slices whose
+    edge ranks see mostly background.  Returns an int64 tensor (CPU); concatenating the ranks' results in this order and
+    scattering by id restores the frame.  No collective is involved."""
+    n, world, tile = int(n), int(world), int(tile)
+    ids = torch.arange(n, dtype=torch.int64)
+    if world == 1:
+        return ids
+    return ids[(ids // tile) % world == rank]

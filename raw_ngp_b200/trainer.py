@@ -182,7 +182,18 @@ class FusedTrainStep:
 
     def __init__(self, model, n_rays, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, loss_scale=128.0, max_samples=None,
                  process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True, loss="mse",
-                 ray_grads=False, pose_optimizer=None, poses=None, pose_lr=1e-3, pose_betas=(0.9, 0.999), pose_eps=1e-8):
+                 ray_grads=False, pose_optimizer=None, poses=None, pose_lr=1e-3, pose_betas=(0.9, 0.999), pose_eps=1e-8,
+                 rgba_targets=False, lossmult=False, loss_weight=False, cam_near_far=False, lambda_entropy=0.0,
+                 adaptive_num_rays=False, num_points=2 ** 18):
+        """The options after pose_eps switch on the remaining pieces of Trainer.train_step (nerf/train_utils.py:481-568), each a
+        static device buffer read by the captured kernels (fill them through set_rays):
+          bg_color="random"   per-ray random background, redrawn on the device every step (:495-496)
+          rgba_targets        targets carry alpha: gt = rgb * a + bg * (1 - a) (:503-506)
+          lossmult, loss_weight  [N, 3] Bayer mask / ground-truth weighting of the HDR loss, normalised by sum(lossmult) (:515-536)
+          cam_near_far        [N, 2] per-ray camera clip of near / far (renderer.py:529-533)
+          lambda_entropy      opacity entropy regulariser (:553-556)
+          adaptive_num_rays   the number of live rays of the next batch follows num_points / samples of this one (:563-564);
+                              n_rays is then the capacity, the live count stays on the device (self.n_rays_dev)"""
         import ctypes
         from . import field as _field
         from .ffmlp import _pad16
@@ -203,7 +214,12 @@ class FusedTrainStep:
             raise ValueError("loss must be 'mse' or 'hdr' (nerf/train_utils.py:512-541)")
         self.loss_mode = 0 if loss == "mse" else 1
         self.perturb = perturb
-        self.bg_color = float(bg_color)
+        self.random_bg = isinstance(bg_color, str)
+        if self.random_bg and bg_color != "random":
+            raise ValueError("bg_color must be a number or 'random'")
+        self.bg_color = 0.0 if self.random_bg else float(bg_color)
+        self.lambda_entropy = float(lambda_entropy)
+        self.adaptive, self.num_points = bool(adaptive_num_rays), int(num_points)
         self.loss_scale = float(loss_scale)
         self.update_extra_interval = update_extra_interval
         self.global_step = 0
@@ -318,6 +334,20 @@ class FusedTrainStep:
         self.rays_ldir = torch.zeros(N, 3, **f32) if self.rfield else None
         self.noises = torch.zeros(N, **f32)
         self.exposure = torch.ones(N, **f32)          # per-ray exposure of the HDR loss (train_utils.py:514)
+        self.bg_rays = torch.zeros(N, 3, **f32) if self.random_bg else None
+        self.target_alpha = torch.ones(N, **f32) if rgba_targets else None
+        self.lossmult = torch.ones(N, 3, **f32) if lossmult else None
+        self.loss_weight = torch.ones(N, 3, **f32) if loss_weight else None
+        self.inv_norm = torch.full((1,), 1.0 / (3 * N), **f32) if lossmult else None
+        self.cam_near_far = torch.tensor([0.0, 1e9], **f32).repeat(N, 1).contiguous() if cam_near_far else None
+        self.n_rays_dev = torch.full((1,), N, device=dev, dtype=torch.int32) if self.adaptive else None
+        self.entropy_ray = torch.zeros(N, **f32) if self.lambda_entropy > 0 else None
+        self.weights_sum, self.depth = torch.zeros(N, **f32), torch.zeros(N, **f32)
+        self.loss_parts = torch.zeros(2, **f32)
+        P0 = lambda t: None if t is None else t.data_ptr()
+        self._loss_opts = _lib.LossOpts(P0(self.bg_rays), P0(self.target_alpha), P0(self.lossmult), P0(self.loss_weight), P0(self.inv_norm),
+                                        P0(self.n_rays_dev), self.lambda_entropy, P0(self.entropy_ray), P0(self.weights_sum),
+                                        P0(self.depth), P0(self.loss_parts))
         self.rays = torch.zeros(N, 2, device=dev, dtype=torch.int32)
         self.counter = torch.zeros(4, device=dev, dtype=torch.int32)
         self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -384,11 +414,13 @@ class FusedTrainStep:
                       self.se3.shape[0], P(self.rays_o), P(self.rays_d), st)
         if self.perturb:
             self.noises.uniform_()
+        if self.random_bg:
+            self.bg_rays.uniform_()          # torch.rand(N, 3) of train_utils.py:496
         aabb = m.aabb_train
-        _lib.call("ngp_march_rays_train_count_aabb", P(self.rays_o), P(self.rays_d), P(aabb), float(m.min_near),
-                  P(m.density_bitfield), float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma), int(opt.max_steps),
-                  N, int(m.cascade), int(m.grid_size), P(self.noises), cap, None, None, P(self.rays), P(self.counter),
-                  P(self.t_scratch), st)
+        _lib.call("ngp_march_rays_train_count_ex", P(self.rays_o), P(self.rays_d), P(aabb), float(m.min_near), P(self.cam_near_far),
+                  P(self.n_rays_dev), P(m.density_bitfield), float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma),
+                  int(opt.max_steps), N, int(m.cascade), int(m.grid_size), P(self.noises), cap, None, None, P(self.rays),
+                  P(self.counter), P(self.t_scratch), st)
         _lib.call("ngp_march_rays_train_write", P(self.rays_o), P(self.rays_d), P(self.rays_ldir), P(m.density_bitfield),
                   float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma), int(opt.max_steps), N, int(m.cascade),
                   int(m.grid_size), None, None, None, P(self.rays), cap, self._m_dev, P(self.t_scratch), P(self.xyzs),
@@ -405,9 +437,12 @@ class FusedTrainStep:
         w1, w2 = self._ptrs(self._w_lp_views[:3]), self._ptrs(self._w_lp_views[3:])
         a1, a2 = self._ptrs(self.acts1), self._ptrs(self.acts2)
         def composite():
-            _lib.call("ngp_composite_train_mse", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
+            _lib.call("ngp_composite_train_loss", P(self.sigma), P(self.rgb), P(self.ts), P(self.rays), cap, self._m_dev, N,
                       float(opt.T_thresh), self.bg_color, P(self.target), self.loss_scale, P(self.image), P(self.ray_loss),
-                      P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), self.loss_mode, P(self.exposure), st)
+                      P(self.loss), P(self.ticket), P(self.d_sigma), P(self.d_rgb), self.loss_mode, P(self.exposure),
+                      ct.byref(self._loss_opts), st)
+            if self.adaptive:      # the live ray count of the NEXT batch (train_utils.py:563-564), from this step's sample count
+                _lib.call("ngp_adaptive_num_rays", P(self.n_rays_dev), self.counter.data_ptr(), self.num_points, N, st)
 
         dw1, dw2 = self._ptrs(self._w_grad_views[:3]), self._ptrs(self._w_grad_views[3:])
         if self.ws:
@@ -627,28 +662,52 @@ class FusedTrainStep:
             out.setdefault(n, []).append(e0.elapsed_time(e1))
         return {n: sum(v) / iters for n, v in out.items()}
 
-    def set_rays(self, rays_o, rays_d, target_rgb, rays_ldir=None, exposure=None):
-        """Copies the step's inputs into the static buffers (pinned host tensors are copied asynchronously)."""
+    def set_rays(self, rays_o, rays_d, target_rgb, rays_ldir=None, exposure=None, **extra):
+        """Copies the step's inputs into the static buffers (pinned host tensors are copied asynchronously).  With rgba_targets
+        target_rgb is [N, 4] (or pass target_alpha=[N]); extra: lossmult, loss_weight [N, 3], cam_near_far [N, 2]."""
+        if target_rgb is not None and target_rgb.shape[-1] == 4:
+            if self.target_alpha is None:
+                raise RuntimeError("FusedTrainStep: RGBA targets need rgba_targets=True")
+            extra.setdefault("target_alpha", target_rgb[..., 3])
+            target_rgb = target_rgb[..., :3]
         for dst, src in ((self.rays_o, rays_o), (self.rays_d, rays_d), (self.target, target_rgb), (self.rays_ldir, rays_ldir),
                          (self.exposure, exposure)):
             if dst is None or src is None or (src.is_cuda and src.data_ptr() == dst.data_ptr()):
                 continue
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
+        self._set_extra(extra)
 
-    def set_camera_rays(self, cam_idx, dirs_cam, target_rgb, exposure=None):
+    def _set_extra(self, extra):
+        for name, src in extra.items():
+            if name not in ("target_alpha", "lossmult", "loss_weight", "cam_near_far"):
+                raise TypeError(f"FusedTrainStep.set_rays: unknown input {name!r}")
+            dst = getattr(self, name)
+            if src is None:
+                continue
+            if dst is None:
+                raise RuntimeError(f"FusedTrainStep: {name} was not enabled at construction")
+            src = torch.as_tensor(src)
+            if name in ("lossmult", "loss_weight"):      # scalars and [N, 1] broadcast like torch.broadcast_to (train_utils.py:518)
+                src = torch.broadcast_to(src.to(dst.device, torch.float32), dst.shape)
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            if name == "lossmult":                       # the normaliser lossmult_tensor.sum() (train_utils.py:536), on the device
+                self.inv_norm.copy_(self.lossmult.sum().reciprocal().reshape(1))
+
+    def set_camera_rays(self, cam_idx, dirs_cam, target_rgb, exposure=None, **extra):
         """Pose mode: the step's rays as (camera index [N], camera-space pixel direction [N, 3]); rays_o / rays_d are produced
         on the device from the refined poses inside the captured step."""
         for dst, src in ((self.cam_idx, cam_idx), (self.dirs_cam, dirs_cam), (self.target, target_rgb), (self.exposure, exposure)):
             if src is None or (src.is_cuda and src.data_ptr() == dst.data_ptr()):
                 continue
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
+        self._set_extra(extra)
 
     @property
     def last_num_points(self):
         return int(self.counter[0].item())
 
     def step(self, rays_o=None, rays_d=None, target_rgb=None, rays_ldir=None, update_grid=True, exposure=None, cam_idx=None,
-             dirs_cam=None):
+             dirs_cam=None, **extra):
         """One optimisation step; returns the (unscaled) loss as a 1-element device tensor (overwritten by the next step).
         The parameter update of this step is applied at the start of the next call (or by flush()).
         Pose mode (pose_optimizer given): pass cam_idx / dirs_cam instead of rays_o / rays_d."""
@@ -657,9 +716,9 @@ class FusedTrainStep:
             self.flush()                       # the density queries of the occupancy update see the updated weights
             model.update_extra_state()
         if rays_o is not None:
-            self.set_rays(rays_o, rays_d, target_rgb, rays_ldir, exposure)
+            self.set_rays(rays_o, rays_d, target_rgb, rays_ldir, exposure, **extra)
         if cam_idx is not None:
-            self.set_camera_rays(cam_idx, dirs_cam, target_rgb, exposure)
+            self.set_camera_rays(cam_idx, dirs_cam, target_rgb, exposure, **extra)
         if self.feat_weights is not None and self._feat_annealing != model.annealing:
             # BARF window: computed on the host, one 128-byte copy (the torch expression is ~10 elementwise kernels)
             self._feat_host.copy_(torch.from_numpy(model._feat_weights_host()))

@@ -102,9 +102,12 @@ def test_backward_matches_reference(case, dtype, ref_grid):
         scale = ref_gx.abs().max().clamp(min=1e-6)
         torch.testing.assert_close(xr.grad / scale, ref_gx / scale, rtol=0, atol=2e-5)
     else:
-        # both sides accumulate in fp16 with atomics in arbitrary order
+        # both sides accumulate in fp16 with atomics in arbitrary order: the reference does not reproduce itself run to run
+        # (max ~ one fp16 ulp of the largest sums on a handful of the 12 M entries, tests/test_gpu_oracle_step.py measures up to
+        # 2.7e-2 at configs[1] size), so the bound is on the mean, with a loose cap on the single worst entry
         scale = ref_ge.float().abs().max().clamp(min=1e-6)
-        torch.testing.assert_close(er.grad.float() / scale, ref_ge.float() / scale, rtol=0, atol=4e-3)
+        err = (er.grad.float() - ref_ge.float()).abs() / scale
+        assert err.max().item() < 1e-2 and err.mean().item() < 1e-5, (err.max().item(), err.mean().item())
         # the reference accumulates dy_dx and the input gradient in half (gridencoder.cu:367-377); ours is fp32
         scale = ref_gx.abs().max().clamp(min=1e-6)
         err = ((xr.grad - ref_gx).abs() / scale)
@@ -197,3 +200,30 @@ def test_module_forward_backward_full_size(ref_grid):
     enc2 = GridEncoder(desired_resolution=2048).cuda()
     enc2.embeddings.data = (enc.embeddings.data.float() * 0.5).half()
     torch.testing.assert_close(enc2(x).float(), out.detach().float() * 0.5, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16], ids=["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("case", [dict(), dict(L=8, log2T=14), dict(gridtype="tiled", log2T=15), dict(L=32, log2T=12, desired=512),
+                                  dict(interpolation="smoothstep", align_corners=True)],
+                         ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "default")
+def test_forward_tile_kernel_equals_point_level_kernels(case, dtype):
+    """The tile kernel (128 points per CTA, thread = (point, level group), rows assembled in shared memory) against the
+    one-thread-per-(point, level) kernel that is itself pinned to the reference above: ragged B, max_level < L (zero fill),
+    out-of-range points, all three table dtypes."""
+    import numpy as np
+    from raw_ngp_b200 import _lib
+    enc, x, emb, off = _setup(dtype=dtype, B=20001, **case)
+    L = enc.num_levels
+    S = float(np.log2(enc.per_level_scale))
+    base_flags = _lib.NGP_GRID_REF_ROUNDING if dtype == torch.float16 else 0
+    for max_level in (L, 7, 1):
+        outs = []
+        for flags in (base_flags, base_flags | _lib.NGP_GRID_POINT_LEVEL_KERNELS):
+            out = torch.full((x.shape[0], L * 2), 7.0, device="cuda", dtype=dtype)
+            _lib.call("ngp_grid_encode_forward", x.data_ptr(), emb.data_ptr(), off.data_ptr(), out.data_ptr(), x.shape[0], 3, 2, L, max_level,
+                      S, enc.base_resolution, None, enc.gridtype_id, int(enc.align_corners), enc.interp_id, _lib.dtype_id(dtype), flags,
+                      _lib.stream())
+            outs.append(out)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), (case, dtype, max_level, (outs[0] != outs[1]).float().mean().item())
+        assert (outs[0][:, 2 * max_level:] == 0).all() and outs[0][64:, :2].abs().max() > 0

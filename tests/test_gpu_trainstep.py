@@ -351,3 +351,85 @@ def test_composite_hdr_loss_kernel_matches_reference_lines():
     torch.testing.assert_close(image, pred, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(loss.item(), float(z["loss"]), rtol=1e-5)
     torch.testing.assert_close(d_rgb / scale, torch.from_numpy(z["d_pred"]).to(dev), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["hdr_random_rgba_bayer_gaussian_entropy", "hdr_white_planck", "hdr_black_hanning_bayer", "mse_random_rgba_entropy"])
+def test_composite_train_loss_kernel_matches_reference_train_step_lines(case):
+    """ngp_composite_train_loss (per-ray background, RGBA ground truth, lossmult / loss_weight, entropy regulariser) against
+    tests/golden/train_step_loss.npz = the reference's own train_step lines (nerf/train_utils.py:494-557) executed on seeded inputs
+    by tools/make_golden_trainstep.py.  Every ray has ONE sample with alpha = the fixture's weights_sum and the fixture's colour, so
+    image, loss and the gradients with respect to the composited colour / opacity map one to one onto the kernel's outputs."""
+    import ctypes
+    import os
+    import numpy as np
+    from raw_ngp_b200 import _lib
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_loss.npz"))
+    f = lambda k: torch.from_numpy(np.ascontiguousarray(z[f"{case}/{k}"])).cuda()
+    colour, ws, images, bg, lossmult, loss_weight = f("colour"), f("ws"), f("images"), f("bg"), f("lossmult"), f("loss_weight")
+    exposure, d_comp, d_ws = f("exposure"), f("d_comp"), f("d_ws")
+    hdr, lam = int(z[f"{case}/hdr"]), float(z[f"{case}/lambda_entropy"])
+    N, dev, dt = ws.shape[0], "cuda", 0.01
+    sigma = (-torch.log1p(-ws.double().clamp(max=1 - 1e-12)) / dt).float()
+    sigma[ws >= 1.0] = 1e8
+    ts = torch.stack([torch.ones(N, device=dev), torch.full((N,), dt, device=dev)], dim=-1).contiguous()
+    rays = torch.stack([torch.arange(N, device=dev), torch.ones(N, device=dev)], dim=-1).int().contiguous()
+    image, ray_loss, loss = torch.zeros(N, 3, device=dev), torch.zeros(N, device=dev), torch.zeros(1, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_sigma, d_rgb = torch.zeros(N, device=dev), torch.zeros(N, 3, device=dev)
+    ent, wso, parts = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(2, device=dev)
+    inv_norm = lossmult.sum().reciprocal().reshape(1)
+    target = images[:, :3].contiguous()
+    alpha_t = images[:, 3].contiguous() if images.shape[1] == 4 else None
+    P = _lib.ptr
+    opts = _lib.LossOpts(P(bg), P(alpha_t), P(lossmult), P(loss_weight), P(inv_norm), None, lam, P(ent), P(wso), None, P(parts))
+    scale = 64.0
+    _lib.call("ngp_composite_train_loss", P(sigma), P(colour), P(ts), P(rays), N, None, N, 1e-8, 0.0, P(target), scale, P(image), P(ray_loss),
+              P(loss), P(ticket), P(d_sigma), P(d_rgb), hdr, P(exposure), ctypes.byref(opts), _lib.stream())
+    torch.cuda.synchronize()
+    alpha = 1 - torch.exp(-sigma * dt)
+    torch.testing.assert_close(wso, ws, rtol=1e-5, atol=2e-7)
+    np.testing.assert_allclose(loss.item(), float(z[f"{case}/loss"]), rtol=2e-5)
+    np.testing.assert_allclose(parts.sum().item(), loss.item(), rtol=1e-6)
+    # d loss / d (composited colour) = grad_rgbs / w ;  d loss / d sigma = dt (1 - alpha) (sum_c dL/dcomp_c colour_c + dL/dws)
+    g_scale = d_comp.abs().max()
+    torch.testing.assert_close(d_rgb / scale, d_comp * alpha[:, None], rtol=1e-4, atol=1e-6 * g_scale.item())
+    exp_sigma = dt * (1 - alpha) * ((d_comp * colour).sum(-1) + d_ws)
+    torch.testing.assert_close(d_sigma / scale, exp_sigma, rtol=2e-4, atol=1e-6 * exp_sigma.abs().max().item())
+
+
+def test_fused_step_extras_cam_near_far_adaptive_rays_and_random_bg():
+    """cam_near_far clamps the marched interval like renderer.py:529-533; the adaptive ray count follows
+    int(round(num_points / samples * num_rays)) (train_utils.py:563-564) on the device; bg_color='random' draws a per-ray background;
+    rays beyond the live count get no samples, no loss, no gradient."""
+    N = 1024
+    model, o, d, tgt = _scene(N)
+    fs = FusedTrainStep(model, N, perturb=False, use_graph=False, cam_near_far=True, adaptive_num_rays=True, num_points=20000,
+                        bg_color="random", lambda_entropy=1e-3)
+    cnf = torch.tensor([1.7, 2.2]).repeat(N, 1).cuda()
+    fs.set_rays(o, d, tgt, cam_near_far=cnf)
+    fs._launch_forward_backward()
+    torch.cuda.synchronize()
+    M0 = fs.last_num_points
+    t = fs.ts[:M0, 0]
+    assert M0 > 0 and t.min().item() >= 1.7 and (t - fs.ts[:M0, 1]).max().item() < 2.2
+    ref = model
+    ref.train()
+    out = ref.render(o, d, bg_color=0, perturb=False, cam_near_far=cnf)
+    assert out["num_points"] == M0
+    torch.testing.assert_close(fs.weights_sum, out["weights_sum"].float(), rtol=2e-3, atol=2e-4)
+    assert fs.bg_rays.min().item() >= 0 and 0.3 < fs.bg_rays.mean().item() < 0.7
+    n1 = int(fs.n_rays_dev.item())
+    assert n1 == max(1, min(N, int(round((20000 / M0) * N))))
+    fs.table_grad.zero_()
+    fs._launch_forward_backward()
+    torch.cuda.synchronize()
+    counts = fs.rays[:, 1]
+    assert (counts[n1:] == 0).all() and counts[:n1].sum().item() == fs.last_num_points
+    assert (fs.image[n1:] == 0).all() and torch.isfinite(fs.loss).all()
+    # graph replay trains with all the options on
+    g = FusedTrainStep(_scene(N)[0], N, use_graph=True, cam_near_far=True, adaptive_num_rays=True, num_points=20000, bg_color="random",
+                       lambda_entropy=1e-3, rgba_targets=True, lossmult=True, loss_weight=True, loss="hdr")
+    rgba = torch.cat([tgt, torch.rand(N, 1, device="cuda")], dim=-1)
+    ls = [g.step(o, d, rgba, update_grid=False, cam_near_far=cnf, lossmult=torch.ones(N, 3, device="cuda"), loss_weight=1.0).item() for _ in range(8)]
+    g.flush()
+    assert all(l == l for l in ls) and 1 <= int(g.n_rays_dev.item()) <= N
