@@ -250,6 +250,7 @@ typedef struct ngp_loss_opts {
     float* weights_sum_out;      /* [N]   composited opacity (renderer results['weights_sum']) */
     float* depth_out;            /* [N]   composited depth (results['depth']) */
     float* parts_out;            /* [2]   data term and entropy term of loss_out */
+    const float* loss_scale_dev; /* [1]   GradScaler scale kept on the device (ngp_grad_scaler_update); NULL: the loss_scale argument */
 } ngp_loss_opts;
 
 /* composite_rays_train forward + background blend + MSE loss + composite_rays_train backward for one training step
@@ -266,7 +267,7 @@ int ngp_composite_train_mse(const float* sigmas, const float* rgbs, const float*
                             float* loss_out, int32_t* ticket, float* grad_sigmas, float* grad_rgbs,
                             int loss_mode, const float* exposure, ngp_stream_t stream);
 
-/* ngp_composite_train_mse with the optional terms of ngp_loss_opts (opts may be NULL). */
+/* ngp_composite_train_mse with the optional terms of the ngp_loss_opts structure; `opts` may be NULL. */
 int ngp_composite_train_loss(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
                              uint32_t M, const int32_t* m_dev, uint32_t N, float T_thresh, float bg_color,
                              const float* target, float loss_scale, float* image_out, float* ray_loss,
@@ -515,6 +516,14 @@ int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int 
  * CUDA graph.  ngp_adam_step_counter increments *step_dev unless *found_inf_dev != 0 (a skipped GradScaler step is not
  * counted, as in torch). */
 int ngp_adam_step_counter(int32_t* step_dev, const float* found_inf_dev, ngp_stream_t stream);
+
+/* torch.amp.GradScaler.update() without a host round trip (nerf/train_utils.py:404, 897-904: the reference trains under a
+ * dynamic GradScaler).  scale_dev [1], inv_scale_dev [1] = 1 / (scale * world) as the fused optimizers read it, state_dev
+ * int32[2] = {clean steps since the last change, skipped steps so far}; found_inf_a / found_inf_b: the inf / nan flags of the
+ * step (either may be NULL).  inf / nan: scale *= backoff_factor; growth_interval clean steps in a row: scale *= growth_factor. */
+int ngp_grad_scaler_update(float* scale_dev, float* inv_scale_dev, int32_t* state_dev, const float* found_inf_a,
+                           const float* found_inf_b, float growth_factor, float backoff_factor, int growth_interval,
+                           uint32_t world, ngp_stream_t stream);
 
 /* Data parallel over NVLink peer memory: reduce-scatter + Adam + all-gather in one kernel.  peer_grads[r] /
  * peer_params_lp[r] (host arrays of `world` device pointers, r = rank) are the SAME buffer on every rank -- gradient

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ngp_pose_rays_forward": [_p, _p, _u32, _p, _p, _u32, _u32, _p, _p, _p],
     "ngp_pose_rays_backward": [_p, _p, _p, _p, _u32, _p, _p, _u32, _u32, _p, _p],
     "ngp_adam_step_counter": [_p, _p, _p],
+    "ngp_grad_scaler_update": [_p, _p, _p, _p, _p, _f32, _f32, _i, _u32, _p],
     "ngp_dp_fused_adam": [_p, _i, _p, _i, _u32, _u32, _p, _p, _p, c_uint64, c_uint64, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
     "ngp_dp_publish_flag": [_p, _p, _u32, _u32, _p],
     "ngp_dp_merge_flags": [_p, _u32, _p, _p],
@@ -86,7 +87,7 @@ _SPECIAL = {
 class LossOpts(ctypes.Structure):
     """ngp_loss_opts of include/ngp_b200.h (optional terms of ngp_composite_train_loss)."""
     _fields_ = [("bg_rays", _p), ("target_alpha", _p), ("lossmult", _p), ("loss_weight", _p), ("inv_norm_dev", _p), ("n_rays_dev", _p),
-                ("lambda_entropy", _f32), ("entropy_ray", _p), ("weights_sum_out", _p), ("depth_out", _p), ("parts_out", _p)]
+                ("lambda_entropy", _f32), ("entropy_ray", _p), ("weights_sum_out", _p), ("depth_out", _p), ("parts_out", _p), ("loss_scale_dev", _p)]
 
 
 _lib = None

@@ -35,6 +35,24 @@ static inline int finish_launch() {
 template <typename T>
 __host__ __device__ __forceinline__ T div_up(T a, T b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: the largest size configured so far is
+// cached per device (a process that drives several GPUs from one thread must set it on each of them).
+constexpr int kMaxDevices = 64;
+struct SmemCache { uint32_t bytes[kMaxDevices]; };
+template <typename F>
+static inline int ensure_dynamic_smem(F kernel, uint32_t smem_bytes, SmemCache& cache) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_last_cuda_error(cudaGetLastError()); return NGP_ERR_CUDA; }
+    const bool cached = dev >= 0 && dev < kMaxDevices;
+    if (cached && smem_bytes <= cache.bytes[dev]) return NGP_OK;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+        set_last_cuda_error(cudaGetLastError());
+        return NGP_ERR_CUDA;
+    }
+    if (cached) cache.bytes[dev] = smem_bytes;
+    return NGP_OK;
+}
+
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // ---- scalar conversions -------------------------------------------------------------------

@@ -439,15 +439,8 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
 #define NGP_LAUNCH_FWD(LD)                                                                                                \
     {                                                                                                                     \
-        static thread_local uint32_t configured = 0;                                                                      \
-        if (smem_bytes > configured) {                                                                                    \
-            if (cudaFuncSetAttribute(field_forward_density_kernel<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                     (int)smem_bytes) != cudaSuccess) {                                                   \
-                set_last_cuda_error(cudaGetLastError());                                                                  \
-                return NGP_ERR_CUDA;                                                                                      \
-            }                                                                                                             \
-            configured = smem_bytes;                                                                                      \
-        }                                                                                                                 \
+        static thread_local SmemCache cache = {};                                                                         \
+        if (const int rc = ensure_dynamic_smem(field_forward_density_kernel<LD>, smem_bytes, cache)) return rc;           \
         field_forward_density_kernel<LD><<<grid, kFieldThreads, smem_bytes, st>>>(xyzs, dirs, ldirs, g, p, M, (__half*)enc_out,   \
                                                                           sigma_out, (__half*)in2, ld2, density_act, beta, \
                                                                           a_off, ctrl_off, m_dev);                        \
@@ -494,14 +487,8 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     const uint32_t last_in_off = in_bytes - kTile * dims[n_layers - 1] * 2;
     const uint32_t smem_bytes = std::max<uint32_t>(ctrl_off + kCtrlPlans + 2 * kMaxLayers * sizeof(MmaPlan), last_in_off + 18 * kPanel);
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
-    static thread_local uint32_t configured = 0;
-    if (smem_bytes > configured) {
-        if (cudaFuncSetAttribute(field_backward_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
-            set_last_cuda_error(cudaGetLastError());
-            return NGP_ERR_CUDA;
-        }
-        configured = smem_bytes;
-    }
+    static thread_local SmemCache cache = {};
+    if (const int rc = ensure_dynamic_smem(field_backward_density_kernel, smem_bytes, cache)) return rc;
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
     field_backward_density_kernel<<<grid, kBwdThreads, smem_bytes, (cudaStream_t)stream>>>(
         xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,

@@ -556,16 +556,9 @@ extern "C" int ngp_field_backward_full(const float* xyzs, const float* d_sigma, 
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
     a.M = M; a.m_dev = m_dev; a.grad_table = (__half*)grad_table;
     a.density_act = density_act; a.color_act = color_act; a.beta = beta;
-    static thread_local uint32_t configured[2] = {0, 0};
-    if (smem_bytes > configured[ig]) {
-        const cudaError_t e = ig ? cudaFuncSetAttribute(field_backward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
-                                 : cudaFuncSetAttribute(field_backward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) {
-            set_last_cuda_error(cudaGetLastError());
-            return NGP_ERR_CUDA;
-        }
-        configured[ig] = smem_bytes;
-    }
+    static thread_local SmemCache cache[2] = {};
+    if (const int rc = ig ? ensure_dynamic_smem(field_backward_ws_kernel<true>, smem_bytes, cache[1])
+                          : ensure_dynamic_smem(field_backward_ws_kernel<false>, smem_bytes, cache[0])) return rc;
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs);
     if (ig) field_backward_ws_kernel<true><<<grid, kBwsThreads, smem_bytes, (cudaStream_t)stream>>>(a);
     else field_backward_ws_kernel<false><<<grid, kBwsThreads, smem_bytes, (cudaStream_t)stream>>>(a);

@@ -379,15 +379,8 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs);
 #define NGP_LAUNCH_WS(LD, DY)                                                                                               \
     {                                                                                                                       \
-        static thread_local uint32_t configured = 0;                                                                        \
-        if (smem_bytes > configured) {                                                                                      \
-            if (cudaFuncSetAttribute(field_forward_ws_kernel<LD, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                     (int)smem_bytes) != cudaSuccess) {                                                     \
-                set_last_cuda_error(cudaGetLastError());                                                                    \
-                return NGP_ERR_CUDA;                                                                                        \
-            }                                                                                                               \
-            configured = smem_bytes;                                                                                        \
-        }                                                                                                                   \
+        static thread_local SmemCache cache = {};                                                                           \
+        if (const int rc = ensure_dynamic_smem(field_forward_ws_kernel<LD, DY>, smem_bytes, cache)) return rc;              \
         field_forward_ws_kernel<LD, DY><<<grid, kWsThreads, smem_bytes, st>>>(a);                                           \
     }
     if (dydx_out) { if (ldirs) NGP_LAUNCH_WS(true, true) else NGP_LAUNCH_WS(false, true) }

@@ -314,14 +314,8 @@ static int mlp_forward_impl(const void* x, uint32_t ldx, const void* const* weig
     const uint32_t a_off = (w_bytes + 127) & ~127u;
     const uint32_t ctrl_off = a_off + kTile * max_k * 2;
     const uint32_t smem_bytes = ctrl_off + 16;
-    static thread_local uint32_t configured = 0;
-    if (smem_bytes > configured) {
-        if (cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
-            set_last_cuda_error(cudaGetLastError());
-            return NGP_ERR_CUDA;
-        }
-        configured = smem_bytes;
-    }
+    static thread_local SmemCache cache = {};
+    if (const int rc = ensure_dynamic_smem(mlp_forward_kernel, smem_bytes, cache)) return rc;
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 4);   // 4 CTAs/SM: 4 x 128 TMEM columns
     mlp_forward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)x, ldx, p, M, (__half*)y, ldy, rgb_out, head_act, a_off, ctrl_off, m_dev);
@@ -382,14 +376,8 @@ static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint3
     const uint32_t last_in_off = in_bytes - kTile * dims[n_layers - 1] * 2;
     const uint32_t smem_bytes = std::max(ctrl_off + 16, last_in_off + 16 * kPanel + 2 * kPanel);
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
-    static thread_local uint32_t configured = 0;
-    if (smem_bytes > configured) {
-        if (cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
-            set_last_cuda_error(cudaGetLastError());
-            return NGP_ERR_CUDA;
-        }
-        configured = smem_bytes;
-    }
+    static thread_local SmemCache cache = {};
+    if (const int rc = ensure_dynamic_smem(mlp_backward_kernel, smem_bytes, cache)) return rc;
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
     mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,

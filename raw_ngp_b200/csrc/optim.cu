@@ -283,10 +283,42 @@ __global__ void adam_step_counter_kernel(int* __restrict__ step_dev, const float
     if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf_dev && *found_inf_dev != 0.f)) *step_dev += 1;
 }
 
+// torch.amp.GradScaler.update() on the device (grad_scaler.py: _amp_update_scale_): state = {scale, inv_scale = 1 / (scale *
+// world), growth tracker, skipped-step count}.  A step whose gradients held inf / nan halves the scale (backoff) and resets the
+// tracker; `growth_interval` clean steps in a row double it.
+__global__ void grad_scaler_update_kernel(float* __restrict__ scale, float* __restrict__ inv_scale, int* __restrict__ state,
+                                          const float* __restrict__ found_a, const float* __restrict__ found_b, float growth, float backoff,
+                                          int growth_interval, float world) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const bool bad = (found_a && *found_a != 0.f) || (found_b && *found_b != 0.f);
+    float sc = *scale;
+    if (bad) {
+        sc *= backoff;
+        state[0] = 0;
+        state[1] += 1;                       // skipped steps, for the host to look at whenever it likes
+    } else if (++state[0] >= growth_interval) {
+        const float grown = sc * growth;
+        if (isfinite(grown)) sc = grown;
+        state[0] = 0;
+    }
+    *scale = sc;
+    *inv_scale = 1.0f / (sc * world);
+}
+
 }  // namespace
 }  // namespace ngp
 
 using namespace ngp;
+
+extern "C" int ngp_grad_scaler_update(float* scale_dev, float* inv_scale_dev, int32_t* state_dev, const float* found_inf_a,
+                                      const float* found_inf_b, float growth_factor, float backoff_factor, int growth_interval,
+                                      uint32_t world, ngp_stream_t stream) {
+    if (!scale_dev || !inv_scale_dev || !state_dev) return NGP_ERR_NULL;
+    if (!(growth_factor >= 1.f) || !(backoff_factor > 0.f && backoff_factor <= 1.f) || growth_interval < 1 || world == 0) return NGP_ERR_BAD_ARG;
+    grad_scaler_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scale_dev, inv_scale_dev, state_dev, found_inf_a, found_inf_b, growth_factor,
+                                                                 backoff_factor, growth_interval, (float)world);
+    return finish_launch();
+}
 
 extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void* grad, int grad_dtype, float* exp_avg,
                               float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2, float eps,

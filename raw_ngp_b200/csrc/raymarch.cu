@@ -775,6 +775,7 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
+    if (x.loss_scale_dev) loss_scale = __ldg(x.loss_scale_dev);      // dynamic GradScaler scale, updated on the device
     // live rays of the batch (adaptive ray count): rays at or beyond it carry no samples, no loss and no gradient
     const uint32_t n_live = x.n_rays_dev ? min(N, (uint32_t)max(__ldg(x.n_rays_dev), 1)) : N;
     if (n < N && n >= n_live) {
@@ -841,7 +842,11 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
             const float cr_ = fminf(1.f, pr_), cg_ = fminf(1.f, pg_), cb_ = fminf(1.f, pb_);
             const float sr = 1.f / (1e-3f + cr_), sg_ = 1.f / (1e-3f + cg_), sb = 1.f / (1e-3f + cb_);
             er = (cr_ - tr) * sr; eg = (cg_ - tgn) * sg_; eb = (cb_ - tb) * sb;
-            dr = (pr_ < 1.f) ? ex * sr : 0.f; dg = (pg_ < 1.f) ? ex * sg_ : 0.f; db = (pb_ < 1.f) ? ex * sb : 0.f;
+            // d min(1, p) / d p: 1 below the clip, 0 above, 1/2 exactly on it (torch.minimum splits the gradient at a tie; a ray
+            // that sees only a white background with exposure 1 sits there)
+            dr = (pr_ < 1.f) ? ex * sr : (pr_ == 1.f ? 0.5f * ex * sr : 0.f);
+            dg = (pg_ < 1.f) ? ex * sg_ : (pg_ == 1.f ? 0.5f * ex * sg_ : 0.f);
+            db = (pb_ < 1.f) ? ex * sb : (pb_ == 1.f ? 0.5f * ex * sb : 0.f);
         } else {
             er = ir - tr; eg = ig - tgn; eb = ib - tb;
         }

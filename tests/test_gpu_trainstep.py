@@ -433,3 +433,56 @@ def test_fused_step_extras_cam_near_far_adaptive_rays_and_random_bg():
     ls = [g.step(o, d, rgba, update_grid=False, cam_near_far=cnf, lossmult=torch.ones(N, 3, device="cuda"), loss_weight=1.0).item() for _ in range(8)]
     g.flush()
     assert all(l == l for l in ls) and 1 <= int(g.n_rays_dev.item()) <= N
+
+
+def test_fused_step_checkpoint_round_trip_and_reference_pth(tmp_path):
+    """Resume: state_dict() / load_state_dict() carry the fp32 masters, Adam moments, device step counters and the loss scale, so a
+    trainer rebuilt from a checkpoint continues like the original.  model_state_dict() is a checkpoint in the REFERENCE's layout
+    (fp32 hash table): saved with torch.save, it loads with strict=True into the reference's own NeRFNetwork (oracle/ref_stack.py)
+    and renders the same image there; loading it back through load_model_state_dict() restores the fp32 master exactly."""
+    import _refstep as R
+    N = 1024
+    model, o, d, tgt = _scene(N)
+    a = FusedTrainStep(model, N, perturb=False, use_graph=True, growth_interval=3)
+    for _ in range(5):
+        a.step(o, d, tgt, update_grid=False)
+    ckpt, msd = a.state_dict(), a.model_state_dict()
+    assert msd["grid_encoder.embeddings"].dtype == torch.float32 and float(ckpt["loss_scale"]) == 256.0      # grew once (3 clean steps)
+    path = tmp_path / "ngp.pth"
+    torch.save({"model": msd, "trainer": ckpt}, path)
+    blob = torch.load(path, map_location="cuda")
+
+    model_b, _, _, _ = _scene(N)
+    model_b.grid_encoder.embeddings.data.zero_()
+    b = FusedTrainStep(model_b, N, perturb=False, use_graph=True, growth_interval=3)
+    b.load_model_state_dict(blob["model"])
+    b.load_state_dict(blob["trainer"])
+    assert torch.equal(b.table_master, a.table_master) and torch.equal(b.w_master, a.w_master)
+    assert torch.equal(model_b.grid_encoder.embeddings.data, a.table_master.half()) and b.opt.step_count == 5
+    la = [a.step(o, d, tgt, update_grid=False).item() for _ in range(4)]
+    lb = [b.step(o, d, tgt, update_grid=False).item() for _ in range(4)]
+    a.flush(); b.flush()
+    assert abs(la[0] - lb[0]) < 1e-6 * max(1.0, abs(la[0])) and abs(la[-1] - lb[-1]) < 2e-3 * abs(la[-1])
+    assert float(b.scale_dev) == float(a.scale_dev) and int(b.opt_step_dev) == int(a.opt_step_dev) == 9
+
+    # a forced overflow: the step is skipped, the scale halves, the skipped-step counter is visible without being polled per step
+    before = b.table_master.clone()
+    b.step(o, d, tgt * float("inf"), update_grid=False)
+    b.flush()
+    torch.cuda.synchronize()
+    assert torch.equal(b.table_master, before) and b.skipped_steps() == 1 and float(b.scale_dev) == 0.5 * float(a.scale_dev)
+
+    # the reference's own network loads the checkpoint (strict) and renders the same image
+    stack = R.stacks().get("ref")
+    kw = {k: getattr(model.opt, k) for k in R.OPT_KEYS if hasattr(model.opt, k)}
+    ref = stack.build_network(stack.make_opt(**kw)).cuda()
+    res = ref.load_state_dict(torch.load(path, map_location="cuda")["model"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys and ref.grid_encoder.embeddings.dtype == torch.float32
+    model_c, _, _, _ = _scene(N)                 # this repository's network from the same file (the trainers above moved on)
+    model_c.load_state_dict(torch.load(path, map_location="cuda")["model"], strict=True)
+    ref.eval(); model_c.eval()
+    oo, dd = synthetic.sphere_rays(2000, seed=8)
+    with torch.no_grad():
+        img_ref = ref.render(oo.cuda(), dd.cuda(), bg_color=1, perturb=False)["image"]
+        img = model_c.render(oo.cuda(), dd.cuda(), bg_color=1, perturb=False)["image"]
+    torch.testing.assert_close(img.float(), img_ref.float(), rtol=2e-3, atol=2e-3)
