@@ -976,8 +976,11 @@ march_infer_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ ra
                    const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, bool contract, float dt_gamma,
                    uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ nears,
                    const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ ts,
-                   const float* __restrict__ noises, bool staged) {
+                   const float* __restrict__ noises, bool staged, const int* __restrict__ ctl) {
     extern __shared__ float s_stage[];
+    // ctl (device-driven loop, ngp_march_rays_dev): the live ray count and the steps per ray of this iteration come from
+    // device memory, the launch was sized for an upper bound of n_alive
+    if (ctl) { n_alive = (uint32_t)__ldg(ctl); n_step = (uint32_t)__ldg(ctl + 1); }
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n0 = n - lane;                           // first ray of the warp
@@ -1060,7 +1063,9 @@ march_infer_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ ra
 __global__ void __launch_bounds__(128)
 composite_infer_kernel(uint32_t n_alive, uint32_t n_step, float T_thresh, int* __restrict__ rays_alive, float* __restrict__ rays_t,
                        const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ts,
-                       float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+                       float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+                       const int* __restrict__ ctl) {
+    if (ctl) { n_alive = (uint32_t)__ldg(ctl); n_step = (uint32_t)__ldg(ctl + 1); }
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_alive) return;
     const int index = rays_alive[n];
@@ -1170,8 +1175,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t cnt, uint32_t*
 }
 
 __global__ void __launch_bounds__(kCompactThreads)
-compact_count_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* __restrict__ block_counts) {
+compact_count_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* __restrict__ block_counts, const int* __restrict__ ctl) {
     __shared__ uint32_t s_warp[kCompactThreads / 32];
+    if (ctl) n_alive = (uint32_t)__ldg(ctl);
     int v[kCompactPer];
     const uint32_t cnt = compact_load(rays_alive, n_alive, blockIdx.x * kCompactTile + threadIdx.x * kCompactPer, v);
     uint32_t total;
@@ -1181,9 +1187,10 @@ compact_count_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* 
 
 __global__ void __launch_bounds__(kCompactThreads)
 compact_write_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, const int* __restrict__ block_counts, int* __restrict__ out,
-                     int* __restrict__ n_out) {
+                     int* __restrict__ n_out, const int* __restrict__ ctl, int* __restrict__ ctl_next, uint32_t n_rays, uint32_t max_steps) {
     __shared__ uint32_t s_warp[kCompactThreads / 32];
     __shared__ uint32_t s_red[kCompactThreads / 32];
+    if (ctl) n_alive = (uint32_t)__ldg(ctl);
     // survivors in the blocks before this one
     uint32_t part = 0;
     for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kCompactThreads) part += (uint32_t)__ldg(block_counts + b);
@@ -1200,7 +1207,19 @@ compact_write_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, const
 #pragma unroll
     for (uint32_t k = 0; k < kCompactPer; k++)
         if (v[k] >= 0) out[pos++] = v[k];
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) n_out[0] = (int)(base + total);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const uint32_t alive = base + total;
+        n_out[0] = (int)alive;
+        if (ctl_next) {
+            // the loop header of run_cuda (renderer.py:588-598, 616) for the NEXT iteration: step += n_step; stop at max_steps or
+            // when no ray is left; n_step = max(min(N // n_alive, 8), 1).  Written to the other control block: the blocks of
+            // this launch still read the current one.
+            const uint32_t step = (uint32_t)__ldg(ctl + 3) + (uint32_t)__ldg(ctl + 1);
+            const uint32_t n_next = (step >= max_steps) ? 0u : alive;
+            const uint32_t ns = n_next ? max(min(n_rays / n_next, 8u), 1u) : 1u;
+            ctl_next[0] = (int)n_next; ctl_next[1] = (int)ns; ctl_next[2] = (int)(n_next * ns); ctl_next[3] = (int)step;
+        }
+    }
 }
 
 }  // namespace
@@ -1428,7 +1447,7 @@ extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* 
     if (!staged) stage_bytes = 0;
     march_infer_kernel<<<div_up(n_alive, 128u), 128, stage_bytes, (cudaStream_t)stream>>>(
         n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, contract != 0, dt_gamma, max_steps, C, H, grid, nears, fars,
-        xyzs, dirs, ts, noises, staged);
+        xyzs, dirs, ts, noises, staged, nullptr);
     return finish_launch();
 }
 
@@ -1439,7 +1458,7 @@ extern "C" int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thr
     if (!rays_alive || !rays_t || !sigmas || !rgbs || !ts || !weights_sum || !depth || !image) return NGP_ERR_NULL;
     if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
     composite_infer_kernel<<<div_up(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(
-        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, ts, weights_sum, depth, image);
+        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, ts, weights_sum, depth, image, nullptr);
     return finish_launch();
 }
 
@@ -1452,8 +1471,50 @@ extern "C" int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_aliv
         return finish_launch();
     }
     const uint32_t blocks = div_up(n_alive, kCompactTile);
-    compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace);
-    compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, alive_out, n_out);
+    compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, nullptr);
+    compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, alive_out, n_out, nullptr, nullptr, 0, 0);
+    return finish_launch();
+}
+
+// ---- the alive-ray loop of run_cuda (renderer.py:588-616) driven from the device ----------------------------------------------
+// ctl = int32[4] {n_alive, n_step, n_alive * n_step, step}: every kernel of an iteration reads its sizes from ctl, the compaction
+// writes the next iteration's block to ctl_next.  Launches are sized for `n_alive_bound` >= the true count (the host's last
+// known value: the count never grows), so the host never has to wait for the device to size a launch.
+extern "C" int ngp_march_rays_dev(const int32_t* ctl, uint32_t n_alive_bound, const int32_t* rays_alive, const float* rays_t,
+                                  const float* rays_o, const float* rays_d, float bound, int contract, float dt_gamma,
+                                  uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* fars, float* xyzs,
+                                  float* dirs, float* ts, const float* noises, ngp_stream_t stream) {
+    if (n_alive_bound == 0) return NGP_OK;
+    if (!ctl || !rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !ts || !noises) return NGP_ERR_NULL;
+    if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
+    if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
+    const uint32_t stage_bytes = 4u * 32u * (5u * 8u + 2u) * (uint32_t)sizeof(float);      // n_step <= 8 (renderer.py:598)
+    march_infer_kernel<<<div_up(n_alive_bound, 128u), 128, stage_bytes, (cudaStream_t)stream>>>(
+        n_alive_bound, 1, rays_alive, rays_t, rays_o, rays_d, bound, contract != 0, dt_gamma, max_steps, C, H, grid, nullptr, fars,
+        xyzs, dirs, ts, noises, true, ctl);
+    return finish_launch();
+}
+
+extern "C" int ngp_composite_rays_dev(const int32_t* ctl, uint32_t n_alive_bound, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                      const float* sigmas, const float* rgbs, const float* ts, float* weights_sum, float* depth,
+                                      float* image, ngp_stream_t stream) {
+    if (n_alive_bound == 0) return NGP_OK;
+    if (!ctl || !rays_alive || !rays_t || !sigmas || !rgbs || !ts || !weights_sum || !depth || !image) return NGP_ERR_NULL;
+    if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
+    composite_infer_kernel<<<div_up(n_alive_bound, 128u), 128, 0, (cudaStream_t)stream>>>(
+        n_alive_bound, 1, T_thresh, rays_alive, rays_t, sigmas, rgbs, ts, weights_sum, depth, image, ctl);
+    return finish_launch();
+}
+
+extern "C" int ngp_compact_rays_alive_dev(const int32_t* ctl, int32_t* ctl_next, uint32_t n_alive_bound, uint32_t n_rays,
+                                          uint32_t max_steps, const int32_t* rays_alive, int32_t* alive_out, int32_t* n_out,
+                                          int32_t* workspace, ngp_stream_t stream) {
+    if (!ctl || !ctl_next || !n_out || !workspace || !rays_alive || !alive_out) return NGP_ERR_NULL;
+    if (!aligned(rays_alive, 16) || n_rays == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
+    const uint32_t blocks = std::max(1u, div_up(n_alive_bound, kCompactTile));
+    compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive_bound, workspace, ctl);
+    compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive_bound, workspace, alive_out, n_out, ctl,
+                                                                             ctl_next, n_rays, max_steps);
     return finish_launch();
 }
 

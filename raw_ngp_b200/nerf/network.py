@@ -117,9 +117,10 @@ class NeRFNetwork(NeRFRenderer):
         dens, col, beta, bound = self._density_act(), _field.COLOR_ACT[self.opt.color_activation], float(self.opt.beta), float(self.bound)
         keep = (w1, w2, fw)      # the launch arguments below hold raw pointers into these
 
-        def field(xyzs, dirs, M, sigmas, rgbs, st, _keep=keep):
+        def field(xyzs, dirs, M, sigmas, rgbs, st, m_dev=None, _keep=keep):
+            # m_dev: device address of the live row count (<= M), see NeRFRenderer._march_composite_loop_fast
             _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
-                      _lib.ptr(fw), bound, S, H, L, gt, ac, ip, a1, c1, a2, c2, M, None, dens, beta, col, None, None, None, None,
+                      _lib.ptr(fw), bound, S, H, L, gt, ac, ip, a1, c1, a2, c2, M, m_dev, dens, beta, col, None, None, None, None,
                       _lib.ptr(sigmas), _lib.ptr(rgbs), None, st)
         return field
 

@@ -162,12 +162,18 @@ class NeRFRenderer(nn.Module):
         """Subclasses whose field is one fused kernel return its launch arguments (see NeRFNetwork); None = generic loop."""
         return None
 
+    LOOKAHEAD = 4          # iterations the host may run ahead of the last alive-ray count it has seen
+
     def _march_composite_loop_fast(self, N, rays_o, rays_d, nears, fars, perturb, weights_sum, depth, image, field):
-        """The alive-ray loop of renderer.py:588-616 with four C-ABI launches per iteration (march, fused field, composite,
-        compaction) on buffers allocated once per frame: n_alive * n_step never exceeds N, the marcher writes every row of
-        its outputs (finished rays as zeros), and the field kernel normalises the directions itself -- so the per-iteration
-        zero fills, the torch normalisation and the autograd / autocast plumbing of the generic loop disappear.  The host
-        still reads the surviving count once per iteration (it sizes the next launches, as in the reference)."""
+        """The alive-ray loop of renderer.py:588-616 driven from the device: four launches per iteration (march, fused field,
+        composite, two-pass compaction) on buffers allocated once per frame, with the loop header -- n_alive, n_step =
+        max(min(N // n_alive, 8), 1), step += n_step, stop at max_steps -- kept in a device control block that the compaction
+        kernel advances (csrc/raymarch.cu: ngp_*_dev).  The reference reads the surviving count back every iteration to size
+        the next launches; here the host only polls, LOOKAHEAD iterations late and without ever idling the GPU, the counts that
+        earlier iterations left in pinned memory: they bound the launch sizes and tell it when to stop enqueuing.  n_alive *
+        n_step never exceeds N, the marcher writes every row of its outputs (finished rays as zeros), and the field kernel
+        normalises the directions itself -- so the per-iteration zero fills, the torch normalisation and the autograd /
+        autocast plumbing of the generic loop disappear as well."""
         from .. import _lib
         P, st = _lib.ptr, _lib.stream()
         dev = rays_o.device
@@ -177,25 +183,41 @@ class NeRFRenderer(nn.Module):
         alive = torch.arange(N, dtype=torch.int32, device=dev)
         alive_next = torch.empty_like(alive)
         rays_t = nears.clone().view(-1).contiguous()
-        nears, fars = nears.view(-1).contiguous(), fars.view(-1).contiguous()
+        fars = fars.view(-1).contiguous()
         zeros = torch.zeros(N, **f32)
         noises = torch.rand(N, **f32) if perturb else zeros
         n_out = torch.zeros(1, dtype=torch.int32, device=dev)
-        ws = torch.empty((N + 4095) // 4096, dtype=torch.int32, device=dev)
-        n_alive, step = N, 0
-        while step < self.opt.max_steps and n_alive > 0:
-            n_step = max(min(N // n_alive, 8), 1)
-            _lib.call("ngp_march_rays", n_alive, n_step, P(alive), P(rays_t), P(rays_o), P(rays_d), float(self.real_bound),
-                      int(bool(self.opt.contract)), float(self.opt.dt_gamma), int(self.opt.max_steps), int(self.cascade),
-                      int(self.grid_size), P(self.density_bitfield), P(nears), P(fars), P(xyzs), P(dirs), P(ts),
-                      P(noises if step == 0 else zeros), st)
-            field(xyzs, dirs, n_alive * n_step, sigmas, rgbs, st)
-            _lib.call("ngp_composite_rays", n_alive, n_step, float(self.opt.T_thresh), P(alive), P(rays_t), P(sigmas), P(rgbs),
-                      P(ts), P(weights_sum), P(depth), P(image), st)
-            _lib.call("ngp_compact_rays_alive", P(alive), n_alive, P(alive_next), P(n_out), P(ws), st)
+        ws = torch.empty((N + 4095) // 4096 + 1, dtype=torch.int32, device=dev)
+        max_steps = int(self.opt.max_steps)
+        n_step0 = max(min(N // max(N, 1), 8), 1)
+        ctl = torch.tensor([[N, n_step0, N * n_step0, 0], [0, 1, 0, 0]], dtype=torch.int32, device=dev)      # ping-pong control blocks
+        L = self.LOOKAHEAD
+        if getattr(self, "_infer_poll", None) is None or self._infer_poll[0].shape[0] != L:
+            self._infer_poll = (torch.zeros(L, 4, dtype=torch.int32).pin_memory(), [torch.cuda.Event() for _ in range(L)])
+        seen, events = self._infer_poll
+        bound = N                     # upper bound of n_alive known to the host
+        it = 0
+        while True:
+            cur, nxt = ctl[it & 1], ctl[(it + 1) & 1]
+            _lib.call("ngp_march_rays_dev", P(cur), bound, P(alive), P(rays_t), P(rays_o), P(rays_d), float(self.real_bound),
+                      int(bool(self.opt.contract)), float(self.opt.dt_gamma), max_steps, int(self.cascade), int(self.grid_size),
+                      P(self.density_bitfield), P(fars), P(xyzs), P(dirs), P(ts), P(noises if it == 0 else zeros), st)
+            field(xyzs, dirs, N, sigmas, rgbs, st, m_dev=cur.data_ptr() + 8)
+            _lib.call("ngp_composite_rays_dev", P(cur), bound, float(self.opt.T_thresh), P(alive), P(rays_t), P(sigmas), P(rgbs), P(ts),
+                      P(weights_sum), P(depth), P(image), st)
+            _lib.call("ngp_compact_rays_alive_dev", P(cur), P(nxt), bound, N, max_steps, P(alive), P(alive_next), P(n_out), P(ws), st)
             alive, alive_next = alive_next, alive
-            n_alive = int(n_out.item())
-            step += n_step
+            seen[it % L].copy_(nxt, non_blocking=True)
+            events[it % L].record()
+            it += 1
+            if it >= L:               # the control block written L - 1 iterations ago: its copy has long landed, the GPU still has work queued
+                j = (it - L) % L
+                events[j].synchronize()
+                bound = int(seen[j, 0])
+                if bound == 0:
+                    break
+            if it > max_steps + L:    # cannot happen: step grows by >= 1 per iteration
+                raise RuntimeError("inference loop did not terminate")
 
     def _march_composite_loop(self, N, rays_o, rays_d, rays_ldir, nears, fars, perturb, shading, amp, weights_sum,
                               depth, image, normals):

@@ -176,3 +176,52 @@ def test_reference_mark_untrained_grid_identical_over_dropin_and_kernel():
         # cuBLAS-vs-FMA rounding difference
         mism = (grids["ours"] != grids["ref"]).float().mean().item()
         assert mism < 1e-4, (vname, mism)
+
+
+def test_reference_proposal_path_identical_over_dropin():
+    """the non-cuda_ray path of the reference (renderer.py:50-136, 405-513: proposal networks -- two small hash
+    grids + MLPs, network.py:59-72,146-149 --, sample_pdf, proposal / distortion losses, contraction), unmodified, over this
+    repository's GridEncoder / SHEncoder: [N, T, 3] inputs, three encoder instances with different level counts, gradients into
+    all three tables.  Training forward + backward and staged inference."""
+    rs = R.stacks()
+    N = 1024
+    extra = dict(cuda_ray=False, num_steps=[64, 32, 16], background="white", lambda_proposal=1, lambda_distort=0, max_ray_batch=512,
+                 bound=2, contract=True, grid_size=32, hashmap_size=15, hashgrid_resolution=128)
+    torch.manual_seed(0)
+    o, d = synthetic.sphere_rays(N, seed=5)
+    o, d = o.cuda(), d.cuda()
+    tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(9)).cuda()
+    models = {}
+    for name in ("ref", "dropin"):
+        st = rs.get(name)
+        torch.manual_seed(1)
+        m = st.build_network(st.make_opt(**extra)).cuda()
+        models[name] = m
+    sd = {k: v.clone() for k, v in models["ref"].state_dict().items()}
+    for k in sd:
+        if k.endswith("embeddings"):
+            sd[k] = torch.empty_like(sd[k]).uniform_(-0.5, 0.5, generator=None)
+    models["ref"].load_state_dict(sd)
+    models["dropin"].load_state_dict(sd)
+    assert type(models["dropin"].prop_encoders[0]).__module__ == "raw_ngp_b200.gridencoder.grid"
+    res = {}
+    for name, m in models.items():
+        m.train()
+        torch.manual_seed(21)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = m.render(o, d, bg_color=1, perturb=True, update_proposal=True)
+        loss = R.mse_loss(out["image"].float(), tgt) + out["proposal_loss"]
+        loss.backward()
+        grads = {k: p.grad.detach().float() for k, p in m.named_parameters() if p.grad is not None}
+        m.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            ev = m.render(o, d, bg_color=1, perturb=False)
+        res[name] = dict(out=out, loss=loss.detach(), grads=grads, ev=ev)
+    a, b = res["ref"], res["dropin"]
+    torch.testing.assert_close(b["out"]["image"].float(), a["out"]["image"].float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(b["loss"], a["loss"], rtol=2e-3, atol=1e-5)
+    torch.testing.assert_close(b["ev"]["image"].float(), a["ev"]["image"].float(), rtol=2e-3, atol=2e-3)
+    assert set(a["grads"]) == set(b["grads"]) and any(k.startswith("prop_encoders.1") for k in a["grads"])
+    for k in a["grads"]:
+        mx, mean = R.err_stats(b["grads"][k], a["grads"][k])
+        assert mx < 2e-2 and mean < 2e-3, (k, mx, mean)
