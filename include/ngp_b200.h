@@ -311,7 +311,10 @@ int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t*
  * pick n_step = max(min(N // n_alive, 8), 1).  Here that loop header lives in a device control block ctl = int32[4]
  * {n_alive, n_step, n_alive * n_step, step}; the three entry points below are ngp_march_rays / ngp_composite_rays /
  * ngp_compact_rays_alive reading their sizes from ctl, launched for `n_alive_bound` >= n_alive rays (any earlier value of the
- * count), and the compaction writes the control block of the NEXT iteration to ctl_next (n_alive = 0 once step >= max_steps).
+ * count), and the compaction writes the control block of the NEXT iteration to ctl_next (n_alive = 0 once step >= max_steps;
+ * n_step = max(min(row_cap // n_alive, step_cap), 1) with step_cap <= 16: row_cap = N, step_cap = 8 is the reference's schedule,
+ * larger values render the same image -- the per-ray sample sequence does not depend on how it is cut into iterations -- in
+ * fewer iterations; the sample buffers hold row_cap rows).
  * Field kernels take ctl + 2 as their m_dev.  Outputs are laid out exactly as by the host-driven entry points. */
 int ngp_march_rays_dev(const int32_t* ctl, uint32_t n_alive_bound, const int32_t* rays_alive, const float* rays_t,
                        const float* rays_o, const float* rays_d, float bound, int contract, float dt_gamma,
@@ -320,9 +323,9 @@ int ngp_march_rays_dev(const int32_t* ctl, uint32_t n_alive_bound, const int32_t
 int ngp_composite_rays_dev(const int32_t* ctl, uint32_t n_alive_bound, float T_thresh, int32_t* rays_alive, float* rays_t,
                            const float* sigmas, const float* rgbs, const float* ts, float* weights_sum, float* depth,
                            float* image, ngp_stream_t stream);
-int ngp_compact_rays_alive_dev(const int32_t* ctl, int32_t* ctl_next, uint32_t n_alive_bound, uint32_t n_rays,
-                               uint32_t max_steps, const int32_t* rays_alive, int32_t* alive_out, int32_t* n_out,
-                               int32_t* workspace, ngp_stream_t stream);
+int ngp_compact_rays_alive_dev(const int32_t* ctl, int32_t* ctl_next, uint32_t n_alive_bound, uint32_t row_cap,
+                               uint32_t step_cap, uint32_t max_steps, const int32_t* rays_alive, int32_t* alive_out,
+                               int32_t* n_out, int32_t* workspace, ngp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Occupancy-grid update  (reference: nerf/renderer.py:811-897, Python loop over torch ops)

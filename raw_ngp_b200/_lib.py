@@ -51,7 +51,7 @@ SIGNATURES = {
     "ngp_compact_rays_alive": [_p, _u32, _p, _p, _p, _p],
     "ngp_march_rays_dev": [_p, _u32, _p, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p],
     "ngp_composite_rays_dev": [_p, _u32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "ngp_compact_rays_alive_dev": [_p, _p, _u32, _u32, _u32, _p, _p, _p, _p, _p],
+    "ngp_compact_rays_alive_dev": [_p, _p, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p],
     "ngp_occ_sample_positions": [_p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_occ_scatter_sigmas": [_p, _p, _u32, _p, _p],
     "ngp_occ_ema_update": [_p, _p, _u32, _f32, _p, _p, _p],

@@ -1187,7 +1187,8 @@ compact_count_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, int* 
 
 __global__ void __launch_bounds__(kCompactThreads)
 compact_write_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, const int* __restrict__ block_counts, int* __restrict__ out,
-                     int* __restrict__ n_out, const int* __restrict__ ctl, int* __restrict__ ctl_next, uint32_t n_rays, uint32_t max_steps) {
+                     int* __restrict__ n_out, const int* __restrict__ ctl, int* __restrict__ ctl_next, uint32_t row_cap, uint32_t step_cap,
+                     uint32_t max_steps) {
     __shared__ uint32_t s_warp[kCompactThreads / 32];
     __shared__ uint32_t s_red[kCompactThreads / 32];
     if (ctl) n_alive = (uint32_t)__ldg(ctl);
@@ -1212,11 +1213,11 @@ compact_write_kernel(const int* __restrict__ rays_alive, uint32_t n_alive, const
         n_out[0] = (int)alive;
         if (ctl_next) {
             // the loop header of run_cuda (renderer.py:588-598, 616) for the NEXT iteration: step += n_step; stop at max_steps or
-            // when no ray is left; n_step = max(min(N // n_alive, 8), 1).  Written to the other control block: the blocks of
-            // this launch still read the current one.
+            // when no ray is left; n_step = max(min(row_cap // n_alive, step_cap), 1) (the reference: row_cap = N, step_cap = 8).
+            // Written to the other control block: the blocks of this launch still read the current one.
             const uint32_t step = (uint32_t)__ldg(ctl + 3) + (uint32_t)__ldg(ctl + 1);
             const uint32_t n_next = (step >= max_steps) ? 0u : alive;
-            const uint32_t ns = n_next ? max(min(n_rays / n_next, 8u), 1u) : 1u;
+            const uint32_t ns = n_next ? max(min(row_cap / n_next, step_cap), 1u) : 1u;
             ctl_next[0] = (int)n_next; ctl_next[1] = (int)ns; ctl_next[2] = (int)(n_next * ns); ctl_next[3] = (int)step;
         }
     }
@@ -1472,9 +1473,11 @@ extern "C" int ngp_compact_rays_alive(const int32_t* rays_alive, uint32_t n_aliv
     }
     const uint32_t blocks = div_up(n_alive, kCompactTile);
     compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, nullptr);
-    compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, alive_out, n_out, nullptr, nullptr, 0, 0);
+    compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, workspace, alive_out, n_out, nullptr, nullptr, 0, 0, 0);
     return finish_launch();
 }
+
+constexpr uint32_t kMaxDevStep = 16;     // largest n_step of the device-driven loop (shared-memory staging of the marcher)
 
 // ---- the alive-ray loop of run_cuda (renderer.py:588-616) driven from the device ----------------------------------------------
 // ctl = int32[4] {n_alive, n_step, n_alive * n_step, step}: every kernel of an iteration reads its sizes from ctl, the compaction
@@ -1488,7 +1491,7 @@ extern "C" int ngp_march_rays_dev(const int32_t* ctl, uint32_t n_alive_bound, co
     if (!ctl || !rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !ts || !noises) return NGP_ERR_NULL;
     if (!aligned(ts, 8)) return NGP_ERR_ALIGN;
     if (max_steps == 0 || H == 0 || C == 0 || H > 1024) return NGP_ERR_BAD_ARG;
-    const uint32_t stage_bytes = 4u * 32u * (5u * 8u + 2u) * (uint32_t)sizeof(float);      // n_step <= 8 (renderer.py:598)
+    const uint32_t stage_bytes = 4u * 32u * (5u * kMaxDevStep + 2u) * (uint32_t)sizeof(float);      // n_step <= kMaxDevStep: 43 KB
     march_infer_kernel<<<div_up(n_alive_bound, 128u), 128, stage_bytes, (cudaStream_t)stream>>>(
         n_alive_bound, 1, rays_alive, rays_t, rays_o, rays_d, bound, contract != 0, dt_gamma, max_steps, C, H, grid, nullptr, fars,
         xyzs, dirs, ts, noises, true, ctl);
@@ -1506,15 +1509,15 @@ extern "C" int ngp_composite_rays_dev(const int32_t* ctl, uint32_t n_alive_bound
     return finish_launch();
 }
 
-extern "C" int ngp_compact_rays_alive_dev(const int32_t* ctl, int32_t* ctl_next, uint32_t n_alive_bound, uint32_t n_rays,
-                                          uint32_t max_steps, const int32_t* rays_alive, int32_t* alive_out, int32_t* n_out,
-                                          int32_t* workspace, ngp_stream_t stream) {
+extern "C" int ngp_compact_rays_alive_dev(const int32_t* ctl, int32_t* ctl_next, uint32_t n_alive_bound, uint32_t row_cap,
+                                          uint32_t step_cap, uint32_t max_steps, const int32_t* rays_alive, int32_t* alive_out,
+                                          int32_t* n_out, int32_t* workspace, ngp_stream_t stream) {
     if (!ctl || !ctl_next || !n_out || !workspace || !rays_alive || !alive_out) return NGP_ERR_NULL;
-    if (!aligned(rays_alive, 16) || n_rays == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
+    if (!aligned(rays_alive, 16) || row_cap == 0 || max_steps == 0 || step_cap == 0 || step_cap > kMaxDevStep) return NGP_ERR_BAD_ARG;
     const uint32_t blocks = std::max(1u, div_up(n_alive_bound, kCompactTile));
     compact_count_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive_bound, workspace, ctl);
     compact_write_kernel<<<blocks, kCompactThreads, 0, (cudaStream_t)stream>>>(rays_alive, n_alive_bound, workspace, alive_out, n_out, ctl,
-                                                                             ctl_next, n_rays, max_steps);
+                                                                             ctl_next, row_cap, step_cap, max_steps);
     return finish_launch();
 }
 

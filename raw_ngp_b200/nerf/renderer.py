@@ -163,6 +163,11 @@ class NeRFRenderer(nn.Module):
         return None
 
     LOOKAHEAD = 4          # iterations the host may run ahead of the last alive-ray count it has seen
+    # Steps per ray and iteration: the reference takes n_step = max(min(N // n_alive, 8), 1) (renderer.py:598) with sample buffers
+    # of N rows.  How a ray's sample sequence is cut into iterations does not change the image (composite_rays continues from
+    # rays_t and the accumulated weights, sample by sample), only the number of iterations: with buffers of INFER_ROWS * N rows
+    # and up to INFER_MAX_STEP steps a 1080p frame takes ~14 iterations instead of ~44.  (1, 8) is the reference's schedule.
+    INFER_ROWS, INFER_MAX_STEP = 4, 16
 
     def _march_composite_loop_fast(self, N, rays_o, rays_d, nears, fars, perturb, weights_sum, depth, image, field):
         """The alive-ray loop of renderer.py:588-616 driven from the device: four launches per iteration (march, fused field,
@@ -178,8 +183,9 @@ class NeRFRenderer(nn.Module):
         P, st = _lib.ptr, _lib.stream()
         dev = rays_o.device
         f32 = dict(dtype=torch.float32, device=dev)
-        xyzs, dirs, ts = torch.empty(N, 3, **f32), torch.empty(N, 3, **f32), torch.empty(N, 2, **f32)
-        sigmas, rgbs = torch.empty(N, **f32), torch.empty(N, 3, **f32)
+        R = N * int(self.INFER_ROWS)              # rows of the sample buffers
+        xyzs, dirs, ts = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, 2, **f32)
+        sigmas, rgbs = torch.empty(R, **f32), torch.empty(R, 3, **f32)
         alive = torch.arange(N, dtype=torch.int32, device=dev)
         alive_next = torch.empty_like(alive)
         rays_t = nears.clone().view(-1).contiguous()
@@ -189,8 +195,8 @@ class NeRFRenderer(nn.Module):
         n_out = torch.zeros(1, dtype=torch.int32, device=dev)
         ws = torch.empty((N + 4095) // 4096 + 1, dtype=torch.int32, device=dev)
         max_steps = int(self.opt.max_steps)
-        n_step0 = max(min(N // max(N, 1), 8), 1)
-        ctl = torch.tensor([[N, n_step0, N * n_step0, 0], [0, 1, 0, 0]], dtype=torch.int32, device=dev)      # ping-pong control blocks
+        # first iteration: one step per ray (most rays of a frame never meet an occupied cell and leave the loop right there)
+        ctl = torch.tensor([[N, 1, N, 0], [0, 1, 0, 0]], dtype=torch.int32, device=dev)      # ping-pong control blocks
         L = self.LOOKAHEAD
         if getattr(self, "_infer_poll", None) is None or self._infer_poll[0].shape[0] != L:
             self._infer_poll = (torch.zeros(L, 4, dtype=torch.int32).pin_memory(), [torch.cuda.Event() for _ in range(L)])
@@ -202,10 +208,11 @@ class NeRFRenderer(nn.Module):
             _lib.call("ngp_march_rays_dev", P(cur), bound, P(alive), P(rays_t), P(rays_o), P(rays_d), float(self.real_bound),
                       int(bool(self.opt.contract)), float(self.opt.dt_gamma), max_steps, int(self.cascade), int(self.grid_size),
                       P(self.density_bitfield), P(fars), P(xyzs), P(dirs), P(ts), P(noises if it == 0 else zeros), st)
-            field(xyzs, dirs, N, sigmas, rgbs, st, m_dev=cur.data_ptr() + 8)
+            field(xyzs, dirs, R, sigmas, rgbs, st, m_dev=cur.data_ptr() + 8)
             _lib.call("ngp_composite_rays_dev", P(cur), bound, float(self.opt.T_thresh), P(alive), P(rays_t), P(sigmas), P(rgbs), P(ts),
                       P(weights_sum), P(depth), P(image), st)
-            _lib.call("ngp_compact_rays_alive_dev", P(cur), P(nxt), bound, N, max_steps, P(alive), P(alive_next), P(n_out), P(ws), st)
+            _lib.call("ngp_compact_rays_alive_dev", P(cur), P(nxt), bound, R, int(self.INFER_MAX_STEP), max_steps, P(alive), P(alive_next),
+                      P(n_out), P(ws), st)
             alive, alive_next = alive_next, alive
             seen[it % L].copy_(nxt, non_blocking=True)
             events[it % L].record()

@@ -205,6 +205,14 @@ def test_fast_inference_loop_matches_generic_loop(kw):
     assert model._fast_infer_args(None, "full") is not None
     for k in ("image", "depth"):
         torch.testing.assert_close(fast[k], slow[k], rtol=2e-3, atol=2e-3)
+    # the iteration schedule (rows of the sample buffers, steps per ray and iteration) does not change a single bit: the
+    # reference's schedule (N rows, <= 8 steps) against the default (4 N rows, <= 16 steps)
+    model.FAST_INFER = True
+    model.INFER_ROWS, model.INFER_MAX_STEP = 1, 8
+    with torch.no_grad():
+        ref_sched = model.render(o, d, bg_color=1.0, perturb=False)
+    for k in ("image", "depth"):
+        assert torch.equal(fast[k], ref_sched[k]), k
     assert (fast["image"] < 0.99).float().mean().item() > 0.1      # the ball is visible
 
 
