@@ -56,6 +56,7 @@ struct WsArgs {
     uint32_t M; const int* m_dev;
     int density_act, color_act; float beta;
     uint32_t n_run;                    // layers to run: 6, or 3 for a density-only query (NeRFNetwork.density)
+    uint32_t rowmajor;                 // saved tensors as plain [M, width] rows (for the kernel-pair backward) instead of tile images
     uint32_t w_off[kWsLayers], a0_off, a0_stage_bytes, h_off[kMlpGroups], ctrl_off;
 };
 
@@ -85,7 +86,7 @@ field_forward_ws_kernel(const WsArgs a) {
         }
         for (uint32_t gI = 0; gI < kMlpGroups; gI++) tc::mbar_init(done_s + 8 * gI, 1);
     }
-    for (uint32_t l = 0; l < a.n_run; l++) tsw::load_weight_tile(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
+    for (uint32_t l = 0; l < a.n_run; l++) tsw::load_weight_tile_r(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kMlpGroups * kWsLayers && (threadIdx.x - 64) % kWsLayers < a.n_run) {
         const uint32_t i = threadIdx.x - 64, gI = i / kWsLayers, l = i % kWsLayers;
         const uint32_t K = a.K[l], N = a.N[l];
@@ -95,8 +96,8 @@ field_forward_ws_kernel(const WsArgs a) {
         pl.idesc = tc::instr_desc(kTile, N, false, false);
         pl.n_steps = K / 16; pl.d_col = gI * kGroupTmemCols; pl.pad = 0;
         for (uint32_t ks = 0; ks < K / 16; ks++) {     // both operands K-major swizzled tiles of width K
-            pl.step[ks].a = tsw::desc_kmajor(a_saddr, K, ks);
-            pl.step[ks].b = tsw::desc_kmajor(w_saddr, K, ks);
+            pl.step[ks].a = tsw::desc_kmajor_r(a_saddr, K, kTile, ks);
+            pl.step[ks].b = tsw::desc_kmajor_r(w_saddr, K, N, ks);
         }
     }
     load_level_consts(s_lv, a.g);
@@ -203,14 +204,29 @@ field_forward_ws_kernel(const WsArgs a) {
                     // image goes to global memory as ONE bulk async copy while the MMA runs.  The commit is issued after the
                     // copy has finished reading shared memory, so "MMA done" also means "tile may be overwritten".
                     __half* save = (l == 0) ? a.enc_out : (l == 3) ? a.in2_out : a.acts[l - 1];
-                    if (save) {
+                    if (save && !a.rowmajor) {
                         const uint32_t bytes = kTile * a.K[l] * 2;
                         const uint32_t src = tc::smem_u32((l == 0) ? smem + a.a0_off + s * a.a0_stage_bytes : h);
                         tc::bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * bytes, src, bytes);
                         tc::bulk_wait_read();
                     }
                     tc::mma_commit(done);
-                    if (l == 0) tc::mma_commit(empty_s + 8 * s);      // ring stage free once layer 0 (and the copy) has read it
+                    if (l == 0 && !a.rowmajor) tc::mma_commit(empty_s + 8 * s);      // ring stage free once layer 0 (and the copy) has read it
+                }
+                if (a.rowmajor) {
+                    // the A operand as plain rows [M, K] (what the kernel-pair backward of field.cu / mlp.cu reads): every thread
+                    // copies its own row out of the tile while the MMA runs
+                    __half* save = (l == 0) ? a.enc_out : (l == 3) ? a.in2_out : a.acts[l - 1];
+                    if (save && live) {
+                        const uint32_t K = a.K[l];
+                        const uint8_t* src = (l == 0) ? smem + a.a0_off + s * a.a0_stage_bytes : h;
+                        uint4* dst = reinterpret_cast<uint4*>(save + (size_t)row * K);
+                        for (uint32_t j = 0; j < K / 8; j++) dst[j] = *reinterpret_cast<const uint4*>(src + tsw::chunk_off_r(K, kTile, tg, j));
+                    }
+                    if (l == 0) {       // the ring stage goes back to the gather warps only after every row has been read
+                        tc::named_bar_sync(1 + gI, kTile);
+                        if (tg == 0) tc::mma_commit(empty_s + 8 * s);
+                    }
                 }
                 tc::mbar_wait(done, ph);
                 ph ^= 1;
@@ -230,7 +246,7 @@ field_forward_ws_kernel(const WsArgs a) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) { ql[i] = __hmax2(ql[i], zero2); qh[i] = __hmax2(qh[i], zero2); }
                         }
-                        const uint32_t o0 = tsw::chunk_off(N, tg, c0 / 8), o1 = tsw::chunk_off(N, tg, c0 / 8 + 1);
+                        const uint32_t o0 = tsw::chunk_off_r(N, kTile, tg, c0 / 8), o1 = tsw::chunk_off_r(N, kTile, tg, c0 / 8 + 1);
                         *reinterpret_cast<uint4*>(h + o0) = lo;
                         *reinterpret_cast<uint4*>(h + o1) = hi;
                     }
@@ -286,7 +302,7 @@ field_forward_ws_kernel(const WsArgs a) {
                         ch[3] = make_uint4(pack2(sh[9], sh[10]), pack2(sh[11], sh[12]), pack2(sh[13], sh[14]), pack2(sh[15], 0.f));
                     }
 #pragma unroll
-                    for (uint32_t c = 0; c < (LDIR ? 6u : 4u); c++) *reinterpret_cast<uint4*>(h + tsw::chunk_off(a.K[3], tg, c)) = ch[c];
+                    for (uint32_t c = 0; c < (LDIR ? 6u : 4u); c++) *reinterpret_cast<uint4*>(h + tsw::chunk_off_r(a.K[3], kTile, tg, c)) = ch[c];
                 } else {
                     // colour head (network.py:131-138): fp16 linear output, `color - 5` in fp16, exp in fp32
                     tc::tmem_ld16(lane_addr, out);
@@ -348,9 +364,11 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
         const uint32_t* d = l < 3 ? grid_dims : view_dims;
         const void* const* w = l < 3 ? grid_weights : view_weights;
         const uint32_t j = l % 3;
-        // every layer input is a swizzled tile of width 16 / 32 / 64 (tile_sw.cuh); wider layers (rfield: 48, 80) use the
-        // two-kernel path of field.cu / mlp.cu
-        if ((d[j] != 16 && d[j] != 32 && d[j] != 64) || d[j + 1] == 0 || d[j + 1] % 16 || d[j + 1] > 128) return NGP_ERR_UNSUPPORTED;
+        // layer inputs are swizzled tiles of width 16 / 32 / 64, or panels of 16 columns for any other multiple of 16 (the
+        // light-stage view_mlp: 48 -> 80 -> 80; tile_sw.cuh).  The tile images of the first kind are what the warp-specialised
+        // backward reads; with other widths the saved tensors are written as plain rows for the kernel-pair backward.
+        if (d[j] == 0 || d[j] % 16 || d[j] > 128 || d[j + 1] == 0 || d[j + 1] % 16 || d[j + 1] > 128) return NGP_ERR_UNSUPPORTED;
+        if (d[j] != 16 && d[j] != 32 && d[j] != 64) a.rowmajor = 1;
         if (!w[j]) return NGP_ERR_NULL;
         if (!aligned(w[j], 16)) return NGP_ERR_ALIGN;
         a.w[l] = (const __half*)w[j];

@@ -48,5 +48,25 @@ __device__ __forceinline__ void load_weight_tile(uint8_t* dst, const __half* __r
 
 __device__ __forceinline__ bool width_ok(uint32_t W) { return W == 16 || W == 32 || W == 64; }
 
+// ---- any width that is a multiple of 16 (the light-stage view_mlp: 48-wide input, 80-wide hidden layers) ------------------
+// A tile of R rows x W columns whose width is not 16 / 32 / 64 is stored as W / 16 PANELS of [R x 16] SWIZZLE_32B tiles, panel
+// p = columns [16 p, 16 p + 16) at byte offset p * R * 32.  One k-step of a K-major operand is exactly one panel, and the
+// MN-major view steps from panel to panel with LBO = R * 32 -- the same two descriptor forms as above with W = 16.
+__device__ __forceinline__ uint32_t chunk_off_r(uint32_t W, uint32_t R, uint32_t r, uint32_t j) {
+    if (width_ok(W)) return chunk_off(W, r, j);
+    return (j >> 1) * (R * 32) + r * 32 + (((j & 1u) ^ ((r >> 2) & 1u)) << 4);
+}
+__device__ __forceinline__ uint64_t desc_kmajor_r(uint32_t tile_saddr, uint32_t W, uint32_t R, uint32_t ks) {
+    if (width_ok(W)) return desc_kmajor(tile_saddr, W, ks);
+    return desc(tile_saddr + ks * R * 32, 16, 8 * 32, 16);
+}
+__device__ __forceinline__ void load_weight_tile_r(uint8_t* dst, const __half* __restrict__ w, uint32_t N, uint32_t K) {
+    const uint32_t chunks = K / 8;
+    for (uint32_t i = threadIdx.x; i < N * chunks; i += blockDim.x) {
+        const uint32_t n = i / chunks, c = i - n * chunks;
+        *reinterpret_cast<uint4*>(dst + chunk_off_r(K, N, n, c)) = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * K + c * 8));
+    }
+}
+
 }  // namespace tsw
 }  // namespace ngp

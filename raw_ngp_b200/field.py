@@ -67,6 +67,14 @@ def _ws_ok(p1, p2):
     return all(d in (16, 32, 64) for d in list(p1[:3]) + list(p2[:3]))
 
 
+def _ws_fwd_ok(p1, p2, L):
+    """The warp-specialised FORWARD takes any layer width that is a multiple of 16 up to 128 (16-column panels, csrc/tile_sw.cuh):
+    the light-stage view_mlp (48 -> 80 -> 80) runs in it, with the saved tensors written as plain rows for the kernel-pair
+    backward.  (The warp-specialised backward keeps all six weight-gradient accumulators in TMEM and both chains' tiles in
+    shared memory; at 80-wide layers neither fits -- 544 of 512 columns, 245 of 227 KB.)"""
+    return L % 8 == 0 and all(d % 16 == 0 and 16 <= d <= 128 for d in list(p1) + list(p2))
+
+
 class _fused_field(Function):
     @staticmethod
     def forward(ctx, xyzs, dirs, ldirs, table, feat_weights, cfg, *weights):
@@ -84,19 +92,20 @@ class _fused_field(Function):
         w2 = [_pad_weight(w, p2[i + 1], p2[i]) for i, w in enumerate(vw)]
         keep = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward; this is the real signal)
         ws = _ws_ok(p1, p2)
+        ws_fwd = ws or _ws_fwd_ok(p1, p2, enc.num_levels)
         f16 = dict(dtype=torch.float16, device=dev)
         Mt = (M + 127) // 128 * 128 if ws else M      # the WS kernels save whole 128-row tiles (tile-panel layout)
         enc_buf = torch.empty(Mt, p1[0], **f16) if keep else None
         acts1 = [torch.empty(Mt, p1[l + 1], **f16) if keep else None for l in range(len(w1) - 1)]
         acts2 = [torch.empty(Mt, p2[l + 1], **f16) if keep else None for l in range(len(w2) - 1)]
-        in2 = torch.empty(Mt, p2[0], **f16) if (keep or not ws) else None
+        in2 = torch.empty(Mt, p2[0], **f16) if (keep or not ws_fwd) else None
         sigma = torch.empty(M, dtype=torch.float32, device=dev)
         rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
         S, H, L, gt, ac, ip = _grid_scalars(enc)
         st = _lib.stream()
         c1 = (ctypes.c_uint32 * len(p1))(*p1)
         c2 = (ctypes.c_uint32 * len(p2))(*p2)
-        if ws:
+        if ws_fwd:
             _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(table), _lib.ptr(enc.offsets),
                       _lib.ptr(feat_weights), float(bound), S, H, L, gt, ac, ip, _ptr_array(w1), c1, _ptr_array(w2), c2, M, None,
                       int(density_act), float(beta), int(color_act), _lib.ptr(enc_buf), _ptr_array(acts1) if keep else None,

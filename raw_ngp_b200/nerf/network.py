@@ -97,7 +97,7 @@ class NeRFNetwork(NeRFRenderer):
         from .. import _lib
         from ..ffmlp import _pad16, _ptr_array
         enc = self.grid_encoder
-        if not (self.FUSED and self.opt.fp16 and not self.opt.rfield and rays_ldir is None and enc.embeddings.is_cuda
+        if not (self.FUSED and self.opt.fp16 and (rays_ldir is not None) == bool(self.opt.rfield) and enc.embeddings.is_cuda
                 and enc.embeddings.dtype == torch.float16 and enc.level_dim == 2 and enc.input_dim == 3 and enc.num_levels % 8 == 0
                 and self.opt.internal_activation == "relu" and self.opt.density_activation in ("clamped_exp", "softplus")
                 and self.opt.color_activation in _field.COLOR_ACT and self.opt.pose_opt in ("none", "barf")
@@ -106,7 +106,7 @@ class NeRFNetwork(NeRFRenderer):
         gw, vw = [l.weight for l in self.grid_mlp.net], [l.weight for l in self.view_mlp.net]
         p1 = [_pad16(d) for d in [gw[0].shape[1]] + [w.shape[0] for w in gw]]
         p2 = [_pad16(d) for d in [vw[0].shape[1]] + [w.shape[0] for w in vw]]
-        if not _field._ws_ok(p1, p2):
+        if not _field._ws_fwd_ok(p1, p2, enc.num_levels):
             return None
         w1 = [_field._pad_weight(w, p1[i + 1], p1[i]) for i, w in enumerate(gw)]
         w2 = [_field._pad_weight(w, p2[i + 1], p2[i]) for i, w in enumerate(vw)]
@@ -116,10 +116,18 @@ class NeRFNetwork(NeRFRenderer):
         fw = self._feat_weights(enc.embeddings.device)
         dens, col, beta, bound = self._density_act(), _field.COLOR_ACT[self.opt.color_activation], float(self.opt.beta), float(self.bound)
         keep = (w1, w2, fw)      # the launch arguments below hold raw pointers into these
+        # light stage (rfield): ONE light direction per frame, repeated for every sample (renderer.py:605)
+        ld_vec = rays_ldir.reshape(-1, 3)[:1].float() if self.opt.rfield else None
+        ld_rows = {}
 
         def field(xyzs, dirs, M, sigmas, rgbs, st, m_dev=None, _keep=keep):
             # m_dev: device address of the live row count (<= M), see NeRFRenderer._march_composite_loop_fast
-            _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), None, _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
+            ldirs = None
+            if ld_vec is not None:
+                if M not in ld_rows:
+                    ld_rows[M] = ld_vec.to(xyzs.device).expand(M, 3).contiguous()
+                ldirs = ld_rows[M]
+            _lib.call("ngp_field_forward_full", _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(ldirs), _lib.ptr(enc.embeddings), _lib.ptr(enc.offsets),
                       _lib.ptr(fw), bound, S, H, L, gt, ac, ip, a1, c1, a2, c2, M, m_dev, dens, beta, col, None, None, None, None,
                       _lib.ptr(sigmas), _lib.ptr(rgbs), None, st)
         return field

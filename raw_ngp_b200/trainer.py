@@ -271,6 +271,8 @@ class FusedTrainStep:
         # widths in {16, 32, 64}: the warp-specialised one-kernel forward / backward; otherwise (rfield: 48-wide view input,
         # 80-wide hidden layers) the density-field + view-MLP kernel pairs, with the same buffers and the same graph
         self.ws = _field._ws_ok(self.p1, self.p2)
+        # any width that is a multiple of 16: the warp-specialised FORWARD still applies (row-major saves for the pair backward)
+        self.ws_fwd = self.ws or _field._ws_fwd_ok(self.p1, self.p2, enc.num_levels)
         # ray_grads: also produce dL/d rays_o and dL/d rays_d (self.d_rays_o / self.d_rays_d, scaled by loss_scale like every
         # gradient of the step) for pose refinement (BARF, --pose_opt barf: rays come from refined poses and require grad)
         # pose_optimizer (raw_ngp_b200.pose.CameraOptimizer) + poses [C, 3|4, 4]: the rays of the step are generated on the
@@ -478,10 +480,15 @@ class FusedTrainStep:
                           P(self.cam_idx), P(self.dirs_cam), N, self.se3.shape[0], P(self.se3_grad), st)
             return
         ld2 = self.p2[0]
-        _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
-                  P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, 3, cap, self._m_dev, self._density_act,
-                  float(opt.beta), P(self.enc_buf), a1, P(self.sigma), P(self.in2), ld2, st)
-        _lib.call("ngp_mlp_forward_rgb", P(self.in2), ld2, w2, c2, 3, cap, self._m_dev, 1, self._color_act, P(self.rgb), a2, st)
+        if self.ws_fwd:       # one warp-specialised forward (16-column panels for the 48 / 80-wide layers), plain-row saves
+            _lib.call("ngp_field_forward_full", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
+                      P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap, self._m_dev, self._density_act,
+                      float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), None, st)
+        else:
+            _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
+                      P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, 3, cap, self._m_dev, self._density_act,
+                      float(opt.beta), P(self.enc_buf), a1, P(self.sigma), P(self.in2), ld2, st)
+            _lib.call("ngp_mlp_forward_rgb", P(self.in2), ld2, w2, c2, 3, cap, self._m_dev, 1, self._color_act, P(self.rgb), a2, st)
         composite()
         _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), ld2, w2, a2, c2, 3, cap,
                   self._m_dev, 1, P(self.d_in2), ld2, dw2, st)
