@@ -32,7 +32,7 @@ constexpr uint32_t kGatherThreads = 512;
 constexpr uint32_t kGatherGroups = kGatherThreads / kTile;
 constexpr uint32_t kMlpGroups = 3;
 constexpr uint32_t kWsThreads = kGatherThreads + kMlpGroups * kTile;     // 768
-constexpr uint32_t kStages = 3;
+constexpr uint32_t kStages = kMlpGroups;      // one ring stage per MLP group: a stage barrier is only ever waited on by its own group (phase parity!)
 constexpr uint32_t kGroupTmemCols = 128;
 constexpr uint32_t kWsTmemCols = 512;
 constexpr uint32_t kWsLayers = 6;
