@@ -414,14 +414,23 @@ int ngp_field_forward_density(const float* xyzs, const float* dirs, const float*
                               float* sigma_out, void* in2, uint32_t ld2, ngp_stream_t stream);
 
 /* d_sigma, sigma [M] fp32; d_in2 [M, ld2] fp16 (columns 0..14 are used); enc / acts as saved by the forward;
- * grad_table [sO, 2] fp16 is ACCUMULATED into; dweights[l] fp32 accumulated with atomics. */
+ * grad_table [sO, 2] fp16 is ACCUMULATED into; dweights[l] fp32 accumulated with atomics.
+ * Input gradients (BARF with the light-stage widths): dydx = the d enc / d x block that ngp_field_forward_full wrote
+ * (dydx_out), d_xyzs [M, 3] fp32 out = d loss / d xyzs (kernel_input_backward, gridencoder.cu:352-378); both or neither. */
 int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
-                               uint32_t ld2, const void* enc, const void* table, const int32_t* offsets,
+                               uint32_t ld2, const void* enc, const void* dydx, const int32_t* offsets,
                                const float* feat_weights, float bound, float S, uint32_t H, uint32_t L,
                                uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
                                const int32_t* m_dev, int density_act, float beta, void* grad_table,
-                               float* const* dweights, ngp_stream_t stream);
+                               float* const* dweights, float* d_xyzs, ngp_stream_t stream);
+
+/* d loss / d dirs [M, 3] from the gradient of the view_mlp input: d_in2 [M, ld2] fp16, columns [col0, col0 + 16) = d SH(dir)
+ * (degree 4), through the SH Jacobian (shencoder.cu:130-350) and the two normalisations of the forward (renderer.py:544,
+ * sphere_harmonics.py:81).  dirs = the marcher's directions.  The warp-specialised backward does this in its V0 group; this
+ * entry point serves the kernel-pair backward. */
+int ngp_sh_dirs_backward(const void* d_in2, uint32_t ld2, uint32_t col0, const float* dirs, uint32_t M,
+                         const int32_t* m_dev, float* d_dirs, ngp_stream_t stream);
 
 /* ngp_mlp_forward whose last epilogue applies the colour activation to output columns 0..2 and writes rgb_out [M,3] fp32 */
 int ngp_mlp_forward_rgb(const void* x, uint32_t ldx, const void* const* weights, const uint32_t* dims,

@@ -59,7 +59,8 @@ SIGNATURES = {
     "ngp_mlp_forward": [_p, _u32, _p, _p, _u32, _u32, _i, _p, _u32, _p, _p],
     "ngp_mlp_backward": [_p, _u32, _p, _u32, _p, _p, _p, _u32, _u32, _i, _p, _u32, _p, _p],
     "ngp_field_forward_density": [_p, _p, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _i, _u32, _p, _p, _u32, _u32, _p, _i, _f32, _p, _p, _p, _p, _u32, _p],
-    "ngp_field_backward_density": [_p, _p, _p, _p, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _i, _u32, _p, _p, _p, _u32, _u32, _p, _i, _f32, _p, _p, _p],
+    "ngp_field_backward_density": [_p, _p, _p, _p, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _i, _u32, _p, _p, _p, _u32, _u32, _p, _i, _f32, _p, _p, _p, _p],
+    "ngp_sh_dirs_backward": [_p, _u32, _u32, _p, _u32, _p, _p, _p],
     "ngp_field_backward_full": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _i, _u32, _p, _p, _p, _p, _u32, _p, _i, _f32, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "ngp_field_forward_full": [_p, _p, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _i, _u32, _p, _p, _p, _p, _u32, _p, _i, _f32, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "ngp_mlp_forward_rgb": [_p, _u32, _p, _p, _u32, _u32, _p, _i, _i, _p, _p, _p],

@@ -224,8 +224,11 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                               const __half* __restrict__ d_in2, uint32_t ld2, const __half* __restrict__ enc, GridArgs g,
                               MlpArgs p, uint32_t M, __half* __restrict__ grad_table, int density_act, float beta,
                               uint32_t dz_off, uint32_t dz_bytes, uint32_t w_base, uint32_t ctrl_off,
-                              const int* __restrict__ m_dev) {
+                              const int* __restrict__ m_dev, const __half* __restrict__ dydx, float* __restrict__ d_xyzs) {
     extern __shared__ __align__(128) uint8_t smem[];
+    // input gradients (dydx != nullptr): the four level groups of a sample add their parts of d loss / d xyz here
+    __shared__ float s_dx[kTile * 3];
+    if (threadIdx.x < kTile * 3) s_dx[threadIdx.x] = 0.f;
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t t = (warp & 3u) * 32u + lane;     // sample row inside the tile == TMEM lane
@@ -360,15 +363,48 @@ field_backward_density_kernel(const float* __restrict__ xyzs, const float* __res
                 // ---- d enc of this thread's sample (TMEM lane) -> hash-table gradient; this group's 4 levels per pass ----
                 float x[3] = {2.f, 2.f, 2.f};
                 if (live) unit_cube(xyzs + (size_t)row * 3, g.bound, x);
+                float dxa[3] = {0.f, 0.f, 0.f};
                 for (uint32_t level = grp; level < g.L; level += kBwdGroups) {     // levels interleaved across the groups
                     float v[2];
                     tc::tmem_ld2(lane_addr + 2 * level, v);
-                    scatter_level(g, s_lv[level], level, x, live, __floats2half2_rn(v[0], v[1]), grad_table, lane);
+                    const __half2 gh = __floats2half2_rn(v[0], v[1]);
+                    if (dydx && live) {
+                        // d loss / d xyz += d enc(level) . d enc / d x, with the dy_dx the warp-specialised forward saved for this
+                        // thread's (row, level group): kernel_input_backward of the reference (gridencoder.cu:352-378); layout and
+                        // arithmetic as in field_bwd_ws.cu
+                        const uint32_t j = (level - grp) / kBwdGroups;
+                        const uint32_t* dy = reinterpret_cast<const uint32_t*>(dydx) +
+                                             (((size_t)(tile * kBwdGroups + grp) * (g.L / 8) + j / 2) * 6 + (j % 2) * 3) * kTile + t;
+                        float2 gf = __half22float2(gh);
+                        if (g.feat_weights) {
+                            const __half2 gw = __floats2half2_rn(gf.x * __ldg(g.feat_weights + 2 * level), gf.y * __ldg(g.feat_weights + 2 * level + 1));
+                            gf = __half22float2(gw);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const uint32_t u = __ldg(dy + d * kTile);
+                            const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&u));
+                            dxa[d] += gf.x * y.x + gf.y * y.y;
+                        }
+                    }
+                    scatter_level(g, s_lv[level], level, x, live, gh, grad_table, lane);
+                }
+                if (dydx) {
+                    const float inv2b = __fdiv_rn(1.0f, 2.0f * g.bound);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) atomicAdd(&s_dx[t * 3 + d], dxa[d] * inv2b);
                 }
             }
             tc::fence_before_sync();
             __syncthreads();
             cur ^= 1;
+        }
+        if (dydx && grp == 0) {      // all four groups have added their parts (barrier above); the next tile adds after another barrier
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                if (live) d_xyzs[(size_t)row * 3 + d] = s_dx[t * 3 + d];
+                s_dx[t * 3 + d] = 0.f;
+            }
         }
     }
     if (iter > 0) {
@@ -451,14 +487,15 @@ extern "C" int ngp_field_forward_density(const float* xyzs, const float* dirs, c
 }
 
 extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigma, const float* sigma, const void* d_in2,
-                                          uint32_t ld2, const void* enc, const void* table_unused, const int32_t* offsets,
+                                          uint32_t ld2, const void* enc, const void* dydx, const int32_t* offsets,
                                           const float* feat_weights, float bound, float S, uint32_t H, uint32_t L,
                                           uint32_t gridtype, int align_corners, uint32_t interp, const void* const* weights,
                                           const void* const* acts, const uint32_t* dims, uint32_t n_layers, uint32_t M,
                                           const int32_t* m_dev, int density_act, float beta, void* grad_table, float* const* dweights,
-                                          ngp_stream_t stream) {
-    (void)table_unused;
+                                          float* d_xyzs, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
+    if ((dydx != nullptr) != (d_xyzs != nullptr)) return NGP_ERR_NULL;
+    if (dydx && (!aligned(dydx, 16) || L % 8 != 0)) return NGP_ERR_BAD_ARG;
     if (!xyzs || !d_sigma || !sigma || !d_in2 || !enc || !offsets || !weights || !dims || !grad_table || !dweights) return NGP_ERR_NULL;
     if (n_layers > 1 && !acts) return NGP_ERR_NULL;
     if (L == 0 || L > kMaxLevels || L % 4 != 0 || gridtype > 1 || interp > 1 || density_act < 0 || density_act > 1) return NGP_ERR_BAD_ARG;
@@ -492,6 +529,6 @@ extern "C" int ngp_field_backward_density(const float* xyzs, const float* d_sigm
     const uint32_t grid = std::min<uint32_t>(div_up(M, kTile), kNumSMs * 2);
     field_backward_density_kernel<<<grid, kBwdThreads, smem_bytes, (cudaStream_t)stream>>>(
         xyzs, d_sigma, sigma, (const __half*)d_in2, ld2, (const __half*)enc, g, p, M, (__half*)grad_table, density_act, beta,
-        dz_off, dz_bytes, w_base, ctrl_off, m_dev);
+        dz_off, dz_bytes, w_base, ctrl_off, m_dev, (const __half*)dydx, d_xyzs);
     return finish_launch();
 }

@@ -146,3 +146,44 @@ extern "C" int ngp_sh_encode_backward(const void* grad, const float* inputs, uin
         default: return NGP_ERR_BAD_DTYPE;
     }
 }
+
+
+namespace ngp {
+namespace {
+__global__ void sh_dirs_backward_kernel(const __half* __restrict__ d_in2, uint32_t ld2, uint32_t col0, const float* __restrict__ dirs,
+                                        uint32_t M, const int* __restrict__ m_dev, float* __restrict__ d_dirs) {
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    float gs[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) gs[k] = __half2float(d_in2[(size_t)row * ld2 + col0 + k]);
+    const float d0 = __ldg(dirs + (size_t)row * 3), d1 = __ldg(dirs + (size_t)row * 3 + 1), d2 = __ldg(dirs + (size_t)row * 3 + 2);
+    const float inv0 = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);            // renderer.py:544
+    const float u0 = d0 * inv0, u1 = d1 * inv0, u2 = d2 * inv0;
+    const float inv1 = 1.0f / sqrtf(u0 * u0 + u1 * u1 + u2 * u2);            // sphere_harmonics.py:81
+    const float x = u0 * inv1, y = u1 * inv1, z = u2 * inv1, zz = z * z;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    constexpr int DEG = 4;
+#define SH_TERM(i, val, ddx, ddy, ddz) gx += gs[i] * (ddx); gy += gs[i] * (ddy); gz += gs[i] * (ddz);
+#include "sh_basis.inc"
+#undef SH_TERM
+    // v = n / |n|  =>  d n = (d v - v (v . d v)) / |n|, twice
+    float t = x * gx + y * gy + z * gz;
+    gx = (gx - x * t) * inv1; gy = (gy - y * t) * inv1; gz = (gz - z * t) * inv1;
+    t = u0 * gx + u1 * gy + u2 * gz;
+    d_dirs[(size_t)row * 3] = (gx - u0 * t) * inv0;
+    d_dirs[(size_t)row * 3 + 1] = (gy - u1 * t) * inv0;
+    d_dirs[(size_t)row * 3 + 2] = (gz - u2 * t) * inv0;
+}
+}  // namespace
+}  // namespace ngp
+
+extern "C" int ngp_sh_dirs_backward(const void* d_in2, uint32_t ld2, uint32_t col0, const float* dirs, uint32_t M,
+                                    const int32_t* m_dev, float* d_dirs, ngp_stream_t stream) {
+    if (M == 0) return NGP_OK;
+    if (!d_in2 || !dirs || !d_dirs) return NGP_ERR_NULL;
+    if (col0 + 16 > ld2) return NGP_ERR_BAD_ARG;
+    ngp::sh_dirs_backward_kernel<<<ngp::div_up(M, 256u), 256, 0, (cudaStream_t)stream>>>((const __half*)d_in2, ld2, col0, dirs, M, m_dev, d_dirs);
+    return ngp::finish_launch();
+}

@@ -164,7 +164,7 @@ class _fused_field(Function):
                       _ptr_array(acts2), c2, n2, M, None, NGP_ACT_RELU, _lib.ptr(d_in2), p2[0], _ptr_array(dw2), st)
             _lib.call("ngp_field_backward_density", _lib.ptr(xyzs), _lib.ptr(d_sigma), _lib.ptr(sigma), _lib.ptr(d_in2), p2[0],
                       _lib.ptr(enc_buf), None, _lib.ptr(enc.offsets), fwp, float(bound), S, H, L, gt, ac, ip, _ptr_array(w1),
-                      _ptr_array(acts1), c1, n1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), st)
+                      _ptr_array(acts1), c1, n1, M, None, int(density_act), float(beta), _lib.ptr(gtable), _ptr_array(dw1), None, st)
         gw = [dw1[l][:d1[l + 1], :d1[l]].to(wdt[l]) for l in range(n1)]
         vw = [dw2[l][:d2[l + 1], :d2[l]].to(wdt[n1 + l]) for l in range(n2)]
         return (None, None, None, None if sink is not None else gtable, None, None, *gw, *vw)

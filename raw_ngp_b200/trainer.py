@@ -273,15 +273,15 @@ class FusedTrainStep:
         self.ws = _field._ws_ok(self.p1, self.p2)
         # any width that is a multiple of 16: the warp-specialised FORWARD still applies (row-major saves for the pair backward)
         self.ws_fwd = self.ws or _field._ws_fwd_ok(self.p1, self.p2, enc.num_levels)
+        self.ray_grads = bool(ray_grads) or pose_optimizer is not None
         # ray_grads: also produce dL/d rays_o and dL/d rays_d (self.d_rays_o / self.d_rays_d, scaled by loss_scale like every
         # gradient of the step) for pose refinement (BARF, --pose_opt barf: rays come from refined poses and require grad)
         # pose_optimizer (raw_ngp_b200.pose.CameraOptimizer) + poses [C, 3|4, 4]: the rays of the step are generated on the
         # device from (camera index, pixel direction) through the refined poses, and se3_refine is trained by its own Adam
         # (torch defaults like barf/camera_optimizers.py:40) with its own inf check (GradScaler checks per optimizer)
         self.pose = pose_optimizer
-        self.ray_grads = bool(ray_grads) or pose_optimizer is not None
-        if self.ray_grads and not self.ws:
-            raise RuntimeError("FusedTrainStep: ray gradients need the warp-specialised kernels (layer widths in {16, 32, 64})")
+        if self.ray_grads and not self.ws_fwd:
+            raise RuntimeError("FusedTrainStep: ray gradients need the warp-specialised forward (layer widths multiples of 16 up to 128)")
         self.w_master = torch.zeros(n_w, device=dev, dtype=torch.float32)
         self.w_lp = torch.zeros(n_w, device=dev, dtype=torch.float16)
         self._w_master_views, self._w_lp_views, self._w_grad_views = [], [], []
@@ -373,7 +373,7 @@ class FusedTrainStep:
         self.acts1 = [torch.empty(cap_t, self.p1[l + 1], **f16) for l in range(2)]
         self.acts2 = [torch.empty(cap_t, self.p2[l + 1], **f16) for l in range(2)]
         self.in2 = torch.empty(cap_t, self.p2[0], **f16)
-        self.d_in2 = None if self.ws else torch.empty(cap, self.p2[0], **f16)
+        self.d_in2 = None if self.ws else torch.empty(cap_t, self.p2[0], **f16)
         self.sigma, self.rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.d_sigma, self.d_rgb = torch.empty(cap, **f32), torch.empty(cap, 3, **f32)
         self.dydx = torch.empty(cap_t, 6 * enc.num_levels, **f16) if self.ray_grads else None   # d enc / d x, saved by the forward
@@ -471,19 +471,14 @@ class FusedTrainStep:
                       w1, c1, w2, c2, cap, self._m_dev, self._density_act, float(opt.beta), self._color_act, P(self.table_grad),
                       dw1, dw2, P(self.dydx), P(self.dirs) if self.ray_grads else None,
                       P(self.d_xyzs), P(self.d_dirs), st)
-            if self.ray_grads:
-                # dL/d rays_o = sum_seg dL/dxyz, dL/d rays_d = sum_seg (dL/dxyz * t + dL/ddirs)  (raymarching.py:319-329)
-                _lib.call("ngp_march_rays_train_backward", P(self.d_xyzs), P(self.d_dirs), P(self.ts), P(self.rays), N, cap,
-                          P(self.d_rays_o), P(self.d_rays_d), st)
-            if self.pose is not None:
-                _lib.call("ngp_pose_rays_backward", P(self.d_rays_o), P(self.d_rays_d), P(self.se3), P(self.poses), self.pose_stride,
-                          P(self.cam_idx), P(self.dirs_cam), N, self.se3.shape[0], P(self.se3_grad), st)
+            self._launch_ray_backward()
             return
         ld2 = self.p2[0]
         if self.ws_fwd:       # one warp-specialised forward (16-column panels for the 48 / 80-wide layers), plain-row saves
             _lib.call("ngp_field_forward_full", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
                       P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, w2, c2, cap, self._m_dev, self._density_act,
-                      float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb), None, st)
+                      float(opt.beta), self._color_act, P(self.enc_buf), a1, P(self.in2), a2, P(self.sigma), P(self.rgb),
+                      P(self.dydx), st)
         else:
             _lib.call("ngp_field_forward_density", P(self.xyzs), P(self.dirs), P(self.ldirs), P(enc.embeddings), P(enc.offsets),
                       P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, c1, 3, cap, self._m_dev, self._density_act,
@@ -492,9 +487,22 @@ class FusedTrainStep:
         composite()
         _lib.call("ngp_mlp_backward_rgb", P(self.d_rgb), P(self.rgb), self._color_act, P(self.in2), ld2, w2, a2, c2, 3, cap,
                   self._m_dev, 1, P(self.d_in2), ld2, dw2, st)
+        if self.ray_grads:      # d dirs from d SH(dir) = d in2[:, 15:31] (the warp-specialised backward does this in its V0 group)
+            _lib.call("ngp_sh_dirs_backward", P(self.d_in2), ld2, 15, P(self.dirs), cap, self._m_dev, P(self.d_dirs), st)
         _lib.call("ngp_field_backward_density", P(self.xyzs), P(self.d_sigma), P(self.sigma), P(self.d_in2), ld2, P(self.enc_buf),
-                  None, P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap, self._m_dev,
-                  self._density_act, float(opt.beta), P(self.table_grad), dw1, st)
+                  P(self.dydx), P(enc.offsets), P(self.feat_weights), float(m.bound), S, H, L, gt, ac, ip, w1, a1, c1, 3, cap, self._m_dev,
+                  self._density_act, float(opt.beta), P(self.table_grad), dw1, P(self.d_xyzs), st)
+        self._launch_ray_backward()
+
+    def _launch_ray_backward(self):
+        """dL/d rays_o = sum_seg dL/dxyz, dL/d rays_d = sum_seg (dL/dxyz * t + dL/ddirs)  (raymarching.py:319-329), then d se3."""
+        P, st, N = _lib.ptr, _lib.stream(), self.N
+        if self.ray_grads:
+            _lib.call("ngp_march_rays_train_backward", P(self.d_xyzs), P(self.d_dirs), P(self.ts), P(self.rays), N, self.cap,
+                      P(self.d_rays_o), P(self.d_rays_d), st)
+        if self.pose is not None:
+            _lib.call("ngp_pose_rays_backward", P(self.d_rays_o), P(self.d_rays_d), P(self.se3), P(self.poses), self.pose_stride,
+                      P(self.cam_idx), P(self.dirs_cam), N, self.se3.shape[0], P(self.se3_grad), st)
 
     def _launch_check(self, count_step=False):
         """inf / nan check of both gradient buffers -> self.found_inf (overwritten) in one launch; count_step: the same kernel

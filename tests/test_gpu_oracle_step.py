@@ -184,3 +184,15 @@ def test_configs4_barf_ray_gradients_vs_reference_stack():
                start_annealing=0.0, end_annealing=0.5)
     ours = _run("configs4", 8192, cfg, ray_grads=True, annealing=0.3)
     assert ours["M"] > 1_000_000
+
+
+def test_light_stage_with_barf_ray_gradients_vs_reference_stack():
+    """The light-stage preset with pose refinement: view_mlp 47 -> 80 -> 80 -> 3 (SH of view and light direction), contraction, HDR
+    loss, BARF window, rays require grad (colmap_provider.py:644-645 switches that on for every light-stage run).  Forward in the
+    warp-specialised kernel on 16-column panels (+ dy_dx), backward in the kernel pairs: d xyz is contracted inside the density
+    backward, d dirs by ngp_sh_dirs_backward."""
+    cfg = dict(bound=2, contract=True, rfield=True, grid_size=128, max_steps=512, hashmap_size=19, hashgrid_resolution=2048,
+               color_activation="clamped_exp", density_activation="clamped_exp", pose_opt="barf", num_cameras=4,
+               start_annealing=0.0, end_annealing=0.5)
+    ours = _run("lightstage_barf", 4096, cfg, loss_kind="hdr", rfield=True, ray_grads=True, annealing=0.3)
+    assert ours["M"] > 1_000_000 and not ours["fs"].ws and ours["fs"].ws_fwd
