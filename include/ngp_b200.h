@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NGP_B200_ABI_VERSION 3
+#define NGP_B200_ABI_VERSION 4
 
 typedef void* ngp_stream_t; /* cudaStream_t */
 
@@ -350,6 +350,15 @@ int ngp_occ_scatter_sigmas(const int32_t* indices, const float* sigmas, uint32_t
  * and zero-filled by the caller. */
 int ngp_occ_ema_update(float* density_grid, const float* tmp_grid, uint32_t n_cells, float decay,
                        double* accum, float* mean_out, ngp_stream_t stream);
+
+/* The sample set of a PARTIAL occupancy update of one cascade (nerf/renderer.py:853-876: H^3/4 uniformly random cells + H^3/4
+ * random occupied cells, jittered positions) without the reference's host sync on the size of the occupied list: the ids of the
+ * cells with density > 0 are compacted from density_grid_cas [H^3] into occ_list [H^3] (count in occ_count[0]; workspace int32
+ * [ceil(H^3 / 4096)]), then u [n, 6] uniforms in [0,1) (n even: first half uniform cells, second half occupied cells) become
+ * xyzs_out [n, 3] and indices_out [n] (Morton ids).  Same distribution as the reference, different random stream. */
+int ngp_occ_sample_partial(const float* density_grid_cas, uint32_t H, float bound, const float* u, uint32_t n,
+                           int32_t* occ_list, int32_t* occ_count, int32_t* workspace, float* xyzs_out,
+                           int32_t* indices_out, ngp_stream_t stream);
 
 /* NeRFRenderer.mark_untrained_grid (nerf/renderer.py:716-809) as one launch: cell (cascade, Morton index) of density_grid
  * [cascade, H^3] is set to -1 unless its centre lies inside aabb [6] grown by half a cell AND inside the frustum of at least

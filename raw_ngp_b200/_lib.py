@@ -55,6 +55,7 @@ SIGNATURES = {
     "ngp_occ_sample_positions": [_p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_occ_scatter_sigmas": [_p, _p, _u32, _p, _p],
     "ngp_occ_ema_update": [_p, _p, _u32, _f32, _p, _p, _p],
+    "ngp_occ_sample_partial": [_p, _u32, _f32, _p, _u32, _p, _p, _p, _p, _p, _p],
     "ngp_mark_untrained_grid": [_p, _p, _u32, _u32, _p, _u32, _p, _f32, _p, _u32, _u32, _f32, _p],
     "ngp_mlp_forward": [_p, _u32, _p, _p, _u32, _u32, _i, _p, _u32, _p, _p],
     "ngp_mlp_backward": [_p, _u32, _p, _u32, _p, _p, _p, _u32, _u32, _i, _p, _u32, _p, _p],

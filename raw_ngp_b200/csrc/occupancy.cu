@@ -99,6 +99,93 @@ occ_ema_kernel(float* __restrict__ density_grid, const float* __restrict__ tmp_g
 }
 
 
+
+// ---- partial update (renderer.py:853-876): H^3/4 uniformly random cells + H^3/4 random OCCUPIED cells per cascade ----------
+// The reference draws them with randint / nonzero / randint / morton3D_invert / cat / rand_like (and a host sync for the size
+// of the occupied list).  Here: the ids of the occupied cells are compacted straight from the density grid (two launches,
+// order preserved, count on the device) and ONE kernel turns 6 uniforms per sample into (cell, jittered position).
+constexpr uint32_t kOccTile = 256 * 16;
+
+__global__ void __launch_bounds__(256)
+occ_count_positive_kernel(const float* __restrict__ grid, uint32_t n, int* __restrict__ block_counts) {
+    const uint32_t first = blockIdx.x * kOccTile + threadIdx.x * 16;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) cnt += (first + k < n && __ldg(grid + first + k) > 0.f) ? 1u : 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    __shared__ uint32_t s_w[8];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        block_counts[blockIdx.x] = (int)t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+occ_write_positive_kernel(const float* __restrict__ grid, uint32_t n, const int* __restrict__ block_counts, int* __restrict__ out,
+                          int* __restrict__ n_out) {
+    __shared__ uint32_t s_w[8], s_red[8];
+    uint32_t part = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 256) part += (uint32_t)__ldg(block_counts + b);
+    part = __reduce_add_sync(0xffffffffu, part);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    const uint32_t first = blockIdx.x * kOccTile + threadIdx.x * 16;
+    uint32_t mask = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) mask |= (first + k < n && __ldg(grid + first + k) > 0.f) ? (1u << k) : 0u;
+    const uint32_t cnt = __popc(mask), lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int sh = 1; sh < 32; sh <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, sh);
+        if (lane >= (uint32_t)sh) incl += u;
+    }
+    if (lane == 31) s_w[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0, base = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) { const uint32_t c = s_w[w]; if (w < wid) before += c; total += c; base += s_red[w]; }
+    uint32_t pos = base + before + incl - cnt;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++)
+        if (mask & (1u << k)) out[pos++] = (int)(first + k);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) n_out[0] = (int)(base + total);
+}
+
+// u [n, 6] uniforms in [0, 1): sample i < n / 2 is a uniformly random cell (u0..2 -> coordinates), sample i >= n / 2 a random
+// entry of the occupied list (u0 -> index; with no occupied cell it revisits the cell of sample i - n / 2, the reference would fail
+// on randint(0, 0)); u3..5 jitter the position inside the cell exactly like occ_sample_kernel.
+__global__ void occ_sample_partial_kernel(const float* __restrict__ u, uint32_t n, const int* __restrict__ occ_list,
+                                          const int* __restrict__ occ_count, uint32_t H, float span, float hgs,
+                                          float* __restrict__ xyzs, int* __restrict__ indices_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* ui = u + (size_t)i * 6;
+    const uint32_t count = (uint32_t)__ldg(occ_count);
+    uint32_t cx, cy, cz, morton;
+    if (i >= n / 2 && count > 0) {
+        const uint32_t k = min((uint32_t)(__ldg(ui) * (float)count), count - 1);
+        morton = (uint32_t)__ldg(occ_list + k);
+        cx = compact3(morton); cy = compact3(morton >> 1); cz = compact3(morton >> 2);
+    } else {
+        const float* uc = (i >= n / 2) ? u + (size_t)(i - n / 2) * 6 : ui;      // no occupied cell: the second half revisits the uniform cells
+        cx = min((uint32_t)(__ldg(uc) * (float)H), H - 1); cy = min((uint32_t)(__ldg(uc + 1) * (float)H), H - 1);
+        cz = min((uint32_t)(__ldg(uc + 2) * (float)H), H - 1);
+        morton = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
+    }
+    const float c[3] = {(float)cx, (float)cy, (float)cz};
+    const float inv_hm1 = __fdiv_rn(1.0f, (float)(H - 1));
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float w = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, c[a]), inv_hm1), -1.0f);
+        const float jitter = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(ui + 3 + a), 2.0f), -1.0f), hgs);
+        xyzs[(size_t)i * 3 + a] = __fadd_rn(__fmul_rn(w, span), jitter);
+    }
+    indices_out[i] = (int)morton;
+}
+
 // renderer.py:716-809: a cell is "trainable" iff it lies inside the training AABB (grown by half a cell) and inside the view
 // frustum of at least one training camera.  The reference evaluates this with a Python loop over 64^3 chunks x cascades x camera
 // batches of torch ops (meshgrid, morton3D, batched matmul, boolean masks, index_put); here one thread owns one cell of one
@@ -217,5 +304,21 @@ extern "C" int ngp_mark_untrained_grid(float* density_grid, const float* poses, 
     mark_untrained_kernel<<<dim3(div_up(H3, 256u), cascade), 256, 0, (cudaStream_t)stream>>>(density_grid, poses, pose_stride, B, half_fov,
                                                                                             n_intr, cam_near, min_near, aabb, H, cascade,
                                                                                             grid_bound);
+    return finish_launch();
+}
+
+extern "C" int ngp_occ_sample_partial(const float* density_grid_cas, uint32_t H, float bound, const float* u, uint32_t n,
+                                      int32_t* occ_list, int32_t* occ_count, int32_t* workspace, float* xyzs_out,
+                                      int32_t* indices_out, ngp_stream_t stream) {
+    if (n == 0) return NGP_OK;
+    if (!density_grid_cas || !u || !occ_list || !occ_count || !workspace || !xyzs_out || !indices_out) return NGP_ERR_NULL;
+    if (H < 2 || H > 1024 || (n & 1u)) return NGP_ERR_BAD_ARG;
+    const uint32_t H3 = H * H * H, blocks = div_up(H3, kOccTile);
+    cudaStream_t st = (cudaStream_t)stream;
+    occ_count_positive_kernel<<<blocks, 256, 0, st>>>(density_grid_cas, H3, workspace);
+    occ_write_positive_kernel<<<blocks, 256, 0, st>>>(density_grid_cas, H3, workspace, occ_list, occ_count);
+    const double hgs = (double)bound / (double)H;
+    occ_sample_partial_kernel<<<div_up(n, 256u), 256, 0, st>>>(u, n, occ_list, occ_count, H, (float)((double)bound - hgs), (float)hgs, xyzs_out,
+                                                             indices_out);
     return finish_launch();
 }

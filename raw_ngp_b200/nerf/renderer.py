@@ -311,27 +311,24 @@ class NeRFRenderer(nn.Module):
             bound = float(min(2 ** cas, self.bound))
             if self.iter_density < 16:
                 n = H3
-                cells = None
                 noise = torch.rand(n, 3, device=dev)
+                xyzs = torch.empty(n, 3, device=dev)
+                indices = torch.empty(n, dtype=torch.int32, device=dev)
+                _lib.call("ngp_occ_sample_positions", None, _lib.ptr(noise), n, H, bound, _lib.ptr(xyzs), _lib.ptr(indices), st)
             else:
-                quarter = H3 // 4
-                coords = torch.randint(0, H, (quarter, 3), device=dev)
-                uniform_idx = raymarching.morton3D(coords)
-                # H^3/4 random OCCUPIED cells (renderer.py:862-866 does nonzero() + randint, a host sync); here the occupied
-                # ids are compacted on the device and drawn with floor(u * count), the count never leaves the GPU.  With no
-                # occupied cell the reference samples the uniform cells only; the second half then repeats them.
-                ids = torch.arange(H3, dtype=torch.int32, device=dev)
-                occ_list, occ_count = raymarching.compact_rays_alive(torch.where(self.density_grid[cas] > 0, ids, -1))
-                pick = (torch.rand(quarter, device=dev) * occ_count.float()).long()
-                pick = torch.minimum(pick, (occ_count.long() - 1).clamp(min=0))
-                occ_cells = torch.where(occ_count > 0, occ_list[pick], uniform_idx)
-                cells = torch.cat([uniform_idx, occ_cells], dim=0).contiguous()
-                n = cells.shape[0]
-                noise = torch.rand(n, 3, device=dev)
-            xyzs = torch.empty(n, 3, device=dev)
-            indices = cells if cells is not None else torch.empty(n, dtype=torch.int32, device=dev)
-            _lib.call("ngp_occ_sample_positions", _lib.ptr(cells), _lib.ptr(noise), n, H, bound, _lib.ptr(xyzs),
-                      None if cells is not None else _lib.ptr(indices), st)
+                # H^3/4 uniform cells + H^3/4 random OCCUPIED cells (renderer.py:853-876 does randint / nonzero / randint /
+                # morton3D_invert / cat, with a host sync on the size of the occupied list): the occupied ids are compacted on the
+                # device, one kernel turns 6 uniforms per sample into (cell, jittered position); the count never leaves the GPU.
+                # With no occupied cell the second half samples uniform cells as well.
+                n = 2 * (H3 // 4)
+                u = torch.rand(n, 6, device=dev)
+                xyzs = torch.empty(n, 3, device=dev)
+                indices = torch.empty(n, dtype=torch.int32, device=dev)
+                occ_list = torch.empty(H3, dtype=torch.int32, device=dev)
+                occ_count = torch.empty(1, dtype=torch.int32, device=dev)
+                ws = torch.empty((H3 + 4095) // 4096, dtype=torch.int32, device=dev)
+                _lib.call("ngp_occ_sample_partial", _lib.ptr(self.density_grid[cas]), H, bound, _lib.ptr(u), n, _lib.ptr(occ_list),
+                          _lib.ptr(occ_count), _lib.ptr(ws), _lib.ptr(xyzs), _lib.ptr(indices), st)
             with amp:
                 sigmas = self.density(xyzs)["sigma"].reshape(-1).detach().float().contiguous()
             _lib.call("ngp_occ_scatter_sigmas", _lib.ptr(indices), _lib.ptr(sigmas), n, _lib.ptr(tmp_grid[cas]), st)

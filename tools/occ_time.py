@@ -1,19 +1,25 @@
-import sys, time, torch
-sys.path.insert(0, '/root/repo')
+import torch, time, sys
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 dev = torch.device("cuda:0")
-model, o, d, tgt = bench.build_scene(dev, 0)
+model = bench.build_model(dev)
 model.grid_encoder.embeddings.data = model.grid_encoder.embeddings.data.half()
-grid0 = model.density_grid.clone(); bits0 = model.density_bitfield.clone()
 for mode, it0 in (("full", 0), ("partial", 16)):
-    for rep in range(3):
-        model.density_grid.copy_(grid0); model.density_bitfield.copy_(bits0); model.iter_density = it0
-        torch.cuda.synchronize(); t0 = time.perf_counter()
+    model.iter_density = it0
+    for _ in range(3):
+        model.iter_density = it0
         model.update_extra_state()
-        torch.cuda.synchronize(); t1 = time.perf_counter()
-    print(mode, f"{(t1 - t0) * 1e3:.3f} ms wall")
-from torch.profiler import profile, ProfilerActivity
-model.iter_density = 0
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    model.update_extra_state(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
+    torch.cuda.synchronize()
+    ts, tw = [], []
+    for _ in range(10):
+        model.iter_density = it0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); e0.record()
+        model.update_extra_state()
+        e1.record(); t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1)); tw.append((t1 - t0) * 1e3)
+    print(mode, "gpu ms", sorted(ts)[5], "host enqueue ms", sorted(tw)[5])
+    if hasattr(model, "update_extra_state_graph"):
+        pass
