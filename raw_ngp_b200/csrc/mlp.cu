@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTile)
 mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* __restrict__ x, uint32_t ldx, MlpArgs p,
                     uint32_t M, __half* __restrict__ dx, uint32_t lddx, const float* __restrict__ d_rgb,
                     const float* __restrict__ rgb, int head_act, uint32_t dz_off, uint32_t dz_bytes,
-                    uint32_t w_base, uint32_t ctrl_off, const int* __restrict__ m_dev) {
+                    uint32_t w_base, uint32_t ctrl_off, const int* __restrict__ m_dev, uint32_t dz_reuse) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, warp = t >> 5;
     const uint32_t L = p.n_layers;
@@ -166,8 +166,17 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
         const uint32_t row = tile * kTile + t;
         uint32_t cur = 0;  // which dZ buffer holds dZ of the layer being processed
+        // Where dZ of layer l lives.  Ping-pong between two buffers of the widest layer, or (dz_reuse: 20 KB less at 80-wide layers,
+        // which is what lets a second CTA share the SM) head buffer | one private buffer | the saved-input tile of layer l + 2,
+        // which is dead once that layer's MMAs have retired and its ReLU mask has been applied.
+        auto dz_of = [&](int l) -> uint8_t* {
+            if (!dz_reuse) return smem + dz_off + (((L - 1 - (uint32_t)l) & 1u) * dz_bytes);
+            if ((uint32_t)l == L - 1) return smem + dz_off;
+            if ((uint32_t)l + 2 == L) return smem + dz_off + dz_bytes;
+            return smem + in_off[l + 2];
+        };
         if (head_act == 0) {
-            load_row_tile(smem + dz_off, dy, lddy, p.dims[L], row, M);
+            load_row_tile(dz_of((int)L - 1), dy, lddy, p.dims[L], row, M);
         } else {
             // d out = d rgb * d act / d out from the activated colour (exp: rgb; clamped exp: rgb below the clamp;
             // sigmoid: rgb (1 - rgb)); columns 3.. of the padded output carry no gradient
@@ -185,7 +194,7 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
                     dz[c] = __float2half_rn(d);
                 }
             }
-            uint8_t* dzt = smem + dz_off;
+            uint8_t* dzt = dz_of((int)L - 1);
             for (uint32_t c = 0; c < p.dims[L] / 8; c++)
                 *reinterpret_cast<uint4*>(dzt + c * kPanel + t * 16) = (c < 2) ? reinterpret_cast<const uint4*>(dz)[c] : make_uint4(0, 0, 0, 0);
         }
@@ -197,7 +206,7 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
         for (int l = (int)L - 1; l >= 0; l--) {
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
             const bool need_dh = (l > 0) || (dx != nullptr);
-            const uint32_t dz_saddr = tc::smem_u32(smem + dz_off + cur * dz_bytes);
+            const uint32_t dz_saddr = tc::smem_u32(dz_of(l));
             if (t == 0) {
                 tc::fence_after_sync();
                 // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]   (both operands MN-major views of row tiles)
@@ -224,7 +233,7 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
             phase ^= 1;
             tc::fence_after_sync();
             if (need_dh) {
-                uint8_t* nxt = smem + dz_off + (cur ^ 1) * dz_bytes;
+                uint8_t* nxt = l > 0 ? dz_of(l - 1) : nullptr;
                 const uint8_t* in_tile = smem + in_off[l];
                 for (uint32_t c0 = 0; c0 < K; c0 += 16) {
                     float v[16];
@@ -367,9 +376,14 @@ static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint3
     }
     for (uint32_t l = 0; l <= n_layers; l++) p.dims[l] = dims[l];
     if (max_k + acc_cols > kBwdTmemCols) return NGP_ERR_UNSUPPORTED;
-    const uint32_t dz_bytes = kTile * std::max(max_n, max_k) * 2;
+    // dZ buffers: two of the widest layer (ping-pong), or -- when every dZ_l with l <= L - 3 fits the saved-input tile of layer
+    // l + 2 -- a head buffer + one private buffer, the deeper dZ tiles reusing dead input tiles (see the kernel)
+    bool reuse = n_layers >= 2;
+    for (uint32_t l = 0; l + 3 <= n_layers; l++) reuse = reuse && dims[l + 1] <= dims[l + 2];
+    uint32_t dz_bytes = kTile * std::max(max_n, max_k) * 2, dz_total = 2 * dz_bytes;
+    if (reuse) { dz_bytes = kTile * dims[n_layers] * 2; dz_total = dz_bytes + kTile * dims[n_layers - 1] * 2; }
     const uint32_t dz_off = in_bytes;
-    const uint32_t w_base = dz_off + 2 * dz_bytes;
+    const uint32_t w_base = dz_off + dz_total;
     const uint32_t ctrl_off = (w_base + w_bytes + 127) & ~127u;
     // the M = 128 MN-major A view of an input tile spans 16 panels (32 KiB) from the tile start: keep that inside the
     // allocation (rows past dims[l] only feed TMEM lanes that are never read)
@@ -381,7 +395,7 @@ static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint3
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
     mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
-                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off, m_dev);
+                                                                          (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off, m_dev, reuse ? 1u : 0u);
     return finish_launch();
 }
 
