@@ -578,7 +578,21 @@ int ngp_dp_fused_adam(const void* const* peer_grads, int grad_dtype, void* const
                       uint32_t world, uint32_t n_store, float* master_shard, float* exp_avg_shard,
                       float* exp_avg_sq_shard, uint64_t lo, uint64_t hi, float lr, float beta1, float beta2, float eps,
                       float weight_decay, const int32_t* step_dev, const float* lr_dev, const float* inv_scale_dev,
-                      const float* found_inf_dev, ngp_stream_t stream);
+                      const float* found_inf_dev, const float* flags, uint32_t n_flags,
+                      ngp_stream_t stream);
+
+/* The slim data-parallel update chain (4 launches + 2 barriers on the side stream instead of 8 + 2):
+ *   ngp_dp_check_publish : ngp_check_finite_multi whose last block also stores this rank's inf / nan flag into slot `rank` of
+ *                          every rank's flag array (peer stores; the caller's barrier orders them)
+ *   ngp_dp_fused_adam    : with flags != NULL the ranks' flags are merged inside the kernel (any flag set: skip) and the update
+ *                          uses step count *step_dev + 1, so no merge / counter launch precedes it
+ *   ngp_dp_finish        : after the second barrier -- merged flag -> found_inf_dev, *step_dev += 1 unless skipped, and both
+ *                          gradient buffers zero-filled (bytes multiples of 16) in one launch */
+int ngp_dp_check_publish(const void* const* grads, const int* dtypes, const uint64_t* counts, uint32_t n_buffers,
+                         float* found_inf_dev, uint32_t* scratch, void* const* peer_flags, uint32_t world, uint32_t rank,
+                         ngp_stream_t stream);
+int ngp_dp_finish(const float* flags, uint32_t world, float* found_inf_dev, int32_t* step_dev, void* grad0, uint64_t bytes0,
+                  void* grad1, uint64_t bytes1, ngp_stream_t stream);
 
 /* GradScaler flag across ranks without a collective: every rank stores its flag into slot `rank` of every rank's float[world]
  * array (peer_flags[r]); after the barrier ngp_dp_merge_flags takes the maximum of the local array. */

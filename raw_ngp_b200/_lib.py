@@ -74,7 +74,9 @@ SIGNATURES = {
     "ngp_pose_rays_backward": [_p, _p, _p, _p, _u32, _p, _p, _u32, _u32, _p, _p],
     "ngp_adam_step_counter": [_p, _p, _p],
     "ngp_grad_scaler_update": [_p, _p, _p, _p, _p, _f32, _f32, _i, _u32, _p],
-    "ngp_dp_fused_adam": [_p, _i, _p, _i, _u32, _u32, _p, _p, _p, c_uint64, c_uint64, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
+    "ngp_dp_fused_adam": [_p, _i, _p, _i, _u32, _u32, _p, _p, _p, c_uint64, c_uint64, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _u32, _p],
+    "ngp_dp_check_publish": [_p, _p, _p, _u32, _p, _p, _p, _u32, _u32, _p],
+    "ngp_dp_finish": [_p, _u32, _p, _p, _p, c_uint64, _p, c_uint64, _p],
     "ngp_dp_publish_flag": [_p, _p, _u32, _u32, _p],
     "ngp_dp_merge_flags": [_p, _u32, _p, _p],
     "ngp_check_finite": [_p, _i, c_uint64, _p, _p],

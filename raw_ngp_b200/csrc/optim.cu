@@ -3,6 +3,7 @@
 // ONE pass over memory (7 streams instead of torch's foreach chain + separate zero_grad + .half() cast).
 // Reference behaviour: torch.optim.Adam(eps=1e-15) (main.py:245) under torch.cuda.amp.GradScaler
 // (nerf/train_utils.py:897-904).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ngp {
@@ -122,11 +123,21 @@ __global__ void __launch_bounds__(256)
 dp_fused_adam_kernel(const PeerPtrs peers, uint32_t world, uint32_t n_store, float* __restrict__ master, float* __restrict__ m,
                      float* __restrict__ v, uint64_t lo, uint64_t hi, float lr, float beta1, float beta2, float eps, float weight_decay,
                      const float* __restrict__ inv_scale_dev, const float* __restrict__ found_inf_dev, const int* __restrict__ step_dev,
-                     const float* __restrict__ lr_dev) {
+                     const float* __restrict__ lr_dev, const float* __restrict__ flags, uint32_t n_flags) {
     if (found_inf_dev && __ldg(found_inf_dev) != 0.f) return;      // GradScaler: the whole step is skipped, on every rank alike
+    // flags != nullptr: the ranks' inf / nan flags (published by peer stores before the barrier) are merged here and the step
+    // count of THIS update is step_dev + 1 -- the counter itself is advanced by ngp_dp_finish after the kernel, so that no
+    // block reads it while another writes it; saves the merge and counter launches on the critical side stream
+    int step_now = __ldg(step_dev);
+    if (flags) {
+        bool bad = false;
+        for (uint32_t r = 0; r < n_flags; r++) bad |= __ldcg(flags + r) != 0.f;
+        if (bad) return;
+        step_now += 1;
+    }
     if (lr_dev) lr = __ldg(lr_dev);
     const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
-    const float t = (float)max(__ldg(step_dev), 1);
+    const float t = (float)max(step_now, 1);
     const float step_size = lr / (1.f - powf(beta1, t)), bias2_sqrt = sqrtf(1.f - powf(beta2, t));
     constexpr uint32_t PER = 16 / sizeof(G);           // elements per 16-byte gradient load
     const uint64_t n_vec = (hi - lo) / PER;            // the shard is a multiple of PER (host-checked)
@@ -180,6 +191,23 @@ dp_fused_adam_kernel(const PeerPtrs peers, uint32_t world, uint32_t n_store, flo
 __global__ void dp_publish_flag_kernel(const float* __restrict__ found_inf_local, PeerPtrs flags, uint32_t world, uint32_t rank) {
     if (threadIdx.x < world) reinterpret_cast<float*>(flags.lp[threadIdx.x])[rank] = *found_inf_local;
 }
+// end of a data-parallel update: merged flag -> found_inf (for the GradScaler update and the host), step counter, and the
+// gradient buffers cleared for the next backward -- one launch instead of merge + counter + two memsets
+__global__ void __launch_bounds__(256)
+dp_finish_kernel(const float* __restrict__ flags, uint32_t world, float* __restrict__ found_inf, int* __restrict__ step_dev,
+                 uint4* __restrict__ g0, uint64_t n0, uint4* __restrict__ g1, uint64_t n1) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float f = 0.f;
+        for (uint32_t r = 0; r < world; r++) f = fmaxf(f, __ldcg(flags + r) != 0.f ? 1.f : 0.f);
+        *found_inf = f;
+        if (f == 0.f) *step_dev += 1;
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += stride) g0[i] = z;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) g1[i] = z;
+}
+
 __global__ void dp_merge_flags_kernel(const float* __restrict__ flags, uint32_t world, float* __restrict__ found_inf) {
     if (threadIdx.x == 0) {
         float f = 0.f;
@@ -221,7 +249,8 @@ __device__ __forceinline__ bool block_has_nonfinite(const G* __restrict__ grad, 
 }
 
 __global__ void __launch_bounds__(256)
-check_finite_multi_kernel(const CheckBuffers b, float* __restrict__ found_inf, int* __restrict__ step_dev, uint32_t* __restrict__ scratch) {
+check_finite_multi_kernel(const CheckBuffers b, float* __restrict__ found_inf, int* __restrict__ step_dev, uint32_t* __restrict__ scratch,
+                          const PeerPtrs peer_flags, uint32_t world, uint32_t rank) {
     uint32_t which = 0;
     while (which + 1 < b.count && blockIdx.x >= b.first_block[which + 1]) which++;
     const uint32_t block = blockIdx.x - b.first_block[which], n_blocks = b.first_block[which + 1] - b.first_block[which];
@@ -237,6 +266,9 @@ check_finite_multi_kernel(const CheckBuffers b, float* __restrict__ found_inf, i
             __threadfence();
             const bool inf = *reinterpret_cast<volatile uint32_t*>(scratch + 1) != 0u;
             *found_inf = inf ? 1.0f : 0.0f;
+            // data parallel: this rank's flag goes into slot `rank` of every rank's flag array (peer stores, ordered by the
+            // barrier that follows on the stream)
+            for (uint32_t r = 0; r < world; r++) reinterpret_cast<float*>(peer_flags.lp[r])[rank] = inf ? 1.0f : 0.0f;
             if (!inf && step_dev) *step_dev += 1;                 // a skipped GradScaler step is not counted
             scratch[0] = 0u; scratch[1] = 0u;
         }
@@ -310,6 +342,20 @@ __global__ void grad_scaler_update_kernel(float* __restrict__ scale, float* __re
 
 using namespace ngp;
 
+// Resident blocks per SM of the streaming optimizer kernels (grid-stride, 256 threads).  They run on the side stream beside the
+// ray marcher of the next step; measured at configs[1] (NGP_ADAM_BLOCKS_PER_SM, step time): 8 -> 0.736 ms, 4 -> 0.740 ms,
+// 2 -> 0.763 ms: the two do not compete for thread slots, the marcher is slowed by memory latency under the optimizer's HBM
+// stream (80 us alone, 120-140 us beside it), so the optimizer keeps the full 8.
+static uint32_t adam_blocks_per_sm() {
+    static const uint32_t v = [] {
+        const char* e = getenv("NGP_ADAM_BLOCKS_PER_SM");
+        const int x = e ? atoi(e) : 8;
+        return (uint32_t)(x >= 1 && x <= 8 ? x : 8);
+    }();
+    return v;
+}
+#define kAdamBlocksPerSM adam_blocks_per_sm()
+
 extern "C" int ngp_grad_scaler_update(float* scale_dev, float* inv_scale_dev, int32_t* state_dev, const float* found_inf_a,
                                       const float* found_inf_b, float growth_factor, float backoff_factor, int growth_interval,
                                       uint32_t world, ngp_stream_t stream) {
@@ -333,7 +379,7 @@ extern "C" int ngp_fused_adam(float* master, void* param_lp, int lp_dtype, void*
         return NGP_ERR_ALIGN;
     const float bias1 = 1.f - powf(beta1, (float)std::max(step, 1u));
     const float bias2_sqrt = sqrtf(1.f - powf(beta2, (float)std::max(step, 1u)));
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(div_up<uint64_t>(n, 4), 256), (uint64_t)kNumSMs * 8);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(div_up<uint64_t>(div_up<uint64_t>(n, 4), 256), (uint64_t)kNumSMs * kAdamBlocksPerSM);
     cudaStream_t st = (cudaStream_t)stream;
 #define NGP_ADAM(G, P, HAS)                                                                                      \
     fused_adam_kernel<G, P, HAS><<<blocks, 256, 0, st>>>(master, (P*)param_lp, (G*)grad, exp_avg, exp_avg_sq, n, lr, \
@@ -356,8 +402,9 @@ extern "C" int ngp_dp_fused_adam(const void* const* peer_grads, int grad_dtype, 
                                  uint32_t world, uint32_t n_store, float* master_shard, float* exp_avg_shard,
                                  float* exp_avg_sq_shard, uint64_t lo, uint64_t hi, float lr, float beta1, float beta2, float eps,
                                  float weight_decay, const int32_t* step_dev, const float* lr_dev, const float* inv_scale_dev,
-                                 const float* found_inf_dev, ngp_stream_t stream) {
+                                 const float* found_inf_dev, const float* flags, uint32_t n_flags, ngp_stream_t stream) {
     if (hi <= lo) return NGP_OK;
+    if (flags && (n_flags == 0 || n_flags > kMaxPeers)) return NGP_ERR_BAD_ARG;
     if (!peer_grads || !peer_params_lp || !master_shard || !exp_avg_shard || !exp_avg_sq_shard || !step_dev) return NGP_ERR_NULL;
     if (world == 0 || world > kMaxPeers || n_store > world) return NGP_ERR_BAD_ARG;
     if (grad_dtype != NGP_F32 && grad_dtype != NGP_F16) return NGP_ERR_BAD_DTYPE;
@@ -379,7 +426,7 @@ extern "C" int ngp_dp_fused_adam(const void* const* peer_grads, int grad_dtype, 
     cudaStream_t st = (cudaStream_t)stream;
 #define NGP_DP(G, P) dp_fused_adam_kernel<G, P><<<blocks, 256, 0, st>>>(pp, world, n_store, master_shard, exp_avg_shard, exp_avg_sq_shard, \
                                                                         lo, hi, lr, beta1, beta2, eps, weight_decay, inv_scale_dev,     \
-                                                                        found_inf_dev, step_dev, lr_dev)
+                                                                        found_inf_dev, step_dev, lr_dev, flags, n_flags)
     if (grad_dtype == NGP_F16 && lp_dtype == NGP_F16) NGP_DP(__half, __half);
     else if (grad_dtype == NGP_F32 && lp_dtype == NGP_F16) NGP_DP(float, __half);
     else if (grad_dtype == NGP_F32 && lp_dtype == NGP_F32) NGP_DP(float, float);
@@ -436,10 +483,44 @@ extern "C" int ngp_check_finite_multi(const void* const* grads, const int* dtype
         if (!aligned(grads[i], 16)) return NGP_ERR_ALIGN;
         b.p[i] = grads[i]; b.n[i] = counts[i]; b.dtype[i] = dtypes[i];
         b.first_block[i] = blocks;
-        blocks += (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(counts[i], 256 * 16), (uint64_t)kNumSMs * 8));
+        blocks += (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(counts[i], 256 * 16), (uint64_t)kNumSMs * kAdamBlocksPerSM));
     }
     b.first_block[n_buffers] = blocks;
-    check_finite_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, found_inf_dev, step_dev, scratch);
+    check_finite_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, found_inf_dev, step_dev, scratch, PeerPtrs{}, 0, 0);
+    return finish_launch();
+}
+
+extern "C" int ngp_dp_check_publish(const void* const* grads, const int* dtypes, const uint64_t* counts, uint32_t n_buffers,
+                                    float* found_inf_dev, uint32_t* scratch, void* const* peer_flags, uint32_t world, uint32_t rank,
+                                    ngp_stream_t stream) {
+    if (!grads || !dtypes || !counts || !found_inf_dev || !scratch || !peer_flags) return NGP_ERR_NULL;
+    if (n_buffers == 0 || n_buffers > 4 || world == 0 || world > kMaxPeers || rank >= world) return NGP_ERR_BAD_ARG;
+    CheckBuffers b = {};
+    b.count = n_buffers;
+    uint32_t blocks = 0;
+    for (uint32_t i = 0; i < n_buffers; i++) {
+        if (counts[i] && !grads[i]) return NGP_ERR_NULL;
+        if (dtypes[i] < NGP_F32 || dtypes[i] > NGP_BF16) return NGP_ERR_BAD_DTYPE;
+        if (!aligned(grads[i], 16)) return NGP_ERR_ALIGN;
+        b.p[i] = grads[i]; b.n[i] = counts[i]; b.dtype[i] = dtypes[i];
+        b.first_block[i] = blocks;
+        blocks += (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(counts[i], 256 * 16), (uint64_t)kNumSMs * kAdamBlocksPerSM));
+    }
+    b.first_block[n_buffers] = blocks;
+    PeerPtrs pf = {};
+    for (uint32_t r = 0; r < world; r++) { if (!peer_flags[r]) return NGP_ERR_NULL; pf.lp[r] = peer_flags[r]; }
+    check_finite_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, found_inf_dev, nullptr, scratch, pf, world, rank);
+    return finish_launch();
+}
+
+extern "C" int ngp_dp_finish(const float* flags, uint32_t world, float* found_inf_dev, int32_t* step_dev, void* grad0, uint64_t bytes0,
+                             void* grad1, uint64_t bytes1, ngp_stream_t stream) {
+    if (!flags || !found_inf_dev || !step_dev) return NGP_ERR_NULL;
+    if (world == 0 || world > kMaxPeers || bytes0 % 16 || bytes1 % 16) return NGP_ERR_BAD_ARG;
+    if ((bytes0 && !aligned(grad0, 16)) || (bytes1 && !aligned(grad1, 16))) return NGP_ERR_ALIGN;
+    const uint64_t n0 = bytes0 / 16, n1 = bytes1 / 16;
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(std::max(n0, n1), 256), (uint64_t)kNumSMs * 8));
+    dp_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(flags, world, found_inf_dev, step_dev, (uint4*)grad0, n0, (uint4*)grad1, n1);
     return finish_launch();
 }
 

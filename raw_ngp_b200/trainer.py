@@ -590,6 +590,22 @@ class FusedTrainStep:
             with torch.cuda.graph(self._graph_field):
                 self._launch_field()
             self.field_kernels = _lib.launch_count - c0
+            # the peer-memory update chain (4 launches + 2 symmetric-memory barriers) as a graph of its own: replayed on the side
+            # stream it costs one launch of host time and no gaps between its small kernels.  NGP_DP_GRAPH=0 keeps it eager.
+            self._graph_update = None
+            if self.peer is not None and os.environ.get("NGP_DP_GRAPH", "1") != "0":
+                n_adam, epoch = self.opt.step_count, _lib.weights_epoch
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    c0 = _lib.launch_count
+                    with torch.cuda.graph(g):
+                        self._peer_update()
+                    self.update_kernels = _lib.launch_count - c0 + 2          # + the two barrier kernels
+                    self._graph_update = g
+                except Exception as e:       # barrier not capturable in this torch build: eager launches, same result
+                    import warnings
+                    warnings.warn(f"FusedTrainStep: the peer update could not be captured ({e!r}); launching it eagerly")
+                self.opt.step_count, _lib.weights_epoch = n_adam, epoch
         self.table_grad.zero_()
         self.w_grad.zero_()
         if self.pose is not None:
@@ -617,28 +633,29 @@ class FusedTrainStep:
     def _peer_update(self):
         """reduce-scatter + Adam + all-gather of the table as ONE kernel over peer memory (and a replicated variant of the same
         kernel for the 57 KB of MLP weights); the GradScaler flag travels through peer stores; two symmetric-memory barriers
-        order the ranks.  No NCCL call, no staging buffer, Adam on 1 / world of the table."""
+        order the ranks.  No NCCL call, no staging buffer, Adam on 1 / world of the table.  Four launches + two barriers:
+        check + flag publish | barrier | Adam(table) | Adam(MLPs) | barrier | finish (merged flag, step count, gradient clear)."""
         st, P, pm = _lib.stream(), _lib.ptr, self.peer
         world, rank = self.world, pm.rank
         _lib.weights_epoch += 1
         self.opt.step_count += 1
         b1, b2 = self.opt.betas
-        self._launch_check()                                       # local gradients -> self.found_inf
-        _lib.call("ngp_dp_publish_flag", P(self.found_inf), pm.ptrs["flags"], world, rank, st)
+        if not hasattr(self, "_chk_args"):
+            self._launch_check()                                   # builds the argument arrays (and is harmless)
+        g, d, n = self._chk_args
+        _lib.call("ngp_dp_check_publish", g, d, n, 2, P(self.found_inf), P(self._chk_scratch), pm.ptrs["flags"], world, rank, st)
         pm.barrier(0)                                              # every rank's gradients and flags are complete
-        _lib.call("ngp_dp_merge_flags", P(self.flags), world, P(self.found_inf), st)
-        _lib.call("ngp_adam_step_counter", P(self.opt_step_dev), P(self.found_inf), st)
         lo, hi = self.shard
         _lib.call("ngp_dp_fused_adam", pm.ptrs["grad"], _lib.NGP_F16, pm.ptrs["table"], _lib.NGP_F16, world, world,
                   P(self.table_master_shard), P(self.shard_m), P(self.shard_v), lo, hi, float(self.opt.lr), float(b1), float(b2),
                   float(self.opt.eps), float(self.opt.weight_decay), P(self.opt_step_dev), P(self.lr_dev), P(self.inv_scale),
-                  P(self.found_inf), st)
+                  None, P(self.flags), world, st)
         _lib.call("ngp_dp_fused_adam", pm.ptrs["w_grad"], _lib.NGP_F32, self._w_lp_local, _lib.NGP_F16, world, 1, P(self.w_master),
                   P(self.w_m), P(self.w_v), 0, self.w_master.numel(), float(self.opt.lr), float(b1), float(b2), float(self.opt.eps),
-                  float(self.opt.weight_decay), P(self.opt_step_dev), P(self.lr_dev), P(self.inv_scale), P(self.found_inf), st)
+                  float(self.opt.weight_decay), P(self.opt_step_dev), P(self.lr_dev), P(self.inv_scale), None, P(self.flags), world, st)
         pm.barrier(1)                                              # all parameter stores have landed, all gradient loads are done
-        self.table_grad.zero_()
-        self.w_grad.zero_()
+        _lib.call("ngp_dp_finish", P(self.flags), world, P(self.found_inf), P(self.opt_step_dev), P(self.table_grad),
+                  self.table_grad.numel() * self.table_grad.element_size(), P(self.w_grad), self.w_grad.numel() * 4, st)
 
     def gather_table_master(self):
         """fp32 master copy of the whole table (checkpoints).  In peer mode every rank holds only its shard: all-gather them."""
@@ -900,7 +917,13 @@ class FusedTrainStep:
                         parallel.all_reduce_gradients([self.se3_grad], None, self.pg)
                     self._side.wait_stream(main)
                     with torch.cuda.stream(self._side):
-                        self._reduce_and_update()
+                        if getattr(self, "_graph_update", None) is not None:
+                            _lib.weights_epoch += 1
+                            self.opt.step_count += 1
+                            self._graph_update.replay()
+                            self.kernels_replayed += self.update_kernels
+                        else:
+                            self._reduce_and_update()
                     if self.pose is not None:
                         self._launch_pose_update()
                 self._graph_march.replay()

@@ -97,7 +97,7 @@ def test_dp_fused_adam_matches_allreduce_then_adam(world):
         for r, sh in enumerate(shards):
             _lib.call("ngp_dp_fused_adam", _ptrs(grads), _lib.NGP_F16, _ptrs(tables), _lib.NGP_F16, world, world, _lib.ptr(sh["master"]),
                       _lib.ptr(sh["m"]), _lib.ptr(sh["v"]), sh["lo"], sh["hi"], 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None,
-                      _lib.ptr(inv_scale), _lib.ptr(found_inf), st)
+                      _lib.ptr(inv_scale), _lib.ptr(found_inf), None, 0, st)
         torch.cuda.synchronize()
         for t in tables[1:]:
             assert torch.equal(t, tables[0])
@@ -110,9 +110,70 @@ def test_dp_fused_adam_matches_allreduce_then_adam(world):
     sh = shards[0]
     _lib.call("ngp_dp_fused_adam", _ptrs(grads), _lib.NGP_F16, _ptrs(tables), _lib.NGP_F16, world, world, _lib.ptr(sh["master"]),
               _lib.ptr(sh["m"]), _lib.ptr(sh["v"]), sh["lo"], sh["hi"], 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None,
-              _lib.ptr(inv_scale), _lib.ptr(found_inf), st)
+              _lib.ptr(inv_scale), _lib.ptr(found_inf), None, 0, st)
     torch.cuda.synchronize()
     assert all(torch.equal(a, b) for a, b in zip(before, tables))
+
+
+@pytest.mark.parametrize("bad_rank", [None, 1])
+def test_dp_slim_chain_check_publish_adam_finish(bad_rank):
+    """The data-parallel update chain as FusedTrainStep._peer_update launches it (check + flag publish | Adam with the flags
+    merged in the kernel and step = counter + 1 | finish: merged flag, counter, gradient clear), `world` ranks emulated on one GPU
+    in the order the barriers impose: every rank's check first, then every rank's Adam, then every rank's finish."""
+    import ctypes
+    torch.manual_seed(5)
+    dev, world, n, nw = "cuda", 3, 8 * 4000, 256
+    per = (n + 8 * world - 1) // (8 * world) * 8
+    master0 = torch.randn(n, device=dev)
+    grads = [(torch.randn(n, device=dev) * 0.1 * 128).half() for _ in range(world)]
+    wgrads = [torch.randn(nw, device=dev) for _ in range(world)]
+    if bad_rank is not None:
+        grads[bad_rank][1234] = float("inf")
+    tables = [master0.half().clone() for _ in range(world)]
+    flags = [torch.zeros(8, device=dev) for _ in range(world)]
+    steps = [torch.full((1,), 4, dtype=torch.int32, device=dev) for _ in range(world)]
+    founds = [torch.full((1,), 9.0, device=dev) for _ in range(world)]
+    scratch = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(world)]
+    inv_scale = torch.full((1,), 1.0 / (128.0 * world), device=dev)
+    st = _lib.stream()
+    shards = []
+    for r in range(world):
+        lo, hi = min(r * per, n), min((r + 1) * per, n)
+        shards.append(dict(lo=lo, hi=hi, master=master0[lo:hi].clone(), m=torch.zeros(hi - lo, device=dev), v=torch.zeros(hi - lo, device=dev)))
+    for r in range(world):
+        args = ((ctypes.c_void_p * 2)(grads[r].data_ptr(), wgrads[r].data_ptr()), (ctypes.c_int * 2)(_lib.NGP_F16, _lib.NGP_F32),
+                (ctypes.c_uint64 * 2)(n, nw))
+        _lib.call("ngp_dp_check_publish", *args, 2, _lib.ptr(founds[r]), _lib.ptr(scratch[r]), _ptrs(flags), world, r, st)
+    for r, sh in enumerate(shards):
+        _lib.call("ngp_dp_fused_adam", _ptrs(grads), _lib.NGP_F16, _ptrs(tables), _lib.NGP_F16, world, world, _lib.ptr(sh["master"]),
+                  _lib.ptr(sh["m"]), _lib.ptr(sh["v"]), sh["lo"], sh["hi"], 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(steps[r]), None,
+                  _lib.ptr(inv_scale), None, _lib.ptr(flags[r]), world, st)
+    for r in range(world):
+        _lib.call("ngp_dp_finish", _lib.ptr(flags[r]), world, _lib.ptr(founds[r]), _lib.ptr(steps[r]), _lib.ptr(grads[r]), n * 2,
+                  _lib.ptr(wgrads[r]), nw * 4, st)
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert flags[r][:world].tolist() == [1.0 if r2 == bad_rank else 0.0 for r2 in range(world)]
+        assert founds[r].item() == (1.0 if bad_rank is not None else 0.0)
+        assert steps[r].item() == (4 if bad_rank is not None else 5)
+        assert grads[r].abs().max().item() == 0 and wgrads[r].abs().max().item() == 0
+    if bad_rank is not None:
+        assert all(torch.equal(t, master0.half()) for t in tables)          # skipped on every rank
+    else:
+        assert all(torch.equal(t, tables[0]) for t in tables[1:]) and not torch.equal(tables[0], master0.half())
+        # the update used step count 5 (= counter + 1): compare with the plain kernel at step 5
+        ref_tables = [master0.half().clone()]
+        ref = dict(master=master0.clone(), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev))
+        # (gradients were cleared by finish: regenerate the same ones)
+        torch.manual_seed(5)
+        _ = torch.randn(n, device=dev)
+        g2 = [(torch.randn(n, device=dev) * 0.1 * 128).half() for _ in range(world)]
+        step5 = torch.full((1,), 5, dtype=torch.int32, device=dev)
+        _lib.call("ngp_dp_fused_adam", _ptrs(g2), _lib.NGP_F16, _ptrs(ref_tables), _lib.NGP_F16, world, 1, _lib.ptr(ref["master"]),
+                  _lib.ptr(ref["m"]), _lib.ptr(ref["v"]), 0, n, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step5), None, _lib.ptr(inv_scale),
+                  None, None, 0, st)
+        torch.cuda.synchronize()
+        assert torch.equal(ref_tables[0], tables[0])
 
 
 def test_dp_flags_and_argument_checks():
@@ -133,10 +194,10 @@ def test_dp_flags_and_argument_checks():
     step_dev = torch.ones(1, dtype=torch.int32, device=dev)
     with pytest.raises(RuntimeError):
         _lib.call("ngp_dp_fused_adam", _ptrs(g), _lib.NGP_F16, _ptrs(t), _lib.NGP_F16, 1, 1, _lib.ptr(m), _lib.ptr(m.clone()), _lib.ptr(m.clone()),
-                  3, 35, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, st)
+                  3, 35, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, None, 0, st)
     with pytest.raises(RuntimeError):
         _lib.call("ngp_dp_fused_adam", _ptrs(g * 9), _lib.NGP_F16, _ptrs(t * 9), _lib.NGP_F16, 9, 9, _lib.ptr(m), _lib.ptr(m.clone()),
-                  _lib.ptr(m.clone()), 0, 64, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, st)
+                  _lib.ptr(m.clone()), 0, 64, 1e-2, 0.9, 0.99, 1e-15, 0.0, _lib.ptr(step_dev), None, None, None, None, 0, st)
 
 
 @pytest.mark.parametrize("bad", [None, ("table", 0), ("table", 12196239), ("mlp", 13000), ("mlp", 3)])
