@@ -71,6 +71,14 @@ class NeRFNetwork(NeRFRenderer):
         ldir_dim = self.view_in_dim if self.opt.rfield else 0
         self.view_mlp = MLP(15 + self.view_in_dim + ldir_dim, 3, 64 + ldir_dim, 3, opt, bias=False)
 
+        if not self.opt.cuda_ray:       # the two proposal fields of the sampling path (network.py:59-72): 5-level grids + 2-layer MLPs
+            self.prop_encoders = nn.ModuleList()
+            self.prop_mlp = nn.ModuleList()
+            for res in (128, 256):
+                enc, dim = get_encoder("hashgrid", input_dim=3, level_dim=2, num_levels=5, log2_hashmap_size=17, desired_resolution=res)
+                self.prop_encoders.append(enc)
+                self.prop_mlp.append(MLP(dim, 1, 16, 2, opt, bias=False))
+
     def _annealing_window(self, L, device):
         start, end = self.opt.start_annealing, self.opt.end_annealing
         k = torch.arange(L, dtype=torch.float32, device=device)
@@ -186,6 +194,9 @@ class NeRFNetwork(NeRFRenderer):
 
     def forward(self, x, d, ld=None, **kwargs):
         # x [N, 3] in [-bound, bound], d [N, 3] unit view directions, ld [N, 3] unit light directions (rfield)
+        if x.dim() == 3:        # [N, T, 3] samples of the proposal path: one flat batch through the same kernels
+            out = self.forward(x.reshape(-1, 3), d.reshape(-1, 3), None if ld is None else ld.reshape(-1, 3), **kwargs)
+            return {"sigma": out["sigma"].view(*x.shape[:-1]), "color": out["color"].view(*x.shape[:-1], 3)}
         if x.dim() == 2 and self._fused_eligible(x, d, ld) and (ld is not None) == bool(self.opt.rfield):
             sigma, color = _field.fused_field(
                 x, d, ld if self.opt.rfield else None, self.grid_encoder, [l.weight for l in self.grid_mlp.net],
@@ -208,6 +219,10 @@ class NeRFNetwork(NeRFRenderer):
         return {"sigma": sigma, "color": color}
 
     def density(self, x, proposal=-1):
+        if proposal >= 0 and not self.opt.cuda_ray and proposal < len(self.prop_encoders):      # network.py:146-149
+            f = self.prop_encoders[proposal](x, bound=self.bound)
+            lead = f.shape[:-1]
+            return {"sigma": trunc_exp(self.prop_mlp[proposal](f.reshape(-1, f.shape[-1])).view(*lead))}
         if x.dim() == 2 and not torch.is_grad_enabled() and self._fused_eligible(x):
             return {"sigma": _field.density_only(self.grid_encoder, [l.weight for l in self.grid_mlp.net], x, self.bound,
                                                  self._density_act(), self.opt.beta, self._feat_weights(x.device))}
@@ -224,8 +239,11 @@ class NeRFNetwork(NeRFRenderer):
         self.annealing = new_value
 
     def get_params(self, lr):
-        return [
+        groups = [
             {"params": self.grid_encoder.parameters(), "lr": lr},
             {"params": self.grid_mlp.parameters(), "lr": lr},
             {"params": self.view_mlp.parameters(), "lr": lr},
         ]
+        if not self.opt.cuda_ray:
+            groups += [{"params": self.prop_encoders.parameters(), "lr": lr}, {"params": self.prop_mlp.parameters(), "lr": lr}]
+        return groups

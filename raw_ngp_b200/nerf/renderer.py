@@ -1,8 +1,8 @@
 """NeRFRenderer -- the cuda_ray rendering path of the reference (nerf/renderer.py) on the B200 operators.
 
 In scope: __init__ (:161-198), update_aabb (:211-217), render/run_cuda (:374-377, :515-676),
-mark_untrained_grid (:716-809), update_extra_state (:811-897) and the differentiable near_far_from_aabb (:139-158).
-The proposal-network path (`run`) and mesh export are not part of the hot path and are not provided.
+mark_untrained_grid (:716-809), update_extra_state (:811-897), the differentiable near_far_from_aabb (:139-158) and the
+proposal-network path `run` (:405-513, `cuda_ray=False`; helpers in nerf/proposal.py).  Mesh export is not provided.
 """
 import math
 from types import SimpleNamespace
@@ -22,6 +22,7 @@ def default_opt(**overrides):
         pose_opt="none", internal_activation="relu", beta=1.0, density_activation="clamped_exp",
         color_activation="clamped_exp", start_annealing=0.0, end_annealing=0.5, lambda_orientation=0,
         compute_normals=False, device="cuda", num_cameras=0, update_extra_interval=16,
+        num_steps=[256, 96, 48], background="black", lambda_proposal=1, lambda_distort=0, max_ray_batch=4096 * 4,
     )
     for k, v in overrides.items():
         setattr(opt, k, v)
@@ -58,8 +59,9 @@ class NeRFRenderer(nn.Module):
         self.register_buffer("aabb_infer", aabb_train.clone())
 
         self.cuda_ray = opt.cuda_ray
-        if not self.cuda_ray:
-            raise NotImplementedError("only the cuda_ray path is part of the B200 hot path")
+        if not self.cuda_ray:           # proposal-network sampling (run): no occupancy grid
+            self._mean_density = 0.0
+            return
         self.register_buffer("density_grid", torch.zeros([self.cascade, self.grid_size ** 3]))
         self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
         self._mean_density = 0.0        # python float or a 1-element device tensor (synced lazily)
@@ -90,7 +92,69 @@ class NeRFRenderer(nn.Module):
         self.aabb_infer = self.aabb_train.clone()
 
     def render(self, rays_o, rays_d, **kwargs):
-        return self.run_cuda(rays_o, rays_d, **kwargs)
+        if self.cuda_ray:
+            return self.run_cuda(rays_o, rays_d, **kwargs)
+        if self.training:
+            return self.run(rays_o, rays_d, **kwargs)
+        # staged inference (renderer.py:378-402): ray batches of opt.max_ray_batch
+        N, B = rays_o.shape[0], int(self.opt.max_ray_batch)
+        parts = [self.run(rays_o[h:h + B], rays_d[h:h + B], **kwargs) for h in range(0, N, B)]
+        return {k: torch.cat([p[k] for p in parts], dim=0) for k in ("depth", "image", "weights_sum")}
+
+    def run(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, shading="full", update_proposal=True, **kwargs):
+        """Hierarchical sampling with the proposal networks (renderer.py:405-513): level 0 samples opt.num_steps[0] uniform bins in
+        the contracted ray parameter, every further level resamples opt.num_steps[i] bins from the previous level's weights; the
+        last level queries the NeRF field and is volume rendered.  rays [N, 3] -> image [N, 3], depth [N], weights_sum [N]."""
+        from . import proposal as P
+        rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
+        N, device = rays_o.shape[0], rays_o.device
+        nears, fars = near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
+        if cam_near_far is not None:
+            nears = torch.maximum(nears, cam_near_far[:, [0]])
+            fars = torch.minimum(fars, cam_near_far[:, [1]])
+        if bg_color is None:
+            bg_color = 1
+        s_near, s_far = P.spacing(nears), P.spacing(fars)
+        steps = list(self.opt.num_steps)
+        history = []                      # (bins, weights) of every level, for the inter-level loss
+        bins = weights = rgbs = mid_t = None
+        for level, T in enumerate(steps):
+            if level == 0:
+                bins = torch.linspace(0, 1, T + 1, device=device).unsqueeze(0).expand(N, -1)
+                if perturb:
+                    bins = (bins + (torch.rand_like(bins) - 0.5) / T).clamp(0, 1)
+            else:
+                bins = P.resample_bins(bins, weights, T + 1, perturb).detach()
+            real_bins = P.spacing_inv(s_near * (1 - bins) + s_far * bins)          # [N, T + 1] in [near, far]
+            mid_t = (real_bins[..., 1:] + real_bins[..., :-1]) / 2
+            xyzs = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * mid_t.unsqueeze(2)
+            pts = P.contract(xyzs) if self.opt.contract else xyzs
+            if level != len(steps) - 1:
+                with torch.set_grad_enabled(update_proposal and torch.is_grad_enabled()):
+                    sigmas = self.density(pts, proposal=level)["sigma"]
+            else:
+                dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+                dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+                out = self(pts, dirs, None, shading=shading)
+                sigmas, rgbs = out["sigma"], out["color"]
+            weights = P.weights_from_sigmas(real_bins, sigmas, opaque_last=self.opt.background == "last_sample")
+            if self.training:
+                history.append((bins, weights))
+        results = {}
+        weights_sum = weights.sum(dim=-1)
+        depth = (weights * mid_t).sum(dim=-1)
+        image = (weights.unsqueeze(-1) * rgbs).sum(dim=-2)
+        if self.training:
+            results["num_points"] = xyzs.shape[0] * xyzs.shape[1]
+            results["weights"] = weights
+            if self.opt.lambda_proposal > 0 and update_proposal:
+                results["proposal_loss"] = P.interlevel_loss([b for b, _ in history], [w for _, w in history])
+            if self.opt.lambda_distort > 0:
+                results["distort_loss"] = P.distortion_loss(bins, weights)
+        results["image"] = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results["weights_sum"] = weights_sum
+        results["depth"] = depth
+        return results
 
     def run_cuda(self, rays_o, rays_d, rays_ldir=None, bg_color=None, perturb=False, cam_near_far=None,
                  update_proposal=True, shading="full", **kwargs):

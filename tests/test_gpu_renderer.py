@@ -231,3 +231,77 @@ def test_train_step_reduces_loss():
     target = torch.rand(2048, 3, generator=torch.Generator().manual_seed(1)).cuda() * 0.2 + 0.4
     losses = [step.step(o, d, target, update_grid=False).item() for _ in range(30)]
     assert math.isfinite(losses[-1]) and losses[-1] < 0.8 * losses[0] and losses[-1] < losses[10] < losses[0], losses[::5]
+
+
+@pytest.mark.parametrize("contract_on", [False, True], ids=["bound2", "contract"])
+def test_proposal_path_matches_reference_run(contract_on):
+    """NeRFRenderer.run (the proposal-network path, cuda_ray=False; nerf/proposal.py) against the REFERENCE's own renderer.py /
+    network.py (unmodified, over its own kernels; oracle/ref_stack.py) on the same parameters and the same torch RNG stream:
+    image, depth, proposal loss, gradients of all five parameter groups; staged inference."""
+    import _refstep as R
+    stack = R.stacks().get("ref")
+    extra = dict(cuda_ray=False, num_steps=[64, 32, 16], background="white", lambda_proposal=1, lambda_distort=0, max_ray_batch=300,
+                 bound=2, contract=contract_on, grid_size=32, hashmap_size=15, hashgrid_resolution=128)
+    torch.manual_seed(1)
+    ours = NeRFNetwork(default_opt(**extra)).cuda()
+    with torch.no_grad():
+        for n, p in ours.named_parameters():
+            if n.endswith("embeddings"):
+                p.uniform_(-0.5, 0.5)
+    ref = stack.build_network(stack.make_opt(**extra)).cuda()
+    res = ref.load_state_dict(ours.state_dict(), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    N = 700
+    o, d = synthetic.sphere_rays(N, seed=5)
+    o, d = o.cuda(), (d * 1.2).cuda()
+    tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(9)).cuda()
+    import contextlib
+    for amp in (True, False):
+        # fp16 autocast (how the trainer calls it): outputs and losses.  fp32: also the gradients -- the inter-level loss is a sum of
+        # max(0, w - bound)^2 over a few violating intervals, so under fp16 its gradient flips with the last bit of a weight
+        out = {}
+        for name, m in (("ref", ref), ("ours", ours)):
+            m.zero_grad(set_to_none=True)
+            m.train()
+            torch.manual_seed(21)
+            ctx = torch.autocast("cuda", dtype=torch.float16) if amp else contextlib.nullcontext()
+            with ctx:
+                r = m.render(o, d, bg_color=1, perturb=True, update_proposal=True)
+            loss = torch.nn.functional.mse_loss(r["image"].float(), tgt) + r["proposal_loss"]
+            loss.backward()
+            grads = {k: p.grad.detach().float().clone() for k, p in m.named_parameters() if p.grad is not None}
+            m.eval()
+            with torch.no_grad(), ctx:
+                ev = m.render(o, d, bg_color=1, perturb=False)
+            out[name] = (r, loss.detach(), grads, ev)
+        (ra, la, ga, ea), (rb, lb, gb, eb) = out["ref"], out["ours"]
+        tol = dict(rtol=2e-3, atol=2e-3) if amp else dict(rtol=1e-4, atol=1e-5)
+        assert ra["num_points"] == rb["num_points"] == N * 16
+        for k in ("image", "depth", "weights_sum"):
+            torch.testing.assert_close(rb[k].float(), ra[k].float(), **tol)
+            torch.testing.assert_close(eb[k].float(), ea[k].float(), **tol)
+        torch.testing.assert_close(rb["proposal_loss"], ra["proposal_loss"], rtol=5e-3 if amp else 1e-4, atol=1e-6)
+        torch.testing.assert_close(lb, la, rtol=2e-3 if amp else 1e-4, atol=1e-6)
+        assert set(ga) == set(gb) and len(ga) == 13
+        if not amp:
+            for k in ga:
+                scale = ga[k].abs().max().clamp(min=1e-12)
+                err = (gb[k] - ga[k]).abs() / scale
+                assert err.max().item() < 2e-3 and err.mean().item() < 1e-4, (k, err.max().item(), err.mean().item())
+
+
+def test_distortion_loss_matches_pairwise_definition():
+    """nerf/proposal.py: the O(T) prefix-sum form against the O(T^2) definition sum_ij w_i w_j |m_i - m_j| + 1/3 sum_i w_i^2 delta_i
+    (what the reference's eff_distloss computes; that package is not installed, so the definition is the pin)."""
+    from raw_ngp_b200.nerf import proposal as P
+    torch.manual_seed(0)
+    bins = torch.sort(torch.rand(64, 33, device="cuda"), dim=-1).values
+    w = torch.rand(64, 32, device="cuda", requires_grad=True)
+    m = (bins[..., 1:] + bins[..., :-1]) / 2
+    dlt = bins[..., 1:] - bins[..., :-1]
+    brute = ((w[..., :, None] * w[..., None, :] * (m[..., :, None] - m[..., None, :]).abs()).sum((-1, -2)) + (w ** 2 * dlt).sum(-1) / 3).mean()
+    fast = P.distortion_loss(bins, w)
+    torch.testing.assert_close(fast, brute, rtol=1e-5, atol=1e-7)
+    g1, = torch.autograd.grad(fast, w, retain_graph=True)
+    g2, = torch.autograd.grad(brute, w)
+    torch.testing.assert_close(g1, g2, rtol=1e-4, atol=1e-6)
