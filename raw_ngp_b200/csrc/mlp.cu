@@ -125,13 +125,31 @@ mlp_forward_kernel(const __half* __restrict__ x, uint32_t ldx, MlpArgs p, uint32
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kBwdTmemCols = 256;
 
-__global__ void __launch_bounds__(kTile)
+// 512 threads per CTA, thread (row, grp) like field_backward_density_kernel: row = (warp % 4) * 32 + lane is the sample (TMEM
+// lane), grp = warp / 4 takes every fourth 16-byte chunk of the saved-activation loads and every fourth 16-column block of the
+// epilogues.  (With 128 threads the per-tile chain -- 26 cp.async per thread, three epilogues of up to 80 columns -- ran on
+// 4-8 warps per SM: 6 % of the warp slots.)
+constexpr uint32_t kMlpBwdThreads = 512, kMlpBwdGroups = kMlpBwdThreads / kTile;
+
+__device__ __forceinline__ void load_row_tile_g(uint8_t* tile, const __half* __restrict__ src, uint32_t ld, uint32_t F, uint32_t row, uint32_t M,
+                                                uint32_t t, uint32_t grp) {
+    if (row < M) {
+        const __half* p = src + (size_t)row * ld;
+        for (uint32_t c = grp; c < F / 8; c += kMlpBwdGroups) tc::cp_async16(tc::smem_u32(tile + c * kPanel + t * 16), p + c * 8);
+    } else {
+        for (uint32_t c = grp; c < F / 8; c += kMlpBwdGroups) *reinterpret_cast<uint4*>(tile + c * kPanel + t * 16) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(kMlpBwdThreads, 2)
 mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* __restrict__ x, uint32_t ldx, MlpArgs p,
                     uint32_t M, __half* __restrict__ dx, uint32_t lddx, const float* __restrict__ d_rgb,
                     const float* __restrict__ rgb, int head_act, uint32_t dz_off, uint32_t dz_bytes,
                     uint32_t w_base, uint32_t ctrl_off, const int* __restrict__ m_dev, uint32_t dz_reuse) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t t = threadIdx.x, warp = t >> 5;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t t = (warp & 3u) * 32u + (threadIdx.x & 31u);     // sample row inside the tile == TMEM lane
+    const uint32_t grp = warp >> 2;
     const uint32_t L = p.n_layers;
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ctrl_off);
@@ -151,14 +169,14 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
         for (uint32_t l = 0; l < L; l++) { acc_col[l] = col; col += p.dims[l + 1]; }
     }
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kBwdTmemCols);
-    if (t == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
+    if (threadIdx.x == 0) tc::mbar_init(tc::smem_u32(mbar), 1);
     for (uint32_t l = 0; l < L; l++) load_weight_tile(smem + w_off[l], p.w[l], p.dims[l + 1], p.dims[l]);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
+    const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t mbar_saddr = tc::smem_u32(mbar);
 
     uint32_t phase = 0, iter = 0;
@@ -176,8 +194,8 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
             return smem + in_off[l + 2];
         };
         if (head_act == 0) {
-            load_row_tile(dz_of((int)L - 1), dy, lddy, p.dims[L], row, M);
-        } else {
+            load_row_tile_g(dz_of((int)L - 1), dy, lddy, p.dims[L], row, M, t, grp);
+        } else if (grp == 0) {
             // d out = d rgb * d act / d out from the activated colour (exp: rgb; clamped exp: rgb below the clamp;
             // sigmoid: rgb (1 - rgb)); columns 3.. of the padded output carry no gradient
             __align__(16) __half dz[16];
@@ -198,8 +216,8 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
             for (uint32_t c = 0; c < p.dims[L] / 8; c++)
                 *reinterpret_cast<uint4*>(dzt + c * kPanel + t * 16) = (c < 2) ? reinterpret_cast<const uint4*>(dz)[c] : make_uint4(0, 0, 0, 0);
         }
-        load_row_tile(smem + in_off[0], x, ldx, p.dims[0], row, M);
-        for (uint32_t l = 1; l < L; l++) load_row_tile(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M);
+        load_row_tile_g(smem + in_off[0], x, ldx, p.dims[0], row, M, t, grp);
+        for (uint32_t l = 1; l < L; l++) load_row_tile_g(smem + in_off[l], p.acts[l - 1], p.dims[l], p.dims[l], row, M, t, grp);
         tc::cp_async_wait_all();
         tc::fence_async_smem();
         __syncthreads();
@@ -207,7 +225,7 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
             const bool need_dh = (l > 0) || (dx != nullptr);
             const uint32_t dz_saddr = tc::smem_u32(dz_of(l));
-            if (t == 0) {
+            if (threadIdx.x == 0) {
                 tc::fence_after_sync();
                 // dW_l^T [K x N] += in_l^T [K x 128] * dZ_l [128 x N]   (both operands MN-major views of row tiles)
                 const uint32_t in_saddr = tc::smem_u32(smem + in_off[l]);
@@ -235,7 +253,7 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
             if (need_dh) {
                 uint8_t* nxt = l > 0 ? dz_of(l - 1) : nullptr;
                 const uint8_t* in_tile = smem + in_off[l];
-                for (uint32_t c0 = 0; c0 < K; c0 += 16) {
+                for (uint32_t c0 = grp * 16; c0 < K; c0 += kMlpBwdGroups * 16) {
                     float v[16];
                     tc::tmem_ld16(lane_addr + c0, v);
                     if (l > 0) {
@@ -272,7 +290,7 @@ mlp_backward_kernel(const __half* __restrict__ dy, uint32_t lddy, const __half* 
         tc::fence_after_sync();
         for (uint32_t l = 0; l < L; l++) {
             const uint32_t K = p.dims[l], N = p.dims[l + 1];
-            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+            for (uint32_t c0 = grp * 16; c0 < N; c0 += kMlpBwdGroups * 16) {
                 float v[16];
                 tc::tmem_ld16(lane_addr + acc_col[l] + c0, v);   // warp-collective: every lane participates
                 if (t < K) {
@@ -394,7 +412,7 @@ static int mlp_backward_impl(const void* dy, uint32_t lddy, const void* x, uint3
     if (const int rc = ensure_dynamic_smem(mlp_backward_kernel, smem_bytes, cache)) return rc;
     const uint32_t n_tiles = div_up(M, kTile);
     const uint32_t grid = std::min<uint32_t>(n_tiles, kNumSMs * 2);   // 2 CTAs/SM: 2 x 256 TMEM columns
-    mlp_backward_kernel<<<grid, kTile, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
+    mlp_backward_kernel<<<grid, kMlpBwdThreads, smem_bytes, (cudaStream_t)stream>>>((const __half*)dy, lddy, (const __half*)x, ldx, p, M,
                                                                           (__half*)dx, lddx, d_rgb, rgb, head_act, dz_off, dz_bytes, w_base, ctrl_off, m_dev, reuse ? 1u : 0u);
     return finish_launch();
 }
