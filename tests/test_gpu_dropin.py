@@ -225,3 +225,26 @@ def test_reference_proposal_path_identical_over_dropin():
     for k in a["grads"]:
         mx, mean = R.err_stats(b["grads"][k], a["grads"][k])
         assert mx < 2e-2 and mean < 2e-3, (k, mx, mean)
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_fast_inference_loop_matches_reference_renderer(perturb):
+    """This repository's own inference path (NeRFRenderer._march_composite_loop_fast: device-driven alive-ray loop, fused field
+    kernel, 4 N-row / 16-step schedule, fp16 table) against the REFERENCE's run_cuda over its own kernels (renderer.py:573-616,
+    fp16 table as well), with and without the first-iteration jitter (the same torch.rand(N) draw on both sides)."""
+    rs = R.stacks()
+    model, _, _, _ = R.build_scene(16, bound=1, grid_size=64, max_steps=256, hashmap_size=15, hashgrid_resolution=256, T_thresh=1e-4, table_scale=1.0)
+    ref = R.reference_model(rs.get("ref"), model, torch.float16)
+    model.grid_encoder.embeddings.data = model.grid_encoder.embeddings.data.half()
+    o, d = synthetic.pinhole_rays(W=160, H=120, fx=150.0, fy=150.0, radius=2.0)
+    o, d = o.cuda(), d.cuda()
+    imgs = {}
+    for name, m in (("ref", ref), ("ours", model)):
+        m.eval()
+        torch.manual_seed(5)
+        with torch.no_grad():
+            imgs[name] = m.render(o, d, bg_color=1, perturb=perturb)
+    assert model._fast_infer_args(None, "full") is not None
+    for k in ("image", "depth"):
+        torch.testing.assert_close(imgs["ours"][k].float(), imgs["ref"][k].float(), rtol=3e-3, atol=3e-3)
+    assert (imgs["ref"]["image"] < 0.99).float().mean().item() > 0.05
