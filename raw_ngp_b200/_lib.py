@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_uint8
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libngp_b200.so")
+LIB_PATH = os.environ.get("NGP_B200_LIB") or os.path.join(_HERE, "lib", "libngp_b200.so")      # the override is for A/B kernel timing (tools/ab_variant.sh)
 
 NGP_F32, NGP_F16, NGP_BF16 = 0, 1, 2
 NGP_GRID_REF_ROUNDING = 1
