@@ -205,6 +205,9 @@ field_backward_ws_kernel(const BwsArgs a) {
         const MmaPlan* pl = plans + ci * kL * 2;
         auto load_tensor = [&](uint32_t tile, uint32_t l) {               // one thread: bulk async copy of one saved tile
             const uint32_t bytes = kTile * c.dims[l] * 2;
+#ifdef NGP_BWS_SKIP_HIDDEN_LOADS      // timing experiment: the hidden tiles are not fetched (what recomputing them would save)
+            if (l > 0) { tc::mbar_arrive(tf + 8 * l); return; }
+#endif
             tc::mbar_arrive_expect_tx(tf + 8 * l, bytes);
             tc::bulk_g2s(tc::smem_u32(smem + c.in_off[l]), c.in[l] + (size_t)tile * (c.dims[l] * kTile), bytes, tf + 8 * l);
         };

@@ -150,6 +150,7 @@ __device__ __forceinline__ void gather_issue(LevelGather& q, const GridArgs& g, 
     corner_rows(lv, base, rows);
     const uint32_t* __restrict__ lvl = reinterpret_cast<const uint32_t*>(g.table) + lv.offset;
 #pragma unroll
+#pragma unroll
     for (uint32_t k = 0; k < 8; k++) q.v[k] = __ldg(lvl + rows[k]);
 }
 __device__ __forceinline__ __half2 gather_finish(const LevelGather& q, const GridArgs& g, uint32_t level, bool inside) {

@@ -32,6 +32,10 @@ using namespace mlpcore;
 using namespace gridcore;
 using namespace fieldcore;
 
+#ifndef NGP_WS_ISOLATE
+#define NGP_WS_ISOLATE 0                // timing experiments only: 1 = the MLP side alone (no gathers), 2 = the gather warps alone,
+                                        // bit 2 (4) = no saves, bit 3 (8) = no st.shared in the hidden epilogues
+#endif
 #ifndef NGP_WS_GATHER_LEVELS
 #define NGP_WS_GATHER_LEVELS 2          // levels a gather thread keeps in flight (8 table rows each)
 #endif
@@ -142,6 +146,12 @@ field_forward_ws_kernel(const WsArgs a) {
             const bool inside = x[0] >= 0 && x[0] <= 1 && x[1] >= 0 && x[1] <= 1 && x[2] >= 0 && x[2] <= 1;
             const float xc[3] = {fminf(fmaxf(x[0], 0.f), 1.f), fminf(fmaxf(x[1], 0.f), 1.f), fminf(fmaxf(x[2], 0.f), 1.f)};
             uint8_t* a0 = smem + a.a0_off + s * a.a0_stage_bytes;
+#if (NGP_WS_ISOLATE & 3) == 1
+            tc::mbar_wait(empty_s + 8 * s, ((it / kStages) & 1u) ^ 1u);
+            tc::fence_async_smem();
+            tc::mbar_arrive(full_s + 8 * s);
+            continue;
+#endif
             bool waited = false;
 #if NGP_WS_GATHER_LEVELS == 4
             // all four levels of the thread (32 table rows) in flight at once
@@ -213,6 +223,14 @@ field_forward_ws_kernel(const WsArgs a) {
             tc::fence_async_smem();
             tc::mbar_arrive(full_s + 8 * s);
         }
+    } else if ((NGP_WS_ISOLATE & 3) == 2) {
+        if (warp >= (kGatherThreads + kMlpGroups * kTile) / 32 && (threadIdx.x & 31u) == 0) {
+            const uint32_t gI = warp - (kGatherThreads + kMlpGroups * kTile) / 32;
+            for (uint32_t it = gI; blockIdx.x + it * gridDim.x < n_tiles; it += kMlpGroups) {
+                tc::mbar_wait(full_s + 8 * (it % kStages), (it / kStages) & 1u);
+                tc::mbar_arrive(empty_s + 8 * (it % kStages));
+            }
+        }
     } else if (warp < (kGatherThreads + kMlpGroups * kTile) / 32) {
         // ================================ MLP groups: epilogues ================================
         const uint32_t gI = (warp - kGatherThreads / 32) / 4;             // group
@@ -266,8 +284,10 @@ field_forward_ws_kernel(const WsArgs a) {
                                 for (int i = 0; i < 4; i++) { ql[i] = __hmax2(ql[i], zero2); qh[i] = __hmax2(qh[i], zero2); }
                             }
                             const uint32_t o0 = tsw::chunk_off_r(N, kTile, tg, c0 / 8), o1 = tsw::chunk_off_r(N, kTile, tg, c0 / 8 + 1);
-                            *reinterpret_cast<uint4*>(h + o0) = lo;
-                            *reinterpret_cast<uint4*>(h + o1) = hi;
+                            if (!(NGP_WS_ISOLATE & 8) || lo.x == 0x12345678u) {
+                                *reinterpret_cast<uint4*>(h + o0) = lo;
+                                *reinterpret_cast<uint4*>(h + o1) = hi;
+                            }
                             if (grow) { grow[c0 / 8] = lo; grow[c0 / 8 + 1] = hi; }
                         }
                     } else if (l == 2) {
@@ -377,7 +397,7 @@ field_forward_ws_kernel(const WsArgs a) {
             tc::mbar_wait(full_s + 8 * st, (it / kStages) & 1u);
             tc::fence_after_sync();
             issue(plans[st * kWsLayers], st * kSlotTmemCols);
-            if (a.enc_out && !a.rowmajor) {
+            if (a.enc_out && !a.rowmajor && !(NGP_WS_ISOLATE & 4)) {
                 const uint32_t bytes = kTile * a.K[0] * 2;
                 tc::bulk_s2g(reinterpret_cast<uint8_t*>(a.enc_out) + (size_t)tile * bytes, tc::smem_u32(smem + a.a0_off + st * a.a0_stage_bytes), bytes);
                 tc::bulk_wait_read();
@@ -404,7 +424,7 @@ field_forward_ws_kernel(const WsArgs a) {
                         // the A operand of layer l + 1 (the tile just written) is what the backward pass needs (h1, h2 | in2, h1',
                         // h2'): its image goes to global memory as ONE bulk async copy while the MMA runs
                         __half* save = (l + 1 == 3) ? a.in2_out : a.acts[l];
-                        if (save && !a.rowmajor) {
+                        if (save && !a.rowmajor && !(NGP_WS_ISOLATE & 4)) {
                             const uint32_t bytes = kTile * a.K[l + 1] * 2;
                             tc::bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile_of[slot] * bytes, tc::smem_u32(smem + a.h_off + st * a.h_bytes), bytes);
                             tc::bulk_wait_read();
