@@ -461,7 +461,7 @@ def run_reference(args):
 def config4_block(device, rank, world, timer, K, R):
     """BASELINE configs[4] / SURVEY 8(d) config 5: data-parallel training with BARF pose refinement -- 8192 rays per GPU
     generated on the device from the refined poses of 100 cameras (different pixels per rank), annealed feature window, ray
-    gradients -> d se3, all-reduce of the se3 gradient + peer-memory exchange of the table / MLP gradients, identical optimizers
+    gradients -> d se3, peer-memory exchange of the table / MLP / se3 gradients (csrc/optim.cu), identical optimizers
     on every rank.  Run at every N (N = 1: the single-GPU base of the scaling curve)."""
     import torch.distributed as dist
     from raw_ngp_b200 import _lib, pose
@@ -492,7 +492,7 @@ def config4_block(device, rank, world, timer, K, R):
     torch.cuda.synchronize()
     ms = r["median"] / K
     out = {"workload": "configs[4] data-parallel BARF step: 8192 rays/GPU from refined poses of 100 cameras, ray gradients -> se3, "
-                       "table/MLP gradient exchange over NVLink peer memory, se3 all-reduce (NCCL)",
+                       "table/MLP and se3 gradient exchange over NVLink peer memory (no NCCL call in the step)",
            "n_gpus": world, "rays_per_gpu": n_rays, "samples_rank0": M, "steps": K, "repeats": R, "ms_per_step": ms,
            "ms_per_step_min": r["min"] / K, "ms_per_step_max": r["max"] / K, "value": world * n_rays / (ms * 1e-3), "unit": "rays/s",
            "dp_mode": "single" if world == 1 else ("peer-memory fused reduce-scatter + Adam + all-gather" if fs.peer is not None else "NCCL all-reduce"),

@@ -607,6 +607,15 @@ int ngp_small_adam(float* master, float* grad, float* exp_avg, float* exp_avg_sq
                    float beta2, float eps, float weight_decay, int32_t* step_dev, const float* lr_dev,
                    const float* inv_scale_dev, float* found_inf_out, ngp_stream_t stream);
 
+/* ngp_small_adam for data-parallel ranks over peer memory: the gradient is the sum over peer_grads[0..world) (every rank's
+ * buffer, mapped into this process; made complete by the caller's barrier), every rank applies the identical update to its own
+ * replica.  The gradient buffers are NOT cleared (peers may still read them: ngp_dp_finish clears after the closing barrier).
+ * Replaces the reference's DDP all-reduce of the pose optimizer's gradient (barf/camera_optimizers.py:40 under
+ * nerf/train_utils.py:386, 900-904). */
+int ngp_dp_small_adam(const void* const* peer_grads, uint32_t world, float* master, float* exp_avg, float* exp_avg_sq, uint32_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev, const float* lr_dev,
+                      const float* inv_scale_dev, float* found_inf_out, ngp_stream_t stream);
+
 /* The GradScaler bookkeeping of a step in one launch: found_inf_dev[0] = 1.0f if any element of any of the n_buffers (<= 4)
  * gradient buffers is inf / nan, else 0.0f (OVERWRITTEN, no zero-fill needed); *step_dev (optional) is incremented when
  * the step is not skipped (like ngp_adam_step_counter).  scratch: device uint32[2], zero before the first call; the

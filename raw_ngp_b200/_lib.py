@@ -81,6 +81,7 @@ SIGNATURES = {
     "ngp_dp_merge_flags": [_p, _u32, _p, _p],
     "ngp_check_finite": [_p, _i, c_uint64, _p, _p],
     "ngp_small_adam": [_p, _p, _p, _p, _u32, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
+    "ngp_dp_small_adam": [_p, _u32, _p, _p, _p, _u32, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
     "ngp_check_finite_multi": [_p, _p, _p, _u32, _p, _p, _p, _p],
 }
 _SPECIAL = {

@@ -310,6 +310,47 @@ small_adam_kernel(float* __restrict__ master, float* __restrict__ grad, float* _
     }
 }
 
+// The same for data parallel ranks over peer memory: the gradient is the SUM of every rank's buffer, read through the peer
+// mappings (the caller's barrier has made them complete); every rank computes the identical update of its own replica, so no
+// broadcast follows.  The buffers are NOT cleared here -- peers may still be reading them (ngp_dp_finish clears after the
+// closing barrier).  Replaces an NCCL all-reduce of 600 floats in front of the ray generation.
+struct SmallPeers { const float* grad[kMaxPeers]; };
+__global__ void __launch_bounds__(256)
+dp_small_adam_kernel(const SmallPeers peers, uint32_t world, float* __restrict__ master, float* __restrict__ m, float* __restrict__ v,
+                     uint32_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int* __restrict__ step_dev,
+                     const float* __restrict__ lr_dev, const float* __restrict__ inv_scale_dev, float* __restrict__ found_inf_out) {
+    bool bad = false;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float g = 0.f;
+        for (uint32_t r = 0; r < world; r++) g += __ldcg(peers.grad[r] + i);      // fixed rank order: bit-identical on every rank
+        bad |= !isfinite(g);
+    }
+    const bool skip = __syncthreads_or(bad);
+    __shared__ int s_step;
+    if (threadIdx.x == 0) {
+        if (!skip) *step_dev += 1;
+        s_step = *step_dev;
+        if (found_inf_out) *found_inf_out = skip ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    if (skip) return;
+    if (lr_dev) lr = __ldg(lr_dev);
+    const float inv_scale = inv_scale_dev ? __ldg(inv_scale_dev) : 1.f;
+    const float t = (float)max(s_step, 1);
+    const float step_size = lr / (1.f - powf(beta1, t)), bias2_sqrt = sqrtf(1.f - powf(beta2, t));
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float g = 0.f;
+        for (uint32_t r = 0; r < world; r++) g += __ldcg(peers.grad[r] + i);
+        g *= inv_scale;
+        const float p = master[i];
+        if (weight_decay != 0.f) g += weight_decay * p;
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi; v[i] = vi;
+        master[i] = p - step_size * (mi / (sqrtf(vi) / bias2_sqrt + eps));
+    }
+}
+
 // GradScaler semantics for a device-side step counter: the optimizer step is counted only when it is not skipped
 __global__ void adam_step_counter_kernel(int* __restrict__ step_dev, const float* __restrict__ found_inf_dev) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && !(found_inf_dev && *found_inf_dev != 0.f)) *step_dev += 1;
@@ -460,6 +501,23 @@ extern "C" int ngp_small_adam(float* master, float* grad, float* exp_avg, float*
     if (n > (1u << 20)) return NGP_ERR_BAD_ARG;      // one block: meant for small tensors
     small_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(master, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                           step_dev, lr_dev, inv_scale_dev, found_inf_out);
+    return finish_launch();
+}
+
+extern "C" int ngp_dp_small_adam(const void* const* peer_grads, uint32_t world, float* master, float* exp_avg, float* exp_avg_sq,
+                                 uint32_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev,
+                                 const float* lr_dev, const float* inv_scale_dev, float* found_inf_out, ngp_stream_t stream) {
+    if (n == 0) return NGP_OK;
+    if (!peer_grads || !master || !exp_avg || !exp_avg_sq || !step_dev) return NGP_ERR_NULL;
+    if (world == 0 || world > kMaxPeers || n > (1u << 20)) return NGP_ERR_BAD_ARG;
+    SmallPeers pp = {};
+    for (uint32_t r = 0; r < world; r++) {
+        if (!peer_grads[r]) return NGP_ERR_NULL;
+        if (!aligned(peer_grads[r], 4)) return NGP_ERR_ALIGN;
+        pp.grad[r] = (const float*)peer_grads[r];
+    }
+    dp_small_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pp, world, master, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                             step_dev, lr_dev, inv_scale_dev, found_inf_out);
     return finish_launch();
 }
 

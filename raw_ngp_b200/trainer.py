@@ -249,9 +249,13 @@ class FusedTrainStep:
                 pm = _PeerMemory(process_group, dev)
                 table_lp = pm.empty_like(self.table_master, torch.float16).copy_(self.table_master)
                 table_grad = pm.empty_like(self.table_master, torch.float16).zero_()
-                w_grad = pm.empty(n_w, torch.float32).zero_()
+                # the se3 gradient of the pose optimizer rides behind the MLP gradients in the same symmetric buffer (one peer
+                # mapping, cleared together by ngp_dp_finish)
+                n_se3 = pose_optimizer.se3_refine.weight.numel() if pose_optimizer is not None else 0
+                w_grad_all = pm.empty(n_w + (n_se3 + 3) // 4 * 4, torch.float32).zero_()
+                w_grad = w_grad_all[:n_w]
                 flags = pm.empty(8, torch.float32).zero_()
-                pm.rendezvous(grad=table_grad, table=table_lp, w_grad=w_grad, flags=flags)
+                pm.rendezvous(grad=table_grad, table=table_lp, w_grad=w_grad_all, flags=flags)
                 self.peer = pm
             except Exception as e:       # no symmetric memory on this system (all ranks fail alike)
                 if not allow_nccl_fallback:
@@ -262,6 +266,7 @@ class FusedTrainStep:
                 warnings.warn(f"FusedTrainStep: peer-memory data parallel path unavailable ({e!r}); using NCCL all-reduce")
         if self.peer is not None:
             enc.embeddings.data, self.table_grad, self.w_grad, self.flags = table_lp, table_grad, w_grad, flags
+            self._w_grad_all, self._n_w = w_grad_all, n_w
         else:
             enc.embeddings.data = self.table_master.half()
             self.table_grad = torch.zeros_like(enc.embeddings.data)
@@ -326,7 +331,12 @@ class FusedTrainStep:
             self.se3 = w.data
             if self.se3.shape[0] != self.poses.shape[0]:
                 raise ValueError("FusedTrainStep: one se3 row per dataset pose")
-            self.se3_grad = torch.zeros_like(self.se3)
+            if self.peer is not None:
+                # summed across ranks by ngp_dp_small_adam through the peer mappings (no NCCL call in front of the ray generation)
+                self.se3_grad = self._w_grad_all[self._n_w:self._n_w + self.se3.numel()].view_as(self.se3)
+                self._se3_peer_ptrs = (ctypes.c_void_p * self.world)(*[int(p) + 4 * self._n_w for p in self.peer.ptrs["w_grad"]])
+            else:
+                self.se3_grad = torch.zeros_like(self.se3)
             self.cam_idx = torch.zeros(N, device=dev, dtype=torch.int32)
             self.dirs_cam = torch.zeros(N, 3, device=dev, dtype=torch.float32)
             self.pose_found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -410,11 +420,19 @@ class FusedTrainStep:
 
     def _launch_pose_update(self):
         """inf check + Adam of se3_refine for the PREVIOUS step's gradients: on the main stream, because the rays of this step
-        are generated from the updated poses (the table / MLP update runs beside the march on the side stream)."""
+        are generated from the updated poses (the table / MLP update runs beside the march on the side stream).
+        Peer-memory data parallel: the gradient is summed over the ranks' buffers inside the kernel; the caller has put a
+        barrier in front (every rank's backward has finished) and ngp_dp_finish clears the buffers afterwards."""
         g = self.pose_opt.groups[0]
         b1, b2 = self.pose_opt.betas
         self.pose_opt.step_count += 1
         _lib.weights_epoch += 1
+        if self.peer is not None:
+            _lib.call("ngp_dp_small_adam", self._se3_peer_ptrs, self.world, _lib.ptr(self.se3), _lib.ptr(g["m"]), _lib.ptr(g["v"]),
+                      self.se3.numel(), float(self.pose_opt.lr), float(b1), float(b2), float(self.pose_opt.eps),
+                      float(self.pose_opt.weight_decay), _lib.ptr(self.pose_step_dev), _lib.ptr(self.pose_lr_dev), _lib.ptr(self.inv_scale),
+                      _lib.ptr(self.pose_found_inf), _lib.stream())
+            return
         _lib.call("ngp_small_adam", _lib.ptr(self.se3), _lib.ptr(self.se3_grad), _lib.ptr(g["m"]), _lib.ptr(g["v"]), self.se3.numel(),
                   float(self.pose_opt.lr), float(b1), float(b2), float(self.pose_opt.eps), float(self.pose_opt.weight_decay),
                   _lib.ptr(self.pose_step_dev), _lib.ptr(self.pose_lr_dev), _lib.ptr(self.inv_scale), _lib.ptr(self.pose_found_inf),
@@ -592,20 +610,45 @@ class FusedTrainStep:
             self.field_kernels = _lib.launch_count - c0
             # the peer-memory update chain (4 launches + 2 symmetric-memory barriers) as a graph of its own: replayed on the side
             # stream it costs one launch of host time and no gaps between its small kernels.  NGP_DP_GRAPH=0 keeps it eager.
-            self._graph_update = None
+            # The peer-memory update chain (4 launches + 2 symmetric-memory barriers) and the march as ONE graph with two branches:
+            #   side:  check + publish | barrier 0 | Adam(table) | Adam(MLPs) | [wait pose] | barrier 1 | finish
+            #   main:  [barrier 2 | pose Adam over the peers' se3 gradients] | march                      -> join
+            # one launch of host time per step and no gaps between the small kernels.  NGP_DP_GRAPH=0 keeps everything eager.
+            self._graph_update = self._graph_um = None
             if self.peer is not None and os.environ.get("NGP_DP_GRAPH", "1") != "0":
                 n_adam, epoch = self.opt.step_count, _lib.weights_epoch
+                n_pose = self.pose_opt.step_count if self.pose is not None else 0
                 try:
+                    if self.pose is None:        # the chain alone, for tools/dp_timeline.py
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._peer_update()
+                        self._graph_update = g
                     g = torch.cuda.CUDAGraph()
                     c0 = _lib.launch_count
                     with torch.cuda.graph(g):
-                        self._peer_update()
-                    self.update_kernels = _lib.launch_count - c0 + 2          # + the two barrier kernels
-                    self._graph_update = g
+                        main = torch.cuda.current_stream()
+                        self._side.wait_stream(main)
+                        ev = None
+                        if self.pose is not None:
+                            self.peer.barrier(2)                   # every rank's se3 gradient is complete
+                            self._launch_pose_update()
+                            ev = torch.cuda.Event()
+                            ev.record(main)
+                        with torch.cuda.stream(self._side):
+                            self._peer_update(pose_event=ev)
+                        self._launch_march()
+                        main.wait_stream(self._side)
+                    self.um_kernels = _lib.launch_count - c0 + 2 + (1 if self.pose is not None else 0) + (1 if self.perturb else 0)
+                    self.update_kernels = self.um_kernels - self.march_kernels
+                    self._graph_um = g
                 except Exception as e:       # barrier not capturable in this torch build: eager launches, same result
                     import warnings
                     warnings.warn(f"FusedTrainStep: the peer update could not be captured ({e!r}); launching it eagerly")
+                    self._graph_update = self._graph_um = None
                 self.opt.step_count, _lib.weights_epoch = n_adam, epoch
+                if self.pose is not None:
+                    self.pose_opt.step_count = n_pose
         self.table_grad.zero_()
         self.w_grad.zero_()
         if self.pose is not None:
@@ -619,22 +662,26 @@ class FusedTrainStep:
         if pose_lr is not None and self.pose is not None:
             self.pose_lr_dev.fill_(float(pose_lr))
 
-    def _reduce_and_update(self):
+    def _reduce_and_update(self, pose_inline=False):
         """Data parallel: all-reduce of the two gradient buffers, inf check, MAX of the flag, fused Adam -- on the current
         (side) stream, so that it overlaps the ray marching of the next step on the main stream."""
         if self.peer is not None:
-            return self._peer_update()
+            return self._peer_update(pose_inline=pose_inline)
         parallel.all_reduce_gradients([self.table_grad, self.w_grad], None, self.pg)
         # The inf / nan check runs on the REDUCED buffers, which are bit-identical on every rank (a non-finite value of any
         # rank survives the SUM), so all ranks take the same skip decision without a second collective for the flag.
         self._launch_check(count_step=True)
         self.opt.step(self.inv_scale, self.found_inf, zero_grad=True, count_step=False)
 
-    def _peer_update(self):
+    def _peer_update(self, pose_inline=False, pose_event=None):
         """reduce-scatter + Adam + all-gather of the table as ONE kernel over peer memory (and a replicated variant of the same
         kernel for the 57 KB of MLP weights); the GradScaler flag travels through peer stores; two symmetric-memory barriers
         order the ranks.  No NCCL call, no staging buffer, Adam on 1 / world of the table.  Four launches + two barriers:
-        check + flag publish | barrier | Adam(table) | Adam(MLPs) | barrier | finish (merged flag, step count, gradient clear)."""
+        check + flag publish | barrier | Adam(table) | Adam(MLPs) | barrier | finish (merged flag, step count, gradient clear).
+        The pose optimizer's se3 gradient lives behind the MLP gradients in the same symmetric buffer: its update
+        (ngp_dp_small_adam, which sums the ranks' buffers itself) runs either inside this chain behind the first barrier
+        (pose_inline, the eager path) or on the main stream behind a barrier of its own, in front of the ray generation; in that
+        case pose_event (recorded behind it) keeps this rank out of the closing barrier until it has read every peer's buffer."""
         st, P, pm = _lib.stream(), _lib.ptr, self.peer
         world, rank = self.world, pm.rank
         _lib.weights_epoch += 1
@@ -645,6 +692,8 @@ class FusedTrainStep:
         g, d, n = self._chk_args
         _lib.call("ngp_dp_check_publish", g, d, n, 2, P(self.found_inf), P(self._chk_scratch), pm.ptrs["flags"], world, rank, st)
         pm.barrier(0)                                              # every rank's gradients and flags are complete
+        if pose_inline and self.pose is not None:
+            self._launch_pose_update()
         lo, hi = self.shard
         _lib.call("ngp_dp_fused_adam", pm.ptrs["grad"], _lib.NGP_F16, pm.ptrs["table"], _lib.NGP_F16, world, world,
                   P(self.table_master_shard), P(self.shard_m), P(self.shard_v), lo, hi, float(self.opt.lr), float(b1), float(b2),
@@ -653,9 +702,11 @@ class FusedTrainStep:
         _lib.call("ngp_dp_fused_adam", pm.ptrs["w_grad"], _lib.NGP_F32, self._w_lp_local, _lib.NGP_F16, world, 1, P(self.w_master),
                   P(self.w_m), P(self.w_v), 0, self.w_master.numel(), float(self.opt.lr), float(b1), float(b2), float(self.opt.eps),
                   float(self.opt.weight_decay), P(self.opt_step_dev), P(self.lr_dev), P(self.inv_scale), None, P(self.flags), world, st)
+        if pose_event is not None:
+            torch.cuda.current_stream().wait_event(pose_event)
         pm.barrier(1)                                              # all parameter stores have landed, all gradient loads are done
         _lib.call("ngp_dp_finish", P(self.flags), world, P(self.found_inf), P(self.opt_step_dev), P(self.table_grad),
-                  self.table_grad.numel() * self.table_grad.element_size(), P(self.w_grad), self.w_grad.numel() * 4, st)
+                  self.table_grad.numel() * self.table_grad.element_size(), P(self._w_grad_all), self._w_grad_all.numel() * 4, st)
 
     def gather_table_master(self):
         """fp32 master copy of the whole table (checkpoints).  In peer mode every rank holds only its shard: all-gather them."""
@@ -788,13 +839,14 @@ class FusedTrainStep:
         k + 1, overlapped with its ray marching).  Call before using the model outside of step()."""
         if not self._pending:
             return
+        peer_pose = self.peer is not None and self.pose is not None
         if self.world > 1:
-            if self.pose is not None:
+            if self.pose is not None and not peer_pose:
                 parallel.all_reduce_gradients([self.se3_grad], None, self.pg)
-            self._reduce_and_update()
+            self._reduce_and_update(pose_inline=peer_pose)
         else:
             self._launch_optimizer()
-        if self.pose is not None:
+        if self.pose is not None and not peer_pose:
             self._launch_pose_update()
         self._launch_scaler_update()
         self._pending = False
@@ -912,26 +964,32 @@ class FusedTrainStep:
             if self.world > 1:
                 # [all-reduce + optimizer update of the previous step, side stream]  ||  [march graph]  ->  field graph
                 main = torch.cuda.current_stream()
-                if self._pending:
-                    if self.pose is not None:      # tiny, and the march below needs the updated poses: main stream, first
-                        parallel.all_reduce_gradients([self.se3_grad], None, self.pg)
-                    self._side.wait_stream(main)
-                    with torch.cuda.stream(self._side):
-                        if getattr(self, "_graph_update", None) is not None:
-                            _lib.weights_epoch += 1
-                            self.opt.step_count += 1
-                            self._graph_update.replay()
-                            self.kernels_replayed += self.update_kernels
-                        else:
-                            self._reduce_and_update()
+                if self._pending and getattr(self, "_graph_um", None) is not None:
+                    _lib.weights_epoch += 1
+                    self.opt.step_count += 1
                     if self.pose is not None:
-                        self._launch_pose_update()
-                self._graph_march.replay()
+                        self.pose_opt.step_count += 1
+                    self._graph_um.replay()                    # update chain || [pose update] march, joined
+                    self.kernels_replayed += self.um_kernels
+                else:
+                    if self._pending:
+                        peer_pose = self.peer is not None and self.pose is not None
+                        if self.pose is not None and not peer_pose:      # tiny, and the march needs the updated poses: main stream, first
+                            parallel.all_reduce_gradients([self.se3_grad], None, self.pg)
+                        self._side.wait_stream(main)
+                        with torch.cuda.stream(self._side):
+                            self._reduce_and_update(pose_inline=peer_pose)
+                        if peer_pose:
+                            main.wait_stream(self._side)           # eager fallback: no overlap with the march
+                        elif self.pose is not None:
+                            self._launch_pose_update()
+                    self._graph_march.replay()
+                    self.kernels_replayed += self.march_kernels
                 main.wait_stream(self._side)
                 if self._pending:
                     self._launch_scaler_update()
                 self._graph_field.replay()
-                self.kernels_replayed += self.march_kernels + self.field_kernels
+                self.kernels_replayed += self.field_kernels
             elif self._pending:
                 _lib.weights_epoch += 1          # the replayed graph contains the optimizer update
                 self._graph_pipe.replay()

@@ -255,3 +255,41 @@ def test_small_adam_matches_torch_and_skips_on_inf():
     grad[577] = float("nan")
     launch()
     assert found.item() == 1.0 and step.item() == 4 and torch.equal(master, before) and grad.abs().max().item() == 0.0
+
+
+def test_dp_small_adam_sums_the_peer_buffers():
+    """ngp_dp_small_adam (the pose optimizer's update in peer-memory data parallel: gradient = sum of every rank's buffer, read
+    through the peer mappings) against torch.optim.Adam on the summed gradient; three local buffers stand in for three ranks.
+    The buffers are left alone (ngp_dp_finish clears them behind the closing barrier); an inf in ANY rank's buffer skips the step."""
+    import ctypes
+    torch.manual_seed(4)
+    dev, n, world = "cuda", 600, 3
+    master = torch.randn(n, device=dev) * 0.01
+    ref = torch.nn.Parameter(master.clone())
+    opt_ref = torch.optim.Adam([ref], lr=1e-3)
+    grads = [torch.zeros(n, device=dev) for _ in range(world)]
+    peers = (ctypes.c_void_p * world)(*[g.data_ptr() for g in grads])
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    lr_dev = torch.full((1,), 1e-3, device=dev)
+    inv_scale = torch.full((1,), 1 / (128.0 * world), device=dev)      # GradScaler scale x world: the mean over ranks
+    found = torch.full((1,), 5.0, device=dev)
+
+    def launch():
+        _lib.call("ngp_dp_small_adam", peers, world, _lib.ptr(master), _lib.ptr(m), _lib.ptr(v), n, 123.0, 0.9, 0.999, 1e-8, 0.0,
+                  _lib.ptr(step), _lib.ptr(lr_dev), _lib.ptr(inv_scale), _lib.ptr(found), _lib.stream())
+
+    for it in range(4):
+        gs = [torch.randn(n, device=dev) for _ in range(world)]
+        for buf, g in zip(grads, gs):
+            buf.copy_(g * 128.0)
+        ref.grad = sum(gs) / world
+        launch()
+        opt_ref.step()
+        assert found.item() == 0.0 and step.item() == it + 1
+        assert all(torch.equal(buf, g * 128.0) for buf, g in zip(grads, gs))
+        torch.testing.assert_close(master, ref.data, rtol=1e-5, atol=1e-7)
+    before = master.clone()
+    grads[2][13] = float("inf")
+    launch()
+    assert found.item() == 1.0 and step.item() == 4 and torch.equal(master, before)

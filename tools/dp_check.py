@@ -67,6 +67,50 @@ def main():
     out["peer_vs_nccl"] = dict(table_max_abs_diff=float(dt.max().item()), table_mean_abs_diff=float(dt.mean().item()),
                                table_mean_abs_update=float(moved.mean().item()),
                                w_max_abs_diff=float((tables["peer"][1] - tables["nccl"][1]).abs().max().item()))
+    # ---- BARF pose refinement (BASELINE configs[4]): the se3 gradient is summed through the peer mappings inside the pose Adam
+    # kernel (peer mode) or all-reduced by NCCL; se3 must be bit-identical across ranks and agree between the modes
+    from raw_ngp_b200 import pose
+    C, n_rays = 100, 4096
+    poses = pose.look_at_poses(C, radius=2.0).to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    idx = torch.randint(0, C, (n_rays,), generator=g).to(dev)
+    ij = torch.randint(0, 800, (n_rays, 2), generator=g).float() + 0.5
+    dirs = pose.pixel_directions(ij[:, 0], ij[:, 1], (1000.0, 1000.0, 400.0, 400.0)).to(dev)
+    tg = torch.rand(n_rays, 3, generator=g).to(dev)
+    se3s = {}
+    for mode in ("peer", "nccl"):
+        os.environ["NGP_DP_PEER"] = "1" if mode == "peer" else "0"
+        model = bench.build_model(dev, pose_opt="barf", start_annealing=0.0, end_annealing=0.5)
+        model.update_annealing(0.25)
+        cam = pose.CameraOptimizer(C, dev)
+        fs = FusedTrainStep(model, n_rays, loss_scale=128.0, pose_optimizer=cam, poses=poses, pose_lr=1e-3, perturb=False,
+                            process_group=dist.group.WORLD)
+        fs.set_camera_rays(idx, dirs, tg)
+        for _ in range(K):
+            fs.step(update_grid=False)
+        fs.flush()
+        torch.cuda.synchronize()
+        se3 = fs.se3.clone()
+        ref = se3.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([float(torch.equal(ref, se3))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            fs.step(update_grid=False)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 200], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        fs.flush(); torch.cuda.synchronize()
+        se3s[mode] = se3
+        out["pose_" + mode] = dict(se3_bit_identical_across_ranks=bool(same.item()), se3_max_abs=float(se3.abs().max().item()),
+                                   pose_steps=int(fs.pose_step_dev.item()), graph=getattr(fs, "_graph_um", None) is not None,
+                                   ms_per_step=round(float(ms.item()), 4))
+        del fs
+    out["pose_peer_vs_nccl"] = dict(se3_max_abs_diff=float((se3s["peer"] - se3s["nccl"]).abs().max().item()))
     if rank == 0:
         print(json.dumps(dict(n_gpus=world, steps=K, **out)), flush=True)
     dist.destroy_process_group()
