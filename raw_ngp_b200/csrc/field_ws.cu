@@ -3,19 +3,15 @@
 //     xyz --gather warps--> hash-grid features --> [A0 ring in shared memory] --MLP warps--> grid_mlp -> sigma, feat
 //                                                                                   SH(dir) -> view_mlp -> colour -> rgb
 //
-// One CTA per SM, 26 warps:
-//   * warps 0-15 (512 threads) only gather: thread (row, g) encodes levels g, g+4, g+8, g+12 of its sample with several levels
-//     (8 table rows each) in flight, writes the fp16 features into stage s of a ring of 128 x 2L tiles and arrives on
-//     full[s].  The gathers are bound by the SM's L1 look-up rate on the L2-resident table, so these warps never wait for
+// One CTA per SM, 28 warps:
+//   * warps 0-15 (512 threads) only gather: thread (row, g) encodes levels g, g+4, g+8, g+12 of its sample with two levels
+//     (16 table rows) in flight, writes the fp16 features into stage s of a 3-deep ring of 128 x 2L tiles and arrives on
+//     full[s].  The gathers are bound by the SM's L1-miss path into the L2-resident table, so these warps never wait for
 //     anything else: the ring decouples them from the tensor-core chain.
-//   * warps 16-23 are two MLP groups (4 warps each), warps 24-25 their MMA issuers (one thread each).  A group keeps TWO
-//     tiles in flight ("slots", each with its own 128 TMEM columns, activation tile and barriers) and alternates between
-//     them layer by layer: its 128 threads run the epilogue of layer l of one slot (TMEM -> registers -> ReLU / fp16 ->
-//     shared memory) and signal ready[slot]; the issuer answers with the tcgen05.mma of layer l+1 (M = 128), the bulk copy
-//     of the tile for the backward pass and a commit on done[slot] -- while the epilogue threads are already busy with the
-//     other slot.  Neither the serial issue sequence nor the MMA latency sits on the epilogue threads' path any more (with
-//     one tile per group and the issue inside the epilogue warps that was 40 % of the MLP warps' time, and the MLP chains,
-//     not the gathers, set the pace of the kernel).
+//   * warps 16-27 are three MLP groups (4 warps each) that take tiles in turn.  A group waits for full[s], then runs the six
+//     layers of grid_mlp and view_mlp as tcgen05.mma (M = 128, accumulators in the group's 128 TMEM columns), with the
+//     fp16 activations going TMEM -> registers -> shared memory between layers; tcgen05.commit on empty[s] hands the ring
+//     stage back to the gather warps as soon as the first layer has consumed it.
 // All tiles are swizzled row-major (tile_sw.cuh: the UMMA SWIZZLE_32B/64B/128B canonical layouts), so the tensor core reads
 // its operands without bank conflicts.  Saved activations (for the backward kernel) are written to global memory as the
 // shared-memory image of the tile ("tile-panel" layout), so that the backward kernel fetches a whole tile with one bulk
@@ -32,35 +28,20 @@ using namespace mlpcore;
 using namespace gridcore;
 using namespace fieldcore;
 
-#ifndef NGP_WS_ISOLATE
-#define NGP_WS_ISOLATE 0                // timing experiments only: 1 = the MLP side alone (no gathers), 2 = the gather warps alone,
-                                        // bit 2 (4) = no saves, bit 3 (8) = no st.shared in the hidden epilogues
-#endif
-#ifndef NGP_WS_GATHER_LEVELS
-#define NGP_WS_GATHER_LEVELS 2          // levels a gather thread keeps in flight (8 table rows each)
-#endif
 constexpr uint32_t kGatherThreads = 512;
 constexpr uint32_t kGatherGroups = kGatherThreads / kTile;
-constexpr uint32_t kMlpGroups = 2;
-constexpr uint32_t kSlots = 2;                                           // tiles in flight per MLP group
-constexpr uint32_t kWsThreads = kGatherThreads + kMlpGroups * kTile + kMlpGroups * 32;     // 832: gather | epilogue | issuers
-// Ring stage <-> (group, slot): tile number `it` of the CTA goes to group it % kMlpGroups, which puts its tiles alternately
-// into its two slots, so stage it % kStages is only ever consumed by one (group, slot) and in order (a waiter two phases
-// early would read the parity of an older phase as "complete").
-constexpr uint32_t kStages = kMlpGroups * kSlots;
-constexpr uint32_t kSlotTmemCols = 128;
+constexpr uint32_t kMlpGroups = 3;
+constexpr uint32_t kWsThreads = kGatherThreads + kMlpGroups * kTile;     // 768
+constexpr uint32_t kStages = kMlpGroups;      // one ring stage per MLP group: a stage barrier is only ever waited on by its own group (phase parity!)
+constexpr uint32_t kGroupTmemCols = 128;
 constexpr uint32_t kWsTmemCols = 512;
 constexpr uint32_t kWsLayers = 6;
-static_assert(kStages * kSlotTmemCols <= kWsTmemCols, "one accumulator per tile in flight");
 
 // control block (byte offsets from ctrl_off)
-constexpr uint32_t kWsFull = 0, kWsEmpty = 8 * kStages, kWsDone = 16 * kStages, kWsReady = 24 * kStages, kWsTmemSlot = 32 * kStages;
+constexpr uint32_t kWsFull = 0, kWsEmpty = 8 * kStages, kWsDone = 16 * kStages, kWsTmemSlot = kWsDone + 8 * kMlpGroups;
 constexpr uint32_t kWsLevels = (kWsTmemSlot + 4 + 15) & ~15u;
 constexpr uint32_t kWsPlans = kWsLevels + kMaxLevels * sizeof(LevelConst);
-// One layer's tcgen05.mma sequence: k-step ks uses descriptors a0 + ks * a_step, b0 + ks * b_step (the start-address field
-// advances by a constant per k-step in every layout of tile_sw.cuh), so the issuer reads 32 bytes per layer.
-struct IssuePlan { uint64_t a0, b0; uint32_t a_step, b_step, idesc, n_steps; };
-constexpr uint32_t kWsCtrlBytes = kWsPlans + kStages * kWsLayers * sizeof(IssuePlan);
+constexpr uint32_t kWsCtrlBytes = kWsPlans + kMlpGroups * kWsLayers * sizeof(MmaPlan);
 
 struct WsArgs {
     const float* xyzs; const float* dirs; const float* ldirs;
@@ -76,7 +57,7 @@ struct WsArgs {
     int density_act, color_act; float beta;
     uint32_t n_run;                    // layers to run: 6, or 3 for a density-only query (NeRFNetwork.density)
     uint32_t rowmajor;                 // saved tensors as plain [M, width] rows (for the kernel-pair backward) instead of tile images
-    uint32_t w_off[kWsLayers], a0_off, a0_stage_bytes, h_off, h_bytes, ctrl_off;
+    uint32_t w_off[kWsLayers], a0_off, a0_stage_bytes, h_off[kMlpGroups], ctrl_off;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_h2(a, b); }
@@ -89,13 +70,12 @@ field_forward_ws_kernel(const WsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t M = a.M;
     if (a.m_dev) M = min(M, (uint32_t)__ldg(a.m_dev));   // sample count produced on the device (no host sync)
-    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint8_t* ctrl = smem + a.ctrl_off;
     const uint32_t full_s = tc::smem_u32(ctrl + kWsFull), empty_s = tc::smem_u32(ctrl + kWsEmpty), done_s = tc::smem_u32(ctrl + kWsDone);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kWsTmemSlot);
     LevelConst* s_lv = reinterpret_cast<LevelConst*>(ctrl + kWsLevels);
-    const uint32_t ready_s = tc::smem_u32(ctrl + kWsReady);
-    IssuePlan* plans = reinterpret_cast<IssuePlan*>(ctrl + kWsPlans);     // [stage = slot * kMlpGroups + group][layer]
+    MmaPlan* plans = reinterpret_cast<MmaPlan*>(ctrl + kWsPlans);     // [group][layer]
 
     // ---- prologue: TMEM, barriers, weights, per-level constants, MMA descriptors -----------------------------------
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), kWsTmemCols);
@@ -103,24 +83,22 @@ field_forward_ws_kernel(const WsArgs a) {
         for (uint32_t s = 0; s < kStages; s++) {
             tc::mbar_init(full_s + 8 * s, kGatherThreads);
             tc::mbar_init(empty_s + 8 * s, 1);
-            tc::mbar_init(done_s + 8 * s, 1);
-            tc::mbar_init(ready_s + 8 * s, kTile);
         }
+        for (uint32_t gI = 0; gI < kMlpGroups; gI++) tc::mbar_init(done_s + 8 * gI, 1);
     }
     for (uint32_t l = 0; l < a.n_run; l++) tsw::load_weight_tile_r(smem + a.w_off[l], a.w[l], a.N[l], a.K[l]);
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + kStages * kWsLayers && (threadIdx.x - 64) % kWsLayers < a.n_run) {
-        const uint32_t i = threadIdx.x - 64, st = i / kWsLayers, l = i % kWsLayers;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kMlpGroups * kWsLayers && (threadIdx.x - 64) % kWsLayers < a.n_run) {
+        const uint32_t i = threadIdx.x - 64, gI = i / kWsLayers, l = i % kWsLayers;
         const uint32_t K = a.K[l], N = a.N[l];
-        // Y = A [128 x K] (K-major) * W_l^T; A = the tile's ring stage for layer 0, else the slot's activation tile
-        const uint32_t a_saddr = tc::smem_u32(smem + (l == 0 ? a.a0_off + st * a.a0_stage_bytes : a.h_off + st * a.h_bytes));
-        const uint32_t w_saddr = tc::smem_u32(smem + a.w_off[l]);
-        IssuePlan& pl = plans[i];
+        // Y = A [128 x K] (K-major) * W_l^T; A = ring stage 0 for layer 0 (the issuer adds the stage offset), else the group's tile
+        const uint32_t a_saddr = tc::smem_u32(smem + (l == 0 ? a.a0_off : a.h_off[gI])), w_saddr = tc::smem_u32(smem + a.w_off[l]);
+        MmaPlan& pl = plans[i];
         pl.idesc = tc::instr_desc(kTile, N, false, false);
-        pl.n_steps = K / 16;
-        pl.a0 = tsw::desc_kmajor_r(a_saddr, K, kTile, 0);     // both operands K-major swizzled tiles of width K
-        pl.b0 = tsw::desc_kmajor_r(w_saddr, K, N, 0);
-        pl.a_step = (uint32_t)(tsw::desc_kmajor_r(a_saddr, K, kTile, 1) - pl.a0);
-        pl.b_step = (uint32_t)(tsw::desc_kmajor_r(w_saddr, K, N, 1) - pl.b0);
+        pl.n_steps = K / 16; pl.d_col = gI * kGroupTmemCols; pl.pad = 0;
+        for (uint32_t ks = 0; ks < K / 16; ks++) {     // both operands K-major swizzled tiles of width K
+            pl.step[ks].a = tsw::desc_kmajor_r(a_saddr, K, kTile, ks);
+            pl.step[ks].b = tsw::desc_kmajor_r(w_saddr, K, N, ks);
+        }
     }
     load_level_consts(s_lv, a.g);
     tc::fence_async_smem();
@@ -146,31 +124,7 @@ field_forward_ws_kernel(const WsArgs a) {
             const bool inside = x[0] >= 0 && x[0] <= 1 && x[1] >= 0 && x[1] <= 1 && x[2] >= 0 && x[2] <= 1;
             const float xc[3] = {fminf(fmaxf(x[0], 0.f), 1.f), fminf(fmaxf(x[1], 0.f), 1.f), fminf(fmaxf(x[2], 0.f), 1.f)};
             uint8_t* a0 = smem + a.a0_off + s * a.a0_stage_bytes;
-#if (NGP_WS_ISOLATE & 3) == 1
-            tc::mbar_wait(empty_s + 8 * s, ((it / kStages) & 1u) ^ 1u);
-            tc::fence_async_smem();
-            tc::mbar_arrive(full_s + 8 * s);
-            continue;
-#endif
             bool waited = false;
-#if NGP_WS_GATHER_LEVELS == 4
-            // all four levels of the thread (32 table rows) in flight at once
-            if (!DYDX && g.L == 4 * kGatherGroups && s_lv[grp].mode != 2 && s_lv[grp + kGatherGroups].mode != 2 &&
-                s_lv[grp + 2 * kGatherGroups].mode != 2 && s_lv[grp + 3 * kGatherGroups].mode != 2) {
-                LevelGather q[4];
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) gather_issue(q[j], g, s_lv[grp + j * kGatherGroups], xc);
-                __half2 f[4];
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) f[j] = gather_finish(q[j], g, grp + j * kGatherGroups, inside);
-                tc::mbar_wait(empty_s + 8 * s, ((it / kStages) & 1u) ^ 1u);
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) {
-                    const uint32_t lv = grp + j * kGatherGroups;
-                    *reinterpret_cast<__half2*>(a0 + tsw::chunk_off(F, r, lv / 4) + (lv % 4) * 4) = f[j];
-                }
-            } else
-#endif
             for (uint32_t level = grp; level < g.L; level += 2 * kGatherGroups) {
                 const uint32_t la = level, lb = level + kGatherGroups;       // L % 8 == 0
                 __half2 f0, f1;
@@ -223,222 +177,156 @@ field_forward_ws_kernel(const WsArgs a) {
             tc::fence_async_smem();
             tc::mbar_arrive(full_s + 8 * s);
         }
-    } else if ((NGP_WS_ISOLATE & 3) == 2) {
-        if (warp >= (kGatherThreads + kMlpGroups * kTile) / 32 && (threadIdx.x & 31u) == 0) {
-            const uint32_t gI = warp - (kGatherThreads + kMlpGroups * kTile) / 32;
-            for (uint32_t it = gI; blockIdx.x + it * gridDim.x < n_tiles; it += kMlpGroups) {
-                tc::mbar_wait(full_s + 8 * (it % kStages), (it / kStages) & 1u);
-                tc::mbar_arrive(empty_s + 8 * (it % kStages));
-            }
-        }
-    } else if (warp < (kGatherThreads + kMlpGroups * kTile) / 32) {
-        // ================================ MLP groups: epilogues ================================
+    } else {
+        // ================================ MLP groups ================================
         const uint32_t gI = (warp - kGatherThreads / 32) / 4;             // group
         const uint32_t tg = threadIdx.x - kGatherThreads - gI * kTile;    // row inside the tile == TMEM lane
-        const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);
-        uint32_t tile_of[kSlots] = {0u, 0u}, ph[kSlots] = {0u, 0u};
-        bool active[kSlots];
-        uint32_t n_next = 0;                                              // index of the group's next tile in its own sequence
-        // the group's tiles go alternately into its two slots: tile number n of the group sits in slot n % kSlots
-        auto next_tile = [&](uint32_t slot) {
-            const uint32_t tile = blockIdx.x + (gI + n_next * kMlpGroups) * gridDim.x;
-            active[slot] = tile < n_tiles;
-            if (active[slot]) { tile_of[slot] = tile; n_next++; }
-        };
-        next_tile(0);
-        next_tile(1);
-        while (active[0] || active[1]) {
+        const uint32_t lane_addr = tmem + (((warp & 3u) * 32u) << 16) + gI * kGroupTmemCols;
+        uint8_t* h = smem + a.h_off[gI];
+        const MmaPlan* pl = plans + gI * kWsLayers;
+        const uint32_t done = done_s + 8 * gI;
+        uint32_t ph = 0;
+        for (uint32_t it = gI;; it += kMlpGroups) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x;
+            if (tile >= n_tiles) break;
+            const uint32_t s = it % kStages;
+            const uint32_t row = tile * kTile + tg;
+            const bool live = row < M;
+            tc::mbar_wait(full_s + 8 * s, (it / kStages) & 1u);
+            float out[16];
             for (uint32_t l = 0; l < a.n_run; l++) {
-#pragma unroll
-                for (uint32_t slot = 0; slot < kSlots; slot++) {
-                    if (!active[slot]) continue;
-                    const uint32_t tile = tile_of[slot], st = slot * kMlpGroups + gI;
-                    const uint32_t row = tile * kTile + tg;
-                    const bool live = row < M;
-                    const uint32_t lane_addr = lane_base + st * kSlotTmemCols;
-                    uint8_t* h = smem + a.h_off + st * a.h_bytes;
-                    tc::mbar_wait(done_s + 8 * st, ph[slot]);             // layer l of this slot has retired (and its operand tile is free)
-                    ph[slot] ^= 1u;
+                if (tg == 0) {
                     tc::fence_after_sync();
-                    if (a.rowmajor && l == 0 && a.enc_out && live) {
-                        // plain-row saves (what the kernel-pair backward of field.cu / mlp.cu reads): the encoder output row by row
-                        // out of the ring stage; the hidden rows below go out straight from the epilogue's registers
-                        const uint8_t* src = smem + a.a0_off + st * a.a0_stage_bytes;
-                        uint4* dst = reinterpret_cast<uint4*>(a.enc_out + (size_t)row * a.K[0]);
-                        for (uint32_t j = 0; j < a.K[0] / 8; j++) dst[j] = *reinterpret_cast<const uint4*>(src + tsw::chunk_off_r(a.K[0], kTile, tg, j));
+                    const uint64_t stage_add = (l == 0) ? (uint64_t)((s * a.a0_stage_bytes) >> 4) : 0ull;
+                    for (uint32_t ks = 0; ks < pl[l].n_steps; ks++)
+                        tc::mma_f16_ss(tmem + pl[l].d_col, pl[l].step[ks].a + stage_add, pl[l].step[ks].b, pl[l].idesc, ks > 0);
+                    // The A operand of this layer is also what the backward pass needs (enc, h1, h2 | in2, h1', h2'): its tile
+                    // image goes to global memory as ONE bulk async copy while the MMA runs.  The commit is issued after the
+                    // copy has finished reading shared memory, so "MMA done" also means "tile may be overwritten".
+                    __half* save = (l == 0) ? a.enc_out : (l == 3) ? a.in2_out : a.acts[l - 1];
+                    if (save && !a.rowmajor) {
+                        const uint32_t bytes = kTile * a.K[l] * 2;
+                        const uint32_t src = tc::smem_u32((l == 0) ? smem + a.a0_off + s * a.a0_stage_bytes : h);
+                        tc::bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * bytes, src, bytes);
+                        tc::bulk_wait_read();
                     }
-                    const uint32_t N = a.N[l];
-                    if (l != 2 && l != 5) {
-                        // hidden layer: ReLU, fp16, next layer's A operand (+ saved for the backward pass)
-                        uint4* grow = (a.rowmajor && a.acts[l] && live) ? reinterpret_cast<uint4*>(a.acts[l] + (size_t)row * N) : nullptr;
-                        for (uint32_t c0 = 0; c0 < N; c0 += 16) {
-                            float v[16];
-                            tc::tmem_ld16(lane_addr + c0, v);
-                            uint4 lo, hi;
-                            pack16(v, lo, hi);
-                            {   // ReLU on the packed halves (8 HMNMX2 instead of 16 FMNMX; rounding is monotone, so the order is immaterial)
-                                const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-                                __half2* ql = reinterpret_cast<__half2*>(&lo);
-                                __half2* qh = reinterpret_cast<__half2*>(&hi);
+                    tc::mma_commit(done);
+                    if (l == 0 && !a.rowmajor) tc::mma_commit(empty_s + 8 * s);      // ring stage free once layer 0 (and the copy) has read it
+                }
+                if (a.rowmajor) {
+                    // the A operand as plain rows [M, K] (what the kernel-pair backward of field.cu / mlp.cu reads): every thread
+                    // copies its own row out of the tile while the MMA runs
+                    __half* save = (l == 0) ? a.enc_out : (l == 3) ? a.in2_out : a.acts[l - 1];
+                    if (save && live) {
+                        const uint32_t K = a.K[l];
+                        const uint8_t* src = (l == 0) ? smem + a.a0_off + s * a.a0_stage_bytes : h;
+                        uint4* dst = reinterpret_cast<uint4*>(save + (size_t)row * K);
+                        for (uint32_t j = 0; j < K / 8; j++) dst[j] = *reinterpret_cast<const uint4*>(src + tsw::chunk_off_r(K, kTile, tg, j));
+                    }
+                    if (l == 0) {       // the ring stage goes back to the gather warps only after every row has been read
+                        tc::named_bar_sync(1 + gI, kTile);
+                        if (tg == 0) tc::mma_commit(empty_s + 8 * s);
+                    }
+                }
+                tc::mbar_wait(done, ph);
+                ph ^= 1;
+                tc::fence_after_sync();
+                const uint32_t N = a.N[l];
+                if (l != 2 && l != 5) {
+                    // hidden layer: ReLU, fp16, next layer's A operand (+ saved for the backward pass)
+                    for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(lane_addr + c0, v);
+                        uint4 lo, hi;
+                        pack16(v, lo, hi);
+                        {   // ReLU on the packed halves (8 HMNMX2 instead of 16 FMNMX; rounding is monotone, so the order is immaterial)
+                            const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+                            __half2* ql = reinterpret_cast<__half2*>(&lo);
+                            __half2* qh = reinterpret_cast<__half2*>(&hi);
 #pragma unroll
-                                for (int i = 0; i < 4; i++) { ql[i] = __hmax2(ql[i], zero2); qh[i] = __hmax2(qh[i], zero2); }
-                            }
-                            const uint32_t o0 = tsw::chunk_off_r(N, kTile, tg, c0 / 8), o1 = tsw::chunk_off_r(N, kTile, tg, c0 / 8 + 1);
-                            if (!(NGP_WS_ISOLATE & 8) || lo.x == 0x12345678u) {
-                                *reinterpret_cast<uint4*>(h + o0) = lo;
-                                *reinterpret_cast<uint4*>(h + o1) = hi;
-                            }
-                            if (grow) { grow[c0 / 8] = lo; grow[c0 / 8 + 1] = hi; }
+                            for (int i = 0; i < 4; i++) { ql[i] = __hmax2(ql[i], zero2); qh[i] = __hmax2(qh[i], zero2); }
                         }
-                    } else if (l == 2) {
-                        // grid_mlp output: sigma (network.py:112-115: fp16 linear output, activation in fp32) and the view_mlp
-                        // input [feat(15), SH(dir)(16), (SH(light dir)(16)), 0]
-                        float out[16];
-                        tc::tmem_ld16(lane_addr, out);
-                        if (live) {
-                            const float o0 = half_round(out[0]);
-                            float sg;
-                            if (a.density_act == 0) sg = expf(o0);
-                            else { const float bx = a.beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / a.beta; }
-                            a.sigma_out[row] = sg;
-                        }
-                        if (a.n_run > 3) {          // (a density-only query has no view branch)
-                            float sh[LDIR ? 32 : 16];
-                            {
-                                float dx = 0.f, dy = 0.f, dz = 1.f;
-                                if (live) { dx = __ldg(a.dirs + (size_t)row * 3); dy = __ldg(a.dirs + (size_t)row * 3 + 1); dz = __ldg(a.dirs + (size_t)row * 3 + 2); }
-                                float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);          // renderer.py:544
-                                dx *= inv; dy *= inv; dz *= inv;
-                                inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);                // SHEncoder.forward, sphere_harmonics.py:81
-                                const float x = dx * inv, y = dy * inv, z = dz * inv, zz = z * z;
-                                constexpr int DEG = 4;
+                        const uint32_t o0 = tsw::chunk_off_r(N, kTile, tg, c0 / 8), o1 = tsw::chunk_off_r(N, kTile, tg, c0 / 8 + 1);
+                        *reinterpret_cast<uint4*>(h + o0) = lo;
+                        *reinterpret_cast<uint4*>(h + o1) = hi;
+                    }
+                } else if (l == 2) {
+                    // grid_mlp output: sigma (network.py:112-115: fp16 linear output, activation in fp32) and the view_mlp
+                    // input [feat(15), SH(dir)(16), (SH(light dir)(16)), 0]
+                    tc::tmem_ld16(lane_addr, out);
+                    if (live) {
+                        const float o0 = half_round(out[0]);
+                        float sg;
+                        if (a.density_act == 0) sg = expf(o0);
+                        else { const float bx = a.beta * o0; sg = (bx > 20.f) ? o0 : log1pf(expf(bx)) / a.beta; }
+                        a.sigma_out[row] = sg;
+                    }
+                    if (a.n_run == 3) {          // density only: no view branch
+                        tc::fence_before_sync();
+                        tc::named_bar_sync(1 + gI, kTile);
+                        continue;
+                    }
+                    float sh[LDIR ? 32 : 16];
+                    {
+                        float dx = 0.f, dy = 0.f, dz = 1.f;
+                        if (live) { dx = __ldg(a.dirs + (size_t)row * 3); dy = __ldg(a.dirs + (size_t)row * 3 + 1); dz = __ldg(a.dirs + (size_t)row * 3 + 2); }
+                        float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);          // renderer.py:544
+                        dx *= inv; dy *= inv; dz *= inv;
+                        inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);                // SHEncoder.forward, sphere_harmonics.py:81
+                        const float x = dx * inv, y = dy * inv, z = dz * inv, zz = z * z;
+                        constexpr int DEG = 4;
 #define SH_TERM(i, v, ddx, ddy, ddz) sh[i] = v;
 #include "sh_basis.inc"
 #undef SH_TERM
-                            }
-                            if (LDIR) {
-                                float dx = 0.f, dy = 0.f, dz = 1.f;
-                                if (live) { dx = __ldg(a.ldirs + (size_t)row * 3); dy = __ldg(a.ldirs + (size_t)row * 3 + 1); dz = __ldg(a.ldirs + (size_t)row * 3 + 2); }
-                                const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);    // SHEncoder.forward only (ldirs are not pre-normalised)
-                                const float x = dx * inv, y = dy * inv, z = dz * inv, zz = z * z;
-                                constexpr int DEG = 4;
+                    }
+                    if (LDIR) {
+                        float dx = 0.f, dy = 0.f, dz = 1.f;
+                        if (live) { dx = __ldg(a.ldirs + (size_t)row * 3); dy = __ldg(a.ldirs + (size_t)row * 3 + 1); dz = __ldg(a.ldirs + (size_t)row * 3 + 2); }
+                        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);    // SHEncoder.forward only (ldirs are not pre-normalised)
+                        const float x = dx * inv, y = dy * inv, z = dz * inv, zz = z * z;
+                        constexpr int DEG = 4;
 #define SH_TERM(i, v, ddx, ddy, ddz) sh[16 + i] = v;
 #include "sh_basis.inc"
 #undef SH_TERM
-                            }
-                            // row = out[1..15], sh[0..15], (sh[16..31]), 0  -> 4 (6) chunks of 8 halves
-                            uint4 ch[LDIR ? 6 : 4];
-                            ch[0] = make_uint4(pack2(out[1], out[2]), pack2(out[3], out[4]), pack2(out[5], out[6]), pack2(out[7], out[8]));
-                            ch[1] = make_uint4(pack2(out[9], out[10]), pack2(out[11], out[12]), pack2(out[13], out[14]), pack2(out[15], sh[0]));
-                            ch[2] = make_uint4(pack2(sh[1], sh[2]), pack2(sh[3], sh[4]), pack2(sh[5], sh[6]), pack2(sh[7], sh[8]));
-                            if (LDIR) {
-                                ch[3] = make_uint4(pack2(sh[9], sh[10]), pack2(sh[11], sh[12]), pack2(sh[13], sh[14]), pack2(sh[15], sh[16]));
-                                ch[4] = make_uint4(pack2(sh[17], sh[18]), pack2(sh[19], sh[20]), pack2(sh[21], sh[22]), pack2(sh[23], sh[24]));
-                                ch[5] = make_uint4(pack2(sh[25], sh[26]), pack2(sh[27], sh[28]), pack2(sh[29], sh[30]), pack2(sh[31], 0.f));
-                            } else {
-                                ch[3] = make_uint4(pack2(sh[9], sh[10]), pack2(sh[11], sh[12]), pack2(sh[13], sh[14]), pack2(sh[15], 0.f));
-                            }
-                            uint4* grow = (a.rowmajor && a.in2_out && live) ? reinterpret_cast<uint4*>(a.in2_out + (size_t)row * a.K[3]) : nullptr;
-#pragma unroll
-                            for (uint32_t c = 0; c < (LDIR ? 6u : 4u); c++) {
-                                *reinterpret_cast<uint4*>(h + tsw::chunk_off_r(a.K[3], kTile, tg, c)) = ch[c];
-                                if (grow) grow[c] = ch[c];
-                            }
-                        }
+                    }
+                    // row = out[1..15], sh[0..15], (sh[16..31]), 0  -> 4 (6) chunks of 8 halves
+                    uint4 ch[LDIR ? 6 : 4];
+                    ch[0] = make_uint4(pack2(out[1], out[2]), pack2(out[3], out[4]), pack2(out[5], out[6]), pack2(out[7], out[8]));
+                    ch[1] = make_uint4(pack2(out[9], out[10]), pack2(out[11], out[12]), pack2(out[13], out[14]), pack2(out[15], sh[0]));
+                    ch[2] = make_uint4(pack2(sh[1], sh[2]), pack2(sh[3], sh[4]), pack2(sh[5], sh[6]), pack2(sh[7], sh[8]));
+                    if (LDIR) {
+                        ch[3] = make_uint4(pack2(sh[9], sh[10]), pack2(sh[11], sh[12]), pack2(sh[13], sh[14]), pack2(sh[15], sh[16]));
+                        ch[4] = make_uint4(pack2(sh[17], sh[18]), pack2(sh[19], sh[20]), pack2(sh[21], sh[22]), pack2(sh[23], sh[24]));
+                        ch[5] = make_uint4(pack2(sh[25], sh[26]), pack2(sh[27], sh[28]), pack2(sh[29], sh[30]), pack2(sh[31], 0.f));
                     } else {
-                        // colour head (network.py:131-138): fp16 linear output, `color - 5` in fp16, exp in fp32
-                        float out[16];
-                        tc::tmem_ld16(lane_addr, out);
-                        if (live) {
+                        ch[3] = make_uint4(pack2(sh[9], sh[10]), pack2(sh[11], sh[12]), pack2(sh[13], sh[14]), pack2(sh[15], 0.f));
+                    }
 #pragma unroll
-                            for (int c = 0; c < 3; c++) {
-                                const float o = half_round(out[c]);
-                                float rc;
-                                if (a.color_act == 2) rc = half_round(1.0f / (1.0f + expf(-o)));
-                                else {
-                                    rc = expf(half_round(o - 5.0f));
-                                    if (a.color_act == 3) rc = fminf(rc, 5.0f);
-                                }
-                                a.rgb_out[(size_t)row * 3 + c] = rc;
+                    for (uint32_t c = 0; c < (LDIR ? 6u : 4u); c++) *reinterpret_cast<uint4*>(h + tsw::chunk_off_r(a.K[3], kTile, tg, c)) = ch[c];
+                } else {
+                    // colour head (network.py:131-138): fp16 linear output, `color - 5` in fp16, exp in fp32
+                    tc::tmem_ld16(lane_addr, out);
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float o = half_round(out[c]);
+                            float rc;
+                            if (a.color_act == 2) rc = half_round(1.0f / (1.0f + expf(-o)));
+                            else {
+                                rc = expf(half_round(o - 5.0f));
+                                if (a.color_act == 3) rc = fminf(rc, 5.0f);
                             }
+                            a.rgb_out[(size_t)row * 3 + c] = rc;
                         }
                     }
-                    // hand the slot to the issuer: the activation tile is written (visible to the tensor core's proxy) and the
-                    // accumulator columns have been read
-                    tc::fence_async_smem();
-                    tc::fence_before_sync();
-                    tc::mbar_arrive(ready_s + 8 * st);
-                    if (l + 1 == a.n_run) next_tile(slot);
                 }
+                if (l != 5) tc::fence_async_smem();
+                tc::fence_before_sync();
+                tc::named_bar_sync(1 + gI, kTile);
             }
         }
-    } else if ((threadIdx.x & 31u) == 0) {
-        // ================================ MMA issuers (one thread per group) ================================
-        const uint32_t gI = warp - (kGatherThreads + kMlpGroups * kTile) / 32;
-        uint32_t tile_of[kSlots] = {0u, 0u}, rph[kSlots] = {0u, 0u};
-        bool active[kSlots];
-        uint32_t n_next = 0;
-        auto issue = [&](const IssuePlan& pl, uint32_t d_col) {
-            uint64_t ad = pl.a0, bd = pl.b0;
-            const uint32_t n = pl.n_steps, as = pl.a_step, bs = pl.b_step, idesc = pl.idesc;
-            for (uint32_t ks = 0; ks < n; ks++, ad += as, bd += bs) tc::mma_f16_ss(tmem + d_col, ad, bd, idesc, ks > 0);
-        };
-        // Take the group's next tile into `slot`: wait for the gather warps, issue layer 0 on the ring stage and the bulk copy
-        // of the stage (the encoder output, saved for the backward pass).  The commits are issued after the copy has finished
-        // reading shared memory, so "layer retired" also means "operand tile may be overwritten".
-        auto start_tile = [&](uint32_t slot) {
-            const uint32_t it = gI + n_next * kMlpGroups;
-            const uint32_t tile = blockIdx.x + it * gridDim.x;
-            active[slot] = tile < n_tiles;
-            if (!active[slot]) return;
-            n_next++;
-            tile_of[slot] = tile;
-            const uint32_t st = it % kStages;                             // == slot * kMlpGroups + gI
-            tc::mbar_wait(full_s + 8 * st, (it / kStages) & 1u);
-            tc::fence_after_sync();
-            issue(plans[st * kWsLayers], st * kSlotTmemCols);
-            if (a.enc_out && !a.rowmajor && !(NGP_WS_ISOLATE & 4)) {
-                const uint32_t bytes = kTile * a.K[0] * 2;
-                tc::bulk_s2g(reinterpret_cast<uint8_t*>(a.enc_out) + (size_t)tile * bytes, tc::smem_u32(smem + a.a0_off + st * a.a0_stage_bytes), bytes);
-                tc::bulk_wait_read();
-            }
-            tc::mma_commit(done_s + 8 * st);
-            // the ring stage goes back to the gather warps once layer 0 (and the copy) has read it; with plain-row saves the
-            // epilogue threads still copy their rows out of it (released below, after their layer-0 epilogue)
-            if (!a.rowmajor) tc::mma_commit(empty_s + 8 * st);
-        };
-        start_tile(0);
-        start_tile(1);
-        while (active[0] || active[1]) {
-            for (uint32_t l = 0; l < a.n_run; l++) {
-#pragma unroll
-                for (uint32_t slot = 0; slot < kSlots; slot++) {
-                    if (!active[slot]) continue;
-                    const uint32_t st = slot * kMlpGroups + gI;
-                    tc::mbar_wait(ready_s + 8 * st, rph[slot]);           // the epilogue of layer l of this slot is finished
-                    rph[slot] ^= 1u;
-                    if (a.rowmajor && l == 0) tc::mbar_arrive(empty_s + 8 * st);
-                    if (l + 1 < a.n_run) {
-                        tc::fence_after_sync();
-                        issue(plans[st * kWsLayers + l + 1], st * kSlotTmemCols);
-                        // the A operand of layer l + 1 (the tile just written) is what the backward pass needs (h1, h2 | in2, h1',
-                        // h2'): its image goes to global memory as ONE bulk async copy while the MMA runs
-                        __half* save = (l + 1 == 3) ? a.in2_out : a.acts[l];
-                        if (save && !a.rowmajor && !(NGP_WS_ISOLATE & 4)) {
-                            const uint32_t bytes = kTile * a.K[l + 1] * 2;
-                            tc::bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile_of[slot] * bytes, tc::smem_u32(smem + a.h_off + st * a.h_bytes), bytes);
-                            tc::bulk_wait_read();
-                        }
-                        tc::mma_commit(done_s + 8 * st);
-                    } else {
-                        start_tile(slot);
-                    }
-                }
-            }
-        }
-        tc::bulk_wait_all();
+        if (tg == 0) tc::bulk_wait_all();
     }
-    __syncwarp();                 // the issuer lanes rejoin their warps before the block-wide barrier
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, kWsTmemCols);
@@ -501,8 +389,7 @@ extern "C" int ngp_field_forward_full(const float* xyzs, const float* dirs, cons
     off = (off + 1023) & ~1023u;      // swizzle atoms are 1024-byte aligned
     a.a0_off = off; a.a0_stage_bytes = kTile * 2 * L * 2;
     off += kStages * a.a0_stage_bytes;
-    a.h_off = off; a.h_bytes = kTile * hmax * 2;      // one activation tile per tile in flight
-    off += kStages * a.h_bytes;
+    for (uint32_t gI = 0; gI < kMlpGroups; gI++) { a.h_off[gI] = off; off += kTile * hmax * 2; }
     a.ctrl_off = off;
     const uint32_t smem_bytes = off + kWsCtrlBytes;
     if (smem_bytes > 227 * 1024) return NGP_ERR_UNSUPPORTED;
