@@ -24,5 +24,6 @@ for rep in range(7):
     e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) / 50)
 print(json.dumps({"lib": os.path.basename(os.environ.get("NGP_B200_LIB", "default")), "fwd_us": round(1e3 * k["ngp_field_forward_full"], 1),
-                  "bwd_us": round(1e3 * k["ngp_field_backward_full"], 1), "step_us": round(1e3 * statistics.median(ts), 1),
+                  "bwd_us": round(1e3 * k["ngp_field_backward_full"], 1), "adam_us": round(1e3 * k["ngp_fused_adam"], 1), "check_us": round(1e3 * k["ngp_check_finite_multi"], 1),
+                  "march_us": round(1e3 * (k["ngp_march_rays_train_count_ex"] + k["ngp_march_rays_train_write"]), 1), "step_us": round(1e3 * statistics.median(ts), 1),
                   "M": fs.last_num_points}))
