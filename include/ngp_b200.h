@@ -213,6 +213,12 @@ int ngp_march_rays_train_count_ex(const float* rays_o, const float* rays_d, cons
                                   const float* noises, uint32_t cap, float* nears_out, float* fars_out, int32_t* rays,
                                   int32_t* counter, float* t_scratch, ngp_stream_t stream);
 
+/* n uniform [0, 1) floats from a counter-based generator (seed, *counter_dev, element index); *counter_dev advances by one per
+ * call, on the device, so the call can sit inside a replayed CUDA graph and still produce a new stream every replay.  Stands in
+ * for the `torch.rand(N)` of the marcher's per-ray jitter (raymarching/raymarching.py:295) and of the random background
+ * (nerf/train_utils.py:496) inside the fused step; the operators themselves still take the noises as an input tensor. */
+int ngp_uniform(float* out, uint32_t n, uint64_t seed, int32_t* counter_dev, ngp_stream_t stream);
+
 /* Adaptive ray count on the device (nerf/train_utils.py:563-564, main.py:59-61): after a step that produced *m_dev samples from
  * *n_rays_dev rays, *n_rays_dev = clamp(round(target_points / m * n), 1, n_max) -- the reference computes the same on the
  * host after reading the sample count back. */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ngp_composite_train_loss": [_p, _p, _p, _p, _u32, _p, _u32, _f32, _f32, _p, _f32, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     "ngp_march_rays_train_count_ex": [_p, _p, _p, _f32, _p, _p, _p, _f32, _i, _f32, _u32, _u32, _u32, _u32, _p, _u32, _p, _p, _p, _p, _p, _p],
     "ngp_adaptive_num_rays": [_p, _p, _u32, _u32, _p],
+    "ngp_uniform": [_p, _u32, c_uint64, _p, _p],
     "ngp_composite_rays_train_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p, _p],
     "ngp_composite_rays_train_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p],
     "ngp_march_rays_train_backward": [_p, _p, _p, _p, _u32, _u32, _p, _p, _p],

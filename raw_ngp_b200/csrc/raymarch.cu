@@ -1538,7 +1538,40 @@ __global__ void adaptive_num_rays_kernel(int* __restrict__ n_rays, const int* __
     *n_rays = (int)max(1ll, min((long long)n_max, r));
 }
 }  // namespace
+// Uniform [0, 1) floats from a counter-based generator (splitmix64 of seed, call counter, element index; 24 random bits each).
+// The per-ray jitter of the marcher and the random background colours are drawn inside the captured step: torch's own
+// generator costs two eager int64 fills in front of every graph replay (seed / offset of its Philox state).
+__global__ void __launch_bounds__(1024)
+uniform_kernel(float* __restrict__ out, uint32_t n, uint64_t seed, int* __restrict__ counter, bool advance) {
+    __shared__ uint32_t s_c;
+    if (threadIdx.x == 0) s_c = (uint32_t)*counter;
+    __syncthreads();
+    const uint64_t base = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)s_c + 1ull);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint64_t z = base + 0xD1B54A32D192ED03ull * ((uint64_t)i + 1ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        out[i] = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+    }
+    if (advance && threadIdx.x == 0) *counter = (int)(s_c + 1u);      // single-block launches only (every thread has read s_c)
+}
+__global__ void counter_advance_kernel(int* __restrict__ counter) { *counter += 1; }
+
 }  // namespace ngp
+
+extern "C" int ngp_uniform(float* out, uint32_t n, uint64_t seed, int32_t* counter_dev, ngp_stream_t stream) {
+    if (n == 0) return NGP_OK;
+    if (!out || !counter_dev) return NGP_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= (1u << 16)) {
+        ngp::uniform_kernel<<<1, 1024, 0, st>>>(out, n, seed, counter_dev, true);
+    } else {
+        ngp::uniform_kernel<<<std::min<uint32_t>(ngp::div_up(n, 1024u), 4u * ngp::kNumSMs), 1024, 0, st>>>(out, n, seed, counter_dev, false);
+        ngp::counter_advance_kernel<<<1, 1, 0, st>>>(counter_dev);
+    }
+    return ngp::finish_launch();
+}
 
 extern "C" int ngp_adaptive_num_rays(int32_t* n_rays_dev, const int32_t* m_dev, uint32_t target_points, uint32_t n_max,
                                      ngp_stream_t stream) {

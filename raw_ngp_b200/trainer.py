@@ -358,6 +358,8 @@ class FusedTrainStep:
         self.rays_o, self.rays_d, self.target = torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32)
         self.rays_ldir = torch.zeros(N, 3, **f32) if self.rfield else None
         self.noises = torch.zeros(N, **f32)
+        self._rng_seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF      # follows torch.manual_seed
+        self._rng_counter = torch.zeros(1, device=dev, dtype=torch.int32)
         self.exposure = torch.ones(N, **f32)          # per-ray exposure of the HDR loss (train_utils.py:514)
         self.bg_rays = torch.zeros(N, 3, **f32) if self.random_bg else None
         self.target_alpha = torch.ones(N, **f32) if rgba_targets else None
@@ -445,10 +447,12 @@ class FusedTrainStep:
         if self.pose is not None:      # provide_refined_poses + get_rays (barf/camera_optimizers.py:92-107, train_utils.py:150-165)
             _lib.call("ngp_pose_rays_forward", P(self.se3), P(self.poses), self.pose_stride, P(self.cam_idx), P(self.dirs_cam), N,
                       self.se3.shape[0], P(self.rays_o), P(self.rays_d), st)
+        # per-ray jitter (raymarching.py:295) and random background (train_utils.py:496) from the library's counter-based generator:
+        # torch's own costs two eager int64 fills (Philox seed / offset) in front of every graph replay
         if self.perturb:
-            self.noises.uniform_()
+            _lib.call("ngp_uniform", P(self.noises), N, self._rng_seed, P(self._rng_counter), st)
         if self.random_bg:
-            self.bg_rays.uniform_()          # torch.rand(N, 3) of train_utils.py:496
+            _lib.call("ngp_uniform", P(self.bg_rays), 3 * N, self._rng_seed ^ 0x5DEECE66D, P(self._rng_counter), st)
         aabb = m.aabb_train
         _lib.call("ngp_march_rays_train_count_ex", P(self.rays_o), P(self.rays_d), P(aabb), float(m.min_near), P(self.cam_near_far),
                   P(self.n_rays_dev), P(m.density_bitfield), float(m.real_bound), int(bool(opt.contract)), float(opt.dt_gamma),
@@ -586,13 +590,13 @@ class FusedTrainStep:
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_fb):
             self._launch_forward_backward()
-        self.graph_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)      # + noises.uniform_
+        self.graph_kernels = _lib.launch_count - c0
         n_adam = self.opt.step_count
         n_pose = self.pose_opt.step_count if self.pose is not None else 0
         c0 = _lib.launch_count
         with torch.cuda.graph(self._graph_pipe):
             self._launch_pipelined()
-        self.pipe_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)        # + noises.uniform_
+        self.pipe_kernels = _lib.launch_count - c0
         self.opt.step_count = n_adam        # capturing is not stepping
         if self.pose is not None:
             self.pose_opt.step_count = n_pose
@@ -603,7 +607,7 @@ class FusedTrainStep:
             c0 = _lib.launch_count
             with torch.cuda.graph(self._graph_march):
                 self._launch_march()
-            self.march_kernels = _lib.launch_count - c0 + (1 if self.perturb else 0)
+            self.march_kernels = _lib.launch_count - c0
             c0 = _lib.launch_count
             with torch.cuda.graph(self._graph_field):
                 self._launch_field()
@@ -639,7 +643,7 @@ class FusedTrainStep:
                             self._peer_update(pose_event=ev)
                         self._launch_march()
                         main.wait_stream(self._side)
-                    self.um_kernels = _lib.launch_count - c0 + 2 + (1 if self.pose is not None else 0) + (1 if self.perturb else 0)
+                    self.um_kernels = _lib.launch_count - c0 + 2 + (1 if self.pose is not None else 0)
                     self.update_kernels = self.um_kernels - self.march_kernels
                     self._graph_um = g
                 except Exception as e:       # barrier not capturable in this torch build: eager launches, same result
@@ -761,7 +765,8 @@ class FusedTrainStep:
         sd = {"table_master": self._full(tm).detach().clone(), "table_exp_avg": self._full(tmm).detach().clone(),
               "table_exp_avg_sq": self._full(tv).detach().clone(), "w_master": self.w_master.clone(), "w_exp_avg": wm.clone(),
               "w_exp_avg_sq": wv.clone(), "opt_step": self.opt_step_dev.clone(), "loss_scale": self.scale_dev.clone(),
-              "scaler_state": self.scaler_state.clone(), "lr": self.lr_dev.clone(), "global_step": self.global_step}
+              "scaler_state": self.scaler_state.clone(), "lr": self.lr_dev.clone(), "global_step": self.global_step,
+              "rng": (self._rng_seed, self._rng_counter.clone())}
         if self.pose is not None:
             g = self.pose_opt.groups[0]
             sd.update({"se3": self.se3.clone(), "se3_exp_avg": g["m"].clone(), "se3_exp_avg_sq": g["v"].clone(),
@@ -793,6 +798,10 @@ class FusedTrainStep:
         self.inv_scale.copy_(1.0 / (self.scale_dev * self.world))
         self.lr_dev.copy_(sd["lr"])
         self.global_step = int(sd["global_step"])
+        if "rng" in sd:      # the jitter / background stream continues where the checkpoint left it
+            self._rng_seed = int(sd["rng"][0])
+            self._rng_counter.copy_(sd["rng"][1])
+            self._graph = None      # the seed is a launch argument of the captured kernels
         if self.pose is not None and "se3" in sd:
             g = self.pose_opt.groups[0]
             self.se3.copy_(sd["se3"])

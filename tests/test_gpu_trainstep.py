@@ -486,3 +486,35 @@ def test_fused_step_checkpoint_round_trip_and_reference_pth(tmp_path):
         img_ref = ref.render(oo.cuda(), dd.cuda(), bg_color=1, perturb=False)["image"]
         img = model_c.render(oo.cuda(), dd.cuda(), bg_color=1, perturb=False)["image"]
     torch.testing.assert_close(img.float(), img_ref.float(), rtol=2e-3, atol=2e-3)
+
+
+def test_library_uniform_generator():
+    """ngp_uniform (the fused step's jitter / background stream, drawn inside the captured graph): values in [0, 1), the moments of a
+    uniform distribution, a new stream per call (device-side counter), the same stream for the same (seed, counter), and the two launch
+    shapes (one block with the counter advance inside; many blocks + a separate advance) agreeing on the common prefix."""
+    from raw_ngp_b200 import _lib
+    dev = "cuda"
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    a, b = torch.empty(65536, device=dev), torch.empty(65536, device=dev)
+    _lib.call("ngp_uniform", _lib.ptr(a), a.numel(), 1234, _lib.ptr(counter), _lib.stream())
+    _lib.call("ngp_uniform", _lib.ptr(b), b.numel(), 1234, _lib.ptr(counter), _lib.stream())
+    assert counter.item() == 2
+    for t in (a, b):
+        assert t.min().item() >= 0.0 and t.max().item() < 1.0
+        assert abs(t.mean().item() - 0.5) < 5e-3 and abs(t.var().item() - 1 / 12) < 2e-3
+    assert (a == b).float().mean().item() < 1e-3                      # a different stream every call
+    corr = ((a - 0.5) * (b - 0.5)).mean().item() * 12
+    lag = ((a[1:] - 0.5) * (a[:-1] - 0.5)).mean().item() * 12
+    assert abs(corr) < 2e-2 and abs(lag) < 2e-2
+    counter.zero_()
+    c = torch.empty(65536, device=dev)
+    _lib.call("ngp_uniform", _lib.ptr(c), c.numel(), 1234, _lib.ptr(counter), _lib.stream())
+    assert torch.equal(a, c)                                          # same (seed, counter) -> same stream
+    counter.zero_()
+    big = torch.empty(3 * 65536 + 5, device=dev)                      # multi-block launch shape
+    _lib.call("ngp_uniform", _lib.ptr(big), big.numel(), 1234, _lib.ptr(counter), _lib.stream())
+    assert counter.item() == 1 and torch.equal(big[:65536], a) and big.max().item() < 1.0
+    d = torch.empty(65536, device=dev)
+    counter.zero_()
+    _lib.call("ngp_uniform", _lib.ptr(d), d.numel(), 99, _lib.ptr(counter), _lib.stream())
+    assert (a == d).float().mean().item() < 1e-3                      # another seed, another stream
