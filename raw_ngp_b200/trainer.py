@@ -563,13 +563,20 @@ class FusedTrainStep:
         Adam streams 366 MB through HBM: on two streams they overlap almost completely."""
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            self._launch_optimizer()
+        ev = None
         if self.pose is not None:
             self._launch_pose_update()
+            ev = torch.cuda.Event()
+            ev.record(main)
+        with torch.cuda.stream(self._side):
+            self._launch_optimizer()
+            # GradScaler.update() behind every consumer of inv_scale (both optimizers), off the main stream: the marcher is
+            # the longer branch, so this launch costs nothing there
+            if ev is not None:
+                self._side.wait_event(ev)
+            self._launch_scaler_update()
         self._launch_march()
         main.wait_stream(self._side)
-        self._launch_scaler_update()
         self._launch_field()
 
     def _capture(self):
@@ -641,6 +648,7 @@ class FusedTrainStep:
                             ev.record(main)
                         with torch.cuda.stream(self._side):
                             self._peer_update(pose_event=ev)
+                            self._launch_scaler_update()
                         self._launch_march()
                         main.wait_stream(self._side)
                     self.um_kernels = _lib.launch_count - c0 + 2 + (1 if self.pose is not None else 0)
@@ -973,13 +981,15 @@ class FusedTrainStep:
             if self.world > 1:
                 # [all-reduce + optimizer update of the previous step, side stream]  ||  [march graph]  ->  field graph
                 main = torch.cuda.current_stream()
+                scaler_done = False
                 if self._pending and getattr(self, "_graph_um", None) is not None:
                     _lib.weights_epoch += 1
                     self.opt.step_count += 1
                     if self.pose is not None:
                         self.pose_opt.step_count += 1
-                    self._graph_um.replay()                    # update chain || [pose update] march, joined
+                    self._graph_um.replay()                    # update chain + GradScaler update || [pose update] march, joined
                     self.kernels_replayed += self.um_kernels
+                    scaler_done = True
                 else:
                     if self._pending:
                         peer_pose = self.peer is not None and self.pose is not None
@@ -995,7 +1005,7 @@ class FusedTrainStep:
                     self._graph_march.replay()
                     self.kernels_replayed += self.march_kernels
                 main.wait_stream(self._side)
-                if self._pending:
+                if self._pending and not scaler_done:
                     self._launch_scaler_update()
                 self._graph_field.replay()
                 self.kernels_replayed += self.field_kernels
