@@ -384,14 +384,15 @@ __global__ void grad_scaler_update_kernel(float* __restrict__ scale, float* __re
 using namespace ngp;
 
 // Resident blocks per SM of the streaming optimizer kernels (grid-stride, 256 threads).  They run on the side stream beside the
-// ray marcher of the next step; measured at configs[1] (NGP_ADAM_BLOCKS_PER_SM, step time): 8 -> 0.736 ms, 4 -> 0.740 ms,
-// 2 -> 0.763 ms: the two do not compete for thread slots, the marcher is slowed by memory latency under the optimizer's HBM
-// stream (80 us alone, 120-140 us beside it), so the optimizer keeps the full 8.
+// ray marcher of the next step.  Measured at configs[1] (NGP_ADAM_BLOCKS_PER_SM, step time between occupancy updates, round 2 with
+// the 512-point marcher window): 8 -> 679.9 us, 6 -> 678.4, 5 -> 677.1, 4 -> 678.3, 3 -> 683.9.  With 8 x 256 threads the inf / nan
+// check that opens the chain fills every thread slot of the SM and the marcher's first blocks wait ~9 us for it to drain; five
+// blocks leave room for them and are still enough to stream at full HBM rate (Adam alone: 76 us with 5, 80 with 8).
 static uint32_t adam_blocks_per_sm() {
     static const uint32_t v = [] {
         const char* e = getenv("NGP_ADAM_BLOCKS_PER_SM");
-        const int x = e ? atoi(e) : 8;
-        return (uint32_t)(x >= 1 && x <= 8 ? x : 8);
+        const int x = e ? atoi(e) : 5;
+        return (uint32_t)(x >= 1 && x <= 8 ? x : 5);
     }();
     return v;
 }
