@@ -796,18 +796,33 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
         const uint32_t offset = (uint32_t)__ldg(rays + (size_t)n * 2), count = (uint32_t)__ldg(rays + (size_t)n * 2 + 1);
         const bool has = count != 0 && offset + count <= M;
         float r = 0, g = 0, b = 0, ws = 0, d = 0;
+        // The kernel lasts as long as its longest ray (a warp walks its ray in chunks of 32 samples, one scan after the other), so
+        // the loads of chunk c + 1 are issued before chunk c is scanned: the L2 round trip leaves the serial chain.
+        struct Chunk { float2 tt; float sg, cr, cg, cb; };
+        auto fetch = [&](uint32_t base) {
+            Chunk c = {make_float2(0.f, 0.f), 0.f, 0.f, 0.f, 0.f};
+            const uint32_t k = base + lane;
+            if (k < count) {
+                const size_t i = (size_t)offset + k;
+                c.tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
+                c.sg = __ldg(sigmas + i);
+                c.cr = __ldg(rgbs + i * 3); c.cg = __ldg(rgbs + i * 3 + 1); c.cb = __ldg(rgbs + i * 3 + 2);
+            }
+            return c;
+        };
         if (has) {
             float T = 1.0f;
+            Chunk nxt = fetch(0);
             for (uint32_t base = 0; base < count; base += 32) {
                 const uint32_t k = base + lane;
                 const bool valid = k < count;
-                const size_t i = (size_t)offset + k;
+                const Chunk cur = nxt;
+                if (base + 32 < count) nxt = fetch(base + 32);
                 float alpha = 0.f, tk = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
                 if (valid) {
-                    const float2 tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
-                    tk = tt.x;
-                    alpha = 1.0f - __expf(-__ldg(sigmas + i) * tt.y);
-                    cr = __ldg(rgbs + i * 3); cg = __ldg(rgbs + i * 3 + 1); cb = __ldg(rgbs + i * 3 + 2);
+                    tk = cur.tt.x;
+                    alpha = 1.0f - __expf(-cur.sg * cur.tt.y);
+                    cr = cur.cr; cg = cur.cg; cb = cur.cb;
                 }
                 const float incl = warp_incl_prod(1.0f - alpha, lane);
                 float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -876,16 +891,18 @@ composite_train_mse_kernel(const float* __restrict__ sigmas, const float* __rest
             const float g_ws = -(bgr * gi_r + bgg * gi_g + bgb * gi_b) + loss_scale * g_ent;
             float T = 1.0f, r0 = 0, g0 = 0, b0 = 0, ws0 = 0;
             uint32_t base = 0;
+            Chunk nxt = fetch(0);
             for (; base < count; base += 32) {
                 const uint32_t k = base + lane;
                 const bool valid = k < count;
                 const size_t i = (size_t)offset + k;
+                const Chunk cur = nxt;
+                if (base + 32 < count) nxt = fetch(base + 32);
                 float alpha = 0.f, dtk = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
                 if (valid) {
-                    const float2 tt = __ldg(reinterpret_cast<const float2*>(ts) + i);
-                    dtk = tt.y;
-                    alpha = 1.0f - __expf(-__ldg(sigmas + i) * dtk);
-                    cr = __ldg(rgbs + i * 3); cg = __ldg(rgbs + i * 3 + 1); cb = __ldg(rgbs + i * 3 + 2);
+                    dtk = cur.tt.y;
+                    alpha = 1.0f - __expf(-cur.sg * dtk);
+                    cr = cur.cr; cg = cur.cg; cb = cur.cb;
                 }
                 const float incl = warp_incl_prod(1.0f - alpha, lane);
                 float excl = __shfl_up_sync(0xffffffffu, incl, 1);
