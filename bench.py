@@ -436,7 +436,19 @@ def run_reference(args):
     rays = CPU_SAMPLE_RAYS
     step = _cpu_step_setup(rays)
     M = 0
-    for _ in range(W):
+    # The whole run has to end within a few minutes on whatever host cores the box has (a step is ~0.2 s on 16 cores, most of it
+    # Adam over the 12.2 M-entry table, which no smaller ray sample would shrink): if the first step says that W + K steps do not
+    # fit NGP_REF_BUDGET_S (default 240 s), fewer steps are run and the line says so (`steps_requested`).
+    budget = float(os.environ.get("NGP_REF_BUDGET_S", "240"))
+    step()                                   # (lazy initialisation: not representative)
+    t0 = time.perf_counter()
+    step()
+    t_first = time.perf_counter() - t0
+    requested = K
+    if (W + K) * t_first > budget:
+        W = min(W, 2)
+        K = max(3, min(K, int(budget / t_first) - W))
+    for _ in range(max(W - 2, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(K):
@@ -452,6 +464,8 @@ def run_reference(args):
                          "sample": f"{rays} rays ({M} samples) per step; the reference has no CPU implementation, this is oracle/cpu_pipeline.py (PyTorch on the host cores)"},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if requested != K:
+        line["steps_requested"] = requested
     print(json.dumps(line), flush=True)
 
 
