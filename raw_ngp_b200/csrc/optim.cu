@@ -24,6 +24,25 @@ template <typename T> __device__ __forceinline__ void store4(T* p, const Vec4<T>
     else *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(r.v);
 }
 
+// The Adam step of one element: p -= step_size * m / (sqrt(v) / bias2_sqrt + eps).  The big streaming kernels run beside the
+// ray marcher, and both are ISSUE bound (56 % / 62 % of the issue slots each when alone): an IEEE square root and two IEEE
+// divisions are ~30 of this kernel's ~45 instructions per element.  NGP_ADAM_FAST_MATH (default) takes sqrt.approx, a
+// multiplication by the reciprocal of bias2_sqrt and div.approx instead: relative error <= 2^-21 of the update, far below the
+// fp16 resolution of the table it feeds (the fp32 master accumulates it like any rounding of the update).
+#ifndef NGP_ADAM_FAST_MATH
+#define NGP_ADAM_FAST_MATH 1
+#endif
+__device__ __forceinline__ float adam_delta(float m, float v, float step_size, float bias2_sqrt, float inv_bias2_sqrt, float eps) {
+#if NGP_ADAM_FAST_MATH
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
+    return step_size * __fdividef(m, s * inv_bias2_sqrt + eps);
+#else
+    (void)inv_bias2_sqrt;
+    return step_size * (m / (sqrtf(v) / bias2_sqrt + eps));
+#endif
+}
+
 template <typename G, typename P, bool HasLP>
 __global__ void __launch_bounds__(256)
 fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __restrict__ grad, float* __restrict__ m,
@@ -39,7 +58,7 @@ fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __res
         bias1 = 1.f - powf(beta1, t);
         bias2_sqrt = sqrtf(1.f - powf(beta2, t));
     }
-    const float step_size = lr / bias1;
+    const float step_size = lr / bias1, inv_bias2_sqrt = 1.f / bias2_sqrt;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n4 = n / 4;      // the buffers are 16-byte aligned (checked by the host wrapper)
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
@@ -54,8 +73,7 @@ fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __res
                 if (weight_decay != 0.f) g += weight_decay * p4.v[k];
                 m4.v[k] = beta1 * m4.v[k] + (1.f - beta1) * g;
                 v4.v[k] = beta2 * v4.v[k] + (1.f - beta2) * g * g;
-                const float denom = sqrtf(v4.v[k]) / bias2_sqrt + eps;
-                p4.v[k] -= step_size * (m4.v[k] / denom);
+                p4.v[k] -= adam_delta(m4.v[k], v4.v[k], step_size, bias2_sqrt, inv_bias2_sqrt, eps);
                 if (HasLP) lp4.v[k] = from_f32<P>(p4.v[k]);
             }
             store4(m + i, m4); store4(v + i, v4); store4(master + i, p4);
@@ -78,8 +96,7 @@ fused_adam_kernel(float* __restrict__ master, P* __restrict__ param_lp, G* __res
             const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
             m[i] = mi;
             v[i] = vi;
-            const float denom = sqrtf(vi) / bias2_sqrt + eps;
-            p -= step_size * (mi / denom);
+            p -= adam_delta(mi, vi, step_size, bias2_sqrt, inv_bias2_sqrt, eps);
             master[i] = p;
             if (HasLP) param_lp[i] = from_f32<P>(p);
         }
@@ -169,7 +186,7 @@ dp_fused_adam_kernel(const PeerPtrs peers, uint32_t world, uint32_t n_store, flo
                 if (weight_decay != 0.f) gg += weight_decay * p4.v[k];
                 m4.v[k] = beta1 * m4.v[k] + (1.f - beta1) * gg;
                 v4.v[k] = beta2 * v4.v[k] + (1.f - beta2) * gg * gg;
-                p4.v[k] -= step_size * (m4.v[k] / (sqrtf(v4.v[k]) / bias2_sqrt + eps));
+                p4.v[k] -= adam_delta(m4.v[k], v4.v[k], step_size, bias2_sqrt, 1.f / bias2_sqrt, eps);
                 out[k0 + k] = from_f32<P>(p4.v[k]);
             }
             store4(m + s + k0, m4); store4(v + s + k0, v4); store4(master + s + k0, p4);
