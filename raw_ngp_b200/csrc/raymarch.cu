@@ -364,6 +364,9 @@ march_train_write_kernel(const float* __restrict__ rays_o, const float* __restri
 #define NGP_MARCH_WINDOW 512
 #endif
 constexpr uint32_t kWin = NGP_MARCH_WINDOW;
+#ifndef NGP_MARCH_JUMP_ROUNDS
+#define NGP_MARCH_JUMP_ROUNDS 2
+#endif
 constexpr uint32_t kCoopWarps = 4;
 
 // tt of an empty probe (raymarching.cu:470-474)
@@ -519,6 +522,23 @@ march_train_count_coop_kernel(const float* __restrict__ rays_o, const float* __r
                 nx[i] = (uint16_t)code;
             }
             __syncwarp();
+            // (2b) pointer jumping: in free space the chase below follows ~80 skips per window, every hop a dependent shared-
+            // memory read executed by all 32 lanes -- a third of the kernel's instructions.  Two rounds of "skip over the next
+            // empty entry" (in parallel over the window) shorten those chains fourfold.  An entry is only skipped if it is empty
+            // AND its own target stays inside the window: a keep entry must be visited, and the last hop of a chain that leaves
+            // the window has to be seen by the chase (exit_skip).  Lanes may read an entry another lane is updating: either value
+            // is a valid target further down the same chain.
+#pragma unroll 1
+            for (uint32_t round = 0; round < NGP_MARCH_JUMP_ROUNDS; round++) {
+                for (uint32_t i = lane; i < cnt; i += 32) {
+                    const uint32_t c = nx[i];
+                    if (!(c & 0x8000u) && c < cnt) {
+                        const uint32_t c2 = nx[c];
+                        if (!(c2 & 0x8000u) && c2 < cnt) nx[i] = (uint16_t)c2;
+                    }
+                }
+                __syncwarp();
+            }
             // (3) pointer chase (uniform over the warp).  A run of consecutive kept lattice points is consumed in one
             // step: its length comes from a ballot over the 32 entries around i and its t's are stored by parallel lanes.
             uint32_t i = 0;
