@@ -7,7 +7,7 @@ set -e
 cd "$(dirname "$0")/.."
 tag=$1; shift
 files=${FILES:-"field field_ws field_bwd_ws"}
-out=raw_ngp_b200/lib/variants; tmp=/tmp/ngp_ab_$tag
+out=raw_ngp_b200/lib/variants; tmp=raw_ngp_b200/_build/ab_$tag
 mkdir -p $out $tmp
 python -m raw_ngp_b200.build >/dev/null
 objs=""
